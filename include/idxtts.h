@@ -1,0 +1,190 @@
+/*
+ * idxtts.h — C-ABI of libidxtts.so, the B200 (sm_100a) compute library behind the
+ * IndexTTS / IndexTTS2 `.infer()` entry points.
+ *
+ * Every entry point replaces one "module-level seam" of the reference pipeline
+ * (SURVEY.md §8b).  The reference file:line each one stands in for is cited on the
+ * declaration.  Rules that hold for every call:
+ *
+ *   - plain C types only: opaque handle, raw pointers, sizes; no torch/C++ types.
+ *   - data pointers may be HOST or DEVICE pointers; the library inspects them with
+ *     cudaPointerGetAttributes and stages host buffers through pinned memory on its
+ *     own stream (the copies are therefore inside any timing of the call).
+ *   - the caller owns every input and output buffer; the engine owns only its packed
+ *     weights, KV cache and work arenas.
+ *   - return value: 0 on success, non-zero error code otherwise; the message is
+ *     available from idx_last_error().  The Python shim turns it into RuntimeError,
+ *     like the reference's AT_ERROR in anti_alias_activation_cuda.cu:214-225.
+ *   - one handle = one CUDA device = one caller thread at a time (the reference is
+ *     not re-entrant either: infer_v2_5.py:268-275, gpt/model_v2.py:88).
+ *   - calls are synchronous with respect to the host unless stated otherwise.
+ */
+#ifndef IDXTTS_H
+#define IDXTTS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct idx_engine idx_engine;
+
+typedef enum {
+  IDX_F32 = 0,
+  IDX_BF16 = 1,
+  IDX_F16 = 2,
+  IDX_I32 = 3,
+  IDX_I64 = 4
+} idx_dtype;
+
+enum {
+  IDX_OK = 0,
+  IDX_ERR_CUDA = 1,     /* a CUDA runtime call or kernel failed                    */
+  IDX_ERR_ARG = 2,      /* bad argument / shape / missing weight                    */
+  IDX_ERR_STATE = 3,    /* call order violated (e.g. generate before finalize)      */
+  IDX_ERR_NOGPU = 4     /* no sm_100 device: there is NO CPU fallback, by design    */
+};
+
+/* ------------------------------------------------------------------ lifecycle -- */
+
+/* Create an engine bound to CUDA device `device`.  Fails with IDX_ERR_NOGPU when no
+ * CUDA device is visible — the product path never falls back to the CPU.           */
+int idx_create(int device, idx_engine** out);
+void idx_destroy(idx_engine* e);
+/* Last error message of this engine (or of the failed idx_create when e == NULL).   */
+const char* idx_last_error(const idx_engine* e);
+/* Library/ABI version and build flags ("sm_100a;...").                              */
+const char* idx_version(void);
+/* Number of kernel launches issued by this engine since creation (bench.py reports
+ * the delta over the timed region as `gpu_launches`).                               */
+int64_t idx_launch_count(const idx_engine* e);
+/* Block until all work queued by this engine has finished.                          */
+int idx_sync(idx_engine* e);
+
+/* -------------------------------------------------------------------- weights -- */
+
+/* Register one tensor of a checkpoint under its reference state-dict name, prefixed
+ * by the module it belongs to ("gpt.", "bigvgan.", "s2mel.", "codec." ...).
+ * Replaces `load_checkpoint` (indextts/utils/checkpoint.py:22-35) + `.to(device)`
+ * (infer_v2_5.py:141-146): the Python loader walks the state dict and calls this
+ * once per tensor.  The engine keeps its own copy (repacked at finalize time), so
+ * the caller may free `data` as soon as the call returns.                           */
+int idx_load_weight(idx_engine* e, const char* name, const void* data, int dtype,
+                    int ndim, const int64_t* shape);
+
+/* ------------------------------------------------------------------------ GPT -- */
+
+/* Geometry of UnifiedVoice (indextts/gpt/model_v2.py:305-420).                      */
+typedef struct {
+  int32_t layers;            /* cfg.gpt.layers                                      */
+  int32_t model_dim;         /* cfg.gpt.model_dim (1280)                            */
+  int32_t heads;             /* cfg.gpt.heads (head_dim must be 64)                 */
+  int32_t number_mel_codes;  /* 8194                                                */
+  int32_t start_mel_token;   /* 8192                                                */
+  int32_t stop_mel_token;    /* 8193                                                */
+  int32_t max_mel_positions; /* rows of mel_pos_embedding.emb.weight                */
+  int32_t max_prompt;        /* longest [cond][text] prompt the KV cache must hold  */
+  int32_t max_batch;         /* concurrent sequences (beams count as sequences)     */
+  int32_t weights_bf16;      /* 1: bf16 weights + autocast rounding points (use_bf16
+                                path, infer_v2_5.py:143-146,758); 0: fp32           */
+} idx_gpt_config;
+
+/* Pack the registered "gpt.*" tensors into the per-SM weight streams of the fused
+ * decode kernel and allocate the KV cache.  Replaces post_init_gpt2_config
+ * (gpt/model_v2.py:422-493).                                                         */
+int idx_gpt_init(idx_engine* e, const idx_gpt_config* cfg);
+
+/* Sampling parameters = the hf_generate_kwargs consumed by
+ * GenerationMixin.generate (gpt/transformers_generation_utils.py:1869-2385), in the
+ * processor order fixed at :900-905,1019-1047.                                      */
+typedef struct {
+  int32_t do_sample;            /* 0: greedy argmax                                  */
+  int32_t num_beams;            /* 1 (beam-sample > 1 not in this round)             */
+  int32_t top_k;                /* 0 = off                                           */
+  float top_p;                  /* 1.0 = off                                         */
+  float temperature;            /* 1.0 = off                                         */
+  float repetition_penalty;     /* 1.0 = off; reference default 10.0                 */
+  float length_penalty;         /* beams only                                        */
+  int32_t max_new_tokens;       /* max_generate_length                               */
+  uint64_t seed;                /* Philox seed of the device sampler                 */
+  int32_t forbid_stop_before;   /* mask stop_mel_token for the first n steps (bench:
+                                   length-deterministic runs); 0 = off   */
+} idx_sampling;
+
+/* One utterance (= one text segment) of a generate call.                            */
+typedef struct {
+  const void* prompt_emb;   /* [prompt_len, model_dim] f32: the [cond][text] embeddings
+                               produced by prepare_gpt_inputs (model_v2.py:648-714),
+                               without left padding                                   */
+  int32_t prompt_len;
+  int32_t* codes_out;       /* [max_new_tokens] generated codes, stop token included  */
+  int32_t* n_codes_out;     /* number of codes written                                */
+  float* logits_out;        /* optional [max_new_tokens, number_mel_codes] f32 of the
+                               processed step logits (tests); NULL to skip            */
+  const int32_t* forced_codes; /* optional teacher forcing: feed these codes instead of
+                               the sampled ones (tests); NULL for free running        */
+} idx_gpt_request;
+
+/* Autoregressive speech-token generation for `nreq` utterances decoded as one batch.
+ * Replaces UnifiedVoice.inference_speech → GPT2InferenceModel.generate
+ * (gpt/model_v2.py:716-825, :121-198) and the HF _sample loop
+ * (transformers_generation_utils.py:3123-3297).                                      */
+int idx_gpt_generate(idx_engine* e, const idx_gpt_request* reqs, int nreq,
+                     const idx_sampling* sp);
+
+/* Build the [cond(3)][start_text, text.., stop_text] prompt embeddings of
+ * prepare_gpt_inputs (gpt/model_v2.py:648-714,754-768) on the device.
+ *   style      [192] f32   campplus embedding (infer_v2_5.py:644-649)
+ *   emo_vec    [model_dim] f32 merged emotion vector (model_v2.py:833-838)
+ *   text_ids   [n_text] i32 (without start/stop), lang id
+ *   out        [3 + n_text + 2, model_dim] f32                                       */
+int idx_gpt_prepare_inputs(idx_engine* e, const float* style, const float* emo_vec,
+                           const int32_t* text_ids, int n_text, int lang, float* out);
+
+/* Timing of the last generate call, measured with CUDA events on the engine stream:
+ * out[0] = prefill ms, out[1] = decode ms, out[2] = decode steps,
+ * out[3] = fused-step kernel launches.                                               */
+int idx_gpt_last_timing(const idx_engine* e, double* out4);
+
+/* ------------------------------------------------------------------- BigVGAN -- */
+
+/* Geometry of the BigVGAN-v2 generator (s2mel/modules/bigvgan/config.json:11-21).    */
+typedef struct {
+  int32_t num_mels;                 /* 80                                            */
+  int32_t upsample_initial_channel; /* 1536                                          */
+  int32_t num_upsamples;            /* 6                                             */
+  int32_t upsample_rates[8];        /* 4,4,2,2,2,2                                   */
+  int32_t upsample_kernel_sizes[8]; /* 8,8,4,4,4,4                                   */
+  int32_t num_kernels;              /* 3                                             */
+  int32_t resblock_kernel_sizes[4]; /* 3,7,11                                        */
+  int32_t resblock_dilations[4][3]; /* 1,3,5 each                                    */
+  int32_t use_tanh_at_final;        /* 0 → clamp(-1,1)                               */
+  int32_t use_bias_at_final;        /* 0                                             */
+  int32_t snake_logscale;           /* 1                                             */
+} idx_bigvgan_config;
+
+/* Fold/pack "bigvgan.*" (weight-norm already removed, as after
+ * bigvgan.remove_weight_norm(), infer_v2_5.py:229-232).                              */
+int idx_bigvgan_init(idx_engine* e, const idx_bigvgan_config* cfg);
+
+/* mel [B, num_mels, F] f32 (reference NCT layout) → wav [B, 1, F*prod(rates)] f32.
+ * Replaces BigVGAN.forward (s2mel/modules/bigvgan/bigvgan.py:360-386), call site
+ * infer_v2_5.py:850.                                                                 */
+int idx_bigvgan_forward(idx_engine* e, const float* mel, int B, int F, float* wav);
+
+/* Standalone anti-aliased SnakeBeta activation: x[B,C,T] f32 → y[B,C,T] f32.
+ * Drop-in for the reference's only native FFI, `fwd_cuda`
+ * (alias_free_activation/cuda/anti_alias_activation_cuda.cu:214-225), with the
+ * torch-path semantics of alias_free_activation/torch/act.py:8-30.
+ * alpha/beta are the log-scale per-channel parameters [C].                           */
+int idx_antialias_snake(idx_engine* e, const float* x, const float* alpha,
+                        const float* beta, int B, int C, int T, int logscale, float* y);
+
+/* Device time of the last idx_bigvgan_forward in ms (CUDA events).                   */
+int idx_bigvgan_last_ms(const idx_engine* e, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IDXTTS_H */

@@ -1,0 +1,129 @@
+// engine.h — internal state of libidxtts.so (not part of the C-ABI; see include/idxtts.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <unordered_map>
+#include <stdexcept>
+#include "../../include/idxtts.h"
+
+struct IdxError : std::runtime_error {
+  int code;
+  IdxError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define IDX_CUDA(call)                                                                    \
+  do {                                                                                    \
+    cudaError_t err__ = (call);                                                           \
+    if (err__ != cudaSuccess)                                                             \
+      throw IdxError(IDX_ERR_CUDA, std::string(#call) + " failed: " +                     \
+                                       cudaGetErrorString(err__) + " at " + __FILE__ +   \
+                                       ":" + std::to_string(__LINE__));                  \
+  } while (0)
+
+#define IDX_CHECK(cond, code, msg)                                                        \
+  do {                                                                                    \
+    if (!(cond)) throw IdxError((code), std::string(msg));                                \
+  } while (0)
+
+struct DevTensor {
+  void* d = nullptr;  // device pointer owned by the engine
+  int dtype = IDX_F32;
+  std::vector<int64_t> shape;
+  size_t numel() const {
+    size_t n = 1;
+    for (auto s : shape) n *= (size_t)s;
+    return n;
+  }
+};
+
+static inline size_t idx_dtype_size(int dt) {
+  switch (dt) {
+    case IDX_F32: return 4;
+    case IDX_BF16: return 2;
+    case IDX_F16: return 2;
+    case IDX_I32: return 4;
+    case IDX_I64: return 8;
+  }
+  return 0;
+}
+
+struct GptState;      // gpt_decode.cu
+struct BigvganState;  // bigvgan.cu
+struct S2melState;    // s2mel.cu
+
+// Bump allocator for per-call activations: reset at the start of each forward call.
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0, high = 0;
+  void* alloc(size_t bytes) {
+    size_t a = (off + 255) & ~(size_t)255;
+    if (a + bytes > cap)
+      throw IdxError(IDX_ERR_ARG, "arena exhausted: need " + std::to_string(a + bytes) +
+                                      " of " + std::to_string(cap));
+    off = a + bytes;
+    if (off > high) high = off;
+    return base + a;
+  }
+  template <typename T>
+  T* get(size_t n) { return (T*)alloc(n * sizeof(T)); }
+  void reset() { off = 0; }
+};
+
+struct idx_engine {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  std::unordered_map<std::string, DevTensor> weights;
+  Arena arena;
+  // pinned staging for host<->device copies
+  void* pinned = nullptr;
+  size_t pinned_cap = 0;
+  GptState* gpt = nullptr;
+  BigvganState* bigvgan = nullptr;
+  S2melState* s2mel = nullptr;
+
+  const DevTensor& W(const std::string& name) const {
+    auto it = weights.find(name);
+    if (it == weights.end()) throw IdxError(IDX_ERR_ARG, "missing weight: " + name);
+    return it->second;
+  }
+  bool has(const std::string& name) const { return weights.find(name) != weights.end(); }
+  // f32 view of a weight (converted copy is made at load time for non-f32 inputs)
+  const float* Wf(const std::string& name) const {
+    const DevTensor& t = W(name);
+    IDX_CHECK(t.dtype == IDX_F32, IDX_ERR_ARG, "weight not f32: " + name);
+    return (const float*)t.d;
+  }
+  void ensure_arena(size_t bytes);
+  void* pinned_buf(size_t bytes);
+};
+
+// true if p is a device (or managed) pointer
+bool idx_is_device_ptr(const void* p);
+// copy `bytes` from a host-or-device pointer into a device buffer on the engine stream
+void idx_to_device(idx_engine* e, void* dst_dev, const void* src, size_t bytes);
+// copy from device buffer to host-or-device pointer (synchronises if dst is host)
+void idx_from_device(idx_engine* e, void* dst, const void* src_dev, size_t bytes);
+
+// module teardown hooks
+void gpt_destroy(GptState*);
+void bigvgan_destroy(BigvganState*);
+void s2mel_destroy(S2melState*);
+
+#define IDX_API_BEGIN try {
+#define IDX_API_END(e)                                     \
+  }                                                        \
+  catch (const IdxError& ex) {                             \
+    if (e) (e)->err = ex.what();                           \
+    return ex.code;                                        \
+  }                                                        \
+  catch (const std::exception& ex) {                       \
+    if (e) (e)->err = ex.what();                           \
+    return IDX_ERR_ARG;                                    \
+  }                                                        \
+  return IDX_OK;

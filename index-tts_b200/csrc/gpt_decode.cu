@@ -1,0 +1,1095 @@
+// gpt_decode.cu — the autoregressive speech-token path of UnifiedVoice as ONE persistent
+// sm_100a kernel per group of decode steps.
+//
+// Replaces, for the v2/v2.5 GPT (SURVEY.md §8a rows a2–a6):
+//   GPT2InferenceModel.forward            indextts/gpt/model_v2.py:121-198
+//   stock HF GPT2Model/Block/Attention/MLP indextts/gpt/transformers_gpt2.py:189-227,571-667
+//   lm_head = Sequential(final_norm, mel_head) model_v2.py:54,408-410   (double LayerNorm, P3)
+//   GenerationMixin._sample greedy loop     transformers_generation_utils.py:3123-3297
+//   RepetitionPenaltyLogitsProcessor        (transformers.generation.logits_process)
+//
+// Design (B200-first, batch-1 decode is pure weight streaming — 965.6 MB bf16 per token):
+//   * one CTA per SM (cooperative launch), 8 compute warps + 1 producer warp;
+//   * every CTA owns a fixed slice of output columns of every GEMV phase; its weights for
+//     ALL layers/phases are pre-packed into one contiguous byte stream in consumption order,
+//     so the producer warp streams it with cp.async.bulk (UBLKCP) into a shared-memory ring,
+//     completely decoupled from the grid barriers — HBM stays busy while the SMs sit at a
+//     barrier or run the tiny attention / LayerNorm / sampling phases;
+//   * 5 grid barriers per layer (QKV | attention | O-proj+res | FC+gelu | proj+res), head,
+//     sampling; repetition penalty, argmax, stop check and the next-token embedding happen on
+//     the device, the host polls one flag per launch (no per-step D2H sync);
+//   * prefill reuses the same kernel: a "step" is then a tile of up to B_TILE consecutive
+//     prompt positions of one sequence (causality falls out of the KV-cache position bound).
+//
+// Numerics follow the reference's bf16 path (infer_v2_5.py:143-146,758 — weights .bfloat16()
+// under autocast): bf16 weights, fp32 accumulation, and a round-to-bf16 at every point where
+// autocast materialises a bf16 tensor (after each Conv1D/Linear, after each elementwise op of
+// NewGELUActivation); LayerNorm is fp32 in / fp32 out; the residual stream is fp32 (the fp32
+// zeros of null_position_embeddings promote it, model_v2.py:23-24 — trap P12); logits are bf16
+// values upcast to fp32 (P5).  See DESIGN.md "GPT numerics".
+#include "engine.h"
+#include "ptx.cuh"
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <cstring>
+#include <cmath>
+
+namespace {
+
+constexpr int NCW = 8;                      // compute warps
+constexpr int NCT = NCW * 32;               // compute threads
+constexpr int NTHREADS = NCT + 32;          // + producer warp
+constexpr int UPC = 8;                      // weight units (one K-segment of D bf16) per chunk
+constexpr int MAXPL = 40;                   // max LayerNorm elements per lane (D <= 1280)
+constexpr int HD = 64;                      // head dim (fixed)
+constexpr int PART_STRIDE = 66;             // attention partial: m, l, o[64]
+
+struct PrefillTile {
+  int seq, pos0, nrows, src_row;
+};
+
+struct GptParams {
+  int L, D, H, V, FF, G;
+  int B;            // valid rows this launch (<= B_TILE)
+  int mode;         // 0 prefill tiles, 1 decode
+  int nsteps;       // steps (or tiles) in this launch
+  int step0;        // decode: global index of the first step of this launch
+  int max_new;      // decode: max tokens per sequence
+  int start_tok, stop_tok, forbid_stop_before;
+  float rep_penalty;
+  int round_bf16;   // 1: emulate autocast bf16 rounding points
+  int nst;          // ring stages
+  // packed weights
+  const __nv_bfloat16* wstream;   // all CTA streams
+  const long long* stream_off;    // [G] unit offset of CTA i's stream
+  // small fp32 parameters
+  const float *ln1_w, *ln1_b, *ln2_w, *ln2_b;      // [L][D]
+  const float *qkv_b, *o_b, *fc_b, *proj_b;        // [L][3D],[L][D],[L][FF],[L][D]
+  const float *lnf_w, *lnf_b, *fn_w, *fn_b, *head_b;
+  const float *mel_emb, *mel_pos;                  // [V][D], [P][D]  (f32 masters)
+  // KV cache [L][nseq][maxpos][D] bf16
+  __nv_bfloat16 *kc, *vc;
+  int nseq, maxpos;
+  // activations (global, L2 resident)
+  float* xg;            // [8][D]   residual stream
+  float* qg;            // [8][D]   q of the current layer
+  __nv_bfloat16* fg;    // [8][FF]  gelu(fc) of the current layer
+  float* part;          // [B*H*nsplit][66] attention partials
+  float* logits;        // [8][V]
+  // per-sequence state
+  int* tok;             // [8] token to feed next
+  int* nout;            // [8] tokens generated so far
+  int* finished;        // [8]
+  int* prompt_len;      // [8]
+  unsigned* seen;       // [8][ceil(V/32)] repetition-penalty bitmap
+  int* codes;           // [8][max_new]
+  const int* forced;    // [8][max_new] or null
+  float* logits_dump;   // [8][max_new][V] or null
+  int* done;            // [1] all sequences finished
+  // prefill
+  const float* prompt;  // [rows][D] f32
+  const PrefillTile* tiles;
+  unsigned* barrier;    // grid barrier counter (zeroed before each launch)
+};
+
+__device__ __forceinline__ float bf16r(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ float rnd(float v, int on) { return on ? bf16r(v) : v; }
+__device__ __forceinline__ float lo_bf(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float hi_bf(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Grid-wide barrier among the compute warps of all CTAs (monotonic counter).
+__device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned& target, int G) {
+  ptx::named_bar_sync(1, NCT);
+  if (threadIdx.x == 0) {
+    target += (unsigned)G;
+    __threadfence();
+    ptx::red_release_gpu_add(ctr, 1u);
+    unsigned spins = 0;
+    while (ptx::ld_acquire_gpu(ctr) < target) {
+      if (++spins > (1u << 28)) __trap();
+    }
+    __threadfence();
+  }
+  ptx::named_bar_sync(1, NCT);
+}
+
+// LayerNorm of one row by one warp, fp32, two-pass from registers.
+// Element i of the row lives in lane (i % 32), slot (i / 32); slots >= npl are unused.
+__device__ __forceinline__ void ln_row(const float (&v_in)[MAXPL], float (&v_out)[MAXPL], int npl,
+                                       int D, const float* w, const float* b, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXPL; ++j)
+    if (j < npl) s += v_in[j];
+  const float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXPL; ++j)
+    if (j < npl) {
+      const float d = v_in[j] - mean;
+      q += d * d;
+    }
+  const float var = warp_sum(q) / (float)D;
+  const float rstd = rsqrtf(var + 1e-5f);
+#pragma unroll
+  for (int j = 0; j < MAXPL; ++j)
+    if (j < npl) {
+      const int i = lane + 32 * j;
+      v_out[j] = (v_in[j] - mean) * rstd * __ldg(w + i) + __ldg(b + i);
+    }
+}
+
+__device__ __forceinline__ void load_row(float (&v)[MAXPL], const float* x, int npl, int lane) {
+#pragma unroll
+  for (int j = 0; j < MAXPL; ++j)
+    if (j < npl) v[j] = __ldcg(x + lane + 32 * j);
+}
+__device__ __forceinline__ void store_row_bf16(const float (&v)[MAXPL], __nv_bfloat16* xs, int npl,
+                                               int lane) {
+#pragma unroll
+  for (int j = 0; j < MAXPL; ++j)
+    if (j < npl) xs[lane + 32 * j] = __float2bfloat16_rn(v[j]);
+}
+
+// NewGELUActivation with a bf16 round after every tensor op (transformers activations.py,
+// evaluated on a bf16 tensor under autocast); plain fp32 formula when rounding is off.
+__device__ __forceinline__ float gelu_new(float x, int r) {
+  float t1 = rnd(x * x * x, r);
+  float t2 = rnd(0.044715f * t1, r);
+  float t3 = rnd(x + t2, r);
+  float t4 = rnd(0.7978845608028654f * t3, r);
+  float t5 = rnd(tanhf(t4), r);
+  float t6 = rnd(1.0f + t5, r);
+  float t7 = rnd(0.5f * x, r);
+  return rnd(t7 * t6, r);
+}
+
+template <int BT>
+struct Smem {
+  // carved from dynamic shared memory
+  __nv_bfloat16* xs;    // [BT][FF]  GEMV input rows (bf16)
+  __nv_bfloat16* ring;  // [nst][UPC][D]
+  float* red;           // [2][UPC][BT] K-split partial sums / attention warp merge [NCW][66]
+  uint64_t* full;       // [nst]
+  uint64_t* empty;      // [nst]
+  int* flags;           // [4]: 0 exit flag for producer, 1 broadcast slot
+};
+
+// One GEMV phase over this CTA's column slice.  `nseg` K-segments of D per column.
+// EPI: 0 QKV, 1 O-proj(+residual), 2 FC(+gelu), 3 PROJ(+residual), 4 HEAD
+template <int BT, int EPI>
+__device__ __forceinline__ void gemv_phase(const GptParams& p, const Smem<BT>& sm, int layer,
+                                           int col0, int ncols, int nseg, unsigned& cons_idx,
+                                           const int* row_seq, const int* row_pos,
+                                           const int* row_valid, int warp, int lane) {
+  const int D = p.D;
+  const int nunits = ncols * nseg;
+  const int nch = (nunits + UPC - 1) / UPC;
+  const int cpl = D / 256;  // 16-byte chunks per lane
+  for (int ch = 0; ch < nch; ++ch) {
+    const int stage = cons_idx % p.nst;
+    const unsigned parity = (cons_idx / p.nst) & 1u;
+    ptx::mbar_wait(&sm.full[stage], parity);
+    const int u = ch * UPC + warp;
+    float acc[BT];
+#pragma unroll
+    for (int b = 0; b < BT; ++b) acc[b] = 0.f;
+    if (u < nunits) {
+      const int seg = u % nseg;
+      const uint4* wrow = (const uint4*)(sm.ring + ((size_t)stage * UPC + warp) * D);
+      for (int j = 0; j < cpl; ++j) {
+        const int c16 = lane + 32 * j;
+        uint4 w = wrow[c16];
+        float wf[8] = {lo_bf(w.x), hi_bf(w.x), lo_bf(w.y), hi_bf(w.y),
+                       lo_bf(w.z), hi_bf(w.z), lo_bf(w.w), hi_bf(w.w)};
+#pragma unroll
+        for (int b = 0; b < BT; ++b) {
+          uint4 xv = ((const uint4*)(sm.xs + (size_t)b * p.FF + (size_t)seg * D))[c16];
+          acc[b] = fmaf(wf[0], lo_bf(xv.x), acc[b]);
+          acc[b] = fmaf(wf[1], hi_bf(xv.x), acc[b]);
+          acc[b] = fmaf(wf[2], lo_bf(xv.y), acc[b]);
+          acc[b] = fmaf(wf[3], hi_bf(xv.y), acc[b]);
+          acc[b] = fmaf(wf[4], lo_bf(xv.z), acc[b]);
+          acc[b] = fmaf(wf[5], hi_bf(xv.z), acc[b]);
+          acc[b] = fmaf(wf[6], lo_bf(xv.w), acc[b]);
+          acc[b] = fmaf(wf[7], hi_bf(xv.w), acc[b]);
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < BT; ++b) acc[b] = warp_sum(acc[b]);
+    }
+    // the weights of this chunk are consumed: hand the stage back to the producer
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&sm.empty[stage]);
+    ++cons_idx;
+
+    int c = -1;  // output column handled by this warp after the (optional) K-split merge
+    if (nseg == 1) {
+      if (u < nunits) c = col0 + u;
+    } else {
+      float* red = sm.red + (size_t)(ch & 1) * UPC * BT;
+      if (lane < BT) {
+        float v = 0.f;
+#pragma unroll
+        for (int b = 0; b < BT; ++b)
+          if (lane == b) v = acc[b];
+        red[warp * BT + lane] = v;
+      }
+      ptx::named_bar_sync(1, NCT);
+      const int cu = ch * UPC + warp * nseg;  // warp w < UPC/nseg merges column w of the chunk
+      if (warp < UPC / nseg && cu < nunits) {
+        c = col0 + cu / nseg;
+        if (lane < BT) {
+          float v = 0.f;
+          for (int s = 0; s < nseg; ++s) v += red[(warp * nseg + s) * BT + lane];
+#pragma unroll
+          for (int b = 0; b < BT; ++b)
+            if (lane == b) acc[b] = v;
+        }
+      }
+    }
+    if (c < 0 || lane >= BT) continue;
+    float a = 0.f;
+#pragma unroll
+    for (int b = 0; b < BT; ++b)
+      if (lane == b) a = acc[b];
+    const int b = lane;
+    if (!row_valid[b]) continue;
+    const int r = p.round_bf16;
+    if (EPI == 0) {
+      float v = rnd(a + __ldg(p.qkv_b + (size_t)layer * 3 * D + c), r);
+      if (c < D) {
+        p.qg[(size_t)b * D + c] = v;
+      } else {
+        size_t base = (((size_t)layer * p.nseq + row_seq[b]) * p.maxpos + row_pos[b]) * D;
+        if (c < 2 * D) p.kc[base + (c - D)] = __float2bfloat16_rn(v);
+        else p.vc[base + (c - 2 * D)] = __float2bfloat16_rn(v);
+      }
+    } else if (EPI == 1) {
+      // the residual stream is fp32 even on the bf16 path (trap P12): only the branch is rounded
+      float o = rnd(a + __ldg(p.o_b + (size_t)layer * D + c), r);
+      float xo = __ldcg(p.xg + (size_t)b * D + c);
+      p.xg[(size_t)b * D + c] = xo + o;
+    } else if (EPI == 2) {
+      float f = rnd(a + __ldg(p.fc_b + (size_t)layer * p.FF + c), r);
+      p.fg[(size_t)b * p.FF + c] = __float2bfloat16_rn(gelu_new(f, r));
+    } else if (EPI == 3) {
+      float o = rnd(a + __ldg(p.proj_b + (size_t)layer * D + c), r);
+      float xo = __ldcg(p.xg + (size_t)b * D + c);
+      p.xg[(size_t)b * D + c] = xo + o;
+    } else {
+      p.logits[(size_t)b * p.V + c] = rnd(a + __ldg(p.head_b + c), r);
+    }
+  }
+}
+
+__device__ __forceinline__ int col_begin(int N, int i, int G) {
+  return (int)(((long long)N * i) / G);
+}
+
+template <int BT>
+__global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int D = p.D, FF = p.FF, G = p.G, L = p.L, H = p.H, V = p.V;
+  const int cta = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  Smem<BT> sm;
+  {
+    unsigned char* q = smem_raw;
+    sm.ring = (__nv_bfloat16*)q;  q += (size_t)p.nst * UPC * D * 2;
+    sm.xs = (__nv_bfloat16*)q;    q += (size_t)BT * FF * 2;
+    sm.red = (float*)q;           q += sizeof(float) * (2 * UPC * BT > NCW * PART_STRIDE ? 2 * UPC * BT : NCW * PART_STRIDE);
+    sm.full = (uint64_t*)q;       q += sizeof(uint64_t) * p.nst;
+    sm.empty = (uint64_t*)q;      q += sizeof(uint64_t) * p.nst;
+    sm.flags = (int*)q;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < p.nst; ++s) {
+      ptx::mbar_init(&sm.full[s], 1);
+      ptx::mbar_init(&sm.empty[s], NCW);
+    }
+    sm.flags[0] = 0;
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+
+  // column slices of this CTA
+  const int q0 = col_begin(3 * D, cta, G), q1 = col_begin(3 * D, cta + 1, G);
+  const int o0 = col_begin(D, cta, G), o1 = col_begin(D, cta + 1, G);
+  const int f0 = col_begin(FF, cta, G), f1 = col_begin(FF, cta + 1, G);
+  const int h0 = col_begin(V, cta, G), h1 = col_begin(V, cta + 1, G);
+  const int nseg_proj = FF / D;
+  const int units_layer = (q1 - q0) + (o1 - o0) + (f1 - f0) + (o1 - o0) * nseg_proj;
+  const int units_head = (p.mode == 1) ? (h1 - h0) : 0;
+
+  // =============================================================== producer warp ====
+  if (warp == NCW) {
+    if (lane == 0) {
+      const uint64_t pol = ptx::policy_evict_first();
+      const __nv_bfloat16* base = p.wstream + (size_t)p.stream_off[cta] * D;
+      unsigned prod_idx = 0;
+      bool stop = false;
+      const int phase_units[4] = {q1 - q0, o1 - o0, f1 - f0, (o1 - o0) * nseg_proj};
+      for (int step = 0; step < p.nsteps && !stop; ++step) {
+        size_t uoff = 0;
+        for (int l = 0; l <= L && !stop; ++l) {
+          const int nph = (l < L) ? 4 : 1;
+          for (int ph = 0; ph < nph && !stop; ++ph) {
+            const int nu = (l < L) ? phase_units[ph] : units_head;
+            for (int u = 0; u < nu; u += UPC) {
+              const int n = min(UPC, nu - u);
+              const int stage = prod_idx % p.nst;
+              const unsigned parity = ((prod_idx / p.nst) & 1u) ^ 1u;
+              unsigned spins = 0;
+              while (!ptx::mbar_try_wait(&sm.empty[stage], parity)) {
+                if (*((volatile int*)&sm.flags[0])) { stop = true; break; }
+                if (++spins > (1u << 26)) __trap();
+              }
+              if (stop) break;
+              const uint32_t bytes = (uint32_t)n * D * 2;
+              ptx::mbar_arrive_expect_tx(&sm.full[stage], bytes);
+              ptx::bulk_g2s(sm.ring + (size_t)stage * UPC * D, base + (uoff + u) * D, bytes,
+                            &sm.full[stage], pol);
+              ++prod_idx;
+            }
+            uoff += nu;
+          }
+        }
+      }
+      sm.flags[2] = (int)prod_idx;  // chunks issued (read by the drain below)
+    }
+    __syncwarp();
+  } else {
+    // ============================================================ compute warps ====
+    unsigned cons_idx = 0;
+    unsigned bar_target = 0;
+    __shared__ int row_seq[8], row_pos[8], row_valid[8], row_posidx[8];
+    const int nsplit = max(1, G / (p.B * H));
+    const int npl = D / 32;
+
+    for (int step = 0; step < p.nsteps; ++step) {
+      // ---- step prologue: row descriptors + input embedding -> xg (own columns only) ----
+      if (tid < 8) {
+        int b = tid;
+        if (p.mode == 0) {
+          PrefillTile t = p.tiles[step];
+          row_seq[b] = t.seq;
+          row_pos[b] = t.pos0 + b;
+          row_valid[b] = (b < t.nrows);
+          row_posidx[b] = t.src_row + b;
+        } else {
+          int k = p.step0 + step;
+          row_seq[b] = b;
+          row_pos[b] = (b < p.B) ? p.prompt_len[b] + k : 0;
+          row_valid[b] = (b < p.B);
+          row_posidx[b] = (k == 0) ? 0 : k + 1;  // P1: mel position k+1 with KV cache
+        }
+      }
+      ptx::named_bar_sync(1, NCT);
+      // every CTA writes the input rows for its own O-proj column slice [o0,o1)
+      for (int idx = tid; idx < BT * (o1 - o0); idx += NCT) {
+        int b = idx / (o1 - o0), c = o0 + idx % (o1 - o0);
+        if (b < BT && row_valid[b]) {
+          float v;
+          if (p.mode == 0) {
+            v = p.prompt[(size_t)row_posidx[b] * D + c];
+          } else {
+            int t = __ldcg(p.tok + b);
+            v = rnd(__ldg(p.mel_emb + (size_t)t * D + c) +
+                        __ldg(p.mel_pos + (size_t)row_posidx[b] * D + c), p.round_bf16);
+          }
+          p.xg[(size_t)b * D + c] = v;
+        }
+      }
+      grid_sync(p.barrier, bar_target, G);
+
+      for (int l = 0; l < L; ++l) {
+        // ---------------- P1: LN1 -> QKV ----------------
+        for (int b = warp; b < BT; b += NCW) {
+          float v[MAXPL], o[MAXPL];
+          load_row(v, p.xg + (size_t)b * D, npl, lane);
+          ln_row(v, o, npl, D, p.ln1_w + (size_t)l * D, p.ln1_b + (size_t)l * D, lane);
+          store_row_bf16(o, sm.xs + (size_t)b * FF, npl, lane);
+        }
+        ptx::named_bar_sync(1, NCT);
+        gemv_phase<BT, 0>(p, sm, l, q0, q1 - q0, 1, cons_idx, row_seq, row_pos, row_valid,
+                          warp, lane);
+        grid_sync(p.barrier, bar_target, G);
+
+        // ---------------- P2: attention over the KV cache ----------------
+        {
+          const int nitems = p.B * H * nsplit;
+          const int g4 = lane >> 3, sub = lane & 7;
+          for (int it = cta; it < nitems; it += G) {
+            const int b = it / (H * nsplit);
+            const int h = (it / nsplit) % H;
+            const int sp = it % nsplit;
+            float* pout = p.part + (size_t)it * PART_STRIDE;
+            if (!row_valid[b]) continue;
+            const int ctx = row_pos[b] + 1;
+            const int k0 = (int)(((long long)ctx * sp) / nsplit);
+            const int k1 = (int)(((long long)ctx * (sp + 1)) / nsplit);
+            float qv[8];
+            {
+              const float* qp = p.qg + (size_t)b * D + h * HD + sub * 8;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) qv[i] = __ldcg(qp + i);
+            }
+            float m = -INFINITY, lsum = 0.f, ov[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ov[i] = 0.f;
+            const size_t cbase = ((size_t)l * p.nseq + row_seq[b]) * p.maxpos;
+            for (int j0 = k0 + warp * 4; j0 < k1; j0 += NCW * 4) {
+              const int j = j0 + g4;
+              const bool valid = j < k1;
+              float s = 0.f;
+              uint4 vv = make_uint4(0, 0, 0, 0);
+              if (valid) {
+                const size_t off = (cbase + j) * D + h * HD + sub * 8;
+                uint4 kk = __ldcg((const uint4*)(p.kc + off));
+                vv = __ldcg((const uint4*)(p.vc + off));
+                s = qv[0] * lo_bf(kk.x) + qv[1] * hi_bf(kk.x) + qv[2] * lo_bf(kk.y) +
+                    qv[3] * hi_bf(kk.y) + qv[4] * lo_bf(kk.z) + qv[5] * hi_bf(kk.z) +
+                    qv[6] * lo_bf(kk.w) + qv[7] * hi_bf(kk.w);
+              }
+              s += __shfl_xor_sync(0xffffffffu, s, 1);
+              s += __shfl_xor_sync(0xffffffffu, s, 2);
+              s += __shfl_xor_sync(0xffffffffu, s, 4);
+              if (valid) {
+                s *= 0.125f;
+                const float mn = fmaxf(m, s);
+                const float corr = __expf(m - mn);
+                const float pr = __expf(s - mn);
+                lsum = lsum * corr + pr;
+                const float vf[8] = {lo_bf(vv.x), hi_bf(vv.x), lo_bf(vv.y), hi_bf(vv.y),
+                                     lo_bf(vv.z), hi_bf(vv.z), lo_bf(vv.w), hi_bf(vv.w)};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) ov[i] = ov[i] * corr + pr * vf[i];
+                m = mn;
+              }
+            }
+            // merge the 4 key groups of the warp
+#pragma unroll
+            for (int xo = 8; xo <= 16; xo <<= 1) {
+              const float m2 = __shfl_xor_sync(0xffffffffu, m, xo);
+              const float l2 = __shfl_xor_sync(0xffffffffu, lsum, xo);
+              const float mn = fmaxf(m, m2);
+              const float c1 = (m == -INFINITY) ? 0.f : __expf(m - mn);
+              const float c2 = (m2 == -INFINITY) ? 0.f : __expf(m2 - mn);
+              lsum = lsum * c1 + l2 * c2;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float o2 = __shfl_xor_sync(0xffffffffu, ov[i], xo);
+                ov[i] = ov[i] * c1 + o2 * c2;
+              }
+              m = mn;
+            }
+            // merge the 8 warps through shared memory
+            float* red = sm.red;
+            ptx::named_bar_sync(1, NCT);  // previous item's merge buffer is free
+            if (lane < 8) {
+              float* rw = red + warp * PART_STRIDE;
+              if (lane == 0) { rw[0] = m; rw[1] = lsum; }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) rw[2 + lane * 8 + i] = ov[i];
+            }
+            ptx::named_bar_sync(1, NCT);
+            if (warp == 0) {
+              float mm = -INFINITY;
+              for (int w = 0; w < NCW; ++w) mm = fmaxf(mm, red[w * PART_STRIDE]);
+              float lt = 0.f, oa = 0.f, ob = 0.f;
+              for (int w = 0; w < NCW; ++w) {
+                const float mw = red[w * PART_STRIDE];
+                const float c = (mw == -INFINITY) ? 0.f : __expf(mw - mm);
+                lt += red[w * PART_STRIDE + 1] * c;
+                oa += red[w * PART_STRIDE + 2 + lane] * c;
+                ob += red[w * PART_STRIDE + 2 + 32 + lane] * c;
+              }
+              if (lane == 0) { pout[0] = mm; pout[1] = lt; }
+              pout[2 + lane] = oa;
+              pout[2 + 32 + lane] = ob;
+            }
+          }
+        }
+        grid_sync(p.barrier, bar_target, G);
+
+        // ---------------- P3: merge attention splits -> O-proj + residual ----------------
+        for (int idx = tid; idx < BT * D; idx += NCT) {
+          const int b = idx / D, c = idx % D;
+          float outv = 0.f;
+          if (b < p.B && row_valid[b]) {
+            const int h = c / HD, d = c % HD;
+            const float* pp = p.part + (size_t)((b * H + h) * nsplit) * PART_STRIDE;
+            float mm = -INFINITY;
+            for (int s = 0; s < nsplit; ++s) mm = fmaxf(mm, __ldcg(pp + s * PART_STRIDE));
+            float lt = 0.f, o = 0.f;
+            for (int s = 0; s < nsplit; ++s) {
+              const float ms = __ldcg(pp + s * PART_STRIDE);
+              const float cc = (ms == -INFINITY) ? 0.f : __expf(ms - mm);
+              lt += __ldcg(pp + s * PART_STRIDE + 1) * cc;
+              o += __ldcg(pp + s * PART_STRIDE + 2 + d) * cc;
+            }
+            outv = o / lt;
+          }
+          sm.xs[(size_t)b * FF + c] = __float2bfloat16_rn(outv);
+        }
+        ptx::named_bar_sync(1, NCT);
+        gemv_phase<BT, 1>(p, sm, l, o0, o1 - o0, 1, cons_idx, row_seq, row_pos, row_valid,
+                          warp, lane);
+        grid_sync(p.barrier, bar_target, G);
+
+        // ---------------- P4: LN2 -> FC + gelu_new ----------------
+        for (int b = warp; b < BT; b += NCW) {
+          float v[MAXPL], o[MAXPL];
+          load_row(v, p.xg + (size_t)b * D, npl, lane);
+          ln_row(v, o, npl, D, p.ln2_w + (size_t)l * D, p.ln2_b + (size_t)l * D, lane);
+          store_row_bf16(o, sm.xs + (size_t)b * FF, npl, lane);
+        }
+        ptx::named_bar_sync(1, NCT);
+        gemv_phase<BT, 2>(p, sm, l, f0, f1 - f0, 1, cons_idx, row_seq, row_pos, row_valid,
+                          warp, lane);
+        grid_sync(p.barrier, bar_target, G);
+
+        // ---------------- P5: proj + residual ----------------
+        {
+          const int n16 = BT * FF / 8;
+          for (int idx = tid; idx < n16; idx += NCT)
+            ((uint4*)sm.xs)[idx] = __ldcg(((const uint4*)p.fg) + idx);
+        }
+        ptx::named_bar_sync(1, NCT);
+        gemv_phase<BT, 3>(p, sm, l, o0, o1 - o0, nseg_proj, cons_idx, row_seq, row_pos,
+                          row_valid, warp, lane);
+        grid_sync(p.barrier, bar_target, G);
+      }
+
+      if (p.mode == 1) {
+        // ---------------- head: ln_f -> final_norm -> mel_head ----------------
+        for (int b = warp; b < BT; b += NCW) {
+          float v[MAXPL], o[MAXPL];
+          load_row(v, p.xg + (size_t)b * D, npl, lane);
+          ln_row(v, o, npl, D, p.lnf_w, p.lnf_b, lane);
+          ln_row(o, v, npl, D, p.fn_w, p.fn_b, lane);
+          store_row_bf16(v, sm.xs + (size_t)b * FF, npl, lane);
+        }
+        ptx::named_bar_sync(1, NCT);
+        gemv_phase<BT, 4>(p, sm, 0, h0, h1 - h0, 1, cons_idx, row_seq, row_pos, row_valid,
+                          warp, lane);
+        grid_sync(p.barrier, bar_target, G);
+
+        // ---------------- sampling: CTA b handles sequence b ----------------
+        if (cta < p.B) {
+          const int b = cta;
+          const int k = p.step0 + step;
+          const float* lg = p.logits + (size_t)b * V;
+          if (p.logits_dump) {
+            float* dst = p.logits_dump + ((size_t)b * p.max_new + k) * V;
+            for (int i = tid; i < V; i += NCT) dst[i] = __ldcg(lg + i);
+          }
+          const unsigned* seen = p.seen + (size_t)b * ((V + 31) / 32);
+          float best = -INFINITY;
+          int besti = 0x7fffffff;
+          for (int i = tid; i < V; i += NCT) {
+            float s = __ldcg(lg + i);
+            if ((seen[i >> 5] >> (i & 31)) & 1u)
+              s = (s < 0.f) ? s * p.rep_penalty : s / p.rep_penalty;
+            if (i == p.stop_tok && k < p.forbid_stop_before) s = -INFINITY;
+            if (s > best || (s == best && i < besti)) { best = s; besti = i; }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float b2 = __shfl_xor_sync(0xffffffffu, best, o);
+            const int i2 = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (b2 > best || (b2 == best && i2 < besti)) { best = b2; besti = i2; }
+          }
+          float* red = sm.red;
+          if (lane == 0) { red[warp * 2] = best; ((int*)red)[warp * 2 + 1] = besti; }
+          ptx::named_bar_sync(1, NCT);
+          if (tid == 0) {
+            for (int w = 1; w < NCW; ++w) {
+              const float b2 = red[w * 2];
+              const int i2 = ((int*)red)[w * 2 + 1];
+              if (b2 > best || (b2 == best && i2 < besti)) { best = b2; besti = i2; }
+            }
+            const int fin = p.finished[b];
+            if (!fin) {
+              p.codes[(size_t)b * p.max_new + k] = besti;
+              p.nout[b] = k + 1;
+              int feed = besti;
+              if (p.forced) feed = p.forced[(size_t)b * p.max_new + k];
+              else if (besti == p.stop_tok) p.finished[b] = 1;
+              if (k + 1 >= p.max_new) p.finished[b] = 1;
+              p.tok[b] = feed;
+              p.seen[(size_t)b * ((V + 31) / 32) + (feed >> 5)] |= 1u << (feed & 31);
+            }
+          }
+          ptx::named_bar_sync(1, NCT);
+        }
+        grid_sync(p.barrier, bar_target, G);
+        // all-finished check (every CTA reads the same flags after the barrier)
+        if (tid == 0) {
+          int alldone = 1;
+          for (int b = 0; b < p.B; ++b) alldone &= __ldcg(p.finished + b);
+          sm.flags[1] = alldone;
+          if (alldone && cta == 0) *p.done = 1;
+        }
+        ptx::named_bar_sync(1, NCT);
+        if (sm.flags[1]) break;
+      }
+    }
+    // tell the producer to stop prefetching
+    if (tid == 0) { *((volatile int*)&sm.flags[0]) = 1; sm.flags[3] = (int)cons_idx; }
+  }
+  __syncthreads();
+  // drain: bulk copies issued beyond what was consumed must land before the CTA exits
+  if (tid == 0) {
+    const unsigned issued = (unsigned)sm.flags[2], consumed = (unsigned)sm.flags[3];
+    for (unsigned n = consumed; n < issued; ++n)
+      ptx::mbar_wait(&sm.full[n % p.nst], (n / p.nst) & 1u);
+  }
+  __syncthreads();
+}
+
+// -------------------------------------------------------------------- packing kernel --
+struct PackUnit {
+  const float* src;
+  long long base;      // element offset of (k = 0)
+  long long kstride;   // element stride along K
+};
+__global__ void pack_units_kernel(const PackUnit* units, __nv_bfloat16* dst, int D, long long n) {
+  long long u = blockIdx.x;
+  if (u >= n) return;
+  PackUnit pu = units[u];
+  for (int k = threadIdx.x; k < D; k += blockDim.x)
+    dst[u * D + k] = __float2bfloat16_rn(pu.src[pu.base + (long long)k * pu.kstride]);
+}
+
+__global__ void round_bf16_kernel(float* x, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = __bfloat162float(__float2bfloat16_rn(x[i]));
+}
+
+__global__ void concat_rows_kernel(float* dst, const float* src, int D, int rows) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (size_t)rows * D) dst[i] = src[i];
+}
+
+// prepare_gpt_inputs (gpt/model_v2.py:648-714 + :754-768) for one utterance.
+__global__ void prepare_inputs_kernel(const float* style, const float* emo_vec,
+                                      const int* text_ids, int n_text, int lang,
+                                      const float* spk_w, const float* spk_b,
+                                      const float* text_emb, const float* text_pos,
+                                      const float* lang_emb, int D, int r, float* out) {
+  const int row = blockIdx.x;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float v = 0.f;
+    if (row == 0) {
+      float acc = 0.f;
+      for (int k = 0; k < 192; ++k) acc += rnd(style[k], r) * spk_w[(size_t)c * 192 + k];
+      v = rnd(rnd(acc + spk_b[c], r) + emo_vec[c], r);
+    } else if (row >= 3) {
+      const int j = row - 3;
+      int id = (j == 0) ? 0 : (j == n_text + 1 ? 1 : text_ids[j - 1]);
+      v = rnd(text_emb[(size_t)id * D + c] + text_pos[(size_t)j * D + c], r);
+      if (lang_emb) v = rnd(v + lang_emb[(size_t)lang * D + c], r);
+    }
+    out[(size_t)row * D + c] = v;
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------ host state --
+struct GptState {
+  idx_gpt_config cfg;
+  int G = 0, FF = 0, nst1 = 0, nst8 = 0;
+  size_t smem1 = 0, smem8 = 0;
+  __nv_bfloat16* wstream = nullptr;
+  long long* stream_off = nullptr;
+  float *ln1_w = nullptr, *ln1_b = nullptr, *ln2_w = nullptr, *ln2_b = nullptr;
+  float *qkv_b = nullptr, *o_b = nullptr, *fc_b = nullptr, *proj_b = nullptr;
+  float *mel_emb = nullptr, *mel_pos = nullptr;
+  __nv_bfloat16 *kc = nullptr, *vc = nullptr;
+  int maxpos = 0;
+  float *xg = nullptr, *qg = nullptr, *part = nullptr, *logits = nullptr;
+  __nv_bfloat16* fg = nullptr;
+  int *tok = nullptr, *nout = nullptr, *finished = nullptr, *prompt_len = nullptr, *done = nullptr;
+  unsigned* seen = nullptr;
+  unsigned* barrier = nullptr;
+  std::vector<void*> owned;
+  double t_prefill_ms = 0, t_decode_ms = 0;
+  int last_steps = 0, last_launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+};
+
+void gpt_destroy(GptState* g) {
+  if (!g) return;
+  for (void* p : g->owned) cudaFree(p);
+  if (g->ev0) cudaEventDestroy(g->ev0);
+  if (g->ev1) cudaEventDestroy(g->ev1);
+  if (g->ev2) cudaEventDestroy(g->ev2);
+  delete g;
+}
+
+template <typename T>
+static T* galloc(GptState* g, size_t n) {
+  T* p = nullptr;
+  IDX_CUDA(cudaMalloc((void**)&p, n * sizeof(T)));
+  IDX_CUDA(cudaMemset(p, 0, n * sizeof(T)));
+  g->owned.push_back(p);
+  return p;
+}
+
+static size_t smem_bytes(int BT, int D, int FF, int nst) {
+  size_t red = sizeof(float) * (size_t)std::max(2 * UPC * BT, NCW * PART_STRIDE);
+  return (size_t)nst * UPC * D * 2 + (size_t)BT * FF * 2 + red + 16 * (size_t)nst + 64;
+}
+
+template <int BT>
+static void launch_fused(idx_engine* e, GptState* g, GptParams& p) {
+  p.nst = (BT == 1) ? g->nst1 : g->nst8;
+  size_t smem = smem_bytes(BT, p.D, p.FF, p.nst);
+  IDX_CUDA(cudaMemsetAsync(g->barrier, 0, sizeof(unsigned), e->stream));
+  void* args[] = {(void*)&p};
+  IDX_CUDA(cudaLaunchCooperativeKernel((void*)gpt_fused_kernel<BT>, dim3(g->G), dim3(NTHREADS),
+                                       args, smem, e->stream));
+  e->launches++;
+  g->last_launches++;
+}
+
+static void launch_fused_bt(idx_engine* e, GptState* g, GptParams& p, int BT) {
+  if (BT == 1) launch_fused<1>(e, g, p);
+  else launch_fused<8>(e, g, p);
+}
+
+extern "C" int idx_gpt_init(idx_engine* e, const idx_gpt_config* cfg) {
+  IDX_API_BEGIN
+  IDX_CHECK(e && cfg, IDX_ERR_ARG, "null argument");
+  IDX_CUDA(cudaSetDevice(e->device));
+  if (e->gpt) { gpt_destroy(e->gpt); e->gpt = nullptr; }
+  GptState* g = new GptState();
+  e->gpt = g;
+  g->cfg = *cfg;
+  const int L = cfg->layers, D = cfg->model_dim, H = cfg->heads, V = cfg->number_mel_codes;
+  const int FF = 4 * D;
+  g->FF = FF;
+  IDX_CHECK(D % 256 == 0 && D <= 32 * MAXPL, IDX_ERR_ARG, "model_dim must be a multiple of 256, <= 1280");
+  IDX_CHECK(D == H * HD, IDX_ERR_ARG, "head_dim must be 64");
+  IDX_CHECK(cfg->max_batch >= 1 && cfg->max_batch <= 8, IDX_ERR_ARG, "max_batch must be 1..8 (per decode group)");
+  IDX_CHECK(cfg->weights_bf16 == 1, IDX_ERR_ARG, "only the bf16 weight path is built in this round");
+  const int G = e->num_sms;
+  g->G = G;
+
+  // ---- ring depth from the shared-memory budget ----
+  int dev_smem = 0;
+  IDX_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
+  auto pick_nst = [&](int BT) {
+    int nst = 2;
+    while (nst < 32 && smem_bytes(BT, D, FF, nst + 1) <= (size_t)dev_smem - 1024) ++nst;
+    return nst;
+  };
+  g->nst1 = pick_nst(1);
+  g->nst8 = pick_nst(8);
+  g->smem1 = smem_bytes(1, D, FF, g->nst1);
+  g->smem8 = smem_bytes(8, D, FF, g->nst8);
+  IDX_CHECK(g->smem8 <= (size_t)dev_smem, IDX_ERR_ARG, "shared memory budget exceeded");
+  IDX_CUDA(cudaFuncSetAttribute(gpt_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem1));
+  IDX_CUDA(cudaFuncSetAttribute(gpt_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem8));
+
+  // ---- build the per-CTA unit table in consumption order ----
+  std::vector<PackUnit> units;
+  std::vector<long long> off(G + 1, 0);
+  auto lname = [&](int l, const char* s) { return "gpt.gpt.h." + std::to_string(l) + "." + s; };
+  for (int l = 0; l < L; ++l) {
+    const DevTensor& wq = e->W(lname(l, "attn.c_attn.weight"));
+    IDX_CHECK(wq.shape.size() == 2 && wq.shape[0] == D && wq.shape[1] == 3 * D, IDX_ERR_ARG, "c_attn.weight shape");
+    const DevTensor& wo = e->W(lname(l, "attn.c_proj.weight"));
+    IDX_CHECK(wo.shape[0] == D && wo.shape[1] == D, IDX_ERR_ARG, "attn.c_proj.weight shape");
+    const DevTensor& wf = e->W(lname(l, "mlp.c_fc.weight"));
+    IDX_CHECK(wf.shape[0] == D && wf.shape[1] == FF, IDX_ERR_ARG, "c_fc.weight shape");
+    const DevTensor& wp = e->W(lname(l, "mlp.c_proj.weight"));
+    IDX_CHECK(wp.shape[0] == FF && wp.shape[1] == D, IDX_ERR_ARG, "mlp.c_proj.weight shape");
+  }
+  const DevTensor& wh = e->W("gpt.mel_head.weight");
+  IDX_CHECK(wh.shape[0] == V && wh.shape[1] == D, IDX_ERR_ARG, "mel_head.weight shape");
+  for (int i = 0; i < G; ++i) {
+    off[i] = (long long)units.size();
+    const int q0 = (int)(((long long)3 * D * i) / G), q1 = (int)(((long long)3 * D * (i + 1)) / G);
+    const int o0 = (int)(((long long)D * i) / G), o1 = (int)(((long long)D * (i + 1)) / G);
+    const int f0 = (int)(((long long)FF * i) / G), f1 = (int)(((long long)FF * (i + 1)) / G);
+    const int h0 = (int)(((long long)V * i) / G), h1 = (int)(((long long)V * (i + 1)) / G);
+    for (int l = 0; l < L; ++l) {
+      const float* wq = (const float*)e->W(lname(l, "attn.c_attn.weight")).d;
+      const float* wo = (const float*)e->W(lname(l, "attn.c_proj.weight")).d;
+      const float* wf = (const float*)e->W(lname(l, "mlp.c_fc.weight")).d;
+      const float* wp = (const float*)e->W(lname(l, "mlp.c_proj.weight")).d;
+      // HF Conv1D keeps weight as [in, out] (P4): element (k, c) at k*N + c
+      for (int c = q0; c < q1; ++c) units.push_back({wq, c, 3LL * D});
+      for (int c = o0; c < o1; ++c) units.push_back({wo, c, (long long)D});
+      for (int c = f0; c < f1; ++c) units.push_back({wf, c, (long long)FF});
+      for (int c = o0; c < o1; ++c)
+        for (int s = 0; s < FF / D; ++s)
+          units.push_back({wp, (long long)s * D * D + c, (long long)D});
+    }
+    // nn.Linear keeps weight as [out, in]
+    for (int c = h0; c < h1; ++c) units.push_back({(const float*)wh.d, (long long)c * D, 1LL});
+  }
+  off[G] = (long long)units.size();
+  const long long nunits = (long long)units.size();
+  PackUnit* d_units = nullptr;
+  IDX_CUDA(cudaMalloc((void**)&d_units, nunits * sizeof(PackUnit)));
+  IDX_CUDA(cudaMemcpyAsync(d_units, units.data(), nunits * sizeof(PackUnit), cudaMemcpyHostToDevice, e->stream));
+  g->wstream = galloc<__nv_bfloat16>(g, (size_t)nunits * D + 64);
+  pack_units_kernel<<<(unsigned)nunits, 128, 0, e->stream>>>(d_units, g->wstream, D, nunits);
+  IDX_CUDA(cudaGetLastError());
+  g->stream_off = galloc<long long>(g, G + 1);
+  IDX_CUDA(cudaMemcpyAsync(g->stream_off, off.data(), (G + 1) * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
+  IDX_CUDA(cudaStreamSynchronize(e->stream));
+  cudaFree(d_units);
+
+  // ---- small parameters gathered into [L][..] arrays ----
+  auto gather = [&](const char* suffix, int n) {
+    float* dst = galloc<float>(g, (size_t)L * n);
+    for (int l = 0; l < L; ++l) {
+      const DevTensor& t = e->W(lname(l, suffix));
+      IDX_CHECK((int)t.numel() == n, IDX_ERR_ARG, std::string("bad size for ") + suffix);
+      IDX_CUDA(cudaMemcpyAsync(dst + (size_t)l * n, t.d, (size_t)n * 4, cudaMemcpyDeviceToDevice, e->stream));
+    }
+    return dst;
+  };
+  g->ln1_w = gather("ln_1.weight", D);
+  g->ln1_b = gather("ln_1.bias", D);
+  g->ln2_w = gather("ln_2.weight", D);
+  g->ln2_b = gather("ln_2.bias", D);
+  g->qkv_b = gather("attn.c_attn.bias", 3 * D);
+  g->o_b = gather("attn.c_proj.bias", D);
+  g->fc_b = gather("mlp.c_fc.bias", FF);
+  g->proj_b = gather("mlp.c_proj.bias", D);
+  // weights .bfloat16(): biases/LN params/embeddings are bf16-valued too
+  auto round_inplace = [&](float* p, size_t n) {
+    round_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(p, n);
+  };
+  for (float* p : {g->ln1_w, g->ln1_b, g->ln2_w, g->ln2_b, g->o_b, g->proj_b}) round_inplace(p, (size_t)L * D);
+  round_inplace(g->qkv_b, (size_t)L * 3 * D);
+  round_inplace(g->fc_b, (size_t)L * FF);
+  auto copy_round = [&](const std::string& name, size_t expect) {
+    const DevTensor& t = e->W(name);
+    IDX_CHECK(expect == 0 || t.numel() == expect, IDX_ERR_ARG, "bad size for " + name);
+    float* dst = galloc<float>(g, t.numel());
+    IDX_CUDA(cudaMemcpyAsync(dst, t.d, t.numel() * 4, cudaMemcpyDeviceToDevice, e->stream));
+    round_inplace(dst, t.numel());
+    return dst;
+  };
+  g->mel_emb = copy_round("gpt.mel_embedding.weight", (size_t)V * D);
+  IDX_CHECK(e->W("gpt.mel_pos_embedding.emb.weight").shape[0] >= cfg->max_mel_positions, IDX_ERR_ARG, "mel_pos rows");
+  g->mel_pos = copy_round("gpt.mel_pos_embedding.emb.weight", 0);
+
+  // ---- KV cache + activations ----
+  g->maxpos = cfg->max_prompt + cfg->max_mel_positions + 8;
+  const size_t kvn = (size_t)L * cfg->max_batch * g->maxpos * D;
+  g->kc = galloc<__nv_bfloat16>(g, kvn);
+  g->vc = galloc<__nv_bfloat16>(g, kvn);
+  g->xg = galloc<float>(g, 8 * (size_t)D);
+  g->qg = galloc<float>(g, 8 * (size_t)D);
+  g->fg = galloc<__nv_bfloat16>(g, 8 * (size_t)FF);
+  g->part = galloc<float>(g, (size_t)(8 * H * std::max(1, G / H) + G) * PART_STRIDE);
+  g->logits = galloc<float>(g, 8 * (size_t)V);
+  g->tok = galloc<int>(g, 8);
+  g->nout = galloc<int>(g, 8);
+  g->finished = galloc<int>(g, 8);
+  g->prompt_len = galloc<int>(g, 8);
+  g->done = galloc<int>(g, 1);
+  g->seen = galloc<unsigned>(g, 8 * (size_t)((V + 31) / 32));
+  g->barrier = galloc<unsigned>(g, 4);
+  IDX_CUDA(cudaEventCreate(&g->ev0));
+  IDX_CUDA(cudaEventCreate(&g->ev1));
+  IDX_CUDA(cudaEventCreate(&g->ev2));
+  IDX_CUDA(cudaStreamSynchronize(e->stream));
+  IDX_API_END(e)
+}
+
+static void fill_common(idx_engine* e, GptState* g, GptParams& p) {
+  const idx_gpt_config& c = g->cfg;
+  memset(&p, 0, sizeof(p));
+  p.L = c.layers; p.D = c.model_dim; p.H = c.heads; p.V = c.number_mel_codes; p.FF = g->FF; p.G = g->G;
+  p.start_tok = c.start_mel_token; p.stop_tok = c.stop_mel_token;
+  p.round_bf16 = c.weights_bf16;
+  p.wstream = g->wstream; p.stream_off = g->stream_off;
+  p.ln1_w = g->ln1_w; p.ln1_b = g->ln1_b; p.ln2_w = g->ln2_w; p.ln2_b = g->ln2_b;
+  p.qkv_b = g->qkv_b; p.o_b = g->o_b; p.fc_b = g->fc_b; p.proj_b = g->proj_b;
+  p.lnf_w = e->Wf("gpt.gpt.ln_f.weight"); p.lnf_b = e->Wf("gpt.gpt.ln_f.bias");
+  p.fn_w = e->Wf("gpt.final_norm.weight"); p.fn_b = e->Wf("gpt.final_norm.bias");
+  p.head_b = e->Wf("gpt.mel_head.bias");
+  p.mel_emb = g->mel_emb; p.mel_pos = g->mel_pos;
+  p.kc = g->kc; p.vc = g->vc; p.nseq = c.max_batch; p.maxpos = g->maxpos;
+  p.xg = g->xg; p.qg = g->qg; p.fg = g->fg; p.part = g->part; p.logits = g->logits;
+  p.tok = g->tok; p.nout = g->nout; p.finished = g->finished; p.prompt_len = g->prompt_len;
+  p.seen = g->seen; p.done = g->done; p.barrier = g->barrier;
+}
+
+extern "C" int idx_gpt_generate(idx_engine* e, const idx_gpt_request* reqs, int nreq,
+                                const idx_sampling* sp) {
+  IDX_API_BEGIN
+  IDX_CHECK(e && e->gpt, IDX_ERR_STATE, "idx_gpt_init has not been called");
+  IDX_CHECK(reqs && sp && nreq >= 1, IDX_ERR_ARG, "bad request");
+  GptState* g = e->gpt;
+  const idx_gpt_config& c = g->cfg;
+  IDX_CHECK(nreq <= c.max_batch, IDX_ERR_ARG, "nreq exceeds max_batch");
+  IDX_CHECK(sp->do_sample == 0 && sp->num_beams == 1, IDX_ERR_ARG,
+            "only greedy decoding (do_sample=False, num_beams=1) is built in this round");
+  IDX_CHECK(sp->max_new_tokens >= 1 && sp->max_new_tokens + 2 <= c.max_mel_positions, IDX_ERR_ARG,
+            "max_new_tokens must satisfy k+1 <= mel_pos rows - 1 (SURVEY A.3)");
+  IDX_CUDA(cudaSetDevice(e->device));
+  const int D = c.model_dim, V = c.number_mel_codes, max_new = sp->max_new_tokens;
+  const int BT = (nreq == 1) ? 1 : 8;
+  g->last_launches = 0;
+
+  // ---- stage prompts ----
+  int total_rows = 0;
+  std::vector<int> plen(8, 0), row0(8, 0);
+  for (int i = 0; i < nreq; ++i) {
+    IDX_CHECK(reqs[i].prompt_emb && reqs[i].prompt_len >= 1 && reqs[i].prompt_len <= c.max_prompt, IDX_ERR_ARG, "bad prompt");
+    IDX_CHECK(reqs[i].prompt_len + max_new + 1 <= g->maxpos, IDX_ERR_ARG, "KV cache too small");
+    plen[i] = reqs[i].prompt_len;
+    row0[i] = total_rows;
+    total_rows += plen[i];
+  }
+  std::vector<PrefillTile> tiles;
+  for (int i = 0; i < nreq; ++i)
+    for (int p0 = 0; p0 < plen[i]; p0 += 8)
+      tiles.push_back({i, p0, std::min(8, plen[i] - p0), row0[i] + p0});
+  const size_t wv = (size_t)((V + 31) / 32);
+  size_t need = (size_t)(total_rows + 8) * D * 4 + tiles.size() * sizeof(PrefillTile) + 8 * (size_t)max_new * 8 + 4096;
+  bool want_logits = false, want_forced = false;
+  for (int i = 0; i < nreq; ++i) { want_logits |= reqs[i].logits_out != nullptr; want_forced |= reqs[i].forced_codes != nullptr; }
+  if (want_logits) need += 8 * (size_t)max_new * V * 4;
+  e->ensure_arena(need + (1 << 20));
+  e->arena.reset();
+  float* d_prompt = e->arena.get<float>((size_t)(total_rows + 8) * D);
+  PrefillTile* d_tiles = e->arena.get<PrefillTile>(tiles.size());
+  int* d_codes = e->arena.get<int>(8 * (size_t)max_new);
+  int* d_forced = want_forced ? e->arena.get<int>(8 * (size_t)max_new) : nullptr;
+  float* d_ldump = want_logits ? e->arena.get<float>(8 * (size_t)max_new * V) : nullptr;
+
+  IDX_CUDA(cudaEventRecord(g->ev0, e->stream));
+  for (int i = 0; i < nreq; ++i)
+    idx_to_device(e, d_prompt + (size_t)row0[i] * D, reqs[i].prompt_emb, (size_t)plen[i] * D * 4);
+  IDX_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(PrefillTile), cudaMemcpyHostToDevice, e->stream));
+  if (want_forced) {
+    IDX_CUDA(cudaMemsetAsync(d_forced, 0, 8 * (size_t)max_new * 4, e->stream));
+    for (int i = 0; i < nreq; ++i) {
+      IDX_CHECK(reqs[i].forced_codes, IDX_ERR_ARG, "forced_codes must be given for all requests or none");
+      idx_to_device(e, d_forced + (size_t)i * max_new, reqs[i].forced_codes, (size_t)max_new * 4);
+    }
+  }
+  // per-sequence state
+  {
+    std::vector<int> h_tok(8, c.start_mel_token), zeros(8, 0);
+    std::vector<unsigned> h_seen(8 * wv, 0u);
+    for (int i = 0; i < nreq; ++i) {
+      // P2: the fake prompt ids [1,...,1, start_mel] are part of input_ids
+      h_seen[i * wv + (1 >> 5)] |= 1u << 1;
+      h_seen[i * wv + (c.start_mel_token >> 5)] |= 1u << (c.start_mel_token & 31);
+    }
+    IDX_CUDA(cudaMemcpyAsync(g->tok, h_tok.data(), 32, cudaMemcpyHostToDevice, e->stream));
+    IDX_CUDA(cudaMemcpyAsync(g->nout, zeros.data(), 32, cudaMemcpyHostToDevice, e->stream));
+    IDX_CUDA(cudaMemcpyAsync(g->finished, zeros.data(), 32, cudaMemcpyHostToDevice, e->stream));
+    IDX_CUDA(cudaMemcpyAsync(g->done, zeros.data(), 4, cudaMemcpyHostToDevice, e->stream));
+    IDX_CUDA(cudaMemcpyAsync(g->prompt_len, plen.data(), 32, cudaMemcpyHostToDevice, e->stream));
+    IDX_CUDA(cudaMemcpyAsync(g->seen, h_seen.data(), h_seen.size() * 4, cudaMemcpyHostToDevice, e->stream));
+    IDX_CUDA(cudaStreamSynchronize(e->stream));  // host vectors go out of scope
+  }
+
+  // ---- prefill: tiles of 8 prompt positions through the same fused kernel ----
+  GptParams p;
+  fill_common(e, g, p);
+  p.B = 8; p.mode = 0; p.nsteps = (int)tiles.size(); p.prompt = d_prompt; p.tiles = d_tiles;
+  p.max_new = max_new; p.rep_penalty = sp->repetition_penalty;
+  launch_fused<8>(e, g, p);
+  IDX_CUDA(cudaEventRecord(g->ev1, e->stream));
+
+  // ---- decode ----
+  fill_common(e, g, p);
+  p.B = nreq; p.mode = 1; p.max_new = max_new; p.rep_penalty = sp->repetition_penalty;
+  p.forbid_stop_before = sp->forbid_stop_before;
+  p.codes = d_codes; p.forced = d_forced; p.logits_dump = d_ldump;
+  const int SPL = 32;  // steps per launch: the host looks at one flag every SPL steps
+  int steps_done = 0;
+  int* h_done = (int*)e->pinned_buf(64);
+  while (steps_done < max_new) {
+    p.step0 = steps_done;
+    p.nsteps = std::min(SPL, max_new - steps_done);
+    launch_fused_bt(e, g, p, BT);
+    IDX_CUDA(cudaMemcpyAsync(h_done, g->done, 4, cudaMemcpyDeviceToHost, e->stream));
+    IDX_CUDA(cudaStreamSynchronize(e->stream));
+    steps_done += p.nsteps;
+    if (*h_done) break;
+  }
+  IDX_CUDA(cudaEventRecord(g->ev2, e->stream));
+
+  // ---- results ----
+  int h_nout[8];
+  IDX_CUDA(cudaMemcpyAsync(h_nout, g->nout, 32, cudaMemcpyDeviceToHost, e->stream));
+  IDX_CUDA(cudaStreamSynchronize(e->stream));
+  int maxn = 0;
+  for (int i = 0; i < nreq; ++i) {
+    maxn = std::max(maxn, h_nout[i]);
+    if (reqs[i].n_codes_out) *reqs[i].n_codes_out = h_nout[i];
+    if (reqs[i].codes_out) idx_from_device(e, reqs[i].codes_out, d_codes + (size_t)i * max_new, (size_t)h_nout[i] * 4);
+    if (reqs[i].logits_out)
+      idx_from_device(e, reqs[i].logits_out, d_ldump + (size_t)i * max_new * V, (size_t)h_nout[i] * V * 4);
+  }
+  IDX_CUDA(cudaStreamSynchronize(e->stream));
+  float ms01 = 0, ms12 = 0;
+  IDX_CUDA(cudaEventElapsedTime(&ms01, g->ev0, g->ev1));
+  IDX_CUDA(cudaEventElapsedTime(&ms12, g->ev1, g->ev2));
+  g->t_prefill_ms = ms01;
+  g->t_decode_ms = ms12;
+  g->last_steps = maxn;
+  IDX_API_END(e)
+}
+
+extern "C" int idx_gpt_last_timing(const idx_engine* e, double* out4) {
+  if (!e || !e->gpt || !out4) return IDX_ERR_STATE;
+  out4[0] = e->gpt->t_prefill_ms;
+  out4[1] = e->gpt->t_decode_ms;
+  out4[2] = e->gpt->last_steps;
+  out4[3] = e->gpt->last_launches;
+  return IDX_OK;
+}
+
+extern "C" int idx_gpt_prepare_inputs(idx_engine* e, const float* style, const float* emo_vec,
+                                      const int32_t* text_ids, int n_text, int lang, float* out) {
+  IDX_API_BEGIN
+  IDX_CHECK(e && e->gpt, IDX_ERR_STATE, "idx_gpt_init has not been called");
+  IDX_CUDA(cudaSetDevice(e->device));
+  GptState* g = e->gpt;
+  const int D = g->cfg.model_dim;
+  const int rows = 3 + n_text + 2;
+  const DevTensor& tpos = e->W("gpt.text_pos_embedding.emb.weight");
+  IDX_CHECK(n_text + 2 <= tpos.shape[0], IDX_ERR_ARG, "text longer than text_pos_embedding");
+  e->ensure_arena((size_t)rows * D * 4 + 4 * (size_t)n_text + 192 * 4 + D * 4 + (1 << 16));
+  e->arena.reset();
+  float* d_style = e->arena.get<float>(192);
+  float* d_emo = e->arena.get<float>(D);
+  int* d_ids = e->arena.get<int>(n_text + 1);
+  float* d_out = e->arena.get<float>((size_t)rows * D);
+  idx_to_device(e, d_style, style, 192 * 4);
+  idx_to_device(e, d_emo, emo_vec, (size_t)D * 4);
+  idx_to_device(e, d_ids, text_ids, (size_t)n_text * 4);
+  const float* lang_emb = e->has("gpt.lang_embedding.weight") ? e->Wf("gpt.lang_embedding.weight") : nullptr;
+  prepare_inputs_kernel<<<rows, 256, 0, e->stream>>>(
+      d_style, d_emo, d_ids, n_text, lang, e->Wf("gpt.spk_emb_proj.weight"), e->Wf("gpt.spk_emb_proj.bias"),
+      e->Wf("gpt.text_embedding.weight"), (const float*)tpos.d, lang_emb, D, g->cfg.weights_bf16, d_out);
+  IDX_CUDA(cudaGetLastError());
+  e->launches++;
+  idx_from_device(e, out, d_out, (size_t)rows * D * 4);
+  IDX_CUDA(cudaStreamSynchronize(e->stream));
+  IDX_API_END(e)
+}

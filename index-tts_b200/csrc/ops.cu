@@ -1,0 +1,163 @@
+// ops.cu — generic multi-tap GEMM (Conv1d / ConvTranspose1d / Linear on channels-last fp32) and
+// layout helpers.  Two back ends behind conv_gemm():
+//   * tcgen05 implicit GEMM (gemm_tc.cu): TMA-staged operands, TMEM accumulators, kind::tf32;
+//   * a plain SIMT fp32 tile kernel (this file): bring-up / odd-shape path and the reference
+//     the tensor-core path is tested against.  Both are CUDA; neither is a CPU fallback.
+#include "ops.h"
+#include <cstdlib>
+
+bool gemm_tc_supported(const ConvGemm& g);
+void gemm_tc_launch(idx_engine* e, const ConvGemm& g);
+
+namespace {
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case ACT_GELU_ERF: return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+    case ACT_SILU: return v / (1.f + __expf(-v));
+    case ACT_MISH: {
+      float sp = (v > 20.f) ? v : log1pf(__expf(v));
+      return v * tanhf(sp);
+    }
+    case ACT_GELU_TANH: {
+      float u = 0.7978845608028654f * (v + 0.044715f * v * v * v);
+      return 0.5f * v * (1.f + tanhf(u));
+    }
+    case ACT_RELU: return v > 0.f ? v : 0.f;
+    default: return v;
+  }
+}
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+__global__ void __launch_bounds__(256) conv_gemm_simt_kernel(const ConvGemm g) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int b = blockIdx.z;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const long long abs_ = g.a_batch_stride ? g.a_batch_stride : (long long)g.Tin * g.K;
+  const int lda = g.lda ? g.lda : g.K;
+  const float* Ab = g.A + (long long)b * abs_;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int ar = tid >> 2, ak = (tid & 3) * 4;   // A tile: row, k offset
+  const int bk = tid >> 4, bn = (tid & 15) * 4;  // B tile: k, n offset
+  for (int tap = 0; tap < g.taps; ++tap) {
+    const int row = m0 + ar;
+    int st = row + tap * g.dil - g.pad;
+    if (g.reflect) {
+      if (st < 0) st = -st;
+      if (st >= g.Tin) st = 2 * (g.Tin - 1) - st;
+    }
+    const bool rvalid = row < g.M && st >= 0 && st < g.Tin;
+    const float* arow = Ab + (long long)st * lda;
+    for (int k0 = 0; k0 < g.K; k0 += BK) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int kk = k0 + ak + i;
+        As[ak + i][ar] = (rvalid && kk < g.K) ? __ldg(arow + kk) : 0.f;
+      }
+      {
+        const int kk = k0 + bk;
+        const float* wrow = g.W + ((long long)tap * g.K + kk) * g.N;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int n = n0 + bn + i;
+          Bs[bk][bn + i] = (kk < g.K && n < g.N) ? __ldg(wrow + n) : 0.f;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        float a[4], w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+  const int ldo = g.ldo ? g.ldo : g.N;
+  const long long obs = g.out_batch_stride ? g.out_batch_stride : (long long)g.M * g.N;
+  const long long valid = g.out_valid ? g.out_valid : (long long)g.M * ldo;
+  const int biasN = g.biasN ? g.biasN : g.N;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= g.N) continue;
+      const long long flat = g.out_off + (long long)m * ldo + n;
+      if (flat < 0 || flat >= valid) continue;
+      float v = acc[i][j];
+      if (g.bias) v += __ldg(g.bias + (n % biasN));
+      v = apply_act(v, g.act);
+      if (g.colscale) v *= __ldg(g.colscale + n);
+      if (g.rowscale) v *= __ldg(g.rowscale + (long long)b * g.M + m);
+      const long long o = (long long)b * obs + flat;
+      if (g.res) v += g.res[o];
+      if (g.accum) v += g.out[o];
+      g.out[o] = v * g.scale;
+    }
+  }
+}
+
+__global__ void transpose_kernel(const float* in, float* out, int R, int Cc) {
+  // in [B][R][Cc] -> out [B][Cc][R]
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const float* ib = in + (long long)b * R * Cc;
+  float* ob = out + (long long)b * R * Cc;
+  int c = blockIdx.x * 32 + threadIdx.x;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    int r = blockIdx.y * 32 + i;
+    if (r < R && c < Cc) tile[i][threadIdx.x] = ib[(long long)r * Cc + c];
+  }
+  __syncthreads();
+  int r = blockIdx.y * 32 + threadIdx.x;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    int cc = blockIdx.x * 32 + i;
+    if (r < R && cc < Cc) ob[(long long)cc * R + r] = tile[threadIdx.x][i];
+  }
+}
+
+}  // namespace
+
+void conv_gemm(idx_engine* e, const ConvGemm& g) {
+  IDX_CHECK(g.A && g.out && g.M > 0 && g.N > 0 && g.K > 0, IDX_ERR_ARG, "conv_gemm: bad arguments");
+  static const bool force_simt = getenv("IDX_FORCE_SIMT") != nullptr;
+  if (!force_simt && g.Wk && gemm_tc_supported(g)) {
+    gemm_tc_launch(e, g);
+    return;
+  }
+  IDX_CHECK(g.W, IDX_ERR_ARG, "conv_gemm: SIMT weight layout missing");
+  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.B);
+  conv_gemm_simt_kernel<<<grid, 256, 0, e->stream>>>(g);
+  IDX_CUDA(cudaGetLastError());
+  e->launches++;
+}
+
+void transpose_bct_to_btc(idx_engine* e, const float* in, float* out, int B, int C, int T) {
+  dim3 grid((T + 31) / 32, (C + 31) / 32, B);
+  transpose_kernel<<<grid, dim3(32, 8), 0, e->stream>>>(in, out, C, T);
+  IDX_CUDA(cudaGetLastError());
+  e->launches++;
+}
+void transpose_btc_to_bct(idx_engine* e, const float* in, float* out, int B, int T, int C) {
+  dim3 grid((C + 31) / 32, (T + 31) / 32, B);
+  transpose_kernel<<<grid, dim3(32, 8), 0, e->stream>>>(in, out, T, C);
+  IDX_CUDA(cudaGetLastError());
+  e->launches++;
+}

@@ -1,0 +1,292 @@
+"""ctypes shim over libidxtts.so (include/idxtts.h).
+
+The library is the product; this file only marshals pointers.  Tensors may be torch tensors
+(CPU or CUDA) or numpy arrays — the library accepts host or device pointers.  There is no CPU
+fallback: `Engine()` raises RuntimeError when no sm_100 device is visible or the library is
+missing.
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+try:  # torch is only a tensor container here
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_PKG, "libidxtts.so")
+HEADER_PATH = os.path.join(_ROOT, "include", "idxtts.h")
+
+IDX_F32, IDX_BF16, IDX_F16, IDX_I32, IDX_I64 = 0, 1, 2, 3, 4
+
+_lib = None
+
+
+class GptConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "layers", "model_dim", "heads", "number_mel_codes", "start_mel_token", "stop_mel_token",
+        "max_mel_positions", "max_prompt", "max_batch", "weights_bf16")]
+
+
+class Sampling(C.Structure):
+    _fields_ = [("do_sample", C.c_int32), ("num_beams", C.c_int32), ("top_k", C.c_int32),
+                ("top_p", C.c_float), ("temperature", C.c_float),
+                ("repetition_penalty", C.c_float), ("length_penalty", C.c_float),
+                ("max_new_tokens", C.c_int32), ("seed", C.c_uint64),
+                ("forbid_stop_before", C.c_int32)]
+
+
+class GptRequest(C.Structure):
+    _fields_ = [("prompt_emb", C.c_void_p), ("prompt_len", C.c_int32),
+                ("codes_out", C.c_void_p), ("n_codes_out", C.c_void_p),
+                ("logits_out", C.c_void_p), ("forced_codes", C.c_void_p)]
+
+
+class BigvganConfig(C.Structure):
+    _fields_ = [("num_mels", C.c_int32), ("upsample_initial_channel", C.c_int32),
+                ("num_upsamples", C.c_int32), ("upsample_rates", C.c_int32 * 8),
+                ("upsample_kernel_sizes", C.c_int32 * 8), ("num_kernels", C.c_int32),
+                ("resblock_kernel_sizes", C.c_int32 * 4),
+                ("resblock_dilations", (C.c_int32 * 3) * 4),
+                ("use_tanh_at_final", C.c_int32), ("use_bias_at_final", C.c_int32),
+                ("snake_logscale", C.c_int32)]
+
+
+def declared_symbols():
+    """Every function the C-ABI header declares (used by the symbol-export test)."""
+    src = open(HEADER_PATH).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(idx_[a-z0-9_]+)\s*\(", src)))
+
+
+def load_library(path: str = None):
+    """dlopen the library and check that it exports everything include/idxtts.h declares."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} not found: build it with `python __graft_entry__.py` — there is no "
+            "CPU/PyTorch fallback for the hot path")
+    lib = C.CDLL(path)
+    missing = [s for s in declared_symbols() if not hasattr(lib, s)]
+    if missing:
+        raise RuntimeError(f"libidxtts.so does not export: {missing}")
+    lib.idx_last_error.restype = C.c_char_p
+    lib.idx_last_error.argtypes = [C.c_void_p]
+    lib.idx_version.restype = C.c_char_p
+    lib.idx_launch_count.restype = C.c_int64
+    lib.idx_launch_count.argtypes = [C.c_void_p]
+    lib.idx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.idx_destroy.argtypes = [C.c_void_p]
+    lib.idx_sync.argtypes = [C.c_void_p]
+    lib.idx_load_weight.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int,
+                                    C.POINTER(C.c_int64)]
+    lib.idx_gpt_init.argtypes = [C.c_void_p, C.POINTER(GptConfig)]
+    lib.idx_gpt_generate.argtypes = [C.c_void_p, C.POINTER(GptRequest), C.c_int,
+                                     C.POINTER(Sampling)]
+    lib.idx_gpt_prepare_inputs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_int, C.c_int, C.c_void_p]
+    lib.idx_gpt_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    lib.idx_bigvgan_init.argtypes = [C.c_void_p, C.POINTER(BigvganConfig)]
+    lib.idx_bigvgan_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.idx_antialias_snake.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.idx_bigvgan_last_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    _lib = lib
+    return lib
+
+
+def _ptr(x):
+    """Raw pointer of a contiguous torch tensor / numpy array (host or device)."""
+    if x is None:
+        return None
+    if torch is not None and isinstance(x, torch.Tensor):
+        assert x.is_contiguous(), "tensor must be contiguous"
+        return x.data_ptr()
+    assert isinstance(x, np.ndarray) and x.flags["C_CONTIGUOUS"]
+    return x.ctypes.data
+
+
+def _as_f32(x):
+    if torch is not None and isinstance(x, torch.Tensor):
+        return x.detach().to(torch.float32).contiguous()
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
+class Engine:
+    """One engine = one CUDA device = one caller thread at a time (include/idxtts.h)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.idx_create(int(device), C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"idx_create failed ({rc}): {self.lib.idx_last_error(None).decode()}")
+        self.h = h
+        self.device = device
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.idx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self.lib.idx_last_error(self.h).decode()}")
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.idx_launch_count(self.h))
+
+    def sync(self):
+        self._check(self.lib.idx_sync(self.h), "idx_sync")
+
+    # ------------------------------------------------------------------ weights --
+    def load_weight(self, name: str, t):
+        t = _as_f32(t)
+        shape = (C.c_int64 * max(1, t.ndim))(*[int(s) for s in t.shape])
+        self._check(self.lib.idx_load_weight(self.h, name.encode(), _ptr(t), IDX_F32, t.ndim, shape),
+                    f"idx_load_weight({name})")
+
+    def load_state_dict(self, prefix: str, sd: dict):
+        """Mirror of load_checkpoint (indextts/utils/checkpoint.py:22-35): every tensor of the
+        state dict is registered under `prefix + key`."""
+        for k, v in sd.items():
+            if hasattr(v, "dtype") and (getattr(v, "is_floating_point", lambda: True)()):
+                self.load_weight(prefix + k, v)
+
+    # ---------------------------------------------------------------------- GPT --
+    def gpt_init(self, layers, model_dim, heads, number_mel_codes=8194, start_mel_token=8192,
+                 stop_mel_token=8193, max_mel_positions=0, max_prompt=640, max_batch=1,
+                 weights_bf16=True):
+        cfg = GptConfig(layers, model_dim, heads, number_mel_codes, start_mel_token,
+                        stop_mel_token, max_mel_positions, max_prompt, max_batch,
+                        1 if weights_bf16 else 0)
+        self._check(self.lib.idx_gpt_init(self.h, C.byref(cfg)), "idx_gpt_init")
+        self.gpt_cfg = cfg
+
+    def gpt_prepare_inputs(self, style, emo_vec, text_ids, lang: int):
+        """prepare_gpt_inputs (gpt/model_v2.py:648-714): returns [3+L+2, D] float32 (numpy)."""
+        style = np.ascontiguousarray(np.asarray(style, dtype=np.float32).reshape(-1))
+        emo_vec = np.ascontiguousarray(np.asarray(emo_vec, dtype=np.float32).reshape(-1))
+        ids = np.ascontiguousarray(np.asarray(text_ids, dtype=np.int32).reshape(-1))
+        # valid_mask of model_v2.py:674: start/stop text tokens inside the padded ids are dropped
+        ids = np.ascontiguousarray(ids[(ids != 0) & (ids != 1)])
+        D = self.gpt_cfg.model_dim
+        out = np.empty((3 + len(ids) + 2, D), dtype=np.float32)
+        self._check(self.lib.idx_gpt_prepare_inputs(self.h, _ptr(style), _ptr(emo_vec), _ptr(ids),
+                                                    len(ids), int(lang), _ptr(out)),
+                    "idx_gpt_prepare_inputs")
+        return out
+
+    def gpt_generate(self, prompts, max_new_tokens, repetition_penalty=10.0, do_sample=False,
+                     num_beams=1, top_k=0, top_p=1.0, temperature=1.0, length_penalty=0.0,
+                     seed=0, forbid_stop_before=0, forced_codes=None, return_logits=False):
+        """Mirror of UnifiedVoice.inference_speech → generate (gpt/model_v2.py:716-825).
+        prompts: list of [S_i, D] float32 arrays (the [cond][text] embeddings, no padding).
+        Returns list of int32 code arrays (stop token included when produced) and, optionally,
+        the raw per-step fp32 logits."""
+        n = len(prompts)
+        V = self.gpt_cfg.number_mel_codes
+        reqs = (GptRequest * n)()
+        keep = []
+        codes = [np.zeros(max_new_tokens, dtype=np.int32) for _ in range(n)]
+        ncodes = [np.zeros(1, dtype=np.int32) for _ in range(n)]
+        logits = [np.zeros((max_new_tokens, V), dtype=np.float32) if return_logits else None
+                  for _ in range(n)]
+        for i, pr in enumerate(prompts):
+            pr = _as_f32(pr)
+            keep.append(pr)
+            reqs[i].prompt_emb = _ptr(pr)
+            reqs[i].prompt_len = int(pr.shape[0])
+            reqs[i].codes_out = _ptr(codes[i])
+            reqs[i].n_codes_out = _ptr(ncodes[i])
+            reqs[i].logits_out = _ptr(logits[i])
+            if forced_codes is not None:
+                fc = np.zeros(max_new_tokens, dtype=np.int32)
+                src = np.asarray(forced_codes[i], dtype=np.int32)[:max_new_tokens]
+                fc[:len(src)] = src
+                keep.append(fc)
+                reqs[i].forced_codes = _ptr(fc)
+        sp = Sampling(int(do_sample), int(num_beams), int(top_k), float(top_p), float(temperature),
+                      float(repetition_penalty), float(length_penalty), int(max_new_tokens),
+                      int(seed), int(forbid_stop_before))
+        self._check(self.lib.idx_gpt_generate(self.h, reqs, n, C.byref(sp)), "idx_gpt_generate")
+        out = [codes[i][: int(ncodes[i][0])].copy() for i in range(n)]
+        if return_logits:
+            return out, [logits[i][: int(ncodes[i][0])] for i in range(n)]
+        return out
+
+    def gpt_last_timing(self):
+        t = (C.c_double * 4)()
+        self._check(self.lib.idx_gpt_last_timing(self.h, t), "idx_gpt_last_timing")
+        return {"prefill_ms": t[0], "decode_ms": t[1], "steps": int(t[2]), "launches": int(t[3])}
+
+    # ------------------------------------------------------------------ BigVGAN --
+    def bigvgan_init(self, h: dict):
+        cfg = BigvganConfig()
+        cfg.num_mels = h.get("num_mels", 80)
+        cfg.upsample_initial_channel = h["upsample_initial_channel"]
+        rates, ks = h["upsample_rates"], h["upsample_kernel_sizes"]
+        cfg.num_upsamples = len(rates)
+        for i, (r, k) in enumerate(zip(rates, ks)):
+            cfg.upsample_rates[i] = r
+            cfg.upsample_kernel_sizes[i] = k
+        rk, rd = h["resblock_kernel_sizes"], h["resblock_dilation_sizes"]
+        cfg.num_kernels = len(rk)
+        for j, (k, ds) in enumerate(zip(rk, rd)):
+            cfg.resblock_kernel_sizes[j] = k
+            for m, d in enumerate(ds):
+                cfg.resblock_dilations[j][m] = d
+        cfg.use_tanh_at_final = int(h.get("use_tanh_at_final", True))
+        cfg.use_bias_at_final = int(h.get("use_bias_at_final", True))
+        cfg.snake_logscale = int(h.get("snake_logscale", True))
+        self._check(self.lib.idx_bigvgan_init(self.h, C.byref(cfg)), "idx_bigvgan_init")
+        self.bigvgan_cfg = cfg
+        self._bigvgan_up = int(np.prod(rates))
+
+    def bigvgan_forward(self, mel, out=None):
+        """BigVGAN.forward (s2mel/modules/bigvgan/bigvgan.py:360-386): mel [B,80,F] f32 →
+        wav [B,1,F*256] f32.  Accepts numpy (host) or torch (host/cuda) buffers."""
+        mel = _as_f32(mel)
+        B, _, F = mel.shape
+        n = F * self._bigvgan_up
+        if out is None:
+            if torch is not None and isinstance(mel, torch.Tensor):
+                out = torch.empty((B, 1, n), dtype=torch.float32, device=mel.device)
+            else:
+                out = np.empty((B, 1, n), dtype=np.float32)
+        self._check(self.lib.idx_bigvgan_forward(self.h, _ptr(mel), B, F, _ptr(out)),
+                    "idx_bigvgan_forward")
+        return out
+
+    def bigvgan_last_ms(self):
+        t = C.c_double()
+        self._check(self.lib.idx_bigvgan_last_ms(self.h, C.byref(t)), "idx_bigvgan_last_ms")
+        return t.value
+
+    def antialias_snake(self, x, alpha, beta, logscale=True):
+        """Activation1d(SnakeBeta) (alias_free_activation/torch/act.py:8-30) on x [B,C,T]."""
+        x = _as_f32(x)
+        alpha, beta = _as_f32(alpha), _as_f32(beta)
+        B, Cc, T = x.shape
+        if torch is not None and isinstance(x, torch.Tensor):
+            y = torch.empty_like(x)
+        else:
+            y = np.empty_like(x)
+        self._check(self.lib.idx_antialias_snake(self.h, _ptr(x), _ptr(alpha), _ptr(beta), B, Cc, T,
+                                                 int(logscale), _ptr(y)), "idx_antialias_snake")
+        return y

@@ -1,0 +1,219 @@
+"""CPU restatement of the IndexTTS v2/v2.5 GPT speech-token path.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product path (index-tts_b200/) never imports it.
+
+Parity status: the reference's own tests pin no numbers for this path (SURVEY.md §4, §8c —
+"parity unpinned" by the reference).  This restatement is pinned instead against stock
+`transformers.GPT2Model` (the block arithmetic the reference executes, gpt/model_v2.py:263)
+run in this container — fp32 and CPU-autocast bf16 — by oracle/validate_gpt_vs_hf.py, and the
+golden vectors in tests/golden/gpt_*.npz were minted from that HF path.
+
+What is restated (reference file:line):
+  prepare_gpt_inputs                       indextts/gpt/model_v2.py:648-714 (+ :754-768 conds)
+  GPT2InferenceModel.forward               indextts/gpt/model_v2.py:121-198
+      prefill: cat(prompt_emb, mel_emb[start] + mel_pos[0])             :146-156, :244-256
+      cached step k>=1: mel_emb[tok] + mel_pos[mask_len - S] = pos k+1  :158-161   (trap P1)
+  GPT2Block / Attention / MLP              indextts/gpt/transformers_gpt2.py:189-227,571-667
+      ln eps 1e-5, Conv1D weight [in,out], gelu_new                     (trap P4)
+  ln_f then lm_head = Sequential(final_norm, mel_head)  model_v2.py:54,186 (trap P3)
+  greedy _sample + RepetitionPenalty over ALL input_ids incl. the fake prompt [1..1, 8192]
+      indextts/gpt/transformers_generation_utils.py:3196-3265; model_v2.py:705-713 (trap P2)
+  logits upcast to fp32 before processors   transformers_generation_utils.py:3220 (trap P5)
+
+bf16 policy (`bf16=True`, the reference's use_bf16 path: infer_v2_5.py:143-146,758): weights
+are bf16 values; every tensor autocast materialises in bf16 is rounded to bf16 (after each
+Conv1D / Linear, after every elementwise op of NewGELUActivation); LayerNorm runs
+fp32-in/fp32-out; attention keeps fp32 scores/softmax and rounds its output.
+Trap P12 (found while pinning against HF): the RESIDUAL STREAM IS FP32 even on the bf16 path —
+`null_position_embeddings` returns fp32 zeros (model_v2.py:23-24), GPT2Model adds them to the
+bf16 inputs_embeds (transformers_gpt2.py:1037-1038) and type promotion makes hidden_states
+fp32; every later `attn_output + residual` (:639, :664) adds a bf16 branch to the fp32 stream
+and stays fp32.  So residual adds are NOT rounded; only the branch outputs are.
+"""
+import math
+
+import numpy as np
+import torch
+
+
+def r16(x: torch.Tensor) -> torch.Tensor:
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def gpt_config(layers=24, model_dim=1280, heads=20, number_mel_codes=8194, start_mel_token=8192,
+               stop_mel_token=8193, max_mel_tokens=1815, max_text_tokens=600,
+               number_text_tokens=12000, n_langs=8):
+    return dict(layers=layers, model_dim=model_dim, heads=heads, number_mel_codes=number_mel_codes,
+                start_mel_token=start_mel_token, stop_mel_token=stop_mel_token,
+                max_mel_tokens=max_mel_tokens, max_text_tokens=max_text_tokens,
+                number_text_tokens=number_text_tokens, n_langs=n_langs,
+                max_mel_positions=max_mel_tokens + 2 + 1)  # model_v2.py:398-400
+
+
+def make_gpt_weights(cfg, seed=1234, bf16=True, head_gain=4.0):
+    """Deterministic synthetic weights under the reference's state-dict names.
+
+    Init follows transformers_gpt2.py:689-714 (normal std 0.02, c_proj std 0.02/sqrt(2L)) and
+    model_v2.py:249,413-417 (embeddings std 0.02), except that biases / LayerNorm affine get
+    small random values so the bias paths are exercised, and the mel head is scaled by
+    `head_gain` so that greedy decisions are not dominated by ties of near-flat logits.
+    """
+    g = torch.Generator().manual_seed(seed)
+    L, D, V = cfg["layers"], cfg["model_dim"], cfg["number_mel_codes"]
+    w = {}
+
+    def n(*shape, std=0.02):
+        return torch.randn(*shape, generator=g) * std
+
+    for l in range(L):
+        p = f"gpt.h.{l}."
+        w[p + "ln_1.weight"] = 1.0 + n(D, std=0.1)
+        w[p + "ln_1.bias"] = n(D, std=0.05)
+        w[p + "attn.c_attn.weight"] = n(D, 3 * D)
+        w[p + "attn.c_attn.bias"] = n(3 * D)
+        w[p + "attn.c_proj.weight"] = n(D, D, std=0.02 / math.sqrt(2 * L))
+        w[p + "attn.c_proj.bias"] = n(D)
+        w[p + "ln_2.weight"] = 1.0 + n(D, std=0.1)
+        w[p + "ln_2.bias"] = n(D, std=0.05)
+        w[p + "mlp.c_fc.weight"] = n(D, 4 * D)
+        w[p + "mlp.c_fc.bias"] = n(4 * D)
+        w[p + "mlp.c_proj.weight"] = n(4 * D, D, std=0.02 / math.sqrt(2 * L))
+        w[p + "mlp.c_proj.bias"] = n(D)
+    w["gpt.ln_f.weight"] = 1.0 + n(D, std=0.1)
+    w["gpt.ln_f.bias"] = n(D, std=0.05)
+    w["final_norm.weight"] = 1.0 + n(D, std=0.1)
+    w["final_norm.bias"] = n(D, std=0.05)
+    w["mel_head.weight"] = n(V, D, std=head_gain / math.sqrt(D))
+    w["mel_head.bias"] = n(V, std=0.1)
+    w["mel_embedding.weight"] = n(V, D)
+    w["mel_pos_embedding.emb.weight"] = n(cfg["max_mel_positions"], D)
+    w["text_embedding.weight"] = n(cfg["number_text_tokens"] + 1, D)
+    w["text_pos_embedding.emb.weight"] = n(cfg["max_text_tokens"] + 2, D)
+    w["lang_embedding.weight"] = n(cfg["n_langs"] + 1, D)
+    w["spk_emb_proj.weight"] = n(D, 192, std=1.0 / math.sqrt(192))
+    w["spk_emb_proj.bias"] = n(D)
+    if bf16:
+        w = {k: r16(v) for k, v in w.items()}
+    return w
+
+
+def prepare_gpt_inputs(w, style, emo_vec, text_ids, lang, bf16=True):
+    """[cond(3)][start_text, text…, stop_text] embeddings (model_v2.py:648-714, :754-768).
+    style [192], emo_vec [D], text_ids 1-D ints (start/stop tokens inside are dropped, :674)."""
+    rr = r16 if bf16 else (lambda x: x)
+    style = torch.as_tensor(style, dtype=torch.float32).reshape(-1)
+    emo_vec = torch.as_tensor(emo_vec, dtype=torch.float32).reshape(-1)
+    ids = torch.as_tensor(np.asarray(text_ids), dtype=torch.long).reshape(-1)
+    ids = ids[(ids != 0) & (ids != 1)]
+    spk = rr(rr(style) @ w["spk_emb_proj.weight"].t() + w["spk_emb_proj.bias"])  # :754
+    cond0 = rr(spk + emo_vec)                                                      # :768
+    D = cond0.shape[0]
+    ids = torch.cat([torch.tensor([0]), ids, torch.tensor([1])])                   # :676-677
+    pos = torch.arange(ids.shape[0])
+    temb = rr(w["text_embedding.weight"][ids] + w["text_pos_embedding.emb.weight"][pos])  # :679
+    if lang is not None:
+        temb = rr(temb + w["lang_embedding.weight"][lang])                         # :681
+    return torch.cat([cond0[None], torch.zeros(2, D), temb], dim=0)
+
+
+def _gelu_new(x, bf16):
+    if not bf16:
+        return 0.5 * x * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (x + 0.044715 * torch.pow(x, 3.0))))
+    # NewGELUActivation on a bf16 tensor: every op materialises a bf16 tensor
+    t1 = r16(x * x * x)
+    t2 = r16(0.044715 * t1)
+    t3 = r16(x + t2)
+    t4 = r16(math.sqrt(2.0 / math.pi) * t3)
+    t5 = r16(torch.tanh(t4))
+    t6 = r16(1.0 + t5)
+    t7 = r16(0.5 * x)
+    return r16(t7 * t6)
+
+
+def _ln(x, w, b):
+    return torch.nn.functional.layer_norm(x, (x.shape[-1],), w, b, 1e-5)
+
+
+class GptOracle:
+    def __init__(self, cfg, weights, bf16=True):
+        self.cfg, self.w, self.bf16 = cfg, weights, bf16
+        self.rr = r16 if bf16 else (lambda x: x)
+        self.reset()
+
+    def reset(self):
+        L = self.cfg["layers"]
+        self.k = [None] * L
+        self.v = [None] * L
+
+    def forward_rows(self, x):
+        """x [T, D] new positions (appended to the KV cache, causal) → final hidden [T, D]."""
+        cfg, w, rr = self.cfg, self.w, self.rr
+        H = cfg["heads"]
+        T, D = x.shape
+        hd = D // H
+        for l in range(cfg["layers"]):
+            p = f"gpt.h.{l}."
+            h = _ln(x, w[p + "ln_1.weight"], w[p + "ln_1.bias"])
+            qkv = rr(rr(h) @ w[p + "attn.c_attn.weight"] + w[p + "attn.c_attn.bias"])
+            q, k, v = qkv.split(D, dim=-1)
+            self.k[l] = k if self.k[l] is None else torch.cat([self.k[l], k], 0)
+            self.v[l] = v if self.v[l] is None else torch.cat([self.v[l], v], 0)
+            K, Vv = self.k[l], self.v[l]
+            S = K.shape[0]
+            qh = q.view(T, H, hd).transpose(0, 1)
+            kh = K.view(S, H, hd).transpose(0, 1)
+            vh = Vv.view(S, H, hd).transpose(0, 1)
+            sc = (qh @ kh.transpose(1, 2)) / math.sqrt(hd)          # transformers_gpt2.py:199-203
+            qpos = torch.arange(S - T, S)[:, None]
+            mask = torch.arange(S)[None, :] <= qpos
+            sc = sc.masked_fill(~mask[None], float("-inf"))
+            a = rr((torch.softmax(sc, dim=-1) @ vh).transpose(0, 1).reshape(T, D))
+            o = rr(a @ w[p + "attn.c_proj.weight"] + w[p + "attn.c_proj.bias"])
+            x = x + o            # residual stream stays fp32 (trap P12, see module docstring)
+            h = _ln(x, w[p + "ln_2.weight"], w[p + "ln_2.bias"])
+            f = rr(rr(h) @ w[p + "mlp.c_fc.weight"] + w[p + "mlp.c_fc.bias"])
+            f = _gelu_new(f, self.bf16)
+            m = rr(f @ w[p + "mlp.c_proj.weight"] + w[p + "mlp.c_proj.bias"])
+            x = x + m
+        return x
+
+    def logits(self, hidden):
+        w, rr = self.w, self.rr
+        h = _ln(hidden, w["gpt.ln_f.weight"], w["gpt.ln_f.bias"])            # GPT2Model ln_f
+        h = _ln(h, w["final_norm.weight"], w["final_norm.bias"])              # lm_head[0]  (P3)
+        return rr(rr(h) @ w["mel_head.weight"].t() + w["mel_head.bias"])      # .float()    (P5)
+
+    @torch.no_grad()
+    def generate(self, prompt_emb, max_new_tokens, repetition_penalty=10.0, forbid_stop_before=0,
+                 forced=None):
+        """Greedy decode. Returns (codes incl. stop token, raw logits [n, V])."""
+        cfg, w, rr = self.cfg, self.w, self.rr
+        start, stop = cfg["start_mel_token"], cfg["stop_mel_token"]
+        self.reset()
+        prompt_emb = torch.as_tensor(prompt_emb, dtype=torch.float32)
+        first = rr(w["mel_embedding.weight"][start] + w["mel_pos_embedding.emb.weight"][0])
+        x = torch.cat([prompt_emb, first[None]], dim=0)                       # model_v2.py:146-156
+        hidden = self.forward_rows(x)[-1:]
+        seen = {1, start}                                                     # fake ids (P2)
+        codes, all_logits = [], []
+        for k in range(max_new_tokens):
+            lg = self.logits(hidden)[0]
+            all_logits.append(lg.clone())
+            s = lg.clone()
+            idx = torch.tensor(sorted(seen))
+            sv = s[idx]
+            s[idx] = torch.where(sv < 0, sv * repetition_penalty, sv / repetition_penalty)
+            if k < forbid_stop_before:
+                s[stop] = float("-inf")
+            tok = int(torch.argmax(s))  # first maximal index on CPU
+            codes.append(tok)
+            feed = tok if forced is None else int(forced[k])
+            if forced is None and tok == stop:
+                break
+            if k + 1 >= max_new_tokens:
+                break
+            seen.add(feed)
+            emb = rr(w["mel_embedding.weight"][feed] + w["mel_pos_embedding.emb.weight"][k + 2])
+            hidden = self.forward_rows(emb[None])                             # position k+2 (P1)
+        return np.array(codes, dtype=np.int32), torch.stack(all_logits).numpy()

@@ -1,0 +1,112 @@
+"""GPU parity tests of the fused GPT decode path (through the C-ABI) against the CPU oracle and
+the golden vectors minted from stock transformers.GPT2Model.
+
+Tolerances (bf16 path): logits are bf16 values (ulp 2^-6 = 0.0156 at |x| in [2,4), 0.031 in
+[4,8)); the reference path itself is only defined up to its rounding noise (HF autocast vs HF
+fp32 on the golden case: rms 0.0185, see oracle/validate_gpt_vs_hf.py).  The engine must agree
+with the oracle to rms <= 0.03 and max-abs <= 0.13 per step under teacher forcing, and its greedy
+pick must equal the oracle's except at near-ties (processed-score gap <= 0.07)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.gpt_common import (GptOracle, check_teacher_forced, gpt_config, load_gpt,
+                              make_gpt_weights, prepare_gpt_inputs, r16)
+from oracle.validate_gpt_vs_hf import small_case
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "gpt_small.npz")
+TOL = dict(max_abs=0.13, max_rms=0.03, tie_tol=0.07)
+
+
+def test_prepare_inputs_matches_oracle(engine):
+    cfg, style, emo, text = small_case()
+    w = make_gpt_weights(cfg, seed=1234, bf16=True)
+    load_gpt(engine, cfg, w)
+    ref = prepare_gpt_inputs(w, style, r16(emo), text, lang=1, bf16=True).numpy()
+    got = engine.gpt_prepare_inputs(style.numpy(), r16(emo).numpy(), text.numpy(), 1)
+    assert got.shape == ref.shape
+    # rows >= 1 are pure gathers + bf16 adds: bit exact; row 0 has a 192-term dot product
+    assert np.array_equal(got[1:], ref[1:])
+    assert np.abs(got[0] - ref[0]).max() <= 2.0 ** -6
+
+
+def test_small_bf16_greedy_vs_hf_golden(engine):
+    g = np.load(GOLD)
+    cfg, style, emo, text = small_case()
+    w = make_gpt_weights(cfg, seed=int(g["weight_seed"]), bf16=True)
+    load_gpt(engine, cfg, w)
+    n = int(g["n_steps"])
+    prompt = g["prompt_bf16"]
+    o_codes, o_logits = g["bf16_codes"], g["bf16_logits"]
+    (e_codes,), (e_logits,) = engine.gpt_generate([prompt], n, 10.0, forbid_stop_before=n,
+                                                  forced_codes=[o_codes], return_logits=True)
+    ties = check_teacher_forced(cfg, o_codes, o_logits, e_codes, e_logits, 10.0, n, **TOL)
+    # free running: identical tokens up to the first near-tie
+    (f_codes,) = engine.gpt_generate([prompt], n, 10.0, forbid_stop_before=n)
+    if ties == 0:
+        assert np.array_equal(f_codes, o_codes)
+    # and the engine is inside the bf16 noise of the real HF autocast path as well
+    d = e_logits - g["hf_autocast_logits"]
+    assert np.sqrt((d ** 2).mean()) < 0.035
+
+
+def test_batched_ragged_prompts_equal_single(engine):
+    """Mirror of the reference's only token-level check (tests/padding_test.py:83-108): the same
+    utterance decoded alone, and inside a batch of ragged prompts, yields the same tokens."""
+    cfg, style, emo, _ = small_case()
+    w = make_gpt_weights(cfg, seed=99, bf16=True)
+    load_gpt(engine, cfg, w, max_batch=4)
+    g = torch.Generator().manual_seed(5)
+    prompts = []
+    for n_text in (3, 9, 17):
+        text = torch.randint(2, 100, (n_text,), generator=g)
+        prompts.append(prepare_gpt_inputs(w, style, r16(emo), text, lang=2, bf16=True).numpy())
+    n = 16
+    singles = [engine.gpt_generate([p], n, 10.0, forbid_stop_before=n, return_logits=True) for p in prompts]
+    codes_b, logits_b = engine.gpt_generate(prompts, n, 10.0, forbid_stop_before=n, return_logits=True,
+                                            forced_codes=[s[0][0] for s in singles])
+    for i in range(3):
+        sc, sl = singles[i][0][0], singles[i][1][0]
+        check_teacher_forced(cfg, sc, sl, codes_b[i], logits_b[i], 10.0, n, **TOL)
+
+
+def test_stop_token_and_lengths(engine):
+    cfg, style, emo, text = small_case()
+    w = make_gpt_weights(cfg, seed=5, bf16=True)
+    w["mel_head.bias"] = w["mel_head.bias"].clone()
+    w["mel_head.bias"][cfg["stop_mel_token"]] += 100.0
+    load_gpt(engine, cfg, w)
+    prompt = prepare_gpt_inputs(w, style, r16(emo), text, lang=0, bf16=True).numpy()
+    (codes,) = engine.gpt_generate([prompt], 40, 10.0, forbid_stop_before=3)
+    assert len(codes) == 4 and codes[-1] == cfg["stop_mel_token"]
+    o_codes, _ = GptOracle(cfg, w, bf16=True).generate(prompt, 40, 10.0, 3)
+    assert len(o_codes) == 4
+    # max_new_tokens bound
+    (codes,) = engine.gpt_generate([prompt], 5, 10.0, forbid_stop_before=100)
+    assert len(codes) == 5
+
+
+def test_full_size_v25_decode_vs_oracle(engine):
+    """IndexTTS-2.5 geometry [ASSUMED 24 x 1280 x 20 heads, V=8194]: 48 greedy steps, S=37."""
+    cfg = gpt_config()
+    w = make_gpt_weights(cfg, seed=2025, bf16=True)
+    load_gpt(engine, cfg, w, max_prompt=64)
+    g = torch.Generator().manual_seed(11)
+    style = torch.randn(192, generator=g)
+    emo = r16(torch.randn(cfg["model_dim"], generator=g) * 0.5)
+    text = torch.randint(2, 12000, (32,), generator=g)
+    prompt = prepare_gpt_inputs(w, style, emo, text, lang=1, bf16=True).numpy()
+    n = 48
+    o_codes, o_logits = GptOracle(cfg, w, bf16=True).generate(prompt, n, 10.0, n)
+    (e_codes,), (e_logits,) = engine.gpt_generate([prompt], n, 10.0, forbid_stop_before=n,
+                                                  forced_codes=[o_codes], return_logits=True)
+    ties = check_teacher_forced(cfg, o_codes, o_logits, e_codes, e_logits, 10.0, n, **TOL)
+    (f_codes,) = engine.gpt_generate([prompt], n, 10.0, forbid_stop_before=n)
+    agree = int((f_codes == o_codes).sum())
+    print(f"full-size: teacher-forced near-tie disagreements {ties}/{n}; free-run agreement {agree}/{n}; "
+          f"timing {engine.gpt_last_timing()}")
+    if ties == 0:
+        assert np.array_equal(f_codes, o_codes)

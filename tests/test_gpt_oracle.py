@@ -1,0 +1,71 @@
+"""CPU: the GPT oracle against the golden vectors minted from stock transformers.GPT2Model
+(oracle/validate_gpt_vs_hf.py), plus the index-bookkeeping traps of SURVEY.md §0/A.3."""
+import os
+
+import numpy as np
+import torch
+
+from oracle.gpt import GptOracle, make_gpt_weights, prepare_gpt_inputs, r16
+from oracle.validate_gpt_vs_hf import small_case
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "gpt_small.npz")
+
+
+def test_fp32_oracle_matches_hf_golden():
+    g = np.load(GOLD)
+    cfg, style, emo, text = small_case()
+    assert np.array_equal(text.numpy(), g["text"])
+    w = make_gpt_weights(cfg, seed=int(g["weight_seed"]), bf16=False)
+    prompt = prepare_gpt_inputs(w, style, emo, text, lang=int(g["lang"]), bf16=False)
+    n = int(g["n_steps"])
+    codes, logits = GptOracle(cfg, w, bf16=False).generate(prompt, n, 10.0, n)
+    assert np.array_equal(codes, g["hf_fp32_codes"])
+    assert np.abs(logits - g["hf_fp32_logits"]).max() < 2e-4
+
+
+def test_bf16_oracle_reproduces_golden_bit_exact():
+    g = np.load(GOLD)
+    cfg, style, emo, text = small_case()
+    w = make_gpt_weights(cfg, seed=int(g["weight_seed"]), bf16=True)
+    prompt = prepare_gpt_inputs(w, style, r16(emo), text, lang=int(g["lang"]), bf16=True)
+    assert np.array_equal(prompt.numpy(), g["prompt_bf16"])
+    n = int(g["n_steps"])
+    codes, logits = GptOracle(cfg, w, bf16=True).generate(prompt, n, 10.0, n)
+    assert np.array_equal(codes, g["bf16_codes"])
+    assert np.array_equal(logits, g["bf16_logits"])
+    # and it sits inside the bf16 noise of the HF autocast path
+    d = logits - g["hf_autocast_logits"]
+    assert np.sqrt((d ** 2).mean()) < 0.03
+
+
+def test_position_rule_and_repetition_penalty_traps():
+    """P1: generated token k is embedded at mel position k+1 (position 1 is never used);
+    P2: codes 1 and start_mel are penalised from step 0."""
+    cfg, style, emo, text = small_case()
+    w = make_gpt_weights(cfg, seed=3, bf16=False)
+    prompt = prepare_gpt_inputs(w, style, emo, text, lang=0, bf16=False)
+    orc = GptOracle(cfg, w, bf16=False)
+    codes, logits = orc.generate(prompt, 4, 10.0, 4)
+    # recompute step 2 by hand with position index 3 for the second generated token
+    orc.reset()
+    first = w["mel_embedding.weight"][cfg["start_mel_token"]] + w["mel_pos_embedding.emb.weight"][0]
+    h = orc.forward_rows(torch.cat([prompt, first[None]], 0))[-1:]
+    h = orc.forward_rows((w["mel_embedding.weight"][int(codes[0])] + w["mel_pos_embedding.emb.weight"][2])[None])
+    h = orc.forward_rows((w["mel_embedding.weight"][int(codes[1])] + w["mel_pos_embedding.emb.weight"][3])[None])
+    assert np.allclose(orc.logits(h)[0].numpy(), logits[2], atol=1e-5)
+    # P2: make token 1 the raw argmax at step 0 and check the penalty removes it
+    w2 = dict(w)
+    w2["mel_head.bias"] = w["mel_head.bias"].clone()
+    w2["mel_head.bias"][1] += 50.0
+    c2, l2 = GptOracle(cfg, w2, bf16=False).generate(prompt, 1, 10.0, 1)
+    assert int(np.argmax(l2[0])) == 1 and int(c2[0]) != 1
+
+
+def test_stop_token_ends_generation():
+    cfg, style, emo, text = small_case()
+    w = make_gpt_weights(cfg, seed=5, bf16=False)
+    w["mel_head.bias"] = w["mel_head.bias"].clone()
+    w["mel_head.bias"][cfg["stop_mel_token"]] += 100.0
+    prompt = prepare_gpt_inputs(w, style, emo, text, lang=0, bf16=False)
+    codes, _ = GptOracle(cfg, w, bf16=False).generate(prompt, 10, 10.0, 3)
+    assert len(codes) == 4 and codes[-1] == cfg["stop_mel_token"]
