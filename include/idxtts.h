@@ -147,6 +147,11 @@ int idx_gpt_prepare_inputs(idx_engine* e, const float* style, const float* emo_v
  * out[3] = fused-step kernel launches.                                               */
 int idx_gpt_last_timing(const idx_engine* e, double* out4);
 
+/* Diagnostic: when `enable` is non-zero the fused kernel records %globaltimer (ns) of CTA 0 at
+ * every phase boundary of the last step of each launch (2 stamps per grid barrier: before and
+ * after).  Copies up to n (<= 256) stamps of the most recent launch into stamps_out.          */
+int idx_gpt_profile(idx_engine* e, int enable, int64_t* stamps_out, int n);
+
 /* ------------------------------------------------------------------- BigVGAN -- */
 
 /* Geometry of the BigVGAN-v2 generator (s2mel/modules/bigvgan/config.json:11-21).    */

@@ -43,6 +43,7 @@ constexpr int UPC = 8;                      // weight units (one K-segment of D 
 constexpr int MAXPL = 40;                   // max LayerNorm elements per lane (D <= 1280)
 constexpr int HD = 64;                      // head dim (fixed)
 constexpr int PART_STRIDE = 66;             // attention partial: m, l, o[64]
+#define RED_FLOATS(BT) ((2 * 5 * UPC * (BT)) > (NCW * PART_STRIDE) ? (2 * 5 * UPC * (BT)) : (NCW * PART_STRIDE))
 
 struct PrefillTile {
   int seq, pos0, nrows, src_row;
@@ -59,6 +60,9 @@ struct GptParams {
   float rep_penalty;
   int round_bf16;   // 1: emulate autocast bf16 rounding points
   int nst;          // ring stages
+  int bar_flavor;   // 0: fence after the grid barrier, 1: none (consumers use ld.cg)
+  int bias_cap;     // floats reserved for the per-CTA bias table
+  int ocap;         // max O-proj columns per CTA
   // packed weights
   const __nv_bfloat16* wstream;   // all CTA streams
   const long long* stream_off;    // [G] unit offset of CTA i's stream
@@ -90,6 +94,7 @@ struct GptParams {
   const float* prompt;  // [rows][D] f32
   const PrefillTile* tiles;
   unsigned* barrier;    // grid barrier counter (zeroed before each launch)
+  long long* prof;      // optional: globaltimer stamps of CTA 0 for the last step of the launch
 };
 
 __device__ __forceinline__ float bf16r(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
@@ -97,64 +102,83 @@ __device__ __forceinline__ float rnd(float v, int on) { return on ? bf16r(v) : v
 __device__ __forceinline__ float lo_bf(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float hi_bf(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
+__device__ __forceinline__ long long gtimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
-// Grid-wide barrier among the compute warps of all CTAs (monotonic counter).
-__device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned& target, int G) {
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ptx::smem_u32(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Grid-wide barrier among the compute warps of all CTAs (monotonic counter).  All cross-CTA
+// data is read with ld.global.cg (L2), so no L1 invalidation is needed on the consumer side.
+// Every thread also drains its cp.async prefetches (LayerNorm parameters of the next phase)
+// before the closing CTA barrier, so they are visible to the whole CTA afterwards.
+__device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned& target, int G, int flavor) {
   ptx::named_bar_sync(1, NCT);
   if (threadIdx.x == 0) {
     target += (unsigned)G;
-    __threadfence();
-    ptx::red_release_gpu_add(ctr, 1u);
+    __threadfence();                      // release: the CTA's stores of this phase
+    atomicAdd(ctr, 1u);
     unsigned spins = 0;
-    while (ptx::ld_acquire_gpu(ctr) < target) {
+    while (ld_relaxed_gpu(ctr) < target) {
       if (++spins > (1u << 28)) __trap();
     }
-    __threadfence();
+    if (flavor == 0) __threadfence();     // acquire
   }
+  cp_async_wait_all();
   ptx::named_bar_sync(1, NCT);
 }
 
 // LayerNorm of one row by one warp, fp32, two-pass from registers.
 // Element i of the row lives in lane (i % 32), slot (i / 32); slots >= npl are unused.
-__device__ __forceinline__ void ln_row(const float (&v_in)[MAXPL], float (&v_out)[MAXPL], int npl,
-                                       int D, const float* w, const float* b, int lane) {
+template <int NPL>
+__device__ __forceinline__ void ln_row(const float (&v_in)[NPL], float (&v_out)[NPL],
+                                       const float* w, const float* b, int lane) {
+  constexpr float invD = 1.0f / (float)(NPL * 32);
   float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < MAXPL; ++j)
-    if (j < npl) s += v_in[j];
-  const float mean = warp_sum(s) / (float)D;
+  for (int j = 0; j < NPL; ++j) s += v_in[j];
+  const float mean = warp_sum(s) * invD;
   float q = 0.f;
 #pragma unroll
-  for (int j = 0; j < MAXPL; ++j)
-    if (j < npl) {
-      const float d = v_in[j] - mean;
-      q += d * d;
-    }
-  const float var = warp_sum(q) / (float)D;
+  for (int j = 0; j < NPL; ++j) {
+    const float d = v_in[j] - mean;
+    q += d * d;
+  }
+  const float var = warp_sum(q) * invD;
   const float rstd = rsqrtf(var + 1e-5f);
 #pragma unroll
-  for (int j = 0; j < MAXPL; ++j)
-    if (j < npl) {
-      const int i = lane + 32 * j;
-      v_out[j] = (v_in[j] - mean) * rstd * __ldg(w + i) + __ldg(b + i);
-    }
+  for (int j = 0; j < NPL; ++j) {
+    const int i = lane + 32 * j;
+    v_out[j] = (v_in[j] - mean) * rstd * w[i] + b[i];
+  }
 }
 
-__device__ __forceinline__ void load_row(float (&v)[MAXPL], const float* x, int npl, int lane) {
+template <int NPL>
+__device__ __forceinline__ void load_row(float (&v)[NPL], const float* x, int lane) {
 #pragma unroll
-  for (int j = 0; j < MAXPL; ++j)
-    if (j < npl) v[j] = __ldcg(x + lane + 32 * j);
+  for (int j = 0; j < NPL; ++j) v[j] = __ldcg(x + lane + 32 * j);
 }
-__device__ __forceinline__ void store_row_bf16(const float (&v)[MAXPL], __nv_bfloat16* xs, int npl,
-                                               int lane) {
+template <int NPL>
+__device__ __forceinline__ void store_row_bf16(const float (&v)[NPL], __nv_bfloat16* xs, int lane) {
 #pragma unroll
-  for (int j = 0; j < MAXPL; ++j)
-    if (j < npl) xs[lane + 32 * j] = __float2bfloat16_rn(v[j]);
+  for (int j = 0; j < NPL; ++j) xs[lane + 32 * j] = __float2bfloat16_rn(v[j]);
 }
 
 // NewGELUActivation with a bf16 round after every tensor op (transformers activations.py,
@@ -179,124 +203,209 @@ struct Smem {
   uint64_t* full;       // [nst]
   uint64_t* empty;      // [nst]
   int* flags;           // [4]: 0 exit flag for producer, 1 broadcast slot
+  float* bias_s;        // per-CTA biases of every layer/phase + head, loaded once per launch
+  float* xres;          // [BT][ocap] this CTA's slice of the fp32 residual stream
+  float* lnp;           // [2][2][D] LayerNorm (weight,bias) double buffer, filled by cp.async
+  unsigned* seen_s;     // [(V+31)/32] repetition-penalty bitmap of the sequence being sampled
 };
 
+// Cooperative LayerNorm of ONE row by all 8 compute warps (batch-1 decode, where a warp-per-row
+// LayerNorm would leave 7 warps idle on the critical path).  Shifted one-pass statistics:
+// S1 = sum(x-K), S2 = sum((x-K)^2) with K = x[0]; thread t owns NPL/8 elements.
+template <int NPL>
+__device__ __forceinline__ void ln_block(float (&v)[NPL / 8], float K, const float* w, const float* b,
+                                         float* red, int warp, int lane) {
+  constexpr int NPT = NPL / 8;
+  constexpr float invD = 1.0f / (float)(NPL * 32);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < NPT; ++j) {
+    const float d = v[j] - K;
+    s1 += d;
+    s2 = fmaf(d, d, s2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (lane == 0) { red[2 * warp] = s1; red[2 * warp + 1] = s2; }
+  ptx::named_bar_sync(1, NCT);
+  float S1 = 0.f, S2 = 0.f;
+#pragma unroll
+  for (int q = 0; q < NCW; ++q) { S1 += red[2 * q]; S2 += red[2 * q + 1]; }
+  const float m1 = S1 * invD;
+  const float mean = K + m1;
+  const float var = fmaxf(S2 * invD - m1 * m1, 0.f);
+  const float rstd = rsqrtf(var + 1e-5f);
+#pragma unroll
+  for (int j = 0; j < NPT; ++j) {
+    const int i = warp * (NPL * 4) + lane + 32 * j;
+    v[j] = (v[j] - mean) * rstd * w[i] + b[i];
+  }
+}
+
 // One GEMV phase over this CTA's column slice.  `nseg` K-segments of D per column.
+// Chunks are consumed in groups of GC so that a warp's GC dot products (one unit per chunk) run
+// interleaved — one dependency chain per phase instead of one per chunk.
 // EPI: 0 QKV, 1 O-proj(+residual), 2 FC(+gelu), 3 PROJ(+residual), 4 HEAD
-template <int BT, int EPI>
+template <int BT, int EPI, int D>
 __device__ __forceinline__ void gemv_phase(const GptParams& p, const Smem<BT>& sm, int layer,
                                            int col0, int ncols, int nseg, unsigned& cons_idx,
                                            const int* row_seq, const int* row_pos,
-                                           const int* row_valid, int warp, int lane) {
-  const int D = p.D;
+                                           const int* row_valid, int warp, int lane,
+                                           const float* bias_ph, int o0, long long* fine = nullptr) {
+  constexpr int GC = (BT == 1) ? 5 : 2;
+  int fi = 0;
+#define FINE() do { if (fine && threadIdx.x == 0 && fi < 12) fine[fi++] = gtimer(); } while (0)
   const int nunits = ncols * nseg;
   const int nch = (nunits + UPC - 1) / UPC;
-  const int cpl = D / 256;  // 16-byte chunks per lane
-  for (int ch = 0; ch < nch; ++ch) {
-    const int stage = cons_idx % p.nst;
-    const unsigned parity = (cons_idx / p.nst) & 1u;
-    ptx::mbar_wait(&sm.full[stage], parity);
-    const int u = ch * UPC + warp;
-    float acc[BT];
+  constexpr int cpl = D / 256;  // 16-byte chunks per lane
+  const int gcap = min(GC, p.nst - 1);
+  for (int ch0 = 0; ch0 < nch; ch0 += gcap) {
+    const int ng = min(gcap, nch - ch0);
+    float acc[GC][BT];
 #pragma unroll
-    for (int b = 0; b < BT; ++b) acc[b] = 0.f;
-    if (u < nunits) {
-      const int seg = u % nseg;
-      const uint4* wrow = (const uint4*)(sm.ring + ((size_t)stage * UPC + warp) * D);
-      for (int j = 0; j < cpl; ++j) {
-        const int c16 = lane + 32 * j;
-        uint4 w = wrow[c16];
-        float wf[8] = {lo_bf(w.x), hi_bf(w.x), lo_bf(w.y), hi_bf(w.y),
-                       lo_bf(w.z), hi_bf(w.z), lo_bf(w.w), hi_bf(w.w)};
+    for (int g = 0; g < GC; ++g)
 #pragma unroll
-        for (int b = 0; b < BT; ++b) {
-          uint4 xv = ((const uint4*)(sm.xs + (size_t)b * p.FF + (size_t)seg * D))[c16];
-          acc[b] = fmaf(wf[0], lo_bf(xv.x), acc[b]);
-          acc[b] = fmaf(wf[1], hi_bf(xv.x), acc[b]);
-          acc[b] = fmaf(wf[2], lo_bf(xv.y), acc[b]);
-          acc[b] = fmaf(wf[3], hi_bf(xv.y), acc[b]);
-          acc[b] = fmaf(wf[4], lo_bf(xv.z), acc[b]);
-          acc[b] = fmaf(wf[5], hi_bf(xv.z), acc[b]);
-          acc[b] = fmaf(wf[6], lo_bf(xv.w), acc[b]);
-          acc[b] = fmaf(wf[7], hi_bf(xv.w), acc[b]);
+      for (int b = 0; b < BT; ++b) acc[g][b] = 0.f;
+    FINE();
+#pragma unroll
+    for (int g = 0; g < GC; ++g)
+      if (g < ng) {
+        const unsigned n = cons_idx + g;
+        ptx::mbar_wait(&sm.full[n % p.nst], (n / p.nst) & 1u);
+      }
+    FINE();
+#pragma unroll
+    for (int g = 0; g < GC; ++g) {
+      const int u = (ch0 + g) * UPC + warp;
+      if (g < ng && u < nunits) {
+        const int stage = (cons_idx + g) % p.nst;
+        const int seg = u % nseg;
+        const uint4* wrow = (const uint4*)(sm.ring + ((size_t)stage * UPC + warp) * D);
+#pragma unroll
+        for (int j = 0; j < cpl; ++j) {
+          const int c16 = lane + 32 * j;
+          const uint4 w = wrow[c16];
+          const float wf[8] = {lo_bf(w.x), hi_bf(w.x), lo_bf(w.y), hi_bf(w.y),
+                               lo_bf(w.z), hi_bf(w.z), lo_bf(w.w), hi_bf(w.w)};
+#pragma unroll
+          for (int b = 0; b < BT; ++b) {
+            const uint4 xv = ((const uint4*)(sm.xs + (size_t)b * (4 * D) + (size_t)seg * D))[c16];
+            float a = acc[g][b];
+            a = fmaf(wf[0], lo_bf(xv.x), a);
+            a = fmaf(wf[1], hi_bf(xv.x), a);
+            a = fmaf(wf[2], lo_bf(xv.y), a);
+            a = fmaf(wf[3], hi_bf(xv.y), a);
+            a = fmaf(wf[4], lo_bf(xv.z), a);
+            a = fmaf(wf[5], hi_bf(xv.z), a);
+            a = fmaf(wf[6], lo_bf(xv.w), a);
+            a = fmaf(wf[7], hi_bf(xv.w), a);
+            acc[g][b] = a;
+          }
         }
       }
-#pragma unroll
-      for (int b = 0; b < BT; ++b) acc[b] = warp_sum(acc[b]);
     }
-    // the weights of this chunk are consumed: hand the stage back to the producer
-    __syncwarp();
-    if (lane == 0) ptx::mbar_arrive(&sm.empty[stage]);
-    ++cons_idx;
-
-    int c = -1;  // output column handled by this warp after the (optional) K-split merge
-    if (nseg == 1) {
-      if (u < nunits) c = col0 + u;
-    } else {
-      float* red = sm.red + (size_t)(ch & 1) * UPC * BT;
-      if (lane < BT) {
-        float v = 0.f;
 #pragma unroll
-        for (int b = 0; b < BT; ++b)
-          if (lane == b) v = acc[b];
-        red[warp * BT + lane] = v;
-      }
-      ptx::named_bar_sync(1, NCT);
-      const int cu = ch * UPC + warp * nseg;  // warp w < UPC/nseg merges column w of the chunk
-      if (warp < UPC / nseg && cu < nunits) {
-        c = col0 + cu / nseg;
-        if (lane < BT) {
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int g = 0; g < GC; ++g)
+#pragma unroll
+        for (int b = 0; b < BT; ++b) acc[g][b] += __shfl_xor_sync(0xffffffffu, acc[g][b], o);
+    FINE();
+    // the weights of these chunks are consumed: hand the stages back to the producer
+    __syncwarp();
+    if (lane == 0)
+      for (int g = 0; g < ng; ++g) ptx::mbar_arrive(&sm.empty[(cons_idx + g) % p.nst]);
+    cons_idx += ng;
+
+    if (nseg > 1) {
+      // K-split: park the partial sums, merge per column after one CTA barrier
+      float* red = sm.red + (size_t)((ch0 / gcap) & 1) * GC * UPC * BT;
+      if (lane < BT) {
+#pragma unroll
+        for (int g = 0; g < GC; ++g) {
           float v = 0.f;
-          for (int s = 0; s < nseg; ++s) v += red[(warp * nseg + s) * BT + lane];
 #pragma unroll
           for (int b = 0; b < BT; ++b)
-            if (lane == b) acc[b] = v;
+            if (lane == b) v = acc[g][b];
+          red[(g * UPC + warp) * BT + lane] = v;
         }
       }
-    }
-    if (c < 0 || lane >= BT) continue;
-    float a = 0.f;
+      ptx::named_bar_sync(1, NCT);
 #pragma unroll
-    for (int b = 0; b < BT; ++b)
-      if (lane == b) a = acc[b];
+      for (int g = 0; g < GC; ++g) {
+        float v = 0.f;
+        if (warp < UPC / nseg && lane < BT)
+          for (int s = 0; s < nseg; ++s) v += red[(g * UPC + warp * nseg + s) * BT + lane];
+#pragma unroll
+        for (int b = 0; b < BT; ++b) acc[g][b] = v;  // only lane b's copy is used below
+      }
+    }
+    if (lane >= BT) continue;
     const int b = lane;
     if (!row_valid[b]) continue;
     const int r = p.round_bf16;
-    if (EPI == 0) {
-      float v = rnd(a + __ldg(p.qkv_b + (size_t)layer * 3 * D + c), r);
-      if (c < D) {
-        p.qg[(size_t)b * D + c] = v;
+#pragma unroll
+    for (int g = 0; g < GC; ++g) {
+      if (g >= ng) continue;
+      int c;
+      if (nseg == 1) {
+        const int u = (ch0 + g) * UPC + warp;
+        if (u >= nunits) continue;
+        c = col0 + u;
       } else {
-        size_t base = (((size_t)layer * p.nseq + row_seq[b]) * p.maxpos + row_pos[b]) * D;
-        if (c < 2 * D) p.kc[base + (c - D)] = __float2bfloat16_rn(v);
-        else p.vc[base + (c - 2 * D)] = __float2bfloat16_rn(v);
+        const int cu = (ch0 + g) * UPC + warp * nseg;  // warp w < UPC/nseg owns column w of chunk g
+        if (warp >= UPC / nseg || cu >= nunits) continue;
+        c = col0 + cu / nseg;
       }
-    } else if (EPI == 1) {
-      // the residual stream is fp32 even on the bf16 path (trap P12): only the branch is rounded
-      float o = rnd(a + __ldg(p.o_b + (size_t)layer * D + c), r);
-      float xo = __ldcg(p.xg + (size_t)b * D + c);
-      p.xg[(size_t)b * D + c] = xo + o;
-    } else if (EPI == 2) {
-      float f = rnd(a + __ldg(p.fc_b + (size_t)layer * p.FF + c), r);
-      p.fg[(size_t)b * p.FF + c] = __float2bfloat16_rn(gelu_new(f, r));
-    } else if (EPI == 3) {
-      float o = rnd(a + __ldg(p.proj_b + (size_t)layer * D + c), r);
-      float xo = __ldcg(p.xg + (size_t)b * D + c);
-      p.xg[(size_t)b * D + c] = xo + o;
-    } else {
-      p.logits[(size_t)b * p.V + c] = rnd(a + __ldg(p.head_b + c), r);
+      float a = 0.f;
+#pragma unroll
+      for (int bb = 0; bb < BT; ++bb)
+        if (lane == bb) a = acc[g][bb];
+      if (EPI == 0) {
+        float v = rnd(a + bias_ph[c - col0], r);
+        if (c < D) {
+          p.qg[(size_t)b * D + c] = v;
+        } else {
+          size_t base = (((size_t)layer * p.nseq + row_seq[b]) * p.maxpos + row_pos[b]) * D;
+          if (c < 2 * D) p.kc[base + (c - D)] = __float2bfloat16_rn(v);
+          else p.vc[base + (c - 2 * D)] = __float2bfloat16_rn(v);
+        }
+      } else if (EPI == 1 || EPI == 3) {
+        // the residual stream is fp32 even on the bf16 path (trap P12): only the branch is rounded
+        float o = rnd(a + bias_ph[c - col0], r);
+        float xn = sm.xres[b * p.ocap + (c - o0)] + o;
+        sm.xres[b * p.ocap + (c - o0)] = xn;
+        p.xg[(size_t)b * D + c] = xn;
+      } else if (EPI == 2) {
+        float f = rnd(a + bias_ph[c - col0], r);
+        p.fg[(size_t)b * (4 * D) + c] = __float2bfloat16_rn(gelu_new(f, r));
+      } else {
+        p.logits[(size_t)b * p.V + c] = rnd(a + bias_ph[c - col0], r);
+      }
     }
   }
+  FINE();
+#undef FINE
 }
+
+#define PROF_STAMP()                                                        \
+  do {                                                                      \
+    if (p.prof && cta == 0 && tid == 0 && step == p.nsteps - 1 && pi < 256) \
+      p.prof[pi++] = gtimer();                                              \
+  } while (0)
 
 __device__ __forceinline__ int col_begin(int N, int i, int G) {
   return (int)(((long long)N * i) / G);
 }
 
-template <int BT>
+template <int BT, int NPL>
 __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int D = p.D, FF = p.FF, G = p.G, L = p.L, H = p.H, V = p.V;
+  constexpr int D = NPL * 32, FF = 4 * D;
+  const int G = p.G, L = p.L, H = p.H, V = p.V;
   const int cta = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -305,10 +414,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
     unsigned char* q = smem_raw;
     sm.ring = (__nv_bfloat16*)q;  q += (size_t)p.nst * UPC * D * 2;
     sm.xs = (__nv_bfloat16*)q;    q += (size_t)BT * FF * 2;
-    sm.red = (float*)q;           q += sizeof(float) * (2 * UPC * BT > NCW * PART_STRIDE ? 2 * UPC * BT : NCW * PART_STRIDE);
+    sm.red = (float*)q;           q += sizeof(float) * RED_FLOATS(BT);
     sm.full = (uint64_t*)q;       q += sizeof(uint64_t) * p.nst;
     sm.empty = (uint64_t*)q;      q += sizeof(uint64_t) * p.nst;
-    sm.flags = (int*)q;
+    sm.flags = (int*)q;           q += 16;
+    sm.bias_s = (float*)q;        q += sizeof(float) * (size_t)p.bias_cap;
+    sm.xres = (float*)q;          q += sizeof(float) * (size_t)BT * p.ocap;
+    sm.seen_s = (unsigned*)q;     q += sizeof(unsigned) * (size_t)((V + 31) / 32);
+    q = (unsigned char*)(((uintptr_t)q + 15) & ~(uintptr_t)15);
+    sm.lnp = (float*)q;
   }
   if (tid == 0) {
     for (int s = 0; s < p.nst; ++s) {
@@ -326,8 +440,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
   const int f0 = col_begin(FF, cta, G), f1 = col_begin(FF, cta + 1, G);
   const int h0 = col_begin(V, cta, G), h1 = col_begin(V, cta + 1, G);
   const int nseg_proj = FF / D;
-  const int units_layer = (q1 - q0) + (o1 - o0) + (f1 - f0) + (o1 - o0) * nseg_proj;
   const int units_head = (p.mode == 1) ? (h1 - h0) : 0;
+  // per-CTA bias table: [L][ qkv | o | fc | proj ] then head — epilogues never wait on L2
+  const int nq = q1 - q0, no = o1 - o0, nf = f1 - f0, nh = h1 - h0;
+  const int bstride = nq + 2 * no + nf;
+  if (warp < NCW) {
+    for (int i = tid; i < L * bstride; i += NCT) {
+      const int l = i / bstride, j = i % bstride;
+      float v;
+      if (j < nq) v = p.qkv_b[(size_t)l * 3 * D + q0 + j];
+      else if (j < nq + no) v = p.o_b[(size_t)l * D + o0 + (j - nq)];
+      else if (j < nq + no + nf) v = p.fc_b[(size_t)l * FF + f0 + (j - nq - no)];
+      else v = p.proj_b[(size_t)l * D + o0 + (j - nq - no - nf)];
+      sm.bias_s[i] = v;
+    }
+    for (int i = tid; i < nh; i += NCT) sm.bias_s[L * bstride + i] = p.head_b[h0 + i];
+  }
+  __syncthreads();
 
   // =============================================================== producer warp ====
   if (warp == NCW) {
@@ -336,7 +465,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
       const __nv_bfloat16* base = p.wstream + (size_t)p.stream_off[cta] * D;
       unsigned prod_idx = 0;
       bool stop = false;
-      const int phase_units[4] = {q1 - q0, o1 - o0, f1 - f0, (o1 - o0) * nseg_proj};
+      const int phase_units[4] = {nq, no, nf, no * nseg_proj};
       for (int step = 0; step < p.nsteps && !stop; ++step) {
         size_t uoff = 0;
         for (int l = 0; l <= L && !stop; ++l) {
@@ -371,10 +500,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
     unsigned cons_idx = 0;
     unsigned bar_target = 0;
     __shared__ int row_seq[8], row_pos[8], row_valid[8], row_posidx[8];
-    const int nsplit = max(1, G / (p.B * H));
-    const int npl = D / 32;
+    const int nsplit = min(8, max(1, G / (p.B * H)));
 
+    int pi = 0;
+    // cp.async prefetch of a LayerNorm (weight, bias) pair into lnp buffer `buf`
+    auto prefetch_ln = [&](int buf, const float* w, const float* b) {
+      float* dst = sm.lnp + (size_t)buf * 2 * D;
+      const int n4 = D / 4;
+      for (int i = tid; i < 2 * n4; i += NCT) {
+        const int which = i / n4, off = (i % n4) * 4;
+        cp_async16(dst + which * D + off, (which ? b : w) + off);
+      }
+    };
+    const float* lnA = sm.lnp;
+    const float* lnB = sm.lnp + 2 * D;
     for (int step = 0; step < p.nsteps; ++step) {
+      PROF_STAMP();
+      if (step == 0) prefetch_ln(0, p.ln1_w, p.ln1_b);
       // ---- step prologue: row descriptors + input embedding -> xg (own columns only) ----
       if (tid < 8) {
         int b = tid;
@@ -406,22 +548,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
                         __ldg(p.mel_pos + (size_t)row_posidx[b] * D + c), p.round_bf16);
           }
           p.xg[(size_t)b * D + c] = v;
+          sm.xres[b * p.ocap + (c - o0)] = v;
         }
       }
-      grid_sync(p.barrier, bar_target, G);
+      PROF_STAMP();
+      grid_sync(p.barrier, bar_target, G, p.bar_flavor);
+      PROF_STAMP();
 
       for (int l = 0; l < L; ++l) {
         // ---------------- P1: LN1 -> QKV ----------------
-        for (int b = warp; b < BT; b += NCW) {
-          float v[MAXPL], o[MAXPL];
-          load_row(v, p.xg + (size_t)b * D, npl, lane);
-          ln_row(v, o, npl, D, p.ln1_w + (size_t)l * D, p.ln1_b + (size_t)l * D, lane);
-          store_row_bf16(o, sm.xs + (size_t)b * FF, npl, lane);
+        prefetch_ln(1, p.ln2_w + (size_t)l * D, p.ln2_b + (size_t)l * D);  // for P4
+        if constexpr (BT == 1) {
+          float v[NPL / 8];
+#pragma unroll
+          for (int j = 0; j < NPL / 8; ++j) v[j] = __ldcg(p.xg + warp * (NPL * 4) + lane + 32 * j);
+          const float K = __ldcg(p.xg);
+          ln_block<NPL>(v, K, lnA, lnA + D, sm.red, warp, lane);
+#pragma unroll
+          for (int j = 0; j < NPL / 8; ++j)
+            sm.xs[warp * (NPL * 4) + lane + 32 * j] = __float2bfloat16_rn(v[j]);
+        } else {
+          for (int b = warp; b < BT; b += NCW) {
+            float v[NPL], o[NPL];
+            load_row<NPL>(v, p.xg + (size_t)b * D, lane);
+            ln_row<NPL>(v, o, lnA, lnA + D, lane);
+            store_row_bf16<NPL>(o, sm.xs + (size_t)b * FF, lane);
+          }
         }
         ptx::named_bar_sync(1, NCT);
-        gemv_phase<BT, 0>(p, sm, l, q0, q1 - q0, 1, cons_idx, row_seq, row_pos, row_valid,
-                          warp, lane);
-        grid_sync(p.barrier, bar_target, G);
+        gemv_phase<BT, 0, D>(p, sm, l, q0, nq, 1, cons_idx, row_seq, row_pos, row_valid,
+                          warp, lane, sm.bias_s + l * bstride, o0,
+                          (p.prof && cta == 0 && l == 1 && step == p.nsteps - 1) ? p.prof + 256 : nullptr);
+        PROF_STAMP();
+        grid_sync(p.barrier, bar_target, G, p.bar_flavor);
+        PROF_STAMP();
 
         // ---------------- P2: attention over the KV cache ----------------
         {
@@ -518,72 +678,133 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
             }
           }
         }
-        grid_sync(p.barrier, bar_target, G);
+        PROF_STAMP();
+        grid_sync(p.barrier, bar_target, G, p.bar_flavor);
+        PROF_STAMP();
 
         // ---------------- P3: merge attention splits -> O-proj + residual ----------------
-        for (int idx = tid; idx < BT * D; idx += NCT) {
-          const int b = idx / D, c = idx % D;
-          float outv = 0.f;
-          if (b < p.B && row_valid[b]) {
-            const int h = c / HD, d = c % HD;
+        // one warp per (row, head): the nsplit partials of a head are contiguous (66 floats
+        // each); every load below is independent so they all fly together (one L2 round trip)
+        for (int bh0 = warp; bh0 < BT * H; bh0 += 3 * NCW) {
+          float ms[3][8], ls[3][8], oa[3][8], ob[3][8];
+#pragma unroll
+          for (int r3 = 0; r3 < 3; ++r3) {
+            const int bh = bh0 + r3 * NCW;
+            const int b = bh / H, h = bh % H;
+            const bool rowon = bh < BT * H && b < p.B && row_valid[b];
             const float* pp = p.part + (size_t)((b * H + h) * nsplit) * PART_STRIDE;
-            float mm = -INFINITY;
-            for (int s = 0; s < nsplit; ++s) mm = fmaxf(mm, __ldcg(pp + s * PART_STRIDE));
-            float lt = 0.f, o = 0.f;
-            for (int s = 0; s < nsplit; ++s) {
-              const float ms = __ldcg(pp + s * PART_STRIDE);
-              const float cc = (ms == -INFINITY) ? 0.f : __expf(ms - mm);
-              lt += __ldcg(pp + s * PART_STRIDE + 1) * cc;
-              o += __ldcg(pp + s * PART_STRIDE + 2 + d) * cc;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+              const bool on = rowon && s < nsplit;
+              ms[r3][s] = on ? __ldcg(pp + s * PART_STRIDE) : -INFINITY;
+              ls[r3][s] = on ? __ldcg(pp + s * PART_STRIDE + 1) : 0.f;
+              oa[r3][s] = on ? __ldcg(pp + s * PART_STRIDE + 2 + lane) : 0.f;
+              ob[r3][s] = on ? __ldcg(pp + s * PART_STRIDE + 34 + lane) : 0.f;
             }
-            outv = o / lt;
           }
-          sm.xs[(size_t)b * FF + c] = __float2bfloat16_rn(outv);
+#pragma unroll
+          for (int r3 = 0; r3 < 3; ++r3) {
+            const int bh = bh0 + r3 * NCW;
+            if (bh >= BT * H) continue;
+            const int b = bh / H, h = bh % H;
+            float mm = -INFINITY;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) mm = fmaxf(mm, ms[r3][s]);
+            float lt = 0.f, o0v = 0.f, o1v = 0.f;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+              const float cc = (ms[r3][s] == -INFINITY) ? 0.f : __expf(ms[r3][s] - mm);
+              lt += ls[r3][s] * cc;
+              o0v += oa[r3][s] * cc;
+              o1v += ob[r3][s] * cc;
+            }
+            const float inv = (lt > 0.f) ? 1.0f / lt : 0.f;
+            sm.xs[(size_t)b * FF + h * HD + lane] = __float2bfloat16_rn(o0v * inv);
+            sm.xs[(size_t)b * FF + h * HD + 32 + lane] = __float2bfloat16_rn(o1v * inv);
+          }
         }
         ptx::named_bar_sync(1, NCT);
-        gemv_phase<BT, 1>(p, sm, l, o0, o1 - o0, 1, cons_idx, row_seq, row_pos, row_valid,
-                          warp, lane);
-        grid_sync(p.barrier, bar_target, G);
+        gemv_phase<BT, 1, D>(p, sm, l, o0, no, 1, cons_idx, row_seq, row_pos, row_valid,
+                          warp, lane, sm.bias_s + l * bstride + nq, o0);
+        PROF_STAMP();
+        grid_sync(p.barrier, bar_target, G, p.bar_flavor);
+        PROF_STAMP();
 
         // ---------------- P4: LN2 -> FC + gelu_new ----------------
-        for (int b = warp; b < BT; b += NCW) {
-          float v[MAXPL], o[MAXPL];
-          load_row(v, p.xg + (size_t)b * D, npl, lane);
-          ln_row(v, o, npl, D, p.ln2_w + (size_t)l * D, p.ln2_b + (size_t)l * D, lane);
-          store_row_bf16(o, sm.xs + (size_t)b * FF, npl, lane);
+        // buffer A was last read in P1 of this layer: refill it for the next LN1 / ln_f
+        if (l + 1 < L) prefetch_ln(0, p.ln1_w + (size_t)(l + 1) * D, p.ln1_b + (size_t)(l + 1) * D);
+        else if (p.mode == 1) prefetch_ln(0, p.lnf_w, p.lnf_b);
+        else prefetch_ln(0, p.ln1_w, p.ln1_b);
+        if constexpr (BT == 1) {
+          float v[NPL / 8];
+#pragma unroll
+          for (int j = 0; j < NPL / 8; ++j) v[j] = __ldcg(p.xg + warp * (NPL * 4) + lane + 32 * j);
+          const float K = __ldcg(p.xg);
+          ln_block<NPL>(v, K, lnB, lnB + D, sm.red, warp, lane);
+#pragma unroll
+          for (int j = 0; j < NPL / 8; ++j)
+            sm.xs[warp * (NPL * 4) + lane + 32 * j] = __float2bfloat16_rn(v[j]);
+        } else {
+          for (int b = warp; b < BT; b += NCW) {
+            float v[NPL], o[NPL];
+            load_row<NPL>(v, p.xg + (size_t)b * D, lane);
+            ln_row<NPL>(v, o, lnB, lnB + D, lane);
+            store_row_bf16<NPL>(o, sm.xs + (size_t)b * FF, lane);
+          }
         }
         ptx::named_bar_sync(1, NCT);
-        gemv_phase<BT, 2>(p, sm, l, f0, f1 - f0, 1, cons_idx, row_seq, row_pos, row_valid,
-                          warp, lane);
-        grid_sync(p.barrier, bar_target, G);
+        gemv_phase<BT, 2, D>(p, sm, l, f0, nf, 1, cons_idx, row_seq, row_pos, row_valid,
+                          warp, lane, sm.bias_s + l * bstride + nq + no, o0,
+                          (p.prof && cta == 0 && l == 1 && step == p.nsteps - 1) ? p.prof + 272 : nullptr);
+        PROF_STAMP();
+        grid_sync(p.barrier, bar_target, G, p.bar_flavor);
+        PROF_STAMP();
 
         // ---------------- P5: proj + residual ----------------
+        if (l + 1 == L && p.mode == 1) prefetch_ln(1, p.fn_w, p.fn_b);  // final_norm for the head
         {
           const int n16 = BT * FF / 8;
           for (int idx = tid; idx < n16; idx += NCT)
             ((uint4*)sm.xs)[idx] = __ldcg(((const uint4*)p.fg) + idx);
         }
         ptx::named_bar_sync(1, NCT);
-        gemv_phase<BT, 3>(p, sm, l, o0, o1 - o0, nseg_proj, cons_idx, row_seq, row_pos,
-                          row_valid, warp, lane);
-        grid_sync(p.barrier, bar_target, G);
+        gemv_phase<BT, 3, D>(p, sm, l, o0, no, nseg_proj, cons_idx, row_seq, row_pos,
+                          row_valid, warp, lane, sm.bias_s + l * bstride + nq + no + nf, o0);
+        PROF_STAMP();
+        grid_sync(p.barrier, bar_target, G, p.bar_flavor);
+        PROF_STAMP();
       }
 
       if (p.mode == 1) {
         // ---------------- head: ln_f -> final_norm -> mel_head ----------------
-        for (int b = warp; b < BT; b += NCW) {
-          float v[MAXPL], o[MAXPL];
-          load_row(v, p.xg + (size_t)b * D, npl, lane);
-          ln_row(v, o, npl, D, p.lnf_w, p.lnf_b, lane);
-          ln_row(o, v, npl, D, p.fn_w, p.fn_b, lane);
-          store_row_bf16(v, sm.xs + (size_t)b * FF, npl, lane);
+        if constexpr (BT == 1) {
+          float v[NPL / 8];
+#pragma unroll
+          for (int j = 0; j < NPL / 8; ++j) v[j] = __ldcg(p.xg + warp * (NPL * 4) + lane + 32 * j);
+          const float K = __ldcg(p.xg);
+          ln_block<NPL>(v, K, lnA, lnA + D, sm.red, warp, lane);
+          ln_block<NPL>(v, 0.f, lnB, lnB + D, sm.red + 2 * NCW, warp, lane);
+#pragma unroll
+          for (int j = 0; j < NPL / 8; ++j)
+            sm.xs[warp * (NPL * 4) + lane + 32 * j] = __float2bfloat16_rn(v[j]);
+        } else {
+          for (int b = warp; b < BT; b += NCW) {
+            float v[NPL], o[NPL];
+            load_row<NPL>(v, p.xg + (size_t)b * D, lane);
+            ln_row<NPL>(v, o, lnA, lnA + D, lane);
+            ln_row<NPL>(o, v, lnB, lnB + D, lane);
+            store_row_bf16<NPL>(v, sm.xs + (size_t)b * FF, lane);
+          }
         }
         ptx::named_bar_sync(1, NCT);
-        gemv_phase<BT, 4>(p, sm, 0, h0, h1 - h0, 1, cons_idx, row_seq, row_pos, row_valid,
-                          warp, lane);
-        grid_sync(p.barrier, bar_target, G);
+        gemv_phase<BT, 4, D>(p, sm, 0, h0, nh, 1, cons_idx, row_seq, row_pos, row_valid,
+                          warp, lane, sm.bias_s + L * bstride, o0);
+        PROF_STAMP();
+        grid_sync(p.barrier, bar_target, G, p.bar_flavor);
+        PROF_STAMP();
 
         // ---------------- sampling: CTA b handles sequence b ----------------
+        prefetch_ln(0, p.ln1_w, p.ln1_b);  // layer 0 of the next step (buffer A is free again)
         if (cta < p.B) {
           const int b = cta;
           const int k = p.step0 + step;
@@ -592,7 +813,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
             float* dst = p.logits_dump + ((size_t)b * p.max_new + k) * V;
             for (int i = tid; i < V; i += NCT) dst[i] = __ldcg(lg + i);
           }
-          const unsigned* seen = p.seen + (size_t)b * ((V + 31) / 32);
+          for (int i = tid; i < (V + 31) / 32; i += NCT)
+            sm.seen_s[i] = p.seen[(size_t)b * ((V + 31) / 32) + i];
+          ptx::named_bar_sync(1, NCT);
+          const unsigned* seen = sm.seen_s;
           float best = -INFINITY;
           int besti = 0x7fffffff;
           for (int i = tid; i < V; i += NCT) {
@@ -631,7 +855,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
           }
           ptx::named_bar_sync(1, NCT);
         }
-        grid_sync(p.barrier, bar_target, G);
+        PROF_STAMP();
+        grid_sync(p.barrier, bar_target, G, p.bar_flavor);
+        PROF_STAMP();
         // all-finished check (every CTA reads the same flags after the barrier)
         if (tid == 0) {
           int alldone = 1;
@@ -708,7 +934,7 @@ __global__ void prepare_inputs_kernel(const float* style, const float* emo_vec,
 // ------------------------------------------------------------------------ host state --
 struct GptState {
   idx_gpt_config cfg;
-  int G = 0, FF = 0, nst1 = 0, nst8 = 0;
+  int G = 0, FF = 0, nst1 = 0, nst8 = 0, bias_cap = 0, ocap = 0, bar_flavor = 0;
   size_t smem1 = 0, smem8 = 0;
   __nv_bfloat16* wstream = nullptr;
   long long* stream_off = nullptr;
@@ -722,6 +948,8 @@ struct GptState {
   int *tok = nullptr, *nout = nullptr, *finished = nullptr, *prompt_len = nullptr, *done = nullptr;
   unsigned* seen = nullptr;
   unsigned* barrier = nullptr;
+  long long* prof = nullptr;
+  int prof_on = 0;
   std::vector<void*> owned;
   double t_prefill_ms = 0, t_decode_ms = 0;
   int last_steps = 0, last_launches = 0;
@@ -746,26 +974,39 @@ static T* galloc(GptState* g, size_t n) {
   return p;
 }
 
-static size_t smem_bytes(int BT, int D, int FF, int nst) {
-  size_t red = sizeof(float) * (size_t)std::max(2 * UPC * BT, NCW * PART_STRIDE);
-  return (size_t)nst * UPC * D * 2 + (size_t)BT * FF * 2 + red + 16 * (size_t)nst + 64;
+static size_t smem_bytes(int BT, int D, int FF, int nst, int bias_cap, int ocap, int V) {
+  size_t red = sizeof(float) * (size_t)RED_FLOATS(BT);
+  return (size_t)nst * UPC * D * 2 + (size_t)BT * FF * 2 + red + 16 * (size_t)nst + 16 +
+         4 * (size_t)bias_cap + 4 * (size_t)BT * ocap + 4 * (size_t)((V + 31) / 32) + 16 +
+         sizeof(float) * 4 * (size_t)D + 64;
 }
 
-template <int BT>
-static void launch_fused(idx_engine* e, GptState* g, GptParams& p) {
+template <int BT, int NPL>
+static void launch_fused_t(idx_engine* e, GptState* g, GptParams& p) {
   p.nst = (BT == 1) ? g->nst1 : g->nst8;
-  size_t smem = smem_bytes(BT, p.D, p.FF, p.nst);
+  p.bias_cap = g->bias_cap;
+  p.ocap = g->ocap;
+  p.bar_flavor = g->bar_flavor;
+  size_t smem = smem_bytes(BT, p.D, p.FF, p.nst, g->bias_cap, g->ocap, p.V);
   IDX_CUDA(cudaMemsetAsync(g->barrier, 0, sizeof(unsigned), e->stream));
   void* args[] = {(void*)&p};
-  IDX_CUDA(cudaLaunchCooperativeKernel((void*)gpt_fused_kernel<BT>, dim3(g->G), dim3(NTHREADS),
+  IDX_CUDA(cudaLaunchCooperativeKernel((void*)gpt_fused_kernel<BT, NPL>, dim3(g->G), dim3(NTHREADS),
                                        args, smem, e->stream));
   e->launches++;
   g->last_launches++;
 }
 
 static void launch_fused_bt(idx_engine* e, GptState* g, GptParams& p, int BT) {
-  if (BT == 1) launch_fused<1>(e, g, p);
-  else launch_fused<8>(e, g, p);
+  // instantiated geometries: model_dim 1280 (IndexTTS GPT) and 256 (unit-test size)
+  const int npl = p.D / 32;
+  if (npl == 40) { if (BT == 1) launch_fused_t<1, 40>(e, g, p); else launch_fused_t<8, 40>(e, g, p); }
+  else if (npl == 8) { if (BT == 1) launch_fused_t<1, 8>(e, g, p); else launch_fused_t<8, 8>(e, g, p); }
+  else throw IdxError(IDX_ERR_ARG, "model_dim must be 1280 or 256 (instantiated kernel geometries)");
+}
+template <int BT>
+static void set_smem_attr(int npl, size_t bytes) {
+  if (npl == 40) IDX_CUDA(cudaFuncSetAttribute(gpt_fused_kernel<BT, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  else IDX_CUDA(cudaFuncSetAttribute(gpt_fused_kernel<BT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
 }
 
 extern "C" int idx_gpt_init(idx_engine* e, const idx_gpt_config* cfg) {
@@ -779,7 +1020,7 @@ extern "C" int idx_gpt_init(idx_engine* e, const idx_gpt_config* cfg) {
   const int L = cfg->layers, D = cfg->model_dim, H = cfg->heads, V = cfg->number_mel_codes;
   const int FF = 4 * D;
   g->FF = FF;
-  IDX_CHECK(D % 256 == 0 && D <= 32 * MAXPL, IDX_ERR_ARG, "model_dim must be a multiple of 256, <= 1280");
+  IDX_CHECK(D == 1280 || D == 256, IDX_ERR_ARG, "model_dim must be 1280 or 256 (instantiated kernel geometries)");
   IDX_CHECK(D == H * HD, IDX_ERR_ARG, "head_dim must be 64");
   IDX_CHECK(cfg->max_batch >= 1 && cfg->max_batch <= 8, IDX_ERR_ARG, "max_batch must be 1..8 (per decode group)");
   IDX_CHECK(cfg->weights_bf16 == 1, IDX_ERR_ARG, "only the bf16 weight path is built in this round");
@@ -789,18 +1030,22 @@ extern "C" int idx_gpt_init(idx_engine* e, const idx_gpt_config* cfg) {
   // ---- ring depth from the shared-memory budget ----
   int dev_smem = 0;
   IDX_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
+  auto cdiv = [](int a, int b) { return (a + b - 1) / b; };
+  g->ocap = cdiv(D, G) + 1;
+  g->bias_cap = L * (cdiv(3 * D, G) + 1 + 2 * g->ocap + cdiv(FF, G) + 1) + cdiv(V, G) + 1;
+  g->bar_flavor = getenv("IDX_GPT_BAR_FLAVOR") ? atoi(getenv("IDX_GPT_BAR_FLAVOR")) : 1;
   auto pick_nst = [&](int BT) {
     int nst = 2;
-    while (nst < 32 && smem_bytes(BT, D, FF, nst + 1) <= (size_t)dev_smem - 1024) ++nst;
+    while (nst < 32 && smem_bytes(BT, D, FF, nst + 1, g->bias_cap, g->ocap, V) <= (size_t)dev_smem - 1024) ++nst;
     return nst;
   };
   g->nst1 = pick_nst(1);
   g->nst8 = pick_nst(8);
-  g->smem1 = smem_bytes(1, D, FF, g->nst1);
-  g->smem8 = smem_bytes(8, D, FF, g->nst8);
+  g->smem1 = smem_bytes(1, D, FF, g->nst1, g->bias_cap, g->ocap, V);
+  g->smem8 = smem_bytes(8, D, FF, g->nst8, g->bias_cap, g->ocap, V);
   IDX_CHECK(g->smem8 <= (size_t)dev_smem, IDX_ERR_ARG, "shared memory budget exceeded");
-  IDX_CUDA(cudaFuncSetAttribute(gpt_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem1));
-  IDX_CUDA(cudaFuncSetAttribute(gpt_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem8));
+  set_smem_attr<1>(D / 32, g->smem1);
+  set_smem_attr<8>(D / 32, g->smem8);
 
   // ---- build the per-CTA unit table in consumption order ----
   std::vector<PackUnit> units;
@@ -907,6 +1152,7 @@ extern "C" int idx_gpt_init(idx_engine* e, const idx_gpt_config* cfg) {
   g->done = galloc<int>(g, 1);
   g->seen = galloc<unsigned>(g, 8 * (size_t)((V + 31) / 32));
   g->barrier = galloc<unsigned>(g, 4);
+  g->prof = galloc<long long>(g, 320);
   IDX_CUDA(cudaEventCreate(&g->ev0));
   IDX_CUDA(cudaEventCreate(&g->ev1));
   IDX_CUDA(cudaEventCreate(&g->ev2));
@@ -931,6 +1177,7 @@ static void fill_common(idx_engine* e, GptState* g, GptParams& p) {
   p.xg = g->xg; p.qg = g->qg; p.fg = g->fg; p.part = g->part; p.logits = g->logits;
   p.tok = g->tok; p.nout = g->nout; p.finished = g->finished; p.prompt_len = g->prompt_len;
   p.seen = g->seen; p.done = g->done; p.barrier = g->barrier;
+  p.prof = g->prof_on ? g->prof : nullptr;
 }
 
 extern "C" int idx_gpt_generate(idx_engine* e, const idx_gpt_request* reqs, int nreq,
@@ -1011,7 +1258,7 @@ extern "C" int idx_gpt_generate(idx_engine* e, const idx_gpt_request* reqs, int 
   fill_common(e, g, p);
   p.B = 8; p.mode = 0; p.nsteps = (int)tiles.size(); p.prompt = d_prompt; p.tiles = d_tiles;
   p.max_new = max_new; p.rep_penalty = sp->repetition_penalty;
-  launch_fused<8>(e, g, p);
+  launch_fused_bt(e, g, p, 8);
   IDX_CUDA(cudaEventRecord(g->ev1, e->stream));
 
   // ---- decode ----
@@ -1091,5 +1338,18 @@ extern "C" int idx_gpt_prepare_inputs(idx_engine* e, const float* style, const f
   e->launches++;
   idx_from_device(e, out, d_out, (size_t)rows * D * 4);
   IDX_CUDA(cudaStreamSynchronize(e->stream));
+  IDX_API_END(e)
+}
+
+extern "C" int idx_gpt_profile(idx_engine* e, int enable, int64_t* stamps_out, int n) {
+  IDX_API_BEGIN
+  IDX_CHECK(e && e->gpt, IDX_ERR_STATE, "idx_gpt_init has not been called");
+  IDX_CUDA(cudaSetDevice(e->device));
+  GptState* g = e->gpt;
+  g->prof_on = enable;
+  if (stamps_out && n > 0) {
+    IDX_CUDA(cudaStreamSynchronize(e->stream));
+    IDX_CUDA(cudaMemcpy(stamps_out, g->prof, sizeof(long long) * (size_t)std::min(n, 320), cudaMemcpyDeviceToHost));
+  }
   IDX_API_END(e)
 }

@@ -93,6 +93,7 @@ def load_library(path: str = None):
     lib.idx_gpt_prepare_inputs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_int, C.c_int, C.c_void_p]
     lib.idx_gpt_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    lib.idx_gpt_profile.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     lib.idx_bigvgan_init.argtypes = [C.c_void_p, C.POINTER(BigvganConfig)]
     lib.idx_bigvgan_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.idx_antialias_snake.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -234,6 +235,13 @@ class Engine:
         t = (C.c_double * 4)()
         self._check(self.lib.idx_gpt_last_timing(self.h, t), "idx_gpt_last_timing")
         return {"prefill_ms": t[0], "decode_ms": t[1], "steps": int(t[2]), "launches": int(t[3])}
+
+    def gpt_profile(self, enable=True, read=False):
+        """Phase-boundary %globaltimer stamps (ns) of CTA 0 for the last step of the last launch."""
+        buf = np.zeros(320, dtype=np.int64)
+        self._check(self.lib.idx_gpt_profile(self.h, int(enable), _ptr(buf) if read else None, 320 if read else 0),
+                    "idx_gpt_profile")
+        return buf
 
     # ------------------------------------------------------------------ BigVGAN --
     def bigvgan_init(self, h: dict):
