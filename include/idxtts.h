@@ -189,6 +189,61 @@ int idx_antialias_snake(idx_engine* e, const float* x, const float* alpha,
 /* Device time of the last idx_bigvgan_forward in ms (CUDA events).                   */
 int idx_bigvgan_last_ms(const idx_engine* e, double* ms);
 
+/* ---------------------------------------------------------------- s2mel + codec -- */
+
+/* Geometry of the s2mel section of config.yaml as MyModel reads it
+ * (s2mel/modules/commons.py:390-414, diffusion_transformer.py:103-184).              */
+typedef struct {
+  int32_t hidden;        /* DiT.hidden_dim (512)                                        */
+  int32_t heads;         /* DiT.num_heads (8; head_dim must be 64)                      */
+  int32_t depth;         /* DiT.depth (13)                                              */
+  int32_t wn_hidden;     /* wavenet.hidden_dim (512, must equal hidden)                 */
+  int32_t wn_layers;     /* wavenet.num_layers (8)                                      */
+  int32_t wn_kernel;     /* wavenet.kernel_size (5)                                     */
+  int32_t in_channels;   /* DiT.in_channels (80 mel bins)                               */
+  int32_t content_dim;   /* DiT.content_dim = length_regulator.channels (512)           */
+  int32_t style_dim;     /* style_encoder.dim (192)                                     */
+  int32_t lr_in;         /* length_regulator.in_channels (1024)                         */
+  int32_t lr_convs;      /* len(length_regulator.sampling_ratios) (4)                   */
+} idx_s2mel_config;
+
+/* Pack "s2mel.cfm.*" and "s2mel.length_regulator.*" (weight norm folded by the loader, the
+ * same tensors load_checkpoint2 reads: s2mel/modules/commons.py:579-635).              */
+int idx_s2mel_init(idx_engine* e, const idx_s2mel_config* cfg);
+
+/* EnhancedCodec geometry (codec/models.py:23-39).                                      */
+typedef struct {
+  int32_t codebook_size, hidden_size, codebook_dim, vocos_dim, vocos_intermediate_dim,
+      vocos_num_layers;
+} idx_codec_config;
+int idx_codec_init(idx_engine* e, const idx_codec_config* cfg);
+
+/* codes [n] i32 → S_infer [2n, hidden_size] f32.  Replaces EnhancedCodec.decode
+ * (codec/models.py:205-231), call site infer_v2_5.py:832.                              */
+int idx_codec_decode(idx_engine* e, const int32_t* codes, int n, float* S_out);
+
+/* S [n_in, lr_in] → cond [ylen, content_dim].  Replaces InterpolateRegulator.forward
+ * (s2mel/modules/length_regulator.py:90-141), call site infer_v2_5.py:835-838
+ * (ylen = int(n_in * 1.72 * duration_factor), computed by the caller).                 */
+int idx_length_regulate(idx_engine* e, const float* S, int n_in, int ylen, float* cond_out);
+
+/* One evaluation of the CFM estimator: x, prompt_x [B,80,T], t [B], style [B,style_dim],
+ * cond [B,T,content_dim] → out [B,80,T].  Replaces DiT.forward
+ * (s2mel/modules/diffusion_transformer.py:186-257); full-length sequences (x_lens = T).  */
+int idx_dit_forward(idx_engine* e, const float* x, const float* prompt_x, const float* t,
+                    const float* style, const float* cond, int B, int T, float* out);
+
+/* Euler solve of the flow-matching ODE with classifier-free guidance:
+ *   mu [T, content_dim], prompt [80, P] (reference mel), style [style_dim], z [80, T] (the
+ *   torch.randn noise the caller drew — trap P6), n_steps (25), cfg_rate (0.7) → mel [80, T]
+ *   with the first P frames zeroed.  Replaces BASECFM.inference / solve_euler
+ *   (s2mel/modules/flow_matching.py:30-115), call site infer_v2_5.py:841-845.           */
+int idx_cfm_solve(idx_engine* e, const float* mu, int T, const float* prompt, int P,
+                  const float* style, const float* z, int n_steps, float cfg_rate, float* mel_out);
+
+/* Device ms of the last codec decode / length regulator / CFM solve (CUDA events).       */
+int idx_s2mel_last_ms(const idx_engine* e, double* ms3);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,401 @@
+// nn_ops.cu — normalisation, pointwise and attention kernels shared by the s2mel / codec paths
+// (channels-last fp32, see ops.h).  Reference semantics cited at each kernel.
+#include "ops.h"
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One warp per row.  MODE 0: LayerNorm (two-pass), MODE 1: RMSNorm (gpt_fast/model.py:317-333).
+template <int MODE>
+__global__ void rownorm_kernel(const float* __restrict__ x, float* __restrict__ y, long long rows, int T,
+                               int C, const float* __restrict__ w, const float* __restrict__ b, float eps,
+                               const float* __restrict__ m0, const float* __restrict__ m1, int mod_stride) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int bidx = (int)(row / T);
+  const float* xr = x + row * C;
+  float* yr = y + row * C;
+  float s = 0.f;
+  for (int i = lane; i < C; i += 32) s += xr[i];
+  float mean = 0.f, q = 0.f;
+  if (MODE == 0) {
+    mean = warp_sum(s) / C;
+    for (int i = lane; i < C; i += 32) { float d = xr[i] - mean; q += d * d; }
+  } else {
+    for (int i = lane; i < C; i += 32) q += xr[i] * xr[i];
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+  for (int i = lane; i < C; i += 32) {
+    float v = (xr[i] - mean) * rstd;
+    if (MODE == 0) {
+      if (w) v = v * w[i] + (b ? b[i] : 0.f);
+      // modulate(x, shift, scale) = x * (1 + scale) + shift   (diffusion_transformer.py:11-12)
+      if (m0) v = v * (1.f + m0[(long long)bidx * mod_stride + i]) + m1[(long long)bidx * mod_stride + i];
+    } else {
+      v *= w[i];
+      // AdaptiveLayerNorm: weight * norm(x) + bias             (gpt_fast/model.py:20-39)
+      if (m0) v = m0[(long long)bidx * mod_stride + i] * v + m1[(long long)bidx * mod_stride + i];
+    }
+    yr[i] = v;
+  }
+}
+
+__global__ void gn_stats_kernel(const float* __restrict__ x, double* stats, long long n_per) {
+  const int b = blockIdx.y;
+  const float* xb = x + (long long)b * n_per;
+  double s = 0, q = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_per; i += (long long)gridDim.x * blockDim.x) {
+    const double v = xb[i];
+    s += v; q += v * v;
+  }
+  __shared__ double ss[256], qq[256];
+  ss[threadIdx.x] = s; qq[threadIdx.x] = q;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { ss[threadIdx.x] += ss[threadIdx.x + o]; qq[threadIdx.x] += qq[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { atomicAdd(&stats[2 * b], ss[0]); atomicAdd(&stats[2 * b + 1], qq[0]); }
+}
+__global__ void gn_apply_mish_kernel(const float* __restrict__ x, float* __restrict__ y, const double* stats,
+                                     long long n_per, int C, const float* __restrict__ w,
+                                     const float* __restrict__ bb, float eps) {
+  const int b = blockIdx.y;
+  const double mean = stats[2 * b] / n_per;
+  const double var = stats[2 * b + 1] / n_per - mean * mean;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float fm = (float)mean;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_per; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    float v = (x[(long long)b * n_per + i] - fm) * rstd * w[c] + bb[c];
+    const float sp = (v > 20.f) ? v : log1pf(expf(v));   // F.mish = x * tanh(softplus(x))
+    y[(long long)b * n_per + i] = v * tanhf(sp);
+  }
+}
+
+__global__ void dwconv_kernel(const float* __restrict__ x, float* __restrict__ y, int T, int C,
+                              const float* __restrict__ w, const float* __restrict__ b, int k) {
+  const int bi = blockIdx.z;
+  const int t = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float* xb = x + (long long)bi * T * C;
+  float acc = b ? b[c] : 0.f;
+  const int pad = (k - 1) / 2;
+  for (int j = 0; j < k; ++j) {
+    const int ts = t + j - pad;
+    if (ts >= 0 && ts < T) acc = fmaf(xb[(long long)ts * C + c], w[c * k + j], acc);
+  }
+  y[((long long)bi * T + t) * C + c] = acc;
+}
+
+__global__ void nearest_kernel(const float* __restrict__ x, float* __restrict__ y, int Tin, int Tout, int C) {
+  const int bi = blockIdx.z, t = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  // aten nearest_idx: scale = (float)in/out; src = min((int)floorf(dst * scale), in - 1)
+  const float scale = (float)Tin / (float)Tout;
+  int src = (int)floorf((float)t * scale);
+  if (src > Tin - 1) src = Tin - 1;
+  y[((long long)bi * Tout + t) * C + c] = x[((long long)bi * Tin + src) * C + c];
+}
+
+__global__ void embedding_kernel(const float* __restrict__ table, const int* __restrict__ ids, float* out, int C) {
+  const int t = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) out[(long long)t * C + c] = table[(long long)ids[t] * C + c];
+}
+
+__global__ void swiglu_kernel(const float* __restrict__ ab, float* __restrict__ y, long long rows, int N) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * N) return;
+  const long long r = i / N;
+  const int c = (int)(i % N);
+  const float a = ab[r * 2 * N + c], b = ab[r * 2 * N + N + c];
+  y[i] = a / (1.f + expf(-a)) * b;   // F.silu(w1 x) * (w3 x)  (gpt_fast/model.py:311-314)
+}
+
+__global__ void wn_gate_kernel(const float* __restrict__ xin, const float* __restrict__ g, int g_stride,
+                               float* __restrict__ y, int T, int N) {
+  // fused_add_tanh_sigmoid_multiply (s2mel/modules/commons.py:132-141)
+  const int bi = blockIdx.z;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)T * N) return;
+  const long long t = i / N;
+  const int c = (int)(i % N);
+  const float* xr = xin + ((long long)bi * T + t) * 2 * N;
+  const float a = xr[c] + g[(long long)bi * g_stride + c];
+  const float s = xr[N + c] + g[(long long)bi * g_stride + N + c];
+  y[((long long)bi * T + t) * N + c] = tanhf(a) * (1.f / (1.f + expf(-s)));
+}
+
+__global__ void copy_cols_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldo,
+                                 int col0, long long rows, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  const long long r = i / C;
+  const int c = (int)(i % C);
+  dst[r * ldo + col0 + c] = src[r * lds + c];
+}
+__global__ void bcast_cols_kernel(const float* __restrict__ vec, float* __restrict__ dst, int ldo, int col0,
+                                  int T, int C) {
+  const int bi = blockIdx.z;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)T * C) return;
+  const long long t = i / C;
+  const int c = (int)(i % C);
+  dst[((long long)bi * T + t) * ldo + col0 + c] = vec[(long long)bi * C + c];
+}
+__global__ void silu_kernel(float* x, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const float v = x[i]; x[i] = v / (1.f + expf(-v)); }
+}
+__global__ void zero_kernel(float* x, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = 0.f;
+}
+__global__ void rope_table_kernel(float* tab, int T, int hd) {
+  const int t = blockIdx.x;
+  const int i = threadIdx.x;
+  if (i >= hd / 2) return;
+  // freqs = 1 / base^(2i/hd); angle = t * freq (fp32), cache = (cos, sin)   (model.py:336-346)
+  const float freq = 1.0f / powf(10000.f, (float)(2 * i) / (float)hd);
+  const float ang = (float)t * freq;
+  tab[((long long)t * (hd / 2) + i) * 2] = cosf(ang);
+  tab[((long long)t * (hd / 2) + i) * 2 + 1] = sinf(ang);
+}
+__global__ void cfg_euler_kernel(float* x, const float* vc, const float* vu, float dt, float rate, int T,
+                                 int C, int P) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)T * C) return;
+  const int t = (int)(i / C);
+  // dphi = (1 + r) * dphi_cond - r * dphi_uncond ; x = x + dt * dphi ; x[:, :, :P] = 0
+  // (flow_matching.py:96-113)
+  const float d = (1.0f + rate) * vc[i] - rate * vu[i];
+  x[i] = (t < P) ? 0.f : x[i] + dt * d;
+}
+
+// ------------------------------------------------------------------------ attention ----
+// fp32 flash attention, 64 queries x 64 keys per tile, head_dim 64, RoPE applied on load
+// (F.scaled_dot_product_attention with a key-padding mask, gpt_fast/model.py:293-306).
+constexpr int AQ = 64, AK = 64, AD = 64;
+__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ qkv, float* __restrict__ out,
+                                                        int T, int H, const float* __restrict__ rope,
+                                                        const int* __restrict__ lens) {
+  extern __shared__ float sm[];
+  float* Qt = sm;                 // [AD][AQ]
+  float* Kt = Qt + AD * AQ;       // [AD][AK]
+  float* Vs = Kt + AD * AK;       // [AK][AD]
+  float* Pt = Vs + AK * AD;       // [AK][AQ]
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AQ;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int ld = 3 * H * AD;
+  const float* base = qkv + (long long)b * T * ld;
+  const int len = lens ? lens[b] : T;
+  // load + rotate Q (pairs), scaled by 1/sqrt(64)
+  for (int i = tid; i < AQ * (AD / 2); i += 256) {
+    const int r = i / (AD / 2), pi = i % (AD / 2);
+    const int t = q0 + r;
+    float a = 0.f, c = 0.f;
+    if (t < T) {
+      const float* qp = base + (long long)t * ld + h * AD + 2 * pi;
+      const float cs = rope[((long long)t * (AD / 2) + pi) * 2], sn = rope[((long long)t * (AD / 2) + pi) * 2 + 1];
+      const float x0 = qp[0], x1 = qp[1];
+      a = (x0 * cs - x1 * sn) * 0.125f;
+      c = (x1 * cs + x0 * sn) * 0.125f;
+    }
+    Qt[(2 * pi) * AQ + r] = a;
+    Qt[(2 * pi + 1) * AQ + r] = c;
+  }
+  float m[4], l[4], o[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m[i] = -INFINITY; l[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+  }
+  for (int k0 = 0; k0 < len; k0 += AK) {
+    __syncthreads();
+    for (int i = tid; i < AK * (AD / 2); i += 256) {
+      const int r = i / (AD / 2), pi = i % (AD / 2);
+      const int t = k0 + r;
+      float a = 0.f, c = 0.f, v0 = 0.f, v1 = 0.f;
+      if (t < len) {
+        const float* kp = base + (long long)t * ld + H * AD + h * AD + 2 * pi;
+        const float cs = rope[((long long)t * (AD / 2) + pi) * 2], sn = rope[((long long)t * (AD / 2) + pi) * 2 + 1];
+        const float x0 = kp[0], x1 = kp[1];
+        a = x0 * cs - x1 * sn;
+        c = x1 * cs + x0 * sn;
+        const float* vp = kp + H * AD;
+        v0 = vp[0]; v1 = vp[1];
+      }
+      Kt[(2 * pi) * AK + r] = a;
+      Kt[(2 * pi + 1) * AK + r] = c;
+      Vs[r * AD + 2 * pi] = v0;
+      Vs[r * AD + 2 * pi + 1] = v1;
+    }
+    __syncthreads();
+    float s[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < AD; ++d) {
+      const float4 qa = *(const float4*)(Qt + d * AQ + ty * 4);
+      const float4 kb = *(const float4*)(Kt + d * AK + tx * 4);
+      const float qv[4] = {qa.x, qa.y, qa.z, qa.w}, kv[4] = {kb.x, kb.y, kb.z, kb.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[i][j] = fmaf(qv[i], kv[j], s[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (k0 + tx * 4 + j >= len) s[i][j] = -INFINITY;
+        mx = fmaxf(mx, s[i][j]);
+      }
+#pragma unroll
+      for (int xo = 1; xo <= 8; xo <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, xo));
+      const float mn = fmaxf(m[i], mx);
+      const float corr = (m[i] == -INFINITY) ? 0.f : __expf(m[i] - mn);
+      float rs = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float p = (s[i][j] == -INFINITY) ? 0.f : __expf(s[i][j] - mn);
+        s[i][j] = p;
+        rs += p;
+      }
+#pragma unroll
+      for (int xo = 1; xo <= 8; xo <<= 1) rs += __shfl_xor_sync(0xffffffffu, rs, xo);
+      l[i] = l[i] * corr + rs;
+      m[i] = mn;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[i][j] *= corr;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Pt[(tx * 4 + j) * AQ + ty * 4 + i] = s[i][j];
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < AK; ++k) {
+      const float4 pa = *(const float4*)(Pt + k * AQ + ty * 4);
+      const float4 vb = *(const float4*)(Vs + k * AD + tx * 4);
+      const float pv[4] = {pa.x, pa.y, pa.z, pa.w}, vv[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[i][j] = fmaf(pv[i], vv[j], o[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int t = q0 + ty * 4 + i;
+    if (t >= T) continue;
+    const float inv = l[i] > 0.f ? 1.f / l[i] : 0.f;
+    float4 r = make_float4(o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv);
+    *(float4*)(out + ((long long)b * T + t) * H * AD + h * AD + tx * 4) = r;
+  }
+}
+
+}  // namespace
+
+#define LAUNCH_CHECK(e)            \
+  do {                             \
+    IDX_CUDA(cudaGetLastError());  \
+    (e)->launches++;               \
+  } while (0)
+
+void layernorm(idx_engine* e, const float* x, float* y, int B, int T, int C, const float* w, const float* b,
+               float eps, const float* scale, const float* shift, int mod_stride) {
+  const long long rows = (long long)B * T;
+  rownorm_kernel<0><<<(unsigned)((rows + 7) / 8), 256, 0, e->stream>>>(x, y, rows, T, C, w, b, eps, scale, shift, mod_stride);
+  LAUNCH_CHECK(e);
+}
+void rmsnorm_adaln(idx_engine* e, const float* x, float* y, int B, int T, int C, const float* nw, const float* mw,
+                   const float* mb, int mod_stride, float eps) {
+  const long long rows = (long long)B * T;
+  rownorm_kernel<1><<<(unsigned)((rows + 7) / 8), 256, 0, e->stream>>>(x, y, rows, T, C, nw, nullptr, eps, mw, mb, mod_stride);
+  LAUNCH_CHECK(e);
+}
+void groupnorm1_mish(idx_engine* e, const float* x, float* y, int B, int T, int C, const float* w, const float* b,
+                     float eps) {
+  double* stats = (double*)e->arena.alloc(sizeof(double) * 2 * B);
+  IDX_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B, e->stream));
+  const long long n_per = (long long)T * C;
+  dim3 grid((unsigned)std::min<long long>(296, (n_per + 255) / 256), B);
+  gn_stats_kernel<<<grid, 256, 0, e->stream>>>(x, stats, n_per);
+  LAUNCH_CHECK(e);
+  gn_apply_mish_kernel<<<grid, 256, 0, e->stream>>>(x, y, stats, n_per, C, w, b, eps);
+  LAUNCH_CHECK(e);
+}
+void dwconv1d(idx_engine* e, const float* x, float* y, int B, int T, int C, const float* w, const float* b, int k) {
+  dim3 grid((C + 127) / 128, T, B);
+  dwconv_kernel<<<grid, 128, 0, e->stream>>>(x, y, T, C, w, b, k);
+  LAUNCH_CHECK(e);
+}
+void nearest_interp(idx_engine* e, const float* x, float* y, int B, int Tin, int Tout, int C) {
+  dim3 grid((C + 127) / 128, Tout, B);
+  nearest_kernel<<<grid, 128, 0, e->stream>>>(x, y, Tin, Tout, C);
+  LAUNCH_CHECK(e);
+}
+void embedding_rows(idx_engine* e, const float* table, const int* ids, float* out, int n, int C) {
+  dim3 grid((C + 127) / 128, n);
+  embedding_kernel<<<grid, 128, 0, e->stream>>>(table, ids, out, C);
+  LAUNCH_CHECK(e);
+}
+void swiglu(idx_engine* e, const float* ab, float* y, long long rows, int N) {
+  swiglu_kernel<<<(unsigned)((rows * N + 255) / 256), 256, 0, e->stream>>>(ab, y, rows, N);
+  LAUNCH_CHECK(e);
+}
+void wn_gate(idx_engine* e, const float* xin, const float* g, int g_stride, float* y, int B, int T, int N) {
+  dim3 grid((unsigned)(((long long)T * N + 255) / 256), 1, B);
+  wn_gate_kernel<<<grid, 256, 0, e->stream>>>(xin, g, g_stride, y, T, N);
+  LAUNCH_CHECK(e);
+}
+void copy_cols(idx_engine* e, const float* src, int lds, float* dst, int ldo, int col0, long long rows, int C) {
+  copy_cols_kernel<<<(unsigned)((rows * C + 255) / 256), 256, 0, e->stream>>>(src, lds, dst, ldo, col0, rows, C);
+  LAUNCH_CHECK(e);
+}
+void bcast_cols(idx_engine* e, const float* vec, float* dst, int ldo, int col0, int B, int T, int C) {
+  dim3 grid((unsigned)(((long long)T * C + 255) / 256), 1, B);
+  bcast_cols_kernel<<<grid, 256, 0, e->stream>>>(vec, dst, ldo, col0, T, C);
+  LAUNCH_CHECK(e);
+}
+void silu_inplace(idx_engine* e, float* x, long long n) {
+  silu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(x, n);
+  LAUNCH_CHECK(e);
+}
+void fill_zero(idx_engine* e, float* x, long long n) {
+  zero_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(x, n);
+  LAUNCH_CHECK(e);
+}
+void rope_table(idx_engine* e, float* tab, int T, int hd) {
+  rope_table_kernel<<<T, 32, 0, e->stream>>>(tab, T, hd);
+  LAUNCH_CHECK(e);
+}
+void attention_rope(idx_engine* e, const float* qkv, float* out, int B, int T, int H, const float* rope,
+                    const int* lens) {
+  static bool attr_set = false;
+  const int smem = 4 * AQ * AD * sizeof(float);
+  if (!attr_set) {
+    IDX_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  dim3 grid((T + AQ - 1) / AQ, H, B);
+  attention_kernel<<<grid, 256, smem, e->stream>>>(qkv, out, T, H, rope, lens);
+  LAUNCH_CHECK(e);
+}
+void cfg_euler(idx_engine* e, float* x, const float* v_cond, const float* v_uncond, float dt, float rate, int T,
+               int C, int P) {
+  cfg_euler_kernel<<<(unsigned)(((long long)T * C + 255) / 256), 256, 0, e->stream>>>(x, v_cond, v_uncond, dt, rate, T, C, P);
+  LAUNCH_CHECK(e);
+}

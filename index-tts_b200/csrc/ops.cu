@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) conv_gemm_simt_kernel(const ConvGemm g) {
   const int b = blockIdx.z;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const long long abs_ = g.a_batch_stride ? g.a_batch_stride : (long long)g.Tin * g.K;
+  const long long abs_ = g.a_bcast ? 0 : (g.a_batch_stride ? g.a_batch_stride : (long long)g.Tin * g.K);
   const int lda = g.lda ? g.lda : g.K;
   const float* Ab = g.A + (long long)b * abs_;
   float acc[4][4];
@@ -160,4 +160,73 @@ void transpose_btc_to_bct(idx_engine* e, const float* in, float* out, int B, int
   transpose_kernel<<<grid, dim3(32, 8), 0, e->stream>>>(in, out, T, C);
   IDX_CUDA(cudaGetLastError());
   e->launches++;
+}
+
+// ------------------------------------------------------------------------ packed weights --
+namespace {
+__global__ void pack_conv_rows_kernel(const float* w, float* wsimt, float* wk, int Co, int Ci, int k, int row0) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long n = (long long)Co * Ci * k;
+  if (i >= n) return;
+  int kk = i % k;
+  int ci = (i / k) % Ci;
+  int co = i / ((long long)k * Ci);
+  float v = w[(long long)row0 * Ci * k + i];
+  wsimt[((long long)kk * Ci + ci) * Co + co] = v;
+  wk[(long long)co * k * Ci + (long long)kk * Ci + ci] = v;
+}
+}  // namespace
+
+float* WeightPool::alloc(size_t n) {
+  float* p = nullptr;
+  IDX_CUDA(cudaMalloc((void**)&p, n * sizeof(float)));
+  owned.push_back(p);
+  return p;
+}
+void WeightPool::release() {
+  for (void* p : owned) cudaFree(p);
+  owned.clear();
+}
+
+PackedW pack_conv1d(idx_engine* e, WeightPool& pool, const std::string& name, int dil, int row0, int rows) {
+  const DevTensor& w = e->W(name + ".weight");
+  IDX_CHECK(w.shape.size() == 3, IDX_ERR_ARG, name + ".weight must be [Co][Ci][k] (fold weight norm first)");
+  PackedW p;
+  const int Co = (int)w.shape[0];
+  p.N = rows < 0 ? Co - row0 : rows;
+  IDX_CHECK(row0 >= 0 && row0 + p.N <= Co, IDX_ERR_ARG, name + ": bad row range");
+  p.K = (int)w.shape[1]; p.taps = (int)w.shape[2]; p.dil = dil;
+  const size_t n = (size_t)p.N * p.K * p.taps;
+  p.wsimt = pool.alloc(n);
+  p.wk = pool.alloc(n);
+  pack_conv_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>((const float*)w.d, p.wsimt, p.wk, p.N, p.K, p.taps, row0);
+  IDX_CUDA(cudaGetLastError());
+  if (e->has(name + ".bias")) p.bias = e->Wf(name + ".bias") + row0;
+  return p;
+}
+
+PackedW pack_linear(idx_engine* e, WeightPool& pool, const std::string& name, int row0, int rows, bool with_bias) {
+  const DevTensor& w = e->W(name + ".weight");
+  IDX_CHECK(w.shape.size() == 2 || (w.shape.size() == 3 && w.shape[2] == 1), IDX_ERR_ARG, name + ".weight must be [N][K]");
+  PackedW p;
+  const int N = (int)w.shape[0];
+  p.N = rows < 0 ? N - row0 : rows;
+  IDX_CHECK(row0 >= 0 && row0 + p.N <= N, IDX_ERR_ARG, name + ": bad row range");
+  p.K = (int)w.shape[1]; p.taps = 1;
+  const size_t n = (size_t)p.N * p.K;
+  p.wsimt = pool.alloc(n);
+  p.wk = pool.alloc(n);
+  pack_conv_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>((const float*)w.d, p.wsimt, p.wk, p.N, p.K, 1, row0);
+  IDX_CUDA(cudaGetLastError());
+  if (with_bias && e->has(name + ".bias")) p.bias = e->Wf(name + ".bias") + row0;
+  return p;
+}
+
+ConvGemm gemm_of(const PackedW& w, const float* A, int B, int T, float* out) {
+  ConvGemm g;
+  g.A = A; g.B = B; g.Tin = T; g.K = w.K;
+  g.W = w.wsimt; g.Wk = w.wk;
+  g.taps = w.taps; g.dil = w.dil; g.pad = (w.taps * w.dil - w.dil) / 2;
+  g.M = T; g.N = w.N; g.bias = w.bias; g.out = out;
+  return g;
 }

@@ -3,6 +3,8 @@
 // rows are time steps, so every Conv1d / Linear is a (multi-tap) GEMM with K = C contiguous.
 #pragma once
 #include "engine.h"
+#include <string>
+#include <vector>
 
 enum { ACT_NONE = 0, ACT_GELU_ERF = 1, ACT_SILU = 2, ACT_MISH = 3, ACT_GELU_TANH = 4, ACT_RELU = 5 };
 
@@ -12,6 +14,7 @@ struct ConvGemm {
   const float* A = nullptr;   // [B][Tin][K]
   int B = 1, Tin = 0, K = 0;
   long long a_batch_stride = 0;  // elements; 0 → Tin*K
+  int a_bcast = 0;               // 1 → every batch entry reads the same A (stride 0)
   int lda = 0;                   // row stride of A in elements; 0 → K
   const float* W = nullptr;   // [taps][K][N]  (N contiguous)  — SIMT layout
   const float* Wk = nullptr;  // [N][taps*K]   (K contiguous)  — tensor-core layout (optional)
@@ -38,3 +41,62 @@ void conv_gemm(idx_engine* e, const ConvGemm& g);
 // [B][C][T] <-> [B][T][C]
 void transpose_bct_to_btc(idx_engine* e, const float* in, float* out, int B, int C, int T);
 void transpose_btc_to_bct(idx_engine* e, const float* in, float* out, int B, int T, int C);
+
+// ---------------------------------------------------------------- normalisation / pointwise --
+// y = LayerNorm(x) [* w + b] [ * (1 + scale[b]) + shift[b] ]   rows of C, x/y [B][T][C]
+void layernorm(idx_engine* e, const float* x, float* y, int B, int T, int C, const float* w,
+               const float* b, float eps, const float* scale, const float* shift, int mod_stride);
+// y = mw[b] * (x * rsqrt(mean(x^2)+eps) * nw) + mb[b]          (AdaptiveLayerNorm over RMSNorm)
+void rmsnorm_adaln(idx_engine* e, const float* x, float* y, int B, int T, int C, const float* nw,
+                   const float* mw, const float* mb, int mod_stride, float eps);
+// GroupNorm(1 group) over each sample's [T][C] block, affine per channel, followed by Mish
+void groupnorm1_mish(idx_engine* e, const float* x, float* y, int B, int T, int C, const float* w,
+                     const float* b, float eps);
+// depthwise Conv1d (groups = C), zero padding (k-1)/2; w [C][k]
+void dwconv1d(idx_engine* e, const float* x, float* y, int B, int T, int C, const float* w,
+              const float* b, int k);
+// y[b][t][:] = x[b][src(t)][:], src(t) = min(floor(t * Tin/Tout), Tin-1)  (F.interpolate nearest)
+void nearest_interp(idx_engine* e, const float* x, float* y, int B, int Tin, int Tout, int C);
+// out[t][:] = table[ids[t]][:]
+void embedding_rows(idx_engine* e, const float* table, const int* ids, float* out, int n, int C);
+// y = silu(a) * b where ab [rows][2*N] holds a | b side by side
+void swiglu(idx_engine* e, const float* ab, float* y, long long rows, int N);
+// y = tanh(a + ga[b]) * sigmoid(c + gc[b]),  xin [B][T][2N] = a | c ; g [B][*] with stride
+void wn_gate(idx_engine* e, const float* xin, const float* g, int g_stride, float* y, int B, int T, int N);
+// copy a [rows][C] block into columns [col0, col0+C) of a [rows][ldo] matrix (concat by columns)
+void copy_cols(idx_engine* e, const float* src, int lds, float* dst, int ldo, int col0, long long rows, int C);
+// broadcast a per-batch vector [B][C] over T rows into columns of dst
+void bcast_cols(idx_engine* e, const float* vec, float* dst, int ldo, int col0, int B, int T, int C);
+// y = silu(x)
+void silu_inplace(idx_engine* e, float* x, long long n);
+// RoPE table [T][hd/2][2] (cos, sin), base 1e4 (gpt_fast/model.py:336-346)
+void rope_table(idx_engine* e, float* tab, int T, int hd);
+// full (non-causal) attention with key-length mask and interleaved-pair RoPE on q,k.
+// qkv [B][T][3*H*64] (q | k | v), out [B][T][H*64]; lens [B] valid keys (device ints) or null
+void attention_rope(idx_engine* e, const float* qkv, float* out, int B, int T, int H, const float* rope,
+                    const int* lens);
+// x[b][t][c] (+)= ... CFG + Euler: x += dt * ((1+r) * v[0] - r * v[1]); rows t < P zeroed. x,v: [T][C]
+void cfg_euler(idx_engine* e, float* x, const float* v_cond, const float* v_uncond, float dt, float rate,
+               int T, int C, int P);
+void fill_zero(idx_engine* e, float* x, long long n);
+
+// ------------------------------------------------------------------------ packed weights --
+struct PackedW {
+  float* wsimt = nullptr;  // [taps][K][N]
+  float* wk = nullptr;     // [N][taps*K]
+  const float* bias = nullptr;
+  int N = 0, K = 0, taps = 1, dil = 1;
+};
+struct WeightPool {
+  std::vector<void*> owned;
+  float* alloc(size_t n);
+  void release();
+};
+// nn.Linear weight [N][K] (optionally only rows [row0, row0+rows))
+PackedW pack_linear(idx_engine* e, WeightPool& pool, const std::string& name, int row0 = 0, int rows = -1,
+                    bool with_bias = true);
+// nn.Conv1d weight [Co][Ci][k] (optionally only output rows [row0, row0+rows))
+PackedW pack_conv1d(idx_engine* e, WeightPool& pool, const std::string& name, int dil = 1, int row0 = 0,
+                    int rows = -1);
+// convenience: D = A·W^T (+bias) for a channels-last activation with optional epilogue fields preset in g
+ConvGemm gemm_of(const PackedW& w, const float* A, int B, int T, float* out);

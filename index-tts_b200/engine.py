@@ -56,6 +56,33 @@ class BigvganConfig(C.Structure):
                 ("snake_logscale", C.c_int32)]
 
 
+class S2melConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("hidden", "heads", "depth", "wn_hidden", "wn_layers", "wn_kernel",
+                                         "in_channels", "content_dim", "style_dim", "lr_in", "lr_convs")]
+
+
+class CodecConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("codebook_size", "hidden_size", "codebook_dim", "vocos_dim",
+                                         "vocos_intermediate_dim", "vocos_num_layers")]
+
+
+def fold_weight_norm(sd):
+    """torch weight_norm (dim=0) folded into a plain `.weight`: w = g * v / ||v|| — what
+    remove_weight_norm() / the parametrisation computes on the fly in the reference."""
+    out = {}
+    for k, v in sd.items():
+        if k.endswith("weight_g"):
+            base = k[: -len("weight_g")]
+            vv = sd[base + "weight_v"].float()
+            norm = vv.reshape(vv.shape[0], -1).norm(dim=1).reshape(-1, *([1] * (vv.dim() - 1)))
+            out[base + "weight"] = v.float() * vv / norm
+        elif k.endswith("weight_v"):
+            continue
+        else:
+            out[k] = v
+    return out
+
+
 def declared_symbols():
     """Every function the C-ABI header declares (used by the symbol-export test)."""
     src = open(HEADER_PATH).read()
@@ -99,6 +126,14 @@ def load_library(path: str = None):
     lib.idx_antialias_snake.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.idx_bigvgan_last_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    lib.idx_s2mel_init.argtypes = [C.c_void_p, C.POINTER(S2melConfig)]
+    lib.idx_codec_init.argtypes = [C.c_void_p, C.POINTER(CodecConfig)]
+    lib.idx_codec_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.idx_length_regulate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.idx_dit_forward.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_void_p]
+    lib.idx_cfm_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                  C.c_int, C.c_float, C.c_void_p]
+    lib.idx_s2mel_last_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     _lib = lib
     return lib
 
@@ -298,3 +333,55 @@ class Engine:
         self._check(self.lib.idx_antialias_snake(self.h, _ptr(x), _ptr(alpha), _ptr(beta), B, Cc, T,
                                                  int(logscale), _ptr(y)), "idx_antialias_snake")
         return y
+
+    # ------------------------------------------------------------- s2mel + codec --
+    def s2mel_init(self, c: dict):
+        cfg = S2melConfig(c["hidden"], c["heads"], c["depth"], c["wn_hidden"], c["wn_layers"], c["wn_kernel"],
+                          c["in_channels"], c["content_dim"], c["style_dim"], c["lr_in"], c["lr_convs"])
+        self._check(self.lib.idx_s2mel_init(self.h, C.byref(cfg)), "idx_s2mel_init")
+        self.s2mel_cfg = cfg
+
+    def codec_init(self, c: dict):
+        cfg = CodecConfig(c["codebook_size"], c["hidden_size"], c["codebook_dim"], c["vocos_dim"],
+                          c["vocos_intermediate_dim"], c["vocos_num_layers"])
+        self._check(self.lib.idx_codec_init(self.h, C.byref(cfg)), "idx_codec_init")
+        self.codec_cfg = cfg
+
+    def codec_decode(self, codes):
+        """EnhancedCodec.decode (codec/models.py:205-231): codes [n] → S_infer [2n, hidden]."""
+        codes = np.ascontiguousarray(np.asarray(codes, dtype=np.int32).reshape(-1))
+        out = np.empty((2 * len(codes), self.codec_cfg.hidden_size), dtype=np.float32)
+        self._check(self.lib.idx_codec_decode(self.h, _ptr(codes), len(codes), _ptr(out)), "idx_codec_decode")
+        return out
+
+    def length_regulate(self, S, ylen):
+        """InterpolateRegulator.forward (length_regulator.py:90-141): S [n, in] → [ylen, C]."""
+        S = _as_f32(S)
+        out = np.empty((int(ylen), self.s2mel_cfg.content_dim), dtype=np.float32)
+        self._check(self.lib.idx_length_regulate(self.h, _ptr(S), int(S.shape[0]), int(ylen), _ptr(out)),
+                    "idx_length_regulate")
+        return out
+
+    def dit_forward(self, x, prompt_x, t, style, cond):
+        """DiT.forward (diffusion_transformer.py:186-257) for full-length sequences."""
+        x, prompt_x, t, style, cond = (_as_f32(a) for a in (x, prompt_x, t, style, cond))
+        B, _, T = x.shape
+        out = np.empty((B, self.s2mel_cfg.in_channels, T), dtype=np.float32)
+        self._check(self.lib.idx_dit_forward(self.h, _ptr(x), _ptr(prompt_x), _ptr(t), _ptr(style), _ptr(cond),
+                                             B, T, _ptr(out)), "idx_dit_forward")
+        return out
+
+    def cfm_solve(self, mu, prompt, style, z, n_steps=25, cfg_rate=0.7):
+        """BASECFM.inference (flow_matching.py:30-115) with caller-supplied noise z [80, T]."""
+        mu, prompt, style, z = (_as_f32(a) for a in (mu, prompt, style, z))
+        T = mu.shape[0]
+        P = prompt.shape[-1]
+        out = np.empty((self.s2mel_cfg.in_channels, T), dtype=np.float32)
+        self._check(self.lib.idx_cfm_solve(self.h, _ptr(mu), T, _ptr(prompt), P, _ptr(style), _ptr(z),
+                                           int(n_steps), float(cfg_rate), _ptr(out)), "idx_cfm_solve")
+        return out
+
+    def s2mel_last_ms(self):
+        t = (C.c_double * 3)()
+        self._check(self.lib.idx_s2mel_last_ms(self.h, t), "idx_s2mel_last_ms")
+        return {"codec_ms": t[0], "length_regulator_ms": t[1], "cfm_ms": t[2]}

@@ -67,3 +67,56 @@ def bigvgan_module(h):
     m.remove_weight_norm()
     m.eval()
     return m
+
+
+class AttrDict(dict):
+    """attribute dictionary with hasattr semantics (missing key → AttributeError)."""
+
+    def __getattr__(self, k):
+        try:
+            v = self[k]
+        except KeyError:
+            raise AttributeError(k)
+        return AttrDict(v) if isinstance(v, dict) and not isinstance(v, AttrDict) else v
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def s2mel_args(hidden=512, heads=8, depth=13, wn_hidden=512, wn_layers=8, content_dim=512,
+               lr_in=1024, style_dim=192):
+    """The s2mel section of checkpoints/config.yaml [ASSUMED dims, SURVEY.md §8] as the reference
+    classes read it (commons.py:390-414, diffusion_transformer.py:103-184)."""
+    return AttrDict(
+        reg_loss_type="l1", dit_type="DiT",
+        DiT=dict(hidden_dim=hidden, num_heads=heads, depth=depth, class_dropout_prob=0.1, block_size=8192,
+                 in_channels=80, style_condition=True, final_layer_type="wavenet", target="mel",
+                 content_dim=content_dim, content_codebook_size=1024, content_type="discrete",
+                 f0_condition=False, n_f0_bins=512, content_codebooks=1, is_causal=False,
+                 long_skip_connection=True, zero_prompt_speech_token=False, time_as_token=False,
+                 style_as_token=False, uvit_skip_connection=True, add_resblock_in_transformer=False),
+        wavenet=dict(hidden_dim=wn_hidden, num_layers=wn_layers, kernel_size=5, dilation_rate=1, p_dropout=0.2,
+                     style_condition=True),
+        style_encoder=dict(dim=style_dim),
+        length_regulator=dict(channels=content_dim, is_discrete=False, in_channels=lr_in,
+                              content_codebook_size=2048, sampling_ratios=[1, 1, 1, 1],
+                              vector_quantize=False, n_codebooks=1, quantizer_dropout=0.0,
+                              f0_condition=False, n_f0_bins=512),
+    )
+
+
+def s2mel_module(args):
+    setup()
+    from indextts.s2mel.modules.commons import MyModel
+    m = MyModel(args)
+    m.eval()
+    m.models["cfm"].estimator.setup_caches(max_batch_size=2, max_seq_length=8192)
+    return m
+
+
+def codec_module(**kw):
+    setup()
+    from indextts.codec.models import EnhancedCodec
+    m = EnhancedCodec(**kw)
+    m.eval()
+    return m

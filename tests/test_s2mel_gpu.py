@@ -1,0 +1,100 @@
+"""GPU parity of the s2mel path (codec decode, length regulator, DiT, CFM solve) through the
+C-ABI against goldens minted from the reference modules and the CPU oracle.
+
+Tolerances: fp32 path; single DiT evaluation <= 1e-2 max-abs (the TRT backend's own --verify bound,
+SURVEY §8c) — measured values are printed and are far smaller on the fp32/SIMT path; CFM solve
+(25 chained evaluations) <= 1e-2 max-abs on mel values of std ~1.4."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from indextts_b200.engine import fold_weight_norm
+from oracle.s2mel import (CODEC_CFG, S2MEL_CFG, cfm_inference, codec_decode, dit_forward, length_regulate,
+                          make_codec_weights, make_s2mel_weights, small_codec_cfg, small_s2mel_cfg)
+from oracle.s2mel import fold_weight_norm as oracle_fold
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _load(engine, c, cc, seed_s, seed_c):
+    w, wc = make_s2mel_weights(c, seed=seed_s), make_codec_weights(cc, seed=seed_c)
+    engine.load_state_dict("s2mel.", {k: v for k, v in fold_weight_norm(w).items() if v.is_floating_point()})
+    engine.load_state_dict("codec.", fold_weight_norm(wc))
+    engine.s2mel_init(c)
+    engine.codec_init(cc)
+    return oracle_fold(w), oracle_fold(wc)
+
+
+def test_small_stages_vs_reference_golden(engine):
+    g = np.load(os.path.join(GOLD, "s2mel_small.npz"))
+    c, cc = small_s2mel_cfg(), small_codec_cfg()
+    _load(engine, c, cc, int(g["seed_s2mel"]), int(g["seed_codec"]))
+    S = engine.codec_decode(g["codes"][0])
+    assert S.shape == g["S_infer"][0].shape
+    print("codec decode max err", np.abs(S - g["S_infer"][0]).max())
+    assert np.abs(S - g["S_infer"][0]).max() < 1e-4
+    cond = engine.length_regulate(g["lr_in"][0], int(g["ylen"]))
+    print("length regulator max err", np.abs(cond - g["cond"][0]).max())
+    assert np.abs(cond - g["cond"][0]).max() < 1e-4
+    T, P = g["mu"].shape[1], g["prompt"].shape[-1]
+    px = np.zeros((1, 80, T), np.float32)
+    px[..., :P] = g["prompt"]
+    d = engine.dit_forward(g["z"], px, g["t"], g["style"], g["mu"])
+    print("DiT forward max err", np.abs(d - g["dit"]).max())
+    assert np.abs(d - g["dit"]).max() < 1e-3
+    mel = engine.cfm_solve(g["mu"][0], g["prompt"][0], g["style"][0], g["z"][0], int(g["n_steps"]), 0.7)
+    print("CFM solve max err", np.abs(mel - g["mel"][0]).max())
+    assert np.abs(mel - g["mel"][0]).max() < 1e-2
+    assert np.all(mel[:, :P] == 0)
+
+
+def test_full_dims_vs_reference_golden_and_oracle(engine):
+    g = np.load(os.path.join(GOLD, "s2mel_full_dit.npz"))
+    c, cc = dict(S2MEL_CFG), dict(CODEC_CFG)
+    w, wc = _load(engine, c, cc, int(g["seed_s2mel"]), int(g["seed_codec"]))
+    S = engine.codec_decode(g["codes"][0])
+    assert np.abs(S - g["S_infer"][0]).max() < 1e-3
+    cond = engine.length_regulate(g["S_infer"][0], int(g["ylen"]))
+    assert np.abs(cond - g["cond"][0]).max() < 1e-3
+    T, P = g["mu"].shape[1], g["prompt"].shape[-1]
+    px = np.zeros((1, 80, T), np.float32)
+    px[..., :P] = g["prompt"]
+    d = engine.dit_forward(g["z"], px, g["t"], g["style"], g["mu"])
+    err = np.abs(d - g["dit"]).max()
+    print(f"full DiT forward (T={T}) max err {err:.2e}")
+    assert err < 1e-2
+    # a longer full-size CFM solve against the CPU oracle: T = 200 frames (60 prompt), 4 steps
+    gen = torch.Generator().manual_seed(3)
+    T, P = 200, 60
+    mu = torch.randn(1, T, c["content_dim"], generator=gen)
+    prompt = torch.randn(1, 80, P, generator=gen) * 1.5 - 4.0
+    style = torch.randn(1, c["style_dim"], generator=gen)
+    z = torch.randn(1, 80, T, generator=gen)
+    ref = cfm_inference(w, c, mu, torch.LongTensor([T]), prompt, style, z, 4, 0.7).numpy()
+    mel = engine.cfm_solve(mu[0].numpy(), prompt[0].numpy(), style[0].numpy(), z[0].numpy(), 4, 0.7)
+    err = np.abs(mel - ref[0]).max()
+    print(f"full CFM 4 steps T={T}: max err {err:.2e}, mel std {ref.std():.2f}, ms {engine.s2mel_last_ms()}")
+    assert err < 1e-2
+
+
+def test_full_size_cfm_properties(engine):
+    """BASELINE-size solve (10 s prompt + 256 tokens: T = 861 + 880, 25 steps): finite output, prompt
+    region zeroed, and linearity of the CFG combine: rate -> the same x when mu/style/prompt are
+    such that cond == uncond is not required; here we check determinism (bit-identical reruns)."""
+    c, cc = dict(S2MEL_CFG), dict(CODEC_CFG)
+    _load(engine, c, cc, 1234, 4321)
+    gen = torch.Generator().manual_seed(8)
+    T, P = 861 + 880, 861
+    mu = torch.randn(T, c["content_dim"], generator=gen).numpy()
+    prompt = (torch.randn(80, P, generator=gen) * 1.5 - 4.0).numpy()
+    style = torch.randn(c["style_dim"], generator=gen).numpy()
+    z = torch.randn(80, T, generator=gen).numpy()
+    mel = engine.cfm_solve(mu, prompt, style, z, 25, 0.7)
+    print("full-size CFM:", engine.s2mel_last_ms())
+    assert mel.shape == (80, T) and np.isfinite(mel).all()
+    assert np.all(mel[:, :P] == 0) and np.abs(mel[:, P:]).max() > 0.1
+    mel2 = engine.cfm_solve(mu, prompt, style, z, 25, 0.7)
+    assert np.array_equal(mel, mel2)
