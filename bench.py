@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py — the IndexTTS-2.5 per-segment hot path on B200 (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--quick]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one utterance through the whole per-segment pipeline of IndexTTS2.infer
+(infer_v2_5.py:749-864): prompt embeddings → GPT prefill + 256 greedy speech tokens (stop masked
+until step 256, repetition_penalty 10) → semantic-codec decode → length regulator (F = 880) →
+cat 10 s reference (P = 861) → CFM 25 Euler steps, CFG 0.7 (T = 1741) → BigVGAN (225 280 samples,
+10.22 s of 22.05 kHz audio) → pcm16.  Speaker conditioning (w2v-BERT / CAMPPlus / mel of the
+reference audio, SURVEY §8f "next") and the emotion vector are cached per speaker exactly as the
+reference caches them (infer_v2_5.py:620-667; trap P11) and are inputs here.
+
+Metric: whole-job speech-tokens/s (higher is better) with RTF alongside.  `value` is measured with
+all inputs resident in HBM; `e2e` through the same public API with HOST buffers (H2D of the
+request, D2H of codes + pcm16 inside the timed region).  Synthetic seeded weights at the
+[ASSUMED] IndexTTS-2.5 shapes (no checkpoints offline) — `data: synthetic`.
+
+N > 1: one process per GPU, utterances shard embarrassingly (weak scaling); NCCL broadcasts the
+speaker latents once and gathers the finished pcm16 waveforms on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_TOKENS = 256
+P_FRAMES = 861          # 10 s reference at 22.05 kHz / hop 256
+N_TEXT = 32
+CFM_STEPS, CFG_RATE = 25, 0.7
+AUDIO_S_PER_TOKEN = 2 * 1.72 * 256 / 22050.0
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+                for nm, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------- workload --
+def make_inputs(seed, cfg_gpt, w_gpt):
+    """Synthetic request of the named shape; conditioning tensors are what the reference caches."""
+    from indextts_b200.synth import r16
+    g = torch.Generator().manual_seed(seed)
+    style = torch.randn(192, generator=g)
+    emo = r16(torch.randn(cfg_gpt["model_dim"], generator=g) * 0.5)
+    text = torch.randint(2, 12000, (N_TEXT,), generator=g)
+    prompt_condition = torch.randn(P_FRAMES, 512, generator=g)
+    ref_mel = torch.randn(80, P_FRAMES, generator=g) * 1.5 - 4.0
+    F = int(2 * N_TOKENS * 1.72)
+    z = torch.randn(80, P_FRAMES + F, generator=g)     # the cfm.inference noise (trap P6)
+    return dict(style=style, emo=emo, text=text, prompt_condition=prompt_condition, ref_mel=ref_mel, z=z, F=F)
+
+
+def build_engine(device):
+    from indextts_b200.engine import Engine, fold_weight_norm
+    from indextts_b200 import synth
+    t0 = time.time()
+    e = Engine(device)
+    cfg = synth.gpt_config()
+    wg = synth.make_gpt_weights(cfg, seed=2025, bf16=True)
+    e.load_state_dict("gpt.", wg)
+    e.gpt_init(cfg["layers"], cfg["model_dim"], cfg["heads"], cfg["number_mel_codes"], cfg["start_mel_token"],
+               cfg["stop_mel_token"], cfg["max_mel_positions"], max_prompt=64, max_batch=1, weights_bf16=True)
+    c, cc = dict(synth.S2MEL_CFG), dict(synth.CODEC_CFG)
+    ws = fold_weight_norm(synth.make_s2mel_weights(c, seed=1234))
+    e.load_state_dict("s2mel.", {k: v for k, v in ws.items() if v.is_floating_point()})
+    e.load_state_dict("codec.", fold_weight_norm(synth.make_codec_weights(cc, seed=4321)))
+    e.s2mel_init(c)
+    e.codec_init(cc)
+    h = dict(synth.BIGVGAN_V2_22K)
+    e.load_state_dict("bigvgan.", synth.make_bigvgan_weights(h, seed=1234))
+    e.bigvgan_init(h)
+    return e, cfg, wg, time.time() - t0
+
+
+def run_utterance(e, inp, prompt_emb, host: bool):
+    """The public-API call sequence of one segment.  host=True: numpy inputs/outputs (H2D/D2H inside)."""
+    (codes,) = e.gpt_generate([prompt_emb], N_TOKENS, 10.0, forbid_stop_before=N_TOKENS)
+    if host:
+        res = e.codes_to_wav(codes, inp["prompt_condition"], inp["ref_mel"], inp["style"], inp["z"], inp["F"],
+                             CFM_STEPS, CFG_RATE, want_wav=False, want_pcm16=True)
+    else:
+        dcodes = torch.from_numpy(codes).to(inp["z_d"].device)
+        res = e.codes_to_wav(dcodes, inp["pc_d"], inp["mel_d"], inp["style_d"], inp["z_d"], inp["F"],
+                             CFM_STEPS, CFG_RATE, want_wav=False, want_pcm16=True)
+    return codes, res["pcm16"]
+
+
+def stage_breakdown(e):
+    g = e.gpt_last_timing()
+    s = e.s2mel_last_ms()
+    return g, s
+
+
+# -------------------------------------------------------------------------- cpu arm --
+def cpu_reference_sample(threads):
+    """The oracle port of the same per-segment path on the host cores, on a bounded sample:
+    16 speech tokens with a 1 s reference (P = 86): GPT prefill + 16 cached steps (full 24x1280
+    geometry, bf16 policy), codec decode, length regulator, CFM 25 steps at T = 86 + 55, BigVGAN
+    F = 55.  Returns tokens/s of that sample."""
+    from indextts_b200 import synth
+    from oracle.gpt import GptOracle, prepare_gpt_inputs
+    from oracle.s2mel import cfm_inference, codec_decode, fold_weight_norm, length_regulate
+    from oracle.bigvgan import bigvgan_forward
+    torch.set_num_threads(threads)
+    cfg = synth.gpt_config()
+    wg = synth.make_gpt_weights(cfg, seed=2025, bf16=True)
+    c, cc, h = dict(synth.S2MEL_CFG), dict(synth.CODEC_CFG), dict(synth.BIGVGAN_V2_22K)
+    ws = fold_weight_norm(synth.make_s2mel_weights(c, seed=1234))
+    wc = fold_weight_norm(synth.make_codec_weights(cc, seed=4321))
+    wb = synth.make_bigvgan_weights(h, seed=1234)
+    g = torch.Generator().manual_seed(0)
+    ntok, P = 16, 86
+    style = torch.randn(192, generator=g)
+    emo = synth.r16(torch.randn(cfg["model_dim"], generator=g) * 0.5)
+    text = torch.randint(2, 12000, (N_TEXT,), generator=g)
+    prompt = prepare_gpt_inputs(wg, style, emo, text, lang=1, bf16=True)
+    F = int(2 * ntok * 1.72)
+    pc = torch.randn(1, P, 512, generator=g)
+    ref_mel = torch.randn(1, 80, P, generator=g) * 1.5 - 4.0
+    z = torch.randn(1, 80, P + F, generator=g)
+
+    def once():
+        t0 = time.perf_counter()
+        codes, _ = GptOracle(cfg, wg, bf16=True).generate(prompt, ntok, 10.0, ntok)
+        S = codec_decode(wc, torch.from_numpy(codes.astype(np.int64))[None])
+        cond = length_regulate(ws, S, F)
+        mu = torch.cat([pc, cond], 1)
+        mel = cfm_inference(ws, c, mu, torch.LongTensor([P + F]), ref_mel, style[None], z, CFM_STEPS, CFG_RATE)
+        wav = bigvgan_forward(h, wb, mel[:, :, P:])
+        assert wav.shape[-1] == F * 256
+        return time.perf_counter() - t0
+    return ntok, once
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    ntok, once = cpu_reference_sample(threads)
+    for _ in range(max(1, min(args.warmup, 1))):
+        once()
+    steps = max(1, min(args.steps, 3))
+    ts = [once() for _ in range(steps)]
+    t = float(np.mean(ts))
+    val = ntok / t
+    sample = (f"{ntok} speech tokens, 1 s reference (P=86), full 24x1280 GPT / 13x512 DiT / BigVGAN-v2 geometry, "
+              f"CFM {CFM_STEPS} steps at T={86 + int(2 * ntok * 1.72)}; oracle port, torch CPU fp32, {threads} threads")
+    line = {"impl": "reference", "metric": "speech_tokens_per_s", "value": val, "unit": "tokens/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": 1, "ms_per_step": t * 1000, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16(gpt)+f32(s2mel,vocoder)", "data": "synthetic",
+            "rtf": t / (ntok * AUDIO_S_PER_TOKEN),
+            "config": {"workload": "IndexTTS-2.5 per-segment pipeline, bounded CPU sample: " + sample},
+            "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------- main --
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    if rank != 0:
+        ge.build()
+    dev = torch.device("cuda", local)
+    e, cfg, wg, t_load = build_engine(local)
+
+    # speaker latents: produced on rank 0, broadcast over NCCL (north-star multi-GPU plumbing)
+    inp = make_inputs(100, cfg, wg)
+    lat = {k: inp[k].to(dev).contiguous() for k in ("prompt_condition", "ref_mel", "style", "emo")}
+    if dist is not None:
+        for k in lat:
+            dist.broadcast(lat[k], src=0)
+    # per-rank utterance: own text and noise
+    mine = make_inputs(1000 + rank, cfg, wg)
+    mine.update({k: lat[k].cpu() for k in lat})
+    prompt_emb = e.gpt_prepare_inputs(mine["style"].numpy(), mine["emo"].numpy(), mine["text"].numpy(), 1)
+    mine["pc_d"], mine["mel_d"], mine["style_d"] = lat["prompt_condition"], lat["ref_mel"], lat["style"]
+    mine["z_d"] = mine["z"].to(dev).contiguous()
+    prompt_emb_d = torch.from_numpy(prompt_emb).to(dev)
+    host_in = {k: np.ascontiguousarray(mine[k].numpy()) for k in ("prompt_condition", "ref_mel", "style", "z")}
+    host_in["F"] = mine["F"]
+
+    def barrier():
+        e.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    # ---- device-resident timing ----
+    for _ in range(W):
+        codes, pcm = run_utterance(e, mine, prompt_emb_d, host=False)
+    assert len(codes) == N_TOKENS and pcm.shape[0] == mine["F"] * 256
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = e.launches
+    e.event_record(0)
+    g_ms = c_ms = 0.0
+    gpt_launch_ms, gpt_launches = 0.0, 0
+    for _ in range(K):
+        run_utterance(e, mine, prompt_emb_d, host=False)
+        g, s = stage_breakdown(e)
+        g_ms += g["prefill_ms"] + g["decode_ms"]
+        gpt_launch_ms += g["decode_ms"]
+        gpt_launches += max(1, g["launches"] - 1)
+        c_ms += s["cfm_ms"]
+    e.event_record(1)
+    barrier()
+    clocks = sampler.stop()
+    t_dev = e.event_elapsed_ms(0, 1) / 1000.0
+    launches = e.launches - l0
+    # ---- end to end: host buffers in, pcm16 out, gather on rank 0 ----
+    for _ in range(2):
+        run_utterance(e, host_in, prompt_emb, host=True)
+    barrier()
+    t0 = time.perf_counter()
+    e.event_record(2)
+    for _ in range(K):
+        codes_h, pcm_h = run_utterance(e, host_in, prompt_emb, host=True)
+        if dist is not None:
+            buf = torch.from_numpy(pcm_h).to(dev)
+            outs = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+            dist.gather(buf, outs, dst=0)
+    e.event_record(3)
+    barrier()
+    t_e2e_wall = time.perf_counter() - t0
+    t_e2e = max(e.event_elapsed_ms(2, 3) / 1000.0, 0.0)
+    t_e2e = max(t_e2e, t_e2e_wall if dist is None else t_e2e)
+    h2d = int(prompt_emb.nbytes + sum(host_in[k].nbytes for k in ("prompt_condition", "ref_mel", "style", "z")) + N_TOKENS * 4)
+    d2h = int(N_TOKENS * 4 + mine["F"] * 256 * 2)
+
+    if dist is not None:
+        t = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    tokens = world * K * N_TOKENS
+    value = tokens / t_dev
+    audio_s = N_TOKENS * AUDIO_S_PER_TOKEN
+    hbm_peak, tc_peak, which = peaks()
+    # roofline of the dominant HBM-bound kernel: the fused GPT decode step
+    L, D, V = cfg["layers"], cfg["model_dim"], cfg["number_mel_codes"]
+    w_bytes = (L * (12 * D * D) + D * V) * 2                       # streamed bf16 weights per step
+    ctx = 3 + N_TEXT + 2 + 1 + N_TOKENS / 2.0                      # mean context over the decode
+    kv_bytes = 2 * L * ctx * D * 2 + 2 * L * D * 2
+    step_us = gpt_launch_ms / (K * N_TOKENS) * 1000.0
+    achieved = (w_bytes + kv_bytes) / (step_us * 1e-6) / 1e9
+    cfm_flop = CFM_STEPS * 0.64e12
+    line = {
+        "metric": "speech_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": t_dev / K * 1000.0, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16(gpt weights, fp32 accumulate)+f32(s2mel, vocoder)", "data": "synthetic",
+        "rtf": (t_dev / K) / audio_s, "e2e_rtf": (t_e2e / K) / audio_s,
+        "config": {"workload": "IndexTTS-2.5 infer_v2_5 batch=1 per GPU: 10 s reference (P=861), 32 text tokens, "
+                               "256 greedy speech tokens, codec->length-regulator->CFM 25 steps CFG 0.7 (T=1741)->BigVGAN "
+                               "(225280 samples); speaker/emotion conditioning cached per speaker as in the reference",
+                   "utterances_per_gpu_per_step": 1, "parallelism": f"dp{world} (utterance sharding)",
+                   "l2": "working set >> L2 (0.97 GB of GPT weights streamed per token, 112 M vocoder weights)"},
+        "stage_ms_per_step": {"gpt": g_ms / K, "cfm": c_ms / K, "other": (t_dev * 1000 - g_ms - c_ms) / K},
+        "roofline": {"kernel": "gpt_fused_kernel (decode step)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                     "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": which,
+                     "us_per_decode_step": step_us,
+                     "algorithmic_bytes_per_step": w_bytes + kv_bytes},
+        "roofline_cfm": {"bound": "tensor", "achieved": cfm_flop / (c_ms / K * 1e-3) / 1e12, "peak": tc_peak,
+                         "unit": "TFLOP/s", "frac": cfm_flop / (c_ms / K * 1e-3) / 1e12 / tc_peak,
+                         "note": "0.64 TFLOP per Euler step at T=1741 (SURVEY §8d); peak is the bf16 figure"},
+        "e2e": {"value": tokens / t_e2e, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches), "clocks": clocks, "weights_load_s": t_load,
+    }
+    if not args.no_cpu_baseline:
+        try:
+            threads = os.cpu_count() or 1
+            ntok, once = cpu_reference_sample(threads)
+            once()
+            tcpu = once()
+            line["cpu_baseline"] = {"value": ntok / tcpu, "unit": "tokens/s", "cores": threads, "kind": "port",
+                                    "sample": f"{ntok} tokens, 1 s reference, full model geometry, oracle port (torch CPU), "
+                                              f"{tcpu:.1f} s wall"}
+        except Exception as ex:  # the bench line must survive a CPU-leg hiccup
+            line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"failed: {ex}"}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

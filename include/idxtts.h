@@ -61,6 +61,10 @@ const char* idx_version(void);
 int64_t idx_launch_count(const idx_engine* e);
 /* Block until all work queued by this engine has finished.                          */
 int idx_sync(idx_engine* e);
+/* CUDA events on the engine's own stream (slots 0..15) — what bench.py times with, since the
+ * engine does not launch on torch's current stream.                                   */
+int idx_event_record(idx_engine* e, int slot);
+int idx_event_elapsed_ms(idx_engine* e, int slot_a, int slot_b, double* ms);
 
 /* -------------------------------------------------------------------- weights -- */
 
@@ -240,6 +244,24 @@ int idx_dit_forward(idx_engine* e, const float* x, const float* prompt_x, const 
  *   (s2mel/modules/flow_matching.py:30-115), call site infer_v2_5.py:841-845.           */
 int idx_cfm_solve(idx_engine* e, const float* mu, int T, const float* prompt, int P,
                   const float* style, const float* z, int n_steps, float cfg_rate, float* mel_out);
+
+/* The per-segment tail of IndexTTS2.infer (infer_v2_5.py:827-856) as one call.            */
+typedef struct {
+  const int32_t* codes;           /* [n_codes] generated codes, cut before stop_mel_token (:809-821) */
+  int32_t n_codes;
+  const float* prompt_condition;  /* [P, content_dim] length-regulated reference features (:651-656)  */
+  const float* ref_mel;           /* [80, P] reference mel (:640)                                     */
+  int32_t P;
+  const float* style;             /* [192] campplus style vector (:644-649)                           */
+  const float* z;                 /* [80, P + F] the torch.randn noise of cfm.inference (trap P6)     */
+  int32_t F;                      /* int(2 * n_codes * 1.72 * duration_factor) (:833)                 */
+  float* wav_out;                 /* optional [F * 256] f32 in [-1, 1]                                */
+  int16_t* pcm16_out;             /* optional [F * 256] clamp(32767*wav) as int16 (:855)              */
+  float* mel_out;                 /* optional [80, F] generated mel (tests)                           */
+} idx_vocode_request;
+
+/* codes → codec decode → length regulator → CFM (n_steps, cfg_rate) → BigVGAN → waveform.     */
+int idx_codes_to_wav(idx_engine* e, const idx_vocode_request* r, int n_steps, float cfg_rate);
 
 /* Device ms of the last codec decode / length regulator / CFM solve (CUDA events).       */
 int idx_s2mel_last_ms(const idx_engine* e, double* ms3);

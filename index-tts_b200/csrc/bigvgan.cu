@@ -16,7 +16,7 @@
 //   * the anti-aliased SnakeBeta is ONE fused kernel (2x FIR upsample → snake → FIR downsample)
 //     that reads x once and writes once; threads map to channels (coalesced) and slide along
 //     time with a 6-sample input window and a 12-sample activated window in registers.
-#include "ops.h"
+#include "stages.h"
 #include <cmath>
 #include <cstring>
 
@@ -364,35 +364,29 @@ static void run_convT(idx_engine* e, const ConvW& c, int u, const float* x, floa
   conv_gemm(e, g);
 }
 
-extern "C" int idx_bigvgan_forward(idx_engine* e, const float* mel, int B, int F, float* wav) {
-  IDX_API_BEGIN
-  IDX_CHECK(e && e->bigvgan, IDX_ERR_STATE, "idx_bigvgan_init has not been called");
-  IDX_CHECK(mel && wav && B >= 1 && F >= 1, IDX_ERR_ARG, "bad arguments");
-  IDX_CUDA(cudaSetDevice(e->device));
-  BigvganState* s = e->bigvgan;
+static size_t bigvgan_maxel(const BigvganState* s, int F) {
+  const idx_bigvgan_config& cfg = s->cfg;
+  size_t maxel = (size_t)F * cfg.upsample_initial_channel;
+  int T = F, ch = cfg.upsample_initial_channel;
+  for (int i = 0; i < cfg.num_upsamples; ++i) {
+    T *= cfg.upsample_rates[i]; ch /= 2;
+    maxel = std::max(maxel, (size_t)T * ch);
+  }
+  return maxel;
+}
+size_t bigvgan_arena_bytes(const BigvganState* s, int B, int F) {
+  return 6 * (size_t)B * bigvgan_maxel(s, F) * 4 + 2 * (size_t)B * s->cfg.num_mels * F * 4 +
+         (size_t)B * F * s->total_up * 4 + (1 << 20);
+}
+int bigvgan_total_up(const BigvganState* s) { return s->total_up; }
+
+void bigvgan_forward_dev(idx_engine* e, BigvganState* s, const float* d_mel, int B, int F, float* d_wav) {
   const idx_bigvgan_config& cfg = s->cfg;
   const int nm = cfg.num_mels;
-  // largest [T][C] activation over the stages
-  size_t maxel = (size_t)F * cfg.upsample_initial_channel;
-  {
-    int T = F, ch = cfg.upsample_initial_channel;
-    for (int i = 0; i < cfg.num_upsamples; ++i) {
-      T *= cfg.upsample_rates[i]; ch /= 2;
-      maxel = std::max(maxel, (size_t)T * ch);
-    }
-  }
-  const size_t bufel = (size_t)B * maxel;
-  const size_t out_n = (size_t)B * F * s->total_up;
-  e->ensure_arena(6 * bufel * 4 + 2 * (size_t)B * nm * F * 4 + out_n * 4 + (1 << 20));
-  e->arena.reset();
-  float* d_mel = e->arena.get<float>((size_t)B * nm * F);
+  const size_t bufel = (size_t)B * bigvgan_maxel(s, F);
   float* d_melT = e->arena.get<float>((size_t)B * nm * F);
   float* buf[6];
   for (int i = 0; i < 6; ++i) buf[i] = e->arena.get<float>(bufel);
-  float* d_wav = e->arena.get<float>(out_n);
-
-  idx_to_device(e, d_mel, mel, (size_t)B * nm * F * 4);
-  IDX_CUDA(cudaEventRecord(s->ev0, e->stream));
   transpose_bct_to_btc(e, d_mel, d_melT, B, nm, F);
   // P: stage input, and — once the transposed conv has consumed it — the accumulator of the
   // resblock outputs (= next stage's input).  Q: the upsampled stage signal read by all blocks.
@@ -435,6 +429,23 @@ extern "C" int idx_bigvgan_forward(idx_engine* e, const float* mel, int B, int F
     IDX_CUDA(cudaGetLastError());
     e->launches++;
   }
+}
+
+extern "C" int idx_bigvgan_forward(idx_engine* e, const float* mel, int B, int F, float* wav) {
+  IDX_API_BEGIN
+  IDX_CHECK(e && e->bigvgan, IDX_ERR_STATE, "idx_bigvgan_init has not been called");
+  IDX_CHECK(mel && wav && B >= 1 && F >= 1, IDX_ERR_ARG, "bad arguments");
+  IDX_CUDA(cudaSetDevice(e->device));
+  BigvganState* s = e->bigvgan;
+  const int nm = s->cfg.num_mels;
+  const size_t out_n = (size_t)B * F * s->total_up;
+  e->ensure_arena(bigvgan_arena_bytes(s, B, F) + (size_t)B * nm * F * 4);
+  e->arena.reset();
+  float* d_mel = e->arena.get<float>((size_t)B * nm * F);
+  float* d_wav = e->arena.get<float>(out_n);
+  idx_to_device(e, d_mel, mel, (size_t)B * nm * F * 4);
+  IDX_CUDA(cudaEventRecord(s->ev0, e->stream));
+  bigvgan_forward_dev(e, s, d_mel, B, F, d_wav);
   IDX_CUDA(cudaEventRecord(s->ev1, e->stream));
   idx_from_device(e, wav, d_wav, out_n * 4);
   IDX_CUDA(cudaStreamSynchronize(e->stream));

@@ -114,6 +114,7 @@ void idx_destroy(idx_engine* e) {
   if (e->bigvgan) bigvgan_destroy(e->bigvgan);
   if (e->s2mel) s2mel_destroy(e->s2mel);
   for (auto& kv : e->weights) cudaFree(kv.second.d);
+  for (auto ev : e->events) if (ev) cudaEventDestroy(ev);
   if (e->arena.base) cudaFree(e->arena.base);
   if (e->pinned) cudaFreeHost(e->pinned);
   cudaStreamDestroy(e->stream);
@@ -131,6 +132,27 @@ int idx_sync(idx_engine* e) {
   IDX_API_BEGIN
   IDX_CUDA(cudaSetDevice(e->device));
   IDX_CUDA(cudaStreamSynchronize(e->stream));
+  IDX_API_END(e)
+}
+
+int idx_event_record(idx_engine* e, int slot) {
+  IDX_API_BEGIN
+  IDX_CHECK(e && slot >= 0 && slot < 16, IDX_ERR_ARG, "bad event slot");
+  IDX_CUDA(cudaSetDevice(e->device));
+  if (!e->events[slot]) IDX_CUDA(cudaEventCreate(&e->events[slot]));
+  IDX_CUDA(cudaEventRecord(e->events[slot], e->stream));
+  IDX_API_END(e)
+}
+
+int idx_event_elapsed_ms(idx_engine* e, int slot_a, int slot_b, double* ms) {
+  IDX_API_BEGIN
+  IDX_CHECK(e && ms && slot_a >= 0 && slot_a < 16 && slot_b >= 0 && slot_b < 16 && e->events[slot_a] && e->events[slot_b],
+            IDX_ERR_ARG, "bad event slots");
+  IDX_CUDA(cudaSetDevice(e->device));
+  IDX_CUDA(cudaEventSynchronize(e->events[slot_b]));
+  float f = 0;
+  IDX_CUDA(cudaEventElapsedTime(&f, e->events[slot_a], e->events[slot_b]));
+  *ms = f;
   IDX_API_END(e)
 }
 

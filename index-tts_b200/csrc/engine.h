@@ -83,6 +83,7 @@ struct idx_engine {
   // pinned staging for host<->device copies
   void* pinned = nullptr;
   size_t pinned_cap = 0;
+  cudaEvent_t events[16] = {};
   GptState* gpt = nullptr;
   BigvganState* bigvgan = nullptr;
   S2melState* s2mel = nullptr;

@@ -16,7 +16,7 @@
 //   * the time-invariant part of cond_x_merge_linear ([prompt | cond | style] columns) is folded
 //     into a per-solve constant C0, so each step starts with a K = 80 GEMM;
 //   * the cond / uncond CFG pair runs as batch 2 exactly like the reference (flow_matching.py:88-104).
-#include "ops.h"
+#include "stages.h"
 #include <cmath>
 #include <cstring>
 
@@ -259,7 +259,7 @@ extern "C" int idx_codec_init(idx_engine* e, const idx_codec_config* cfg) {
 
 // ------------------------------------------------------------------ device-side stages --
 // codes (device int32 [n]) -> S_infer (device [2n][hidden])
-static void codec_decode_dev(idx_engine* e, S2melState* s, const int* d_codes, int n, float* d_out) {
+void codec_decode_dev(idx_engine* e, S2melState* s, const int* d_codes, int n, float* d_out) {
   const idx_codec_config& c = s->ccfg;
   const int Hs = c.hidden_size, Vd = c.vocos_dim, Vi = c.vocos_intermediate_dim;
   float* emb = e->arena.get<float>((size_t)n * c.codebook_dim);
@@ -289,7 +289,7 @@ static void codec_decode_dev(idx_engine* e, S2melState* s, const int* d_codes, i
 }
 
 // S (device [n_in][lr_in]) -> cond (device rows written at d_out with row stride = content_dim)
-static void length_regulate_dev(idx_engine* e, S2melState* s, const float* d_S, int n_in, int ylen, float* d_out) {
+void length_regulate_dev(idx_engine* e, S2melState* s, const float* d_S, int n_in, int ylen, float* d_out) {
   const idx_s2mel_config& c = s->cfg;
   const int C = c.content_dim;
   float* a = e->arena.get<float>((size_t)n_in * C);
@@ -483,7 +483,7 @@ static void euler_times(int n, std::vector<float>& t, std::vector<float>& dt) {
 
 // full solve on device buffers. d_mu [T][content], d_prompt [80][P] (NCT), d_style [style],
 // d_z [80][T] (NCT) -> d_mel [80][T] (NCT).
-static void cfm_solve_dev(idx_engine* e, S2melState* s, const float* d_mu, int T, const float* d_prompt, int P,
+void cfm_solve_dev(idx_engine* e, S2melState* s, const float* d_mu, int T, const float* d_prompt, int P,
                           const float* d_style, const float* d_z, int n_steps, float rate, float* d_mel) {
   const idx_s2mel_config& c = s->cfg;
   const int C = c.in_channels, H = c.hidden, Cd = c.content_dim, Sd = c.style_dim;
@@ -525,6 +525,23 @@ static void cfm_solve_dev(idx_engine* e, S2melState* s, const float* d_mu, int T
   (void)H;
 }
 
+size_t codec_arena_bytes(const S2melState* s, int n) {
+  const idx_codec_config& c = s->ccfg;
+  return 4 * (size_t)n * (c.codebook_dim + 5 * c.hidden_size + 2 * c.vocos_dim + c.vocos_intermediate_dim) + (1 << 20);
+}
+size_t lr_arena_bytes(const S2melState* s, int n_in, int ylen) {
+  const idx_s2mel_config& c = s->cfg;
+  return 4 * ((size_t)n_in * (c.lr_in + c.content_dim) + 4 * (size_t)ylen * c.content_dim) + (1 << 20);
+}
+size_t cfm_arena_bytes(const S2melState* s, int T, int n_steps) {
+  const idx_s2mel_config& c = s->cfg;
+  return dit_arena_bytes(s, 2, T) + 4 * (size_t)T * (8 * c.in_channels + 3 * c.content_dim + 6 * c.hidden + 2 * c.style_dim) +
+         4 * (size_t)n_steps * (s->mod_width + 2 * c.wn_hidden * (c.wn_layers + 1) + 6 * c.hidden + 512) + (4 << 20);
+}
+int s2mel_content_dim(const S2melState* s) { return s->cfg.content_dim; }
+int s2mel_codec_hidden(const S2melState* s) { return s->ccfg.hidden_size; }
+bool s2mel_ready(const S2melState* s) { return s && s->has_s2mel && s->has_codec; }
+
 // ------------------------------------------------------------------------------ C-ABI --
 extern "C" int idx_codec_decode(idx_engine* e, const int32_t* codes, int n, float* S_out) {
   IDX_API_BEGIN
@@ -533,7 +550,7 @@ extern "C" int idx_codec_decode(idx_engine* e, const int32_t* codes, int n, floa
   IDX_CUDA(cudaSetDevice(e->device));
   S2melState* s = e->s2mel;
   const idx_codec_config& c = s->ccfg;
-  e->ensure_arena(4 * (size_t)n * (c.codebook_dim + 5 * c.hidden_size + 2 * c.vocos_dim + c.vocos_intermediate_dim) + (1 << 20));
+  e->ensure_arena(codec_arena_bytes(s, n) + 8 * (size_t)n * c.hidden_size);
   e->arena.reset();
   int* d_codes = e->arena.get<int>(n);
   float* d_out = e->arena.get<float>((size_t)2 * n * c.hidden_size);

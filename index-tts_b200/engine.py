@@ -66,6 +66,12 @@ class CodecConfig(C.Structure):
                                          "vocos_intermediate_dim", "vocos_num_layers")]
 
 
+class VocodeRequest(C.Structure):
+    _fields_ = [("codes", C.c_void_p), ("n_codes", C.c_int32), ("prompt_condition", C.c_void_p),
+                ("ref_mel", C.c_void_p), ("P", C.c_int32), ("style", C.c_void_p), ("z", C.c_void_p),
+                ("F", C.c_int32), ("wav_out", C.c_void_p), ("pcm16_out", C.c_void_p), ("mel_out", C.c_void_p)]
+
+
 def fold_weight_norm(sd):
     """torch weight_norm (dim=0) folded into a plain `.weight`: w = g * v / ||v|| — what
     remove_weight_norm() / the parametrisation computes on the fly in the reference."""
@@ -112,6 +118,8 @@ def load_library(path: str = None):
     lib.idx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     lib.idx_destroy.argtypes = [C.c_void_p]
     lib.idx_sync.argtypes = [C.c_void_p]
+    lib.idx_event_record.argtypes = [C.c_void_p, C.c_int]
+    lib.idx_event_elapsed_ms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
     lib.idx_load_weight.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int,
                                     C.POINTER(C.c_int64)]
     lib.idx_gpt_init.argtypes = [C.c_void_p, C.POINTER(GptConfig)]
@@ -134,6 +142,7 @@ def load_library(path: str = None):
     lib.idx_cfm_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_float, C.c_void_p]
     lib.idx_s2mel_last_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    lib.idx_codes_to_wav.argtypes = [C.c_void_p, C.POINTER(VocodeRequest), C.c_int, C.c_float]
     _lib = lib
     return lib
 
@@ -189,6 +198,14 @@ class Engine:
 
     def sync(self):
         self._check(self.lib.idx_sync(self.h), "idx_sync")
+
+    def event_record(self, slot: int):
+        self._check(self.lib.idx_event_record(self.h, int(slot)), "idx_event_record")
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        t = C.c_double()
+        self._check(self.lib.idx_event_elapsed_ms(self.h, int(a), int(b), C.byref(t)), "idx_event_elapsed_ms")
+        return t.value
 
     # ------------------------------------------------------------------ weights --
     def load_weight(self, name: str, t):
@@ -385,3 +402,32 @@ class Engine:
         t = (C.c_double * 3)()
         self._check(self.lib.idx_s2mel_last_ms(self.h, t), "idx_s2mel_last_ms")
         return {"codec_ms": t[0], "length_regulator_ms": t[1], "cfm_ms": t[2]}
+
+    def codes_to_wav(self, codes, prompt_condition, ref_mel, style, z, F, n_steps=25, cfg_rate=0.7,
+                     want_wav=True, want_pcm16=False, want_mel=False, out=None):
+        """infer_v2_5.py:827-856 for one segment.  Host or device (torch.cuda) buffers.
+        Returns dict(wav=[F*256] f32, pcm16=..., mel=[80,F])."""
+        on_dev = torch is not None and isinstance(z, torch.Tensor) and z.is_cuda
+        if on_dev:
+            codes_t = codes.to(torch.int32).contiguous()
+        else:
+            codes_t = np.ascontiguousarray(np.asarray(codes, dtype=np.int32).reshape(-1))
+        pc, rm, st, zz = (_as_f32(a) for a in (prompt_condition, ref_mel, style, z))
+        P = int(rm.shape[-1])
+        up = self._bigvgan_up
+        res = {}
+
+        def mk(shape, dtype_np, dtype_t):
+            if on_dev:
+                return torch.empty(shape, dtype=dtype_t, device=z.device)
+            return np.empty(shape, dtype=dtype_np)
+        if want_wav:
+            res["wav"] = mk((F * up,), np.float32, torch.float32 if torch else None)
+        if want_pcm16:
+            res["pcm16"] = mk((F * up,), np.int16, torch.int16 if torch else None)
+        if want_mel:
+            res["mel"] = mk((80, F), np.float32, torch.float32 if torch else None)
+        r = VocodeRequest(_ptr(codes_t), int(codes_t.shape[0]), _ptr(pc), _ptr(rm), P, _ptr(st), _ptr(zz), int(F),
+                          _ptr(res.get("wav")), _ptr(res.get("pcm16")), _ptr(res.get("mel")))
+        self._check(self.lib.idx_codes_to_wav(self.h, C.byref(r), int(n_steps), float(cfg_rate)), "idx_codes_to_wav")
+        return res

@@ -37,65 +37,11 @@ import numpy as np
 import torch
 
 
-def r16(x: torch.Tensor) -> torch.Tensor:
-    return x.to(torch.bfloat16).to(torch.float32)
+from indextts_b200.synth import gpt_config, make_gpt_weights, r16  # noqa: F401,E402
 
 
-def gpt_config(layers=24, model_dim=1280, heads=20, number_mel_codes=8194, start_mel_token=8192,
-               stop_mel_token=8193, max_mel_tokens=1815, max_text_tokens=600,
-               number_text_tokens=12000, n_langs=8):
-    return dict(layers=layers, model_dim=model_dim, heads=heads, number_mel_codes=number_mel_codes,
-                start_mel_token=start_mel_token, stop_mel_token=stop_mel_token,
-                max_mel_tokens=max_mel_tokens, max_text_tokens=max_text_tokens,
-                number_text_tokens=number_text_tokens, n_langs=n_langs,
-                max_mel_positions=max_mel_tokens + 2 + 1)  # model_v2.py:398-400
 
 
-def make_gpt_weights(cfg, seed=1234, bf16=True, head_gain=4.0):
-    """Deterministic synthetic weights under the reference's state-dict names.
-
-    Init follows transformers_gpt2.py:689-714 (normal std 0.02, c_proj std 0.02/sqrt(2L)) and
-    model_v2.py:249,413-417 (embeddings std 0.02), except that biases / LayerNorm affine get
-    small random values so the bias paths are exercised, and the mel head is scaled by
-    `head_gain` so that greedy decisions are not dominated by ties of near-flat logits.
-    """
-    g = torch.Generator().manual_seed(seed)
-    L, D, V = cfg["layers"], cfg["model_dim"], cfg["number_mel_codes"]
-    w = {}
-
-    def n(*shape, std=0.02):
-        return torch.randn(*shape, generator=g) * std
-
-    for l in range(L):
-        p = f"gpt.h.{l}."
-        w[p + "ln_1.weight"] = 1.0 + n(D, std=0.1)
-        w[p + "ln_1.bias"] = n(D, std=0.05)
-        w[p + "attn.c_attn.weight"] = n(D, 3 * D)
-        w[p + "attn.c_attn.bias"] = n(3 * D)
-        w[p + "attn.c_proj.weight"] = n(D, D, std=0.02 / math.sqrt(2 * L))
-        w[p + "attn.c_proj.bias"] = n(D)
-        w[p + "ln_2.weight"] = 1.0 + n(D, std=0.1)
-        w[p + "ln_2.bias"] = n(D, std=0.05)
-        w[p + "mlp.c_fc.weight"] = n(D, 4 * D)
-        w[p + "mlp.c_fc.bias"] = n(4 * D)
-        w[p + "mlp.c_proj.weight"] = n(4 * D, D, std=0.02 / math.sqrt(2 * L))
-        w[p + "mlp.c_proj.bias"] = n(D)
-    w["gpt.ln_f.weight"] = 1.0 + n(D, std=0.1)
-    w["gpt.ln_f.bias"] = n(D, std=0.05)
-    w["final_norm.weight"] = 1.0 + n(D, std=0.1)
-    w["final_norm.bias"] = n(D, std=0.05)
-    w["mel_head.weight"] = n(V, D, std=head_gain / math.sqrt(D))
-    w["mel_head.bias"] = n(V, std=0.1)
-    w["mel_embedding.weight"] = n(V, D)
-    w["mel_pos_embedding.emb.weight"] = n(cfg["max_mel_positions"], D)
-    w["text_embedding.weight"] = n(cfg["number_text_tokens"] + 1, D)
-    w["text_pos_embedding.emb.weight"] = n(cfg["max_text_tokens"] + 2, D)
-    w["lang_embedding.weight"] = n(cfg["n_langs"] + 1, D)
-    w["spk_emb_proj.weight"] = n(D, 192, std=1.0 / math.sqrt(192))
-    w["spk_emb_proj.bias"] = n(D)
-    if bf16:
-        w = {k: r16(v) for k, v in w.items()}
-    return w
 
 
 def prepare_gpt_inputs(w, style, emo_vec, text_ids, lang, bf16=True):

@@ -27,21 +27,13 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-S2MEL_CFG = dict(hidden=512, heads=8, depth=13, wn_hidden=512, wn_layers=8, wn_kernel=5,
-                 in_channels=80, content_dim=512, style_dim=192, lr_in=1024, lr_convs=4)
-CODEC_CFG = dict(codebook_size=8192, hidden_size=1024, codebook_dim=8, vocos_dim=384,
-                 vocos_intermediate_dim=2048, vocos_num_layers=12)
+from indextts_b200.synth import (CODEC_CFG, S2MEL_CFG, make_codec_weights, make_s2mel_weights,  # noqa: F401,E402
+                                  small_codec_cfg, small_s2mel_cfg)
 
 
-def small_s2mel_cfg():
-    c = dict(S2MEL_CFG)
-    c.update(hidden=128, heads=2, depth=5, wn_hidden=128, wn_layers=3, content_dim=64, lr_in=96)  # FinalLayer needs wn_hidden == hidden
-    return c
 
 
-def small_codec_cfg():
-    return dict(codebook_size=64, hidden_size=96, codebook_dim=8, vocos_dim=48,
-                vocos_intermediate_dim=128, vocos_num_layers=3)
+
 
 
 def fold_weight_norm(sd):
@@ -61,126 +53,8 @@ def fold_weight_norm(sd):
 
 
 # ------------------------------------------------------------------------------ weights --
-def make_s2mel_weights(c, seed=1234):
-    """Seeded synthetic weights under the reference names (as stored in a checkpoint: weight-norm
-    layers keep weight_g/weight_v).  1/sqrt(fan_in) scaling keeps activations O(1); adaLN
-    projections are biased to (scale~1, shift~0) like a trained model."""
-    g = torch.Generator().manual_seed(seed)
-    w = {}
-    H, Dn, WH, NL, C = c["hidden"], c["depth"], c["wn_hidden"], c["wn_layers"], c["in_channels"]
-    inter = ((int(2 * 4 * H / 3) + 255) // 256) * 256
-
-    def lin(name, co, ci, bias=True, gain=1.0):
-        w[name + ".weight"] = torch.randn(co, ci, generator=g) * (gain / math.sqrt(ci))
-        if bias:
-            w[name + ".bias"] = torch.randn(co, generator=g) * 0.05
-
-    def wn(name, shape, bias=True, gain=1.0):
-        v = torch.randn(*shape, generator=g) * (1.0 / math.sqrt(np.prod(shape[1:])))
-        w[name + ".weight_v"] = v
-        w[name + ".weight_g"] = (v.reshape(shape[0], -1).norm(dim=1) * gain *
-                                 (1.0 + 0.1 * torch.randn(shape[0], generator=g))).reshape(shape[0], *([1] * (len(shape) - 1)))
-        if bias:
-            w[name + ".bias"] = torch.randn(shape[0], generator=g) * 0.05
-
-    def adaln(name, dim):
-        w[name + ".project_layer.weight"] = torch.randn(2 * dim, dim, generator=g) * (0.3 / math.sqrt(dim))
-        b = torch.randn(2 * dim, generator=g) * 0.05
-        b[:dim] += 1.0
-        w[name + ".project_layer.bias"] = b
-        w[name + ".norm.weight"] = 1.0 + 0.1 * torch.randn(dim, generator=g)
-
-    e = "cfm.estimator."
-    for l in range(Dn):
-        p = e + f"transformer.layers.{l}."
-        lin(p + "attention.wqkv", 3 * H, H, bias=False)
-        lin(p + "attention.wo", H, H, bias=False, gain=0.5)
-        lin(p + "feed_forward.w1", inter, H, bias=False)
-        lin(p + "feed_forward.w3", inter, H, bias=False)
-        lin(p + "feed_forward.w2", H, inter, bias=False, gain=0.5)
-        adaln(p + "ffn_norm", H)
-        adaln(p + "attention_norm", H)
-        lin(p + "skip_in_linear", H, 2 * H)
-    adaln(e + "transformer.norm", H)
-    wn(e + "x_embedder", (H, C))                      # present in checkpoints, unused by forward
-    w[e + "cond_embedder.weight"] = torch.randn(1024, H, generator=g) * 0.02
-    lin(e + "cond_projection", H, c["content_dim"])
-    for te, dim in (("t_embedder", H), ("t_embedder2", WH)):
-        half = 128
-        w[e + te + ".freqs"] = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half)
-        lin(e + te + ".mlp.0", dim, 256)
-        lin(e + te + ".mlp.2", dim, dim)
-    lin(e + "conv1", WH, H)
-    w[e + "conv2.weight"] = torch.randn(C, WH, 1, generator=g) * (1.0 / math.sqrt(WH))
-    w[e + "conv2.bias"] = torch.randn(C, generator=g) * 0.05
-    for i in range(NL):
-        wn(e + f"wavenet.in_layers.{i}.conv.conv", (2 * WH, WH, c["wn_kernel"]))
-        co = 2 * WH if i < NL - 1 else WH
-        wn(e + f"wavenet.res_skip_layers.{i}.conv.conv", (co, WH, 1), gain=0.5)
-    wn(e + "wavenet.cond_layer.conv.conv", (2 * WH * NL, WH, 1))
-    wn(e + "final_layer.linear", (WH, WH))
-    lin(e + "final_layer.adaLN_modulation.1", 2 * WH, WH, gain=0.3)
-    lin(e + "res_projection", WH, H)
-    w[e + "content_mask_embedder.weight"] = torch.zeros(1, H)
-    lin(e + "skip_linear", H, H + C)
-    lin(e + "cond_x_merge_linear", H, H + 2 * C + c["style_dim"])
-    w[e + "input_pos"] = torch.arange(16384)
-    # length regulator
-    r = "length_regulator."
-    ch = c["content_dim"]
-    w[r + "mask_token"] = torch.zeros(1, ch)
-    w[r + "embedding.weight"] = torch.randn(2048, ch, generator=g) * 0.02
-    lin(r + "content_in_proj", ch, c["lr_in"])
-    for i in range(c["lr_convs"]):
-        w[r + f"model.{3 * i}.weight"] = torch.randn(ch, ch, 3, generator=g) * (1.0 / math.sqrt(3 * ch))
-        w[r + f"model.{3 * i}.bias"] = torch.randn(ch, generator=g) * 0.05
-        w[r + f"model.{3 * i + 1}.weight"] = 1.0 + 0.1 * torch.randn(ch, generator=g)
-        w[r + f"model.{3 * i + 1}.bias"] = torch.randn(ch, generator=g) * 0.05
-    k = 3 * c["lr_convs"]
-    w[r + f"model.{k}.weight"] = torch.randn(ch, ch, 1, generator=g) * (1.0 / math.sqrt(ch))
-    w[r + f"model.{k}.bias"] = torch.randn(ch, generator=g) * 0.05
-    return w
 
 
-def make_codec_weights(c, seed=4321):
-    g = torch.Generator().manual_seed(seed)
-    w = {}
-    Hs, Cd, Vd, Vi = c["hidden_size"], c["codebook_dim"], c["vocos_dim"], c["vocos_intermediate_dim"]
-
-    def t(*shape, std):
-        return torch.randn(*shape, generator=g) * std
-
-    q = "quantizer.quantizers.0."
-    w[q + "codebook.weight"] = t(c["codebook_size"], Cd, std=1.0)
-    for nm, (co, ci) in (("in_project", (Cd, Hs)), ("out_project", (Hs, Cd))):
-        v = t(co, ci, 1, std=1.0 / math.sqrt(ci))
-        w[q + nm + ".weight_v"] = v
-        w[q + nm + ".weight_g"] = v.reshape(co, -1).norm(dim=1).reshape(co, 1, 1) * (1 + 0.1 * torch.randn(co, generator=g)).reshape(co, 1, 1)
-        w[q + nm + ".bias"] = t(co, std=0.05)
-    for part in ("encoder", "decoder"):
-        b = part + ".0."
-        w[b + "embed.weight"] = t(Vd, Hs, 7, std=1.0 / math.sqrt(7 * Hs))
-        w[b + "embed.bias"] = t(Vd, std=0.05)
-        for nm in ("norm", "final_layer_norm"):
-            w[b + nm + ".weight"] = 1.0 + t(Vd, std=0.1)
-            w[b + nm + ".bias"] = t(Vd, std=0.05)
-        for l in range(c["vocos_num_layers"]):
-            p = b + f"convnext.{l}."
-            w[p + "dwconv.weight"] = t(Vd, 1, 7, std=1.0 / math.sqrt(7))
-            w[p + "dwconv.bias"] = t(Vd, std=0.05)
-            w[p + "norm.weight"] = 1.0 + t(Vd, std=0.1)
-            w[p + "norm.bias"] = t(Vd, std=0.05)
-            w[p + "pwconv1.weight"] = t(Vi, Vd, std=1.0 / math.sqrt(Vd))
-            w[p + "pwconv1.bias"] = t(Vi, std=0.05)
-            w[p + "pwconv2.weight"] = t(Vd, Vi, std=1.0 / math.sqrt(Vi))
-            w[p + "pwconv2.bias"] = t(Vd, std=0.05)
-            w[p + "gamma"] = 0.3 + t(Vd, std=0.05)
-        w[part + ".1.weight"] = t(Hs, Vd, std=1.0 / math.sqrt(Vd))
-        w[part + ".1.bias"] = t(Hs, std=0.05)
-    for nm in ("down", "up"):
-        w[nm + ".weight"] = t(Hs, Hs, 3, std=1.0 / math.sqrt(3 * Hs))
-        w[nm + ".bias"] = t(Hs, std=0.05)
-    return w
 
 
 # -------------------------------------------------------------------------------- codec --
