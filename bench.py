@@ -275,7 +275,7 @@ def main():
     sampler.start()
     l0 = e.launches
     e.event_record(0)
-    g_ms = c_ms = 0.0
+    g_ms = c_ms = v_ms = 0.0
     gpt_launch_ms, gpt_launches = 0.0, 0
     for _ in range(K):
         run_utterance(e, mine, prompt_emb_d, host=False)
@@ -284,6 +284,7 @@ def main():
         gpt_launch_ms += g["decode_ms"]
         gpt_launches += max(1, g["launches"] - 1)
         c_ms += s["cfm_ms"]
+        v_ms += e.bigvgan_last_ms()
     e.event_record(1)
     barrier()
     clocks = sampler.stop()
@@ -340,7 +341,8 @@ def main():
                                "(225280 samples); speaker/emotion conditioning cached per speaker as in the reference",
                    "utterances_per_gpu_per_step": 1, "parallelism": f"dp{world} (utterance sharding)",
                    "l2": "working set >> L2 (0.97 GB of GPT weights streamed per token, 112 M vocoder weights)"},
-        "stage_ms_per_step": {"gpt": g_ms / K, "cfm": c_ms / K, "other": (t_dev * 1000 - g_ms - c_ms) / K},
+        "stage_ms_per_step": {"gpt": g_ms / K, "cfm": c_ms / K, "bigvgan": v_ms / K,
+                              "other": (t_dev * 1000 - g_ms - c_ms - v_ms) / K},
         "roofline": {"kernel": "gpt_fused_kernel (decode step)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                      "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": which,
                      "us_per_decode_step": step_us,
@@ -348,6 +350,9 @@ def main():
         "roofline_cfm": {"bound": "tensor", "achieved": cfm_flop / (c_ms / K * 1e-3) / 1e12, "peak": tc_peak,
                          "unit": "TFLOP/s", "frac": cfm_flop / (c_ms / K * 1e-3) / 1e12 / tc_peak,
                          "note": "0.64 TFLOP per Euler step at T=1741 (SURVEY §8d); peak is the bf16 figure"},
+        "roofline_bigvgan": {"bound": "tensor", "achieved": 1.8037e9 * mine["F"] / (v_ms / K * 1e-3) / 1e12, "peak": tc_peak,
+                             "unit": "TFLOP/s", "frac": 1.8037e9 * mine["F"] / (v_ms / K * 1e-3) / 1e12 / tc_peak,
+                             "note": "1.8037 GFLOP per mel frame (SURVEY §8d)"},
         "e2e": {"value": tokens / t_e2e, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches), "clocks": clocks, "weights_load_s": t_load,
     }

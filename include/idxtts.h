@@ -193,6 +193,17 @@ int idx_antialias_snake(idx_engine* e, const float* x, const float* alpha,
 /* Device time of the last idx_bigvgan_forward in ms (CUDA events).                   */
 int idx_bigvgan_last_ms(const idx_engine* e, double* ms);
 
+/* Diagnostic (tests): one multi-tap channels-last GEMM — the building block of every Conv1d /
+ * ConvTranspose1d / Linear of the vocoder and s2mel paths — through a chosen back end
+ * (backend 1 = SIMT fp32, 2 = tcgen05 tf32, 0 = automatic).  wk is K-major [N][taps*K];
+ * D[b][m][n] = scale*(act(sum + bias) + res + (accum ? out : 0)) stored at
+ * out[b*out_elems_per_batch + out_off + m*ldo + n] where 0 <= flat < out_valid.            */
+int idx_debug_conv_gemm(idx_engine* e, const float* A, int B, int Tin, int K, const float* wk,
+                        int taps, int dil, int pad, int M, int N, const float* bias, int biasN,
+                        int act, const float* res, int accum, float scale, long long out_off,
+                        int ldo, long long out_valid, long long out_elems_per_batch, int backend,
+                        float* out);
+
 /* ---------------------------------------------------------------- s2mel + codec -- */
 
 /* Geometry of the s2mel section of config.yaml as MyModel reads it

@@ -379,6 +379,7 @@ size_t bigvgan_arena_bytes(const BigvganState* s, int B, int F) {
          (size_t)B * F * s->total_up * 4 + (1 << 20);
 }
 int bigvgan_total_up(const BigvganState* s) { return s->total_up; }
+void bigvgan_set_ms(BigvganState* s, double ms) { s->last_ms = ms; }
 
 void bigvgan_forward_dev(idx_engine* e, BigvganState* s, const float* d_mel, int B, int F, float* d_wav) {
   const idx_bigvgan_config& cfg = s->cfg;

@@ -1,4 +1,287 @@
-// gemm_tc.cu — tcgen05 implicit-GEMM back end of conv_gemm() (placeholder until the kernel lands).
+// gemm_tc.cu — tcgen05 implicit-GEMM back end of conv_gemm() for sm_100a.
+//
+//   D[b][m][n] = epi( sum_tap sum_k A[b][m + tap*dil - pad][k] * Wk[n][tap*K + k] )
+//
+// One CTA computes a 128 x BN output tile (M = time rows, N = output channels):
+//   warp 0      TMA producer: per (tap, k-chunk) one 3-D box of the activations [B][T][K]
+//               (32 fp32 x 128 rows, SWIZZLE_128B; rows outside [0,T) and columns >= K are
+//               zero-filled by TMA = Conv1d zero padding / ragged K for free) and one 2-D box of the
+//               K-major weights, into a ring of shared-memory stages (mbarrier full/empty);
+//   warp 1      allocates TMEM, issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8 per instruction,
+//               4 per stage) from shared-memory descriptors, commits to the stage's empty barrier;
+//               the fp32 accumulator tile lives in TMEM (BN columns x 128 lanes);
+//   warps 2..5  epilogue: tcgen05.ld the accumulator (each warp its 32-lane quarter), apply
+//               bias / activation / layer-scale / residual / accumulate / scale, store with the
+//               generic (out_off, ldo, out_valid) mapping that also serves ConvTranspose1d.
+// Operands are fp32 in HBM; the tensor maps use TFLOAT32 so the TMA unit rounds to tf32 on load.
 #include "ops.h"
-bool gemm_tc_supported(const ConvGemm&) { return false; }
-void gemm_tc_launch(idx_engine*, const ConvGemm&) { throw IdxError(IDX_ERR_STATE, "tcgen05 GEMM not built"); }
+#include "ptx.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <map>
+#include <tuple>
+#include <cstdlib>
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 32;   // fp32 elements = 128 bytes = one SWIZZLE_128B row
+
+__device__ __forceinline__ float apply_act_tc(float v, int act) {
+  switch (act) {
+    case ACT_GELU_ERF: return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+    case ACT_SILU: return v / (1.f + __expf(-v));
+    case ACT_MISH: {
+      float sp = (v > 20.f) ? v : log1pf(__expf(v));
+      return v * tanhf(sp);
+    }
+    case ACT_GELU_TANH: {
+      float u = 0.7978845608028654f * (v + 0.044715f * v * v * v);
+      return 0.5f * v * (1.f + tanhf(u));
+    }
+    case ACT_RELU: return v > 0.f ? v : 0.f;
+    default: return v;
+  }
+}
+
+struct TcParams {
+  int M, N, K, taps, dil, pad, a_bcast;
+  int n_kchunks;        // ceil(K / BK)
+  const float* bias; int biasN; int act;
+  const float* res; const float* rowscale; const float* colscale;
+  int accum; float scale;
+  float* out; long long out_batch_stride, out_off, out_valid; int ldo;
+  int stages;
+};
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B: start address (>>4), LBO (unused for
+// swizzled K-major, set to 1), SBO = 1024 B (8 rows x 128 B), version = 1 (sm_100), layout = 2.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const TcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // carve: stages x (A 16 KB | B BN*128 B), then barriers
+  unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int A_BYTES = BM * BK * 4;
+  constexpr int B_BYTES = BN * BK * 4;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  uint64_t* full = (uint64_t*)(base + (size_t)p.stages * STAGE_BYTES);
+  uint64_t* empty = full + p.stages;
+  uint64_t* accum_full = empty + p.stages;
+  uint32_t* tmem_slot = (uint32_t*)(accum_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, b = blockIdx.z;
+  const int n_iters = p.taps * p.n_kchunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    ptx::mbar_init(accum_full, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+  }
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::prefetch_tensormap(&tmA);
+      ptx::prefetch_tensormap(&tmB);
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1u;
+        ptx::mbar_wait(&empty[s], ph ^ 1u);
+        const int tap = it / p.n_kchunks, kc = it % p.n_kchunks;
+        unsigned char* sa = base + (size_t)s * STAGE_BYTES;
+        unsigned char* sb = sa + A_BYTES;
+        ptx::mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+        ptx::tma_load_3d(sa, &tmA, &full[s], kc * BK, m0 + tap * p.dil - p.pad, p.a_bcast ? 0 : b);
+        ptx::tma_load_2d(sb, &tmB, &full[s], tap * p.K + kc * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3, M>>4
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(BM >> 4) << 24);
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1u;
+        ptx::mbar_wait(&full[s], ph);
+        ptx::tcgen05_fence_after();
+        const uint32_t sa = ptx::smem_u32(base + (size_t)s * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+        const uint64_t da = make_desc(sa), db = make_desc(sb);
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          // advance 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
+          ptx::umma_tf32(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                         (it > 0 || k > 0) ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty[s]);
+      }
+      ptx::umma_commit(accum_full);
+    }
+  } else {
+    // ---------------- epilogue warps (2..5): TMEM lane quarter = warp % 4 ----------------
+    const int q = warp & 3;
+    ptx::mbar_wait(accum_full, 0);
+    ptx::tcgen05_fence_after();
+    const int m = m0 + q * 32 + lane;
+    const long long obs = p.out_batch_stride;
+    const int biasN = p.biasN ? p.biasN : p.N;
+    const float rs = (p.rowscale && m < p.M) ? p.rowscale[(long long)b * p.M + m] : 1.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      ptx::tmem_ld_wait();
+      if (m < p.M) {
+        const long long rowflat = p.out_off + (long long)m * p.ldo;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = n0 + c0 + j;
+          if (n >= p.N) break;
+          const long long flat = rowflat + n;
+          if (flat < 0 || flat >= p.out_valid) continue;
+          float v = __uint_as_float(r[j]);
+          if (p.bias) v += __ldg(p.bias + (n % biasN));
+          v = apply_act_tc(v, p.act);
+          if (p.colscale) v *= __ldg(p.colscale + n);
+          v *= rs;
+          const long long o = (long long)b * obs + flat;
+          if (p.res) v += p.res[o];
+          if (p.accum) v += p.out[o];
+          p.out[o] = v * p.scale;
+        }
+      }
+    }
+    ptx::tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+  }
+}
+
+PFN_cuTensorMapEncodeTiled get_encode() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) != cudaSuccess || !f)
+      throw IdxError(IDX_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    fn = (PFN_cuTensorMapEncodeTiled)f;
+  }
+  return fn;
+}
+
+using MapKey = std::tuple<const void*, long long, long long, long long, long long, int, int>;
+std::map<MapKey, CUtensorMap>& map_cache() {
+  static std::map<MapKey, CUtensorMap> c;
+  return c;
+}
+
+CUtensorMap make_map(const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                     const cuuint32_t* box) {
+  static const bool plain_f32 = getenv("IDX_TMA_F32") != nullptr;
+  MapKey key(ptr, (long long)dims[0], (long long)dims[1], rank > 2 ? (long long)dims[2] : 0,
+             (long long)strides_bytes[0] ^ ((rank > 2 ? (long long)strides_bytes[1] : 0) << 20), (int)box[1], rank);
+  auto& cache = map_cache();
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  CUtensorMap m;
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = get_encode()(&m, plain_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32,
+                            (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    throw IdxError(IDX_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  if (cache.size() > 20000) cache.clear();
+  cache.emplace(key, m);
+  return m;
+}
+
+template <int BN>
+void launch_bn(idx_engine* e, const ConvGemm& g, const CUtensorMap& tmA, const CUtensorMap& tmB) {
+  TcParams p;
+  p.M = g.M; p.N = g.N; p.K = g.K; p.taps = g.taps; p.dil = g.dil; p.pad = g.pad; p.a_bcast = g.a_bcast;
+  p.n_kchunks = (g.K + BK - 1) / BK;
+  p.bias = g.bias; p.biasN = g.biasN; p.act = g.act;
+  p.res = g.res; p.rowscale = g.rowscale; p.colscale = g.colscale;
+  p.accum = g.accum; p.scale = g.scale; p.out = g.out;
+  p.ldo = g.ldo ? g.ldo : g.N;
+  p.out_batch_stride = g.out_batch_stride ? g.out_batch_stride : (long long)g.M * g.N;
+  p.out_off = g.out_off;
+  p.out_valid = g.out_valid ? g.out_valid : (long long)g.M * p.ldo;
+  constexpr int STAGE = BM * BK * 4 + BN * BK * 4;
+  const int n_iters = p.taps * p.n_kchunks;
+  int stages = (200 * 1024) / STAGE;
+  if (stages > 8) stages = 8;
+  if (stages > n_iters) stages = n_iters < 2 ? 2 : n_iters;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * STAGE + 1024 + (2 * stages + 1) * 8 + 16;
+  static bool attr_done = false;
+  if (!attr_done) {
+    IDX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.B);
+  gemm_tc_kernel<BN><<<grid, 192, smem, e->stream>>>(tmA, tmB, p);
+  IDX_CUDA(cudaGetLastError());
+  e->launches++;
+}
+
+}  // namespace
+
+bool gemm_tc_supported(const ConvGemm& g) {
+  static const bool off = getenv("IDX_NO_TC") != nullptr;
+  if (off || g.reflect || !g.Wk) return false;
+  if (g.K % 4 != 0) return false;                             // 16-byte global strides
+  const int lda = g.lda ? g.lda : g.K;
+  if (lda % 4 != 0) return false;
+  if (((uintptr_t)g.A & 15) || ((uintptr_t)g.Wk & 15)) return false;
+  const long long abs_ = g.a_batch_stride ? g.a_batch_stride : (long long)g.Tin * lda;
+  if (abs_ % 4 != 0) return false;
+  if ((long long)g.M * g.N * g.K * g.taps < (1 << 18)) return false;   // tiny problems: SIMT
+  return true;
+}
+
+void gemm_tc_launch(idx_engine* e, const ConvGemm& g) {
+  const int lda = g.lda ? g.lda : g.K;
+  const long long abs_ = g.a_bcast ? (long long)g.Tin * lda : (g.a_batch_stride ? g.a_batch_stride : (long long)g.Tin * lda);
+  // A: [B][Tin][K] fp32, dims (K, Tin, B)
+  cuuint64_t adims[3] = {(cuuint64_t)g.K, (cuuint64_t)g.Tin, (cuuint64_t)(g.a_bcast ? 1 : g.B)};
+  cuuint64_t astr[2] = {(cuuint64_t)lda * 4, (cuuint64_t)abs_ * 4};
+  cuuint32_t abox[3] = {BK, BM, 1};
+  CUtensorMap tmA = make_map(g.A, 3, adims, astr, abox);
+  // B: Wk [N][taps*K] fp32, dims (taps*K, N)
+  cuuint64_t bdims[2] = {(cuuint64_t)g.taps * g.K, (cuuint64_t)g.N};
+  cuuint64_t bstr[1] = {(cuuint64_t)g.taps * g.K * 4};
+  const int BN = g.N <= 32 ? 32 : (g.N <= 64 ? 64 : 128);
+  cuuint32_t bbox[2] = {BK, (cuuint32_t)BN};
+  CUtensorMap tmB = make_map(g.Wk, 2, bdims, bstr, bbox);
+  if (BN == 32) launch_bn<32>(e, g, tmA, tmB);
+  else if (BN == 64) launch_bn<64>(e, g, tmA, tmB);
+  else launch_bn<128>(e, g, tmA, tmB);
+}

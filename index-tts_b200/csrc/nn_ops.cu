@@ -156,6 +156,16 @@ __global__ void silu_kernel(float* x, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { const float v = x[i]; x[i] = v / (1.f + expf(-v)); }
 }
+__global__ void reflect_pad_kernel(const float* __restrict__ x, float* __restrict__ y, int T, int C, int left,
+                                   int Tout) {
+  const int bi = blockIdx.z, i = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  int t = i - left;
+  if (t < 0) t = -t;
+  if (t >= T) t = 2 * (T - 1) - t;
+  y[((long long)bi * Tout + i) * C + c] = x[((long long)bi * T + t) * C + c];
+}
 __global__ void zero_kernel(float* x, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) x[i] = 0.f;
@@ -376,6 +386,12 @@ void silu_inplace(idx_engine* e, float* x, long long n) {
 }
 void fill_zero(idx_engine* e, float* x, long long n) {
   zero_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(x, n);
+  LAUNCH_CHECK(e);
+}
+void reflect_pad_rows(idx_engine* e, const float* x, float* y, int B, int T, int C, int left, int right) {
+  const int Tout = T + left + right;
+  dim3 grid((C + 127) / 128, Tout, B);
+  reflect_pad_kernel<<<grid, 128, 0, e->stream>>>(x, y, T, C, left, Tout);
   LAUNCH_CHECK(e);
 }
 void rope_table(idx_engine* e, float* tab, int T, int hd) {

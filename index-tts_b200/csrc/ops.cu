@@ -135,10 +135,17 @@ __global__ void transpose_kernel(const float* in, float* out, int R, int Cc) {
 
 }  // namespace
 
+static int g_force_backend = 0;  // 0 auto, 1 SIMT, 2 tensor core (diagnostics)
+
 void conv_gemm(idx_engine* e, const ConvGemm& g) {
   IDX_CHECK(g.A && g.out && g.M > 0 && g.N > 0 && g.K > 0, IDX_ERR_ARG, "conv_gemm: bad arguments");
   static const bool force_simt = getenv("IDX_FORCE_SIMT") != nullptr;
-  if (!force_simt && g.Wk && gemm_tc_supported(g)) {
+  if (g_force_backend == 2) {
+    IDX_CHECK(g.Wk && !g.reflect, IDX_ERR_ARG, "conv_gemm: tensor-core path not applicable");
+    gemm_tc_launch(e, g);
+    return;
+  }
+  if (!force_simt && g_force_backend != 1 && g.Wk && gemm_tc_supported(g)) {
     gemm_tc_launch(e, g);
     return;
   }
@@ -229,4 +236,55 @@ ConvGemm gemm_of(const PackedW& w, const float* A, int B, int T, float* out) {
   g.taps = w.taps; g.dil = w.dil; g.pad = (w.taps * w.dil - w.dil) / 2;
   g.M = T; g.N = w.N; g.bias = w.bias; g.out = out;
   return g;
+}
+
+namespace {
+__global__ void kmajor_to_simt_kernel(const float* wk, float* ws, int N, int KT) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * KT) return;
+  int n = (int)(i / KT), k = (int)(i % KT);
+  ws[(long long)k * N + n] = wk[i];
+}
+}  // namespace
+
+// Diagnostic entry (tests): run one multi-tap GEMM through a chosen back end.
+// wk is the K-major weight [N][taps*K]; out is [B][out_rows][ldo]-shaped via (out_off, ldo, out_valid).
+extern "C" int idx_debug_conv_gemm(idx_engine* e, const float* A, int B, int Tin, int K, const float* wk, int taps,
+                                   int dil, int pad, int M, int N, const float* bias, int biasN, int act,
+                                   const float* res, int accum, float scale, long long out_off, int ldo,
+                                   long long out_valid, long long out_elems_per_batch, int backend, float* out) {
+  IDX_API_BEGIN
+  IDX_CHECK(e && A && wk && out, IDX_ERR_ARG, "null argument");
+  IDX_CUDA(cudaSetDevice(e->device));
+  const size_t na = (size_t)B * Tin * K, nw = (size_t)N * taps * K, no = (size_t)B * out_elems_per_batch;
+  e->ensure_arena(4 * (na + 2 * nw + 2 * no + (size_t)N) + (1 << 20));
+  e->arena.reset();
+  float* dA = e->arena.get<float>(na);
+  float* dWk = e->arena.get<float>(nw);
+  float* dWs = e->arena.get<float>(nw);
+  float* dOut = e->arena.get<float>(no);
+  float* dRes = res ? e->arena.get<float>(no) : nullptr;
+  float* dBias = bias ? e->arena.get<float>(biasN ? biasN : N) : nullptr;
+  idx_to_device(e, dA, A, na * 4);
+  idx_to_device(e, dWk, wk, nw * 4);
+  idx_to_device(e, dOut, out, no * 4);   // initial contents matter for accum
+  if (res) idx_to_device(e, dRes, res, no * 4);
+  if (bias) idx_to_device(e, dBias, bias, (size_t)(biasN ? biasN : N) * 4);
+  kmajor_to_simt_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, e->stream>>>(dWk, dWs, N, taps * K);
+  IDX_CUDA(cudaGetLastError());
+  ConvGemm g;
+  g.A = dA; g.B = B; g.Tin = Tin; g.K = K; g.W = dWs; g.Wk = dWk; g.taps = taps; g.dil = dil; g.pad = pad;
+  g.M = M; g.N = N; g.bias = dBias; g.biasN = biasN; g.act = act; g.res = dRes; g.accum = accum; g.scale = scale;
+  g.out = dOut; g.out_off = out_off; g.ldo = ldo; g.out_valid = out_valid; g.out_batch_stride = out_elems_per_batch;
+  g_force_backend = backend;
+  try {
+    conv_gemm(e, g);
+  } catch (...) {
+    g_force_backend = 0;
+    throw;
+  }
+  g_force_backend = 0;
+  idx_from_device(e, out, dOut, no * 4);
+  IDX_CUDA(cudaStreamSynchronize(e->stream));
+  IDX_API_END(e)
 }

@@ -79,6 +79,8 @@ void attention_rope(idx_engine* e, const float* qkv, float* out, int B, int T, i
 void cfg_euler(idx_engine* e, float* x, const float* v_cond, const float* v_uncond, float dt, float rate,
                int T, int C, int P);
 void fill_zero(idx_engine* e, float* x, long long n);
+// y[b][i][:] = x[b][reflect(i - left)][:], i in [0, T + left + right)   (F.pad mode='reflect')
+void reflect_pad_rows(idx_engine* e, const float* x, float* y, int B, int T, int C, int left, int right);
 
 // ------------------------------------------------------------------------ packed weights --
 struct PackedW {

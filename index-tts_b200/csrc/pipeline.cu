@@ -54,12 +54,21 @@ extern "C" int idx_codes_to_wav(idx_engine* e, const idx_vocode_request* r, int 
   }
   idx_to_device(e, d_style, r->style, 192 * 4);
   idx_to_device(e, d_z, r->z, (size_t)C * T * 4);
+  auto stamp = [&](int slot) {
+    if (!e->events[slot]) IDX_CUDA(cudaEventCreate(&e->events[slot]));
+    IDX_CUDA(cudaEventRecord(e->events[slot], e->stream));
+  };
+  stamp(10);
   codec_decode_dev(e, s, d_codes, n, d_S);                              // infer_v2_5.py:832
+  stamp(11);
   length_regulate_dev(e, s, d_S, 2 * n, F, d_mu + (size_t)P * Cd);      // :835-840 (cat with prompt_condition)
+  stamp(12);
   cfm_solve_dev(e, s, d_mu, T, d_prompt, P, d_style, d_z, n_steps, cfg_rate, d_mel);   // :841-845
+  stamp(13);
   crop_cols_kernel<<<(unsigned)(((long long)C * F + 255) / 256), 256, 0, e->stream>>>(d_mel, T, P, d_melF, F, C);  // :846
   IDX_CUDA(cudaGetLastError()); e->launches++;
   bigvgan_forward_dev(e, bv, d_melF, 1, F, d_wav);                      // :850
+  stamp(14);
   if (r->mel_out) idx_from_device(e, r->mel_out, d_melF, (size_t)C * F * 4);
   if (r->wav_out) idx_from_device(e, r->wav_out, d_wav, (size_t)F * up * 4);
   if (r->pcm16_out) {
@@ -68,5 +77,12 @@ extern "C" int idx_codes_to_wav(idx_engine* e, const idx_vocode_request* r, int 
     idx_from_device(e, r->pcm16_out, d_pcm, (size_t)F * up * 2);
   }
   IDX_CUDA(cudaStreamSynchronize(e->stream));
+  float m0, m1, m2, m3;
+  IDX_CUDA(cudaEventElapsedTime(&m0, e->events[10], e->events[11]));
+  IDX_CUDA(cudaEventElapsedTime(&m1, e->events[11], e->events[12]));
+  IDX_CUDA(cudaEventElapsedTime(&m2, e->events[12], e->events[13]));
+  IDX_CUDA(cudaEventElapsedTime(&m3, e->events[13], e->events[14]));
+  s2mel_set_ms(s, m0, m1, m2);
+  bigvgan_set_ms(bv, m3);
   IDX_API_END(e)
 }

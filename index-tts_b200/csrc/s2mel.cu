@@ -305,7 +305,7 @@ void length_regulate_dev(idx_engine* e, S2melState* s, const float* d_S, int n_i
 }
 
 struct DitBuffers {
-  float *h[16], *a, *qkv, *att, *ff, *cat, *xres, *wy, *wxin, *wacts, *wout, *z, *v, *rope;
+  float *h[16], *a, *qkv, *att, *ff, *cat, *xres, *wy, *wpad, *wxin, *wacts, *wout, *z, *v, *rope;
   int* lens;
 };
 
@@ -367,8 +367,12 @@ static void dit_eval(idx_engine* e, S2melState* s, DitBuffers& b, int Bn, int T,
   // WaveNet (wavenet.py:132-166), masks are all-ones for full-length sequences
   fill_zero(e, b.wout, (long long)Bn * T * WH);
   for (int i = 0; i < NL; ++i) {
-    ConvGemm gi = gemm_of(s->wn_in[i], b.wy, Bn, T, b.wxin);
-    gi.reflect = 1;   // SConv1d pad_mode='reflect' (encodec.py:196-229)
+    // SConv1d pad_mode='reflect' (encodec.py:196-229): materialise the reflected halo rows so the
+    // conv is a plain zero-pad-free multi-tap GEMM (tensor-core path; TMA cannot reflect)
+    const int kk = s->wn_in[i].taps, pl = (kk - 1) - (kk - 1) / 2, pr = (kk - 1) / 2;
+    reflect_pad_rows(e, b.wy, b.wpad, Bn, T, WH, pl, pr);
+    ConvGemm gi = gemm_of(s->wn_in[i], b.wpad, Bn, T + kk - 1, b.wxin);
+    gi.pad = 0; gi.M = T;
     conv_gemm(e, gi);
     wn_gate(e, b.wxin, wncond + (size_t)i * 2 * WH, 0, b.wacts, Bn, T, WH);
     if (i < NL - 1) {
@@ -403,6 +407,7 @@ static void alloc_dit(idx_engine* e, S2melState* s, DitBuffers& b, int Bn, int T
   b.cat = e->arena.get<float>(bt * 2 * H);
   b.xres = e->arena.get<float>(bt * H);
   b.wy = e->arena.get<float>(bt * WH);
+  b.wpad = e->arena.get<float>((size_t)Bn * (T + 8) * WH);
   b.wxin = e->arena.get<float>(bt * 2 * WH);
   b.wacts = e->arena.get<float>(bt * WH);
   b.wout = e->arena.get<float>(bt * WH);
@@ -415,7 +420,7 @@ static void alloc_dit(idx_engine* e, S2melState* s, DitBuffers& b, int Bn, int T
 static size_t dit_arena_bytes(const S2melState* s, int Bn, int T) {
   const idx_s2mel_config& c = s->cfg;
   const size_t bt = (size_t)Bn * T;
-  return 4 * (bt * c.hidden * (12 + 1 + 3 + 1 + 2 + 1) + bt * 3 * s->inter + bt * c.wn_hidden * 6 + bt * c.in_channels +
+  return 4 * (bt * c.hidden * (12 + 1 + 3 + 1 + 2 + 1) + bt * 3 * s->inter + bt * c.wn_hidden * 7 + (size_t)Bn * 8 * c.wn_hidden + bt * c.in_channels +
               (size_t)T * 64) + 64 * 256;
 }
 
@@ -541,6 +546,7 @@ size_t cfm_arena_bytes(const S2melState* s, int T, int n_steps) {
 int s2mel_content_dim(const S2melState* s) { return s->cfg.content_dim; }
 int s2mel_codec_hidden(const S2melState* s) { return s->ccfg.hidden_size; }
 bool s2mel_ready(const S2melState* s) { return s && s->has_s2mel && s->has_codec; }
+void s2mel_set_ms(S2melState* s, double codec, double lr, double cfm) { s->ms_codec = codec; s->ms_lr = lr; s->ms_cfm = cfm; }
 
 // ------------------------------------------------------------------------------ C-ABI --
 extern "C" int idx_codec_decode(idx_engine* e, const int32_t* codes, int n, float* S_out) {

@@ -21,3 +21,5 @@ size_t bigvgan_arena_bytes(const BigvganState* s, int B, int F);
 int bigvgan_total_up(const BigvganState* s);
 // d_mel [B][num_mels][F] (NCT) -> d_wav [B][F*total_up]
 void bigvgan_forward_dev(idx_engine* e, BigvganState* s, const float* d_mel, int B, int F, float* d_wav);
+void s2mel_set_ms(S2melState* s, double codec, double lr, double cfm);
+void bigvgan_set_ms(BigvganState* s, double ms);

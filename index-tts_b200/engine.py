@@ -134,6 +134,9 @@ def load_library(path: str = None):
     lib.idx_antialias_snake.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.idx_bigvgan_last_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    lib.idx_debug_conv_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                        C.c_float, C.c_longlong, C.c_int, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p]
     lib.idx_s2mel_init.argtypes = [C.c_void_p, C.POINTER(S2melConfig)]
     lib.idx_codec_init.argtypes = [C.c_void_p, C.POINTER(CodecConfig)]
     lib.idx_codec_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -431,3 +434,26 @@ class Engine:
                           _ptr(res.get("wav")), _ptr(res.get("pcm16")), _ptr(res.get("mel")))
         self._check(self.lib.idx_codes_to_wav(self.h, C.byref(r), int(n_steps), float(cfg_rate)), "idx_codes_to_wav")
         return res
+
+    # --------------------------------------------------------------- diagnostics --
+    def debug_conv_gemm(self, A, wk, taps=1, dil=1, pad=0, M=None, bias=None, act=0, res=None, accum=False,
+                        scale=1.0, out_off=0, ldo=None, out_valid=None, out_rows=None, backend=0, out_init=None,
+                        biasN=0):
+        """One channels-last multi-tap GEMM through a chosen back end (1 SIMT, 2 tcgen05)."""
+        A = np.ascontiguousarray(A, dtype=np.float32)
+        wk = np.ascontiguousarray(wk, dtype=np.float32)
+        B, Tin, K = A.shape
+        N = wk.shape[0]
+        M = Tin if M is None else M
+        ldo = N if ldo is None else ldo
+        out_rows = M if out_rows is None else out_rows
+        per = out_rows * ldo if out_valid is None else int(out_valid)
+        out_valid = per
+        out = np.zeros((B, per), dtype=np.float32) if out_init is None else np.ascontiguousarray(out_init, dtype=np.float32).reshape(B, per).copy()
+        b_ = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
+        r_ = None if res is None else np.ascontiguousarray(res, dtype=np.float32).reshape(B, per)
+        self._check(self.lib.idx_debug_conv_gemm(self.h, _ptr(A), B, Tin, K, _ptr(wk), taps, dil, pad, M, N, _ptr(b_),
+                                                 biasN, act, _ptr(r_), int(accum), float(scale), int(out_off), ldo,
+                                                 int(out_valid), int(per), int(backend), _ptr(out)),
+                    "idx_debug_conv_gemm")
+        return out
