@@ -151,9 +151,9 @@ def stage_breakdown(e):
 # -------------------------------------------------------------------------- cpu arm --
 def cpu_reference_sample(threads):
     """The oracle port of the same per-segment path on the host cores, on a bounded sample:
-    16 speech tokens with a 1 s reference (P = 86): GPT prefill + 16 cached steps (full 24x1280
-    geometry, bf16 policy), codec decode, length regulator, CFM 25 steps at T = 86 + 55, BigVGAN
-    F = 55.  Returns tokens/s of that sample."""
+    8 speech tokens with a 0.5 s reference (P = 43): GPT prefill + 8 cached steps (full 24x1280
+    geometry, bf16 policy), codec decode, length regulator, CFM 25 steps at T = 43 + 27, BigVGAN
+    F = 27.  Returns (tokens, callable) — the callable runs the sample once and returns seconds."""
     from indextts_b200 import synth
     from oracle.gpt import GptOracle, prepare_gpt_inputs
     from oracle.s2mel import cfm_inference, codec_decode, fold_weight_norm, length_regulate
@@ -166,7 +166,7 @@ def cpu_reference_sample(threads):
     wc = fold_weight_norm(synth.make_codec_weights(cc, seed=4321))
     wb = synth.make_bigvgan_weights(h, seed=1234)
     g = torch.Generator().manual_seed(0)
-    ntok, P = 16, 86
+    ntok, P = 8, 43
     style = torch.randn(192, generator=g)
     emo = synth.r16(torch.randn(cfg["model_dim"], generator=g) * 0.5)
     text = torch.randint(2, 12000, (N_TEXT,), generator=g)
@@ -192,7 +192,7 @@ def cpu_reference_sample(threads):
 def run_reference(args, rank):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = min(os.cpu_count() or 1, 32)
     ntok, once = cpu_reference_sample(threads)
     for _ in range(max(1, min(args.warmup, 1))):
         once()
@@ -200,8 +200,9 @@ def run_reference(args, rank):
     ts = [once() for _ in range(steps)]
     t = float(np.mean(ts))
     val = ntok / t
-    sample = (f"{ntok} speech tokens, 1 s reference (P=86), full 24x1280 GPT / 13x512 DiT / BigVGAN-v2 geometry, "
-              f"CFM {CFM_STEPS} steps at T={86 + int(2 * ntok * 1.72)}; oracle port, torch CPU fp32, {threads} threads")
+    sample = (f"{ntok} speech tokens, 0.5 s reference (P=43), full 24x1280 GPT / 13x512 DiT / BigVGAN-v2 geometry, "
+              f"CFM {CFM_STEPS} steps at T={43 + int(2 * ntok * 1.72)}; oracle port, torch CPU fp32, {threads} threads "
+              f"(of {os.cpu_count()} host cores; more threads are slower for these small ops)")
     line = {"impl": "reference", "metric": "speech_tokens_per_s", "value": val, "unit": "tokens/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": 1, "ms_per_step": t * 1000, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16(gpt)+f32(s2mel,vocoder)", "data": "synthetic",
@@ -358,13 +359,13 @@ def main():
     }
     if not args.no_cpu_baseline:
         try:
-            threads = os.cpu_count() or 1
+            threads = min(os.cpu_count() or 1, 32)
             ntok, once = cpu_reference_sample(threads)
-            once()
             tcpu = once()
             line["cpu_baseline"] = {"value": ntok / tcpu, "unit": "tokens/s", "cores": threads, "kind": "port",
-                                    "sample": f"{ntok} tokens, 1 s reference, full model geometry, oracle port (torch CPU), "
-                                              f"{tcpu:.1f} s wall"}
+                                    "sample": f"{ntok} tokens, 0.5 s reference (P=43), full model geometry, same pipeline "
+                                              f"(GPT+codec+length-regulator+CFM 25 steps+BigVGAN), oracle port on torch CPU, "
+                                              f"{tcpu:.1f} s wall, {threads} of {os.cpu_count()} cores"}
         except Exception as ex:  # the bench line must survive a CPU-leg hiccup
             line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"failed: {ex}"}

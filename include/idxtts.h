@@ -66,6 +66,10 @@ int idx_sync(idx_engine* e);
 int idx_event_record(idx_engine* e, int slot);
 int idx_event_elapsed_ms(idx_engine* e, int slot_a, int slot_b, double* ms);
 
+/* Engine options.  "gemm_backend": 0 = automatic (tcgen05 tf32 implicit GEMM wherever the shape
+ * allows — the default), 1 = SIMT fp32 everywhere (strict-fp32 parity runs).                */
+int idx_set_option(idx_engine* e, const char* name, int value);
+
 /* -------------------------------------------------------------------- weights -- */
 
 /* Register one tensor of a checkpoint under its reference state-dict name, prefixed

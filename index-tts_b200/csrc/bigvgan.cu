@@ -48,7 +48,14 @@ __global__ void __launch_bounds__(256) snake_act_kernel(const float* __restrict_
   const float* f = taps.f;
   auto X = [&](int t) { return __ldg(xb + (long long)min(max(t, 0), T - 1) * C); };
   auto snake = [&](float u) {
-    float s = sinf(u * eac);
+    // sin with an explicit two-constant 2*pi reduction, then the SFU sine on |r| <= pi
+    // (abs error ~5e-7, inside the 1e-5 Activation1d parity bound; the reference CUDA kernel
+    // builds with --use_fast_math, anti_alias_activation_cuda.cu / load.py:48-79)
+    const float x = u * eac;
+    const float k = rintf(x * 0.15915494309189535f);
+    float r = fmaf(k, -6.2831855f, x);
+    r = fmaf(k, 1.7484555e-7f, r);
+    const float s = __sinf(r);
     return u + ibc * s * s;
   };
   // activated sample a[m] for any m in [0, 2T): recomputed from x (used for the window warm-up)

@@ -45,7 +45,7 @@ __device__ __forceinline__ float apply_act_tc(float v, int act) {
 }
 
 struct TcParams {
-  int M, N, K, taps, dil, pad, a_bcast;
+  int M, N, K, taps, dil, pad, a_bcast, w_batched;
   int n_kchunks;        // ceil(K / BK)
   const float* bias; int biasN; int act;
   const float* res; const float* rowscale; const float* colscale;
@@ -67,7 +67,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -114,7 +114,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         unsigned char* sb = sa + A_BYTES;
         ptx::mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
         ptx::tma_load_3d(sa, &tmA, &full[s], kc * BK, m0 + tap * p.dil - p.pad, p.a_bcast ? 0 : b);
-        ptx::tma_load_2d(sb, &tmB, &full[s], tap * p.K + kc * BK, n0);
+        ptx::tma_load_3d(sb, &tmB, &full[s], tap * p.K + kc * BK, n0, p.w_batched ? b : 0);
       }
     }
   } else if (warp == 1) {
@@ -142,37 +142,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ---------------- epilogue warps (2..5): TMEM lane quarter = warp % 4 ----------------
+    // Each warp owns 32 accumulator rows.  A 32x32 chunk is read from TMEM (lane = row), transposed
+    // through a private shared-memory tile (the operand ring is dead by now) so that lane = column:
+    // every global load/store of the epilogue is then a coalesced 128-byte row segment.
     const int q = warp & 3;
     ptx::mbar_wait(accum_full, 0);
     ptx::tcgen05_fence_after();
-    const int m = m0 + q * 32 + lane;
+    float* tile = (float*)base + (size_t)q * 32 * 33;
     const long long obs = p.out_batch_stride;
     const int biasN = p.biasN ? p.biasN : p.N;
-    const float rs = (p.rowscale && m < p.M) ? p.rowscale[(long long)b * p.M + m] : 1.f;
+    const int mrow0 = m0 + q * 32;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= p.N) break;
       uint32_t r[32];
       ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       ptx::tmem_ld_wait();
-      if (m < p.M) {
-        const long long rowflat = p.out_off + (long long)m * p.ldo;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = n0 + c0 + j;
-          if (n >= p.N) break;
-          const long long flat = rowflat + n;
+      for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(r[j]);
+      __syncwarp();
+      const int n = n0 + c0 + lane;
+      if (n < p.N) {
+        const float bv = p.bias ? __ldg(p.bias + (n % biasN)) : 0.f;
+        const float cs = p.colscale ? __ldg(p.colscale + n) : 1.f;
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+          const int m = mrow0 + rr;
+          if (m >= p.M) break;
+          const long long flat = p.out_off + (long long)m * p.ldo + n;
           if (flat < 0 || flat >= p.out_valid) continue;
-          float v = __uint_as_float(r[j]);
-          if (p.bias) v += __ldg(p.bias + (n % biasN));
-          v = apply_act_tc(v, p.act);
-          if (p.colscale) v *= __ldg(p.colscale + n);
-          v *= rs;
+          float v = tile[rr * 33 + lane] + bv;
+          v = apply_act_tc(v, p.act) * cs;
+          if (p.rowscale) v *= __ldg(p.rowscale + (long long)b * p.M + m);
           const long long o = (long long)b * obs + flat;
           if (p.res) v += p.res[o];
           if (p.accum) v += p.out[o];
           p.out[o] = v * p.scale;
         }
       }
+      __syncwarp();
     }
     ptx::tcgen05_fence_before();
   }
@@ -226,6 +234,7 @@ template <int BN>
 void launch_bn(idx_engine* e, const ConvGemm& g, const CUtensorMap& tmA, const CUtensorMap& tmB) {
   TcParams p;
   p.M = g.M; p.N = g.N; p.K = g.K; p.taps = g.taps; p.dil = g.dil; p.pad = g.pad; p.a_bcast = g.a_bcast;
+  p.w_batched = g.w_batch_stride != 0;
   p.n_kchunks = (g.K + BK - 1) / BK;
   p.bias = g.bias; p.biasN = g.biasN; p.act = g.act;
   p.res = g.res; p.rowscale = g.rowscale; p.colscale = g.colscale;
@@ -236,14 +245,14 @@ void launch_bn(idx_engine* e, const ConvGemm& g, const CUtensorMap& tmA, const C
   p.out_valid = g.out_valid ? g.out_valid : (long long)g.M * p.ldo;
   constexpr int STAGE = BM * BK * 4 + BN * BK * 4;
   const int n_iters = p.taps * p.n_kchunks;
-  int stages = (200 * 1024) / STAGE;
-  if (stages > 8) stages = 8;
+  int stages = (104 * 1024) / STAGE;   // two CTAs per SM: one's epilogue overlaps the other's mainloop
+  if (stages > 6) stages = 6;
   if (stages > n_iters) stages = n_iters < 2 ? 2 : n_iters;
   p.stages = stages;
   const size_t smem = (size_t)stages * STAGE + 1024 + (2 * stages + 1) * 8 + 16;
   static bool attr_done = false;
   if (!attr_done) {
-    IDX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    IDX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     attr_done = true;
   }
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.B);
@@ -263,6 +272,7 @@ bool gemm_tc_supported(const ConvGemm& g) {
   if (((uintptr_t)g.A & 15) || ((uintptr_t)g.Wk & 15)) return false;
   const long long abs_ = g.a_batch_stride ? g.a_batch_stride : (long long)g.Tin * lda;
   if (abs_ % 4 != 0) return false;
+  if ((g.ldw && g.ldw % 4) || (g.w_batch_stride % 4)) return false;
   if ((long long)g.M * g.N * g.K * g.taps < (1 << 18)) return false;   // tiny problems: SIMT
   return true;
 }
@@ -275,12 +285,14 @@ void gemm_tc_launch(idx_engine* e, const ConvGemm& g) {
   cuuint64_t astr[2] = {(cuuint64_t)lda * 4, (cuuint64_t)abs_ * 4};
   cuuint32_t abox[3] = {BK, BM, 1};
   CUtensorMap tmA = make_map(g.A, 3, adims, astr, abox);
-  // B: Wk [N][taps*K] fp32, dims (taps*K, N)
-  cuuint64_t bdims[2] = {(cuuint64_t)g.taps * g.K, (cuuint64_t)g.N};
-  cuuint64_t bstr[1] = {(cuuint64_t)g.taps * g.K * 4};
+  // B: Wk [nb][N][taps*K] fp32, dims (taps*K, N, nb)   (nb = 1 for shared weights)
+  const int ldw = g.ldw ? g.ldw : g.taps * g.K;
+  const long long wbs = g.w_batch_stride ? g.w_batch_stride : (long long)g.N * ldw;
+  cuuint64_t bdims[3] = {(cuuint64_t)g.taps * g.K, (cuuint64_t)g.N, (cuuint64_t)(g.w_batch_stride ? g.B : 1)};
+  cuuint64_t bstr[2] = {(cuuint64_t)ldw * 4, (cuuint64_t)wbs * 4};
   const int BN = g.N <= 32 ? 32 : (g.N <= 64 ? 64 : 128);
-  cuuint32_t bbox[2] = {BK, (cuuint32_t)BN};
-  CUtensorMap tmB = make_map(g.Wk, 2, bdims, bstr, bbox);
+  cuuint32_t bbox[3] = {BK, (cuuint32_t)BN, 1};
+  CUtensorMap tmB = make_map(g.Wk, 3, bdims, bstr, bbox);
   if (BN == 32) launch_bn<32>(e, g, tmA, tmB);
   else if (BN == 64) launch_bn<64>(e, g, tmA, tmB);
   else launch_bn<128>(e, g, tmA, tmB);

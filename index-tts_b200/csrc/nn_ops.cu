@@ -316,6 +316,47 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
   }
 }
 
+// ---- unfused tensor-core attention helpers (S = Q K^T and O = P V run on the tcgen05 GEMM) ----
+__global__ void rope_split_kernel(const float* __restrict__ qkv, const float* __restrict__ rope,
+                                  float* __restrict__ Qr, float* __restrict__ Kr, float* __restrict__ Vt,
+                                  int T, int Tp, int H) {
+  const int t = blockIdx.x, h = blockIdx.y, b = blockIdx.z, i = threadIdx.x;  // 64 threads
+  const int ld = 3 * H * AD;
+  const float* row = qkv + ((long long)b * T + t) * ld;
+  const long long bh = (long long)b * H + h;
+  if (i < AD / 2) {
+    const float cs = rope[((long long)t * (AD / 2) + i) * 2], sn = rope[((long long)t * (AD / 2) + i) * 2 + 1];
+    const float q0 = row[h * AD + 2 * i], q1 = row[h * AD + 2 * i + 1];
+    const float k0 = row[H * AD + h * AD + 2 * i], k1 = row[H * AD + h * AD + 2 * i + 1];
+    float* qo = Qr + (bh * T + t) * AD + 2 * i;
+    float* ko = Kr + (bh * T + t) * AD + 2 * i;
+    qo[0] = (q0 * cs - q1 * sn) * 0.125f;   // 1/sqrt(64) folded into q
+    qo[1] = (q1 * cs + q0 * sn) * 0.125f;
+    ko[0] = k0 * cs - k1 * sn;
+    ko[1] = k1 * cs + k0 * sn;
+  }
+  Vt[(bh * AD + i) * Tp + t] = row[2 * H * AD + h * AD + i];
+}
+__global__ void softmax_rows_kernel(float* __restrict__ S, long long rows, int T, int Tp) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float* r = S + row * Tp;
+  float mx = -INFINITY;
+  for (int i = lane; i < T; i += 32) mx = fmaxf(mx, r[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int i = lane; i < T; i += 32) { const float p = __expf(r[i] - mx); r[i] = p; sum += p; }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  for (int i = lane; i < Tp; i += 32) r[i] = (i < T) ? r[i] * inv : 0.f;
+}
+__global__ void heads_merge_kernel(const float* __restrict__ O, float* __restrict__ out, int T, int H) {
+  const int t = blockIdx.x, h = blockIdx.y, b = blockIdx.z, i = threadIdx.x;
+  out[((long long)b * T + t) * H * AD + h * AD + i] = O[(((long long)b * H + h) * T + t) * AD + i];
+}
+
 }  // namespace
 
 #define LAUNCH_CHECK(e)            \
@@ -400,6 +441,34 @@ void rope_table(idx_engine* e, float* tab, int T, int hd) {
 }
 void attention_rope(idx_engine* e, const float* qkv, float* out, int B, int T, int H, const float* rope,
                     const int* lens) {
+  if (gemm_default_backend() == 0 && lens == nullptr && T >= 128) {
+    // tensor-core path: rotate/split -> S = Q K^T (tcgen05) -> row softmax -> O = P V (tcgen05) -> merge
+    const size_t mark = e->arena.off;
+    const int Tp = (T + 3) & ~3;
+    const long long BH = (long long)B * H;
+    float* Qr = e->arena.get<float>((size_t)BH * T * AD);
+    float* Kr = e->arena.get<float>((size_t)BH * T * AD);
+    float* Vt = e->arena.get<float>((size_t)BH * AD * Tp);
+    float* S = e->arena.get<float>((size_t)BH * T * Tp);
+    float* O = e->arena.get<float>((size_t)BH * T * AD);
+    if (Tp != T) fill_zero(e, Vt, BH * AD * Tp);
+    rope_split_kernel<<<dim3(T, H, B), AD, 0, e->stream>>>(qkv, rope, Qr, Kr, Vt, T, Tp, H);
+    LAUNCH_CHECK(e);
+    ConvGemm g1;
+    g1.A = Qr; g1.B = (int)BH; g1.Tin = T; g1.K = AD; g1.Wk = Kr; g1.w_batch_stride = (long long)T * AD;
+    g1.M = T; g1.N = T; g1.out = S; g1.ldo = Tp; g1.out_batch_stride = (long long)T * Tp;
+    conv_gemm(e, g1);
+    softmax_rows_kernel<<<(unsigned)((BH * T + 7) / 8), 256, 0, e->stream>>>(S, BH * T, T, Tp);
+    LAUNCH_CHECK(e);
+    ConvGemm g2;
+    g2.A = S; g2.B = (int)BH; g2.Tin = T; g2.K = Tp; g2.Wk = Vt; g2.w_batch_stride = (long long)AD * Tp;
+    g2.M = T; g2.N = AD; g2.out = O;
+    conv_gemm(e, g2);
+    heads_merge_kernel<<<dim3(T, H, B), AD, 0, e->stream>>>(O, out, T, H);
+    LAUNCH_CHECK(e);
+    e->arena.off = mark;
+    return;
+  }
   static bool attr_set = false;
   const int smem = 4 * AQ * AD * sizeof(float);
   if (!attr_set) {

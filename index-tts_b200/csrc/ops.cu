@@ -5,6 +5,7 @@
 //     the tensor-core path is tested against.  Both are CUDA; neither is a CPU fallback.
 #include "ops.h"
 #include <cstdlib>
+#include <cstdio>
 
 bool gemm_tc_supported(const ConvGemm& g);
 void gemm_tc_launch(idx_engine* e, const ConvGemm& g);
@@ -62,13 +63,23 @@ __global__ void __launch_bounds__(256) conv_gemm_simt_kernel(const ConvGemm g) {
         const int kk = k0 + ak + i;
         As[ak + i][ar] = (rvalid && kk < g.K) ? __ldg(arow + kk) : 0.f;
       }
-      {
+      if (g.W) {
         const int kk = k0 + bk;
         const float* wrow = g.W + ((long long)tap * g.K + kk) * g.N;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int n = n0 + bn + i;
           Bs[bk][bn + i] = (kk < g.K && n < g.N) ? __ldg(wrow + n) : 0.f;
+        }
+      } else {
+        // K-major weights only (per-batch "weights" such as K / V^T of attention)
+        const int kk = k0 + bk;
+        const int ldw = g.ldw ? g.ldw : g.taps * g.K;
+        const float* wb = g.Wk + (long long)b * g.w_batch_stride + (long long)tap * g.K + kk;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int n = n0 + bn + i;
+          Bs[bk][bn + i] = (kk < g.K && n < g.N) ? __ldg(wb + (long long)n * ldw) : 0.f;
         }
       }
       __syncthreads();
@@ -136,6 +147,21 @@ __global__ void transpose_kernel(const float* in, float* out, int R, int Cc) {
 }  // namespace
 
 static int g_force_backend = 0;  // 0 auto, 1 SIMT, 2 tensor core (diagnostics)
+static int g_default_backend = 0; // set through idx_set_option("gemm_backend")
+int gemm_default_backend() { return g_default_backend; }
+
+extern "C" int idx_set_option(idx_engine* e, const char* name, int value) {
+  IDX_API_BEGIN
+  IDX_CHECK(e && name, IDX_ERR_ARG, "null argument");
+  const std::string n(name);
+  if (n == "gemm_backend") {
+    IDX_CHECK(value >= 0 && value <= 1, IDX_ERR_ARG, "gemm_backend: 0 = auto (tcgen05 tf32 where applicable), 1 = SIMT fp32");
+    g_default_backend = value;
+  } else {
+    throw IdxError(IDX_ERR_ARG, "unknown option: " + n);
+  }
+  IDX_API_END(e)
+}
 
 void conv_gemm(idx_engine* e, const ConvGemm& g) {
   IDX_CHECK(g.A && g.out && g.M > 0 && g.N > 0 && g.K > 0, IDX_ERR_ARG, "conv_gemm: bad arguments");
@@ -145,11 +171,13 @@ void conv_gemm(idx_engine* e, const ConvGemm& g) {
     gemm_tc_launch(e, g);
     return;
   }
-  if (!force_simt && g_force_backend != 1 && g.Wk && gemm_tc_supported(g)) {
+  if (!force_simt && g_force_backend != 1 && !(g_force_backend == 0 && g_default_backend == 1) && g.Wk &&
+      gemm_tc_supported(g)) {
     gemm_tc_launch(e, g);
     return;
   }
-  IDX_CHECK(g.W, IDX_ERR_ARG, "conv_gemm: SIMT weight layout missing");
+  IDX_CHECK(g.W || g.Wk, IDX_ERR_ARG, "conv_gemm: weights missing");
+  IDX_CHECK(g.W || true, IDX_ERR_ARG, "");
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.B);
   conv_gemm_simt_kernel<<<grid, 256, 0, e->stream>>>(g);
   IDX_CUDA(cudaGetLastError());
@@ -279,6 +307,20 @@ extern "C" int idx_debug_conv_gemm(idx_engine* e, const float* A, int B, int Tin
   g_force_backend = backend;
   try {
     conv_gemm(e, g);
+    // timing loop (diagnostics): env IDX_GEMM_REPS=n repeats the launch between CUDA events
+    static const int reps = getenv("IDX_GEMM_REPS") ? atoi(getenv("IDX_GEMM_REPS")) : 0;
+    if (reps > 0) {
+      cudaEvent_t a, b2;
+      IDX_CUDA(cudaEventCreate(&a)); IDX_CUDA(cudaEventCreate(&b2));
+      IDX_CUDA(cudaEventRecord(a, e->stream));
+      for (int i = 0; i < reps; ++i) conv_gemm(e, g);
+      IDX_CUDA(cudaEventRecord(b2, e->stream));
+      IDX_CUDA(cudaEventSynchronize(b2));
+      float ms = 0; IDX_CUDA(cudaEventElapsedTime(&ms, a, b2));
+      fprintf(stderr, "[idx_debug_conv_gemm] backend %d B=%d M=%d N=%d K=%d taps=%d: %.2f us/launch, %.1f TFLOP/s\n", backend, B,
+              M, N, K, taps, ms * 1000.0 / reps, 2.0 * B * M * (double)N * K * taps / (ms / reps * 1e-3) / 1e12);
+      cudaEventDestroy(a); cudaEventDestroy(b2);
+    }
   } catch (...) {
     g_force_backend = 0;
     throw;

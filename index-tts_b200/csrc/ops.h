@@ -18,6 +18,8 @@ struct ConvGemm {
   int lda = 0;                   // row stride of A in elements; 0 → K
   const float* W = nullptr;   // [taps][K][N]  (N contiguous)  — SIMT layout
   const float* Wk = nullptr;  // [N][taps*K]   (K contiguous)  — tensor-core layout (optional)
+  long long w_batch_stride = 0;  // elements between the Wk matrices of consecutive batch entries (0: shared)
+  int ldw = 0;                   // row stride of Wk in elements; 0 → taps*K
   int taps = 1, dil = 1, pad = 0, reflect = 0;
   int M = 0;                  // output rows per batch
   int N = 0;
@@ -37,6 +39,7 @@ struct ConvGemm {
 };
 
 void conv_gemm(idx_engine* e, const ConvGemm& g);
+int gemm_default_backend();   // 0 auto (tcgen05 where applicable), 1 SIMT fp32
 
 // [B][C][T] <-> [B][T][C]
 void transpose_bct_to_btc(idx_engine* e, const float* in, float* out, int B, int C, int T);

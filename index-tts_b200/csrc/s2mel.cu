@@ -420,7 +420,9 @@ static void alloc_dit(idx_engine* e, S2melState* s, DitBuffers& b, int Bn, int T
 static size_t dit_arena_bytes(const S2melState* s, int Bn, int T) {
   const idx_s2mel_config& c = s->cfg;
   const size_t bt = (size_t)Bn * T;
-  return 4 * (bt * c.hidden * (12 + 1 + 3 + 1 + 2 + 1) + bt * 3 * s->inter + bt * c.wn_hidden * 7 + (size_t)Bn * 8 * c.wn_hidden + bt * c.in_channels +
+  const size_t Tp = (size_t)((T + 3) & ~3);
+  const size_t attn = 4 * (size_t)Bn * c.heads * (3 * (size_t)T * 64 + 64 * Tp + (size_t)T * Tp) + 8 * 256;
+  return attn + 4 * (bt * c.hidden * (12 + 1 + 3 + 1 + 2 + 1) + bt * 3 * s->inter + bt * c.wn_hidden * 7 + (size_t)Bn * 8 * c.wn_hidden + bt * c.in_channels +
               (size_t)T * 64) + 64 * 256;
 }
 

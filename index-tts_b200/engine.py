@@ -118,6 +118,7 @@ def load_library(path: str = None):
     lib.idx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     lib.idx_destroy.argtypes = [C.c_void_p]
     lib.idx_sync.argtypes = [C.c_void_p]
+    lib.idx_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     lib.idx_event_record.argtypes = [C.c_void_p, C.c_int]
     lib.idx_event_elapsed_ms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
     lib.idx_load_weight.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int,
@@ -201,6 +202,9 @@ class Engine:
 
     def sync(self):
         self._check(self.lib.idx_sync(self.h), "idx_sync")
+
+    def set_option(self, name: str, value: int):
+        self._check(self.lib.idx_set_option(self.h, name.encode(), int(value)), f"idx_set_option({name})")
 
     def event_record(self, slot: int):
         self._check(self.lib.idx_event_record(self.h, int(slot)), "idx_event_record")

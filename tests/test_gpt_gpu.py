@@ -5,9 +5,10 @@ Tolerances (bf16 path): logits are bf16 values (ulp 2^-6 = 0.0156 at |x| in [2,4
 [4,8), 0.0625 in [8,16)); the reference path itself is only defined up to its rounding noise
 (HF autocast vs HF fp32 on the 2-layer golden case: rms 0.0185 at logit std 4.1, see
 oracle/validate_gpt_vs_hf.py; the 24-layer geometry accumulates ~1.5x that).  Under teacher
-forcing the engine must agree with the oracle per step to rms <= 0.035 and
-|diff| <= 0.05 + |logit|/64 (2 bf16 ulps of the logit's binade) and its greedy pick must equal
-the oracle's except at near-ties (processed-score gap <= 0.07)."""
+forcing the engine must agree with the oracle per step to rms <= 0.035 and max-abs <= 0.16
+(4.5 sigma of that noise over 8194 logits x 48 steps, plus the final bf16 quantisation of a logit
+of magnitude up to 16) and its greedy pick must equal the oracle's except at near-ties
+(processed-score gap <= 0.07)."""
 import os
 
 import numpy as np
@@ -20,7 +21,7 @@ from oracle.validate_gpt_vs_hf import small_case
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "gpt_small.npz")
-TOL = dict(max_abs=0.05, max_rms=0.035, tie_tol=0.07)
+TOL = dict(max_abs=0.16, max_rms=0.035, tie_tol=0.07)
 
 
 def test_prepare_inputs_matches_oracle(engine):
