@@ -249,8 +249,8 @@ def main():
     inp = make_inputs(100, cfg, wg)
     lat = {k: inp[k].to(dev).contiguous() for k in ("prompt_condition", "ref_mel", "style", "emo")}
     if dist is not None:
-        for k in lat:
-            dist.broadcast(lat[k], src=0)
+        from indextts_b200.sharding import broadcast_latents
+        broadcast_latents(dist, lat, src=0)
     # per-rank utterance: own text and noise
     mine = make_inputs(1000 + rank, cfg, wg)
     mine.update({k: lat[k].cpu() for k in lat})
@@ -300,9 +300,8 @@ def main():
     for _ in range(K):
         codes_h, pcm_h = run_utterance(e, host_in, prompt_emb, host=True)
         if dist is not None:
-            buf = torch.from_numpy(pcm_h).to(dev)
-            outs = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
-            dist.gather(buf, outs, dst=0)
+            from indextts_b200.sharding import gather_wavs
+            gather_wavs(dist, torch.from_numpy(pcm_h).to(dev), rank, world, dst=0)
     e.event_record(3)
     barrier()
     t_e2e_wall = time.perf_counter() - t0
@@ -345,7 +344,10 @@ def main():
         "stage_ms_per_step": {"gpt": g_ms / K, "cfm": c_ms / K, "bigvgan": v_ms / K,
                               "other": (t_dev * 1000 - g_ms - c_ms - v_ms) / K},
         "roofline": {"kernel": "gpt_fused_kernel (decode step)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                     "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": which,
+                     "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": 944.2e6, "traffic_note": "dram read+write per step of the same weight stream, ncu --set full, "
+                                                         "profiles/r01_gpt_fused_ncu.md (prefill instantiation; head phase +21 MB)",
+                     "peak_source": which,
                      "us_per_decode_step": step_us,
                      "algorithmic_bytes_per_step": w_bytes + kv_bytes},
         "roofline_cfm": {"bound": "tensor", "achieved": cfm_flop / (c_ms / K * 1e-3) / 1e12, "peak": tc_peak,

@@ -1,0 +1,138 @@
+"""Drop-in binding for the reference pipeline classes.
+
+`attach(tts)` takes a live reference object — `indextts.infer_v2_5.IndexTTS2` (or `infer_v2.IndexTTS2`)
+built by the reference's own constructor, i.e. with its own config/checkpoint loaders — registers the
+weights of its modules with a B200 engine and rebinds the module-level seams of `infer_generator`
+ to the C-ABI:
+
+    tts.gpt.inference_speech          → idx_gpt_prepare_inputs + idx_gpt_generate   (model_v2.py:716-825)
+    tts.semantic_codec.decode         → idx_codec_decode                            (codec/models.py:205-231)
+    tts.s2mel.models['length_regulator'](…)  → idx_length_regulate                  (length_regulator.py:90-141)
+    tts.s2mel.models['cfm'].inference → idx_cfm_solve                               (flow_matching.py:30-115)
+    tts.bigvgan(mel)                  → idx_bigvgan_forward                         (bigvgan.py:360-386)
+
+`infer_v2_5.py` itself is not modified: `.infer()` keeps its signature, text front-end, prompt caching,
+segment loop and timing prints, and simply reaches these callables instead of the PyTorch modules.  Tensors
+stay torch tensors (containers); the engine receives raw device pointers.  Nothing here falls back to
+PyTorch compute: if the engine cannot be created the call raises.
+"""
+import types
+
+import numpy as np
+import torch
+
+from .engine import Engine, fold_weight_norm
+
+
+def _sd(module):
+    # `inference_model.*` re-exports the same tensors (GPT2InferenceModel shares the blocks, model_v2.py:466-474)
+    return {k: v.detach() for k, v in module.state_dict().items()
+            if torch.is_floating_point(v) and not k.startswith("inference_model.")}
+
+
+def load_reference_weights(engine: Engine, tts, max_batch: int = 1):
+    """Register the weights the reference loaded (checkpoint.py:22-35, commons.py:579-635,
+    codec/models.py:233-247, bigvgan.py:413-492) and size the engine from the modules' own shapes."""
+    gpt = tts.gpt
+    sd = _sd(gpt)
+    engine.load_state_dict("gpt.", sd)
+    layers = len(gpt.gpt.h)
+    D = gpt.model_dim
+    engine.gpt_init(layers, D, gpt.heads, gpt.number_mel_codes, gpt.start_mel_token, gpt.stop_mel_token,
+                    sd["mel_pos_embedding.emb.weight"].shape[0],
+                    max_prompt=sd["text_pos_embedding.emb.weight"].shape[0] + 8, max_batch=max_batch,
+                    weights_bf16=True)
+    # s2mel (weight-norm parametrised layers are folded: g * v / ||v||)
+    s2 = {k[len("models."):]: v for k, v in _sd(tts.s2mel).items()}
+    s2 = fold_weight_norm(s2)
+    engine.load_state_dict("s2mel.", s2)
+    est = "cfm.estimator."
+    H = s2[est + "cond_projection.weight"].shape[0]
+    depth = 1 + max(int(k.split(".")[4]) for k in s2 if k.startswith(est + "transformer.layers."))
+    wn_layers = 1 + max(int(k.split(".")[4]) for k in s2 if k.startswith(est + "wavenet.in_layers."))
+    lr_convs = sum(1 for k in s2 if k.startswith("length_regulator.model.") and k.endswith(".weight")
+                   and s2[k].dim() == 3 and s2[k].shape[-1] == 3)
+    engine.s2mel_init(dict(hidden=H, heads=H // 64, depth=depth, wn_hidden=s2[est + "conv1.weight"].shape[0],
+                           wn_layers=wn_layers, wn_kernel=s2[est + "wavenet.in_layers.0.conv.conv.weight"].shape[-1],
+                           in_channels=s2[est + "conv2.weight"].shape[0],
+                           content_dim=s2[est + "cond_projection.weight"].shape[1],
+                           style_dim=s2[est + "cond_x_merge_linear.weight"].shape[1] - H - 2 * s2[est + "conv2.weight"].shape[0],
+                           lr_in=s2["length_regulator.content_in_proj.weight"].shape[1], lr_convs=lr_convs))
+    cd = fold_weight_norm(_sd(tts.semantic_codec))
+    engine.load_state_dict("codec.", cd)
+    q = "quantizer.quantizers.0."
+    engine.codec_init(dict(codebook_size=cd[q + "codebook.weight"].shape[0], hidden_size=cd["decoder.1.weight"].shape[0],
+                           codebook_dim=cd[q + "codebook.weight"].shape[1], vocos_dim=cd["decoder.1.weight"].shape[1],
+                           vocos_intermediate_dim=cd["decoder.0.convnext.0.pwconv1.weight"].shape[0],
+                           vocos_num_layers=1 + max(int(k.split(".")[3]) for k in cd if k.startswith("decoder.0.convnext."))))
+    bv = fold_weight_norm(_sd(tts.bigvgan))
+    engine.load_state_dict("bigvgan.", bv)
+    engine.bigvgan_init(dict(tts.bigvgan.h))
+    return engine
+
+
+def attach(tts, engine: Engine = None, device: int = 0):
+    """Rebind the compute seams of a reference IndexTTS2 instance to the B200 engine (see module doc)."""
+    engine = engine or Engine(device)
+    load_reference_weights(engine, tts)
+    dev = torch.device("cuda", engine.device)
+    gpt = tts.gpt
+
+    def inference_speech(self, speech_condition, text_inputs, langs=None, emo_speech_condition=None, cond_lengths=None,
+                         emo_cond_lengths=None, emo_vec=None, use_speed=False, campplus_embedding=None, wav=None,
+                         input_tokens=None, num_return_sequences=1, max_generate_length=None, typical_sampling=False,
+                         typical_mass=.9, **hf):
+        # same argument meaning as gpt/model_v2.py:716-825; emo_vec comes from merge_emovec (:833-838)
+        if emo_vec is None or campplus_embedding is None:
+            raise ValueError("the B200 path needs emo_vec and campplus_embedding (what infer_v2_5.py:759-791 passes)")
+        if hf.get("num_beams", 1) != 1 or hf.get("do_sample", False):
+            raise NotImplementedError("round 1 builds greedy decoding (do_sample=False, num_beams=1)")
+        lang = int(langs.reshape(-1)[0]) if langs is not None else 0
+        outs = []
+        for i in range(text_inputs.shape[0]):
+            prompt = engine.gpt_prepare_inputs(campplus_embedding.reshape(-1, 192)[min(i, campplus_embedding.reshape(-1, 192).shape[0] - 1)].float().cpu().numpy(),
+                                               emo_vec.reshape(-1, self.model_dim)[0].float().cpu().numpy(),
+                                               text_inputs[i].cpu().numpy(), lang)
+            max_new = max_generate_length if max_generate_length is not None else self.max_mel_tokens - 1
+            (codes,) = engine.gpt_generate([prompt], int(max_new),
+                                           repetition_penalty=float(hf.get("repetition_penalty", 1.0)))
+            outs.append(torch.from_numpy(codes.astype(np.int64)))
+        n = max(len(o) for o in outs)
+        pad = torch.full((len(outs), n), self.stop_mel_token, dtype=torch.long)
+        for i, o in enumerate(outs):
+            pad[i, : len(o)] = o
+        return pad.to(dev), None
+
+    gpt.inference_speech = types.MethodType(inference_speech, gpt)
+
+    def codec_decode(self, codes):
+        c = codes.reshape(-1, codes.shape[-1])
+        out = [torch.from_numpy(engine.codec_decode(c[i].cpu().numpy())) for i in range(c.shape[0])]
+        return torch.stack(out).to(dev)
+
+    tts.semantic_codec.decode = types.MethodType(codec_decode, tts.semantic_codec)
+
+    class _LengthRegulator(torch.nn.Module):
+        def forward(self, x, ylens=None, n_quantizers=None, f0=None):
+            y = engine.length_regulate(x[0].float().contiguous(), int(ylens.max()))
+            return torch.from_numpy(y)[None].to(dev), ylens, None, None, None
+
+    tts.s2mel.models["length_regulator"] = _LengthRegulator()
+
+    cfm = tts.s2mel.models["cfm"]
+
+    def cfm_inference(self, mu, x_lens, prompt, style, f0, n_timesteps, temperature=1.0, inference_cfg_rate=0.5):
+        B, T = mu.size(0), mu.size(1)
+        z = torch.randn([B, self.in_channels, T], device=mu.device) * temperature   # same RNG call (trap P6)
+        out = engine.cfm_solve(mu[0].float().contiguous(), prompt[0].float().contiguous(), style[0].float().contiguous(),
+                               z[0].contiguous(), n_timesteps, inference_cfg_rate)
+        return torch.from_numpy(out)[None].to(mu.device)
+
+    cfm.inference = types.MethodType(cfm_inference, cfm)
+
+    def bigvgan_forward(mel):
+        return engine.bigvgan_forward(mel.float().contiguous())
+
+    tts.bigvgan.forward = bigvgan_forward
+    tts._b200_engine = engine
+    return tts
