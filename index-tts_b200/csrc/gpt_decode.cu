@@ -43,7 +43,7 @@ constexpr int UPC = 8;                      // weight units (one K-segment of D 
 constexpr int MAXPL = 40;                   // max LayerNorm elements per lane (D <= 1280)
 constexpr int HD = 64;                      // head dim (fixed)
 constexpr int PART_STRIDE = 66;             // attention partial: m, l, o[64]
-#define RED_FLOATS(BT) ((2 * 5 * UPC * (BT)) > (NCW * PART_STRIDE) ? (2 * 5 * UPC * (BT)) : (NCW * PART_STRIDE))
+#define RED_FLOATS(BT) (((BT) == 1 ? 7 * NCW * 8 : 2 * NCW * 64) > (NCW * PART_STRIDE) ? ((BT) == 1 ? 7 * NCW * 8 : 2 * NCW * 64) : (NCW * PART_STRIDE))
 
 struct PrefillTile {
   int seq, pos0, nrows, src_row;
@@ -175,10 +175,29 @@ __device__ __forceinline__ void load_row(float (&v)[NPL], const float* x, int la
 #pragma unroll
   for (int j = 0; j < NPL; ++j) v[j] = __ldcg(x + lane + 32 * j);
 }
+// Activation rows in shared memory (the B operand of the GEMV MMAs) are stored with the 16-byte
+// chunk index XOR-ed by (row & 7), like the weight rows in the ring: the 8 row addresses of an
+// ldmatrix 8x8 tile then hit 8 different bank groups (rows are 10 KB / 2.5 KB apart = 0 mod 128 B).
+__device__ __forceinline__ int xs_idx(int b, int k) { return (((k >> 3) ^ (b & 7)) << 3) | (k & 7); }
+
 template <int NPL>
-__device__ __forceinline__ void store_row_bf16(const float (&v)[NPL], __nv_bfloat16* xs, int lane) {
+__device__ __forceinline__ void store_row_bf16(const float (&v)[NPL], __nv_bfloat16* xs_row, int b, int lane) {
 #pragma unroll
-  for (int j = 0; j < NPL; ++j) xs[lane + 32 * j] = __float2bfloat16_rn(v[j]);
+  for (int j = 0; j < NPL; ++j) xs_row[xs_idx(b, lane + 32 * j)] = __float2bfloat16_rn(v[j]);
+}
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
 // NewGELUActivation with a bf16 round after every tensor op (transformers activations.py,
@@ -245,9 +264,14 @@ __device__ __forceinline__ void ln_block(float (&v)[NPL / 8], float K, const flo
   }
 }
 
-// One GEMV phase over this CTA's column slice.  `nseg` K-segments of D per column.
-// Chunks are consumed in groups of GC so that a warp's GC dot products (one unit per chunk) run
-// interleaved — one dependency chain per phase instead of one per chunk.
+// One GEMV phase over this CTA's column slice on the tensor cores (mma.sync m16n8k16, bf16 in,
+// fp32 accumulate).  The slice is cut into groups of <= 8 columns; one ring chunk holds the 8 weight
+// rows of a group for one K-segment of D (pre-swizzled at pack time).  The MMA's M = 16 rows are the 8
+// weight rows (rows 8..15 alias them), N = 8 are the activation rows of the step (batch / prompt
+// positions; a 1-row step aliases row 0), K runs over the segment: warp w owns k-steps
+// [w*KS, (w+1)*KS), so every warp issues KS x (ldmatrix A, ldmatrix B, mma) per chunk and the 8 partial
+// accumulators are summed through shared memory.  A tile of M = 8 weight rows per 20 KB stage is what
+// keeps the prefetch ring deep; tcgen05's minimum M = 64 would need 160 KB stages.
 // EPI: 0 QKV, 1 O-proj(+residual), 2 FC(+gelu), 3 PROJ(+residual), 4 HEAD
 template <int BT, int EPI, int D>
 __device__ __forceinline__ void gemv_phase(const GptParams& p, const Smem<BT>& sm, int layer,
@@ -255,117 +279,79 @@ __device__ __forceinline__ void gemv_phase(const GptParams& p, const Smem<BT>& s
                                            const int* row_seq, const int* row_pos,
                                            const int* row_valid, int warp, int lane,
                                            const float* bias_ph, int o0, long long* fine = nullptr) {
-  constexpr int GC = (BT == 1) ? 5 : 2;
-  int fi = 0;
-#define FINE() do { if (fine && threadIdx.x == 0 && fi < 12) fine[fi++] = gtimer(); } while (0)
-  const int nunits = ncols * nseg;
-  const int nch = (nunits + UPC - 1) / UPC;
-  constexpr int cpl = D / 256;  // 16-byte chunks per lane
-  const int gcap = min(GC, p.nst - 1);
-  for (int ch0 = 0; ch0 < nch; ch0 += gcap) {
-    const int ng = min(gcap, nch - ch0);
-    float acc[GC][BT];
+  constexpr int GMAX = (BT == 1) ? 7 : 2;           // column groups in flight
+  constexpr int KS = (D / 16) / NCW;                // k-steps per warp per segment
+  constexpr int FFc = 4 * D;
+  const int ngroups = (ncols + 7) >> 3;
+  const int gpb = max(1, min(GMAX, (p.nst - 1) / nseg));
+  // per-lane ldmatrix coordinates
+  const int a_r = lane & 7, a_hi = (lane >> 4) & 1;            // A: row in tile, k-half (matrices 2,3)
+  const int b_n = min(lane & 7, BT - 1), b_hi = (lane >> 3) & 1;
+  const uint32_t ring_base = ptx::smem_u32(sm.ring);
+  const uint32_t xs_base = ptx::smem_u32(sm.xs) + (uint32_t)b_n * FFc * 2;
+  const int g = lane >> 2, t4 = lane & 3;
+  (void)fine;
+  for (int g0 = 0; g0 < ngroups; g0 += gpb) {
+    const int nb = min(gpb, ngroups - g0);
+    float acc[GMAX][4];
 #pragma unroll
-    for (int g = 0; g < GC; ++g)
+    for (int gi = 0; gi < GMAX; ++gi) { acc[gi][0] = acc[gi][1] = acc[gi][2] = acc[gi][3] = 0.f; }
 #pragma unroll
-      for (int b = 0; b < BT; ++b) acc[g][b] = 0.f;
-    FINE();
+    for (int gi = 0; gi < GMAX; ++gi) {
+      if (gi < nb) {
+        for (int sgi = 0; sgi < nseg; ++sgi) {
+          const unsigned n = cons_idx + gi * nseg + sgi;
+          const int stage = n % p.nst;
+          ptx::mbar_wait(&sm.full[stage], (n / p.nst) & 1u);
+          const uint32_t a_row = ring_base + (uint32_t)((stage * UPC + a_r) * D * 2);
+          const uint32_t b_row = xs_base + (uint32_t)(sgi * D * 2);
 #pragma unroll
-    for (int g = 0; g < GC; ++g)
-      if (g < ng) {
-        const unsigned n = cons_idx + g;
-        ptx::mbar_wait(&sm.full[n % p.nst], (n / p.nst) & 1u);
-      }
-    FINE();
-#pragma unroll
-    for (int g = 0; g < GC; ++g) {
-      const int u = (ch0 + g) * UPC + warp;
-      if (g < ng && u < nunits) {
-        const int stage = (cons_idx + g) % p.nst;
-        const int seg = u % nseg;
-        const uint4* wrow = (const uint4*)(sm.ring + ((size_t)stage * UPC + warp) * D);
-#pragma unroll
-        for (int j = 0; j < cpl; ++j) {
-          const int c16 = lane + 32 * j;
-          const uint4 w = wrow[c16];
-          const float wf[8] = {lo_bf(w.x), hi_bf(w.x), lo_bf(w.y), hi_bf(w.y),
-                               lo_bf(w.z), hi_bf(w.z), lo_bf(w.w), hi_bf(w.w)};
-#pragma unroll
-          for (int b = 0; b < BT; ++b) {
-            const uint4 xv = ((const uint4*)(sm.xs + (size_t)b * (4 * D) + (size_t)seg * D))[c16];
-            float a = acc[g][b];
-            a = fmaf(wf[0], lo_bf(xv.x), a);
-            a = fmaf(wf[1], hi_bf(xv.x), a);
-            a = fmaf(wf[2], lo_bf(xv.y), a);
-            a = fmaf(wf[3], hi_bf(xv.y), a);
-            a = fmaf(wf[4], lo_bf(xv.z), a);
-            a = fmaf(wf[5], hi_bf(xv.z), a);
-            a = fmaf(wf[6], lo_bf(xv.w), a);
-            a = fmaf(wf[7], hi_bf(xv.w), a);
-            acc[g][b] = a;
+          for (int ks = 0; ks < KS; ++ks) {
+            const int kc = 2 * (warp * KS + ks);                 // 16-byte chunk index of k0
+            uint32_t a0, a1, a2, a3, b0, b1;
+            ldmatrix_x4(a_row + (uint32_t)(((kc + a_hi) ^ a_r) << 4), a0, a1, a2, a3);
+            ldmatrix_x2(b_row + (uint32_t)(((kc + b_hi) ^ (b_n & 7)) << 4), b0, b1);
+            // x4 matrix order is (rows, k-lo), (rows+8, k-lo), (rows, k-hi), (rows+8, k-hi): the lane ->
+            // address map above gives matrices 0,1 the k-lo chunk and 2,3 the k-hi chunk of the same rows
+            mma_bf16_16816(acc[gi], a0, a1, a2, a3, b0, b1);
           }
         }
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-      for (int g = 0; g < GC; ++g)
-#pragma unroll
-        for (int b = 0; b < BT; ++b) acc[g][b] += __shfl_xor_sync(0xffffffffu, acc[g][b], o);
-    FINE();
     // the weights of these chunks are consumed: hand the stages back to the producer
     __syncwarp();
     if (lane == 0)
-      for (int g = 0; g < ng; ++g) ptx::mbar_arrive(&sm.empty[(cons_idx + g) % p.nst]);
-    cons_idx += ng;
+      for (int i = 0; i < nb * nseg; ++i) ptx::mbar_arrive(&sm.empty[(cons_idx + i) % p.nst]);
+    cons_idx += nb * nseg;
 
-    if (nseg > 1) {
-      // K-split: park the partial sums, merge per column after one CTA barrier
-      float* red = sm.red + (size_t)((ch0 / gcap) & 1) * GC * UPC * BT;
-      if (lane < BT) {
+    // cross-warp K reduction: red[gi][warp][row g][col]
+    float* red = sm.red;
 #pragma unroll
-        for (int g = 0; g < GC; ++g) {
-          float v = 0.f;
-#pragma unroll
-          for (int b = 0; b < BT; ++b)
-            if (lane == b) v = acc[g][b];
-          red[(g * UPC + warp) * BT + lane] = v;
+    for (int gi = 0; gi < GMAX; ++gi) {
+      if (gi < nb) {
+        if (BT == 1) {
+          if (t4 == 0) red[(gi * NCW + warp) * 8 + g] = acc[gi][0];
+        } else {
+          float* rp = red + ((gi * NCW + warp) * 8 + g) * 8 + 2 * t4;
+          rp[0] = acc[gi][0];
+          rp[1] = acc[gi][1];
         }
       }
-      ptx::named_bar_sync(1, NCT);
-#pragma unroll
-      for (int g = 0; g < GC; ++g) {
-        float v = 0.f;
-        if (warp < UPC / nseg && lane < BT)
-          for (int s = 0; s < nseg; ++s) v += red[(g * UPC + warp * nseg + s) * BT + lane];
-#pragma unroll
-        for (int b = 0; b < BT; ++b) acc[g][b] = v;  // only lane b's copy is used below
-      }
     }
-    if (lane >= BT) continue;
-    const int b = lane;
-    if (!row_valid[b]) continue;
-    const int r = p.round_bf16;
-#pragma unroll
-    for (int g = 0; g < GC; ++g) {
-      if (g >= ng) continue;
-      int c;
-      if (nseg == 1) {
-        const int u = (ch0 + g) * UPC + warp;
-        if (u >= nunits) continue;
-        c = col0 + u;
-      } else {
-        const int cu = (ch0 + g) * UPC + warp * nseg;  // warp w < UPC/nseg owns column w of chunk g
-        if (warp >= UPC / nseg || cu >= nunits) continue;
-        c = col0 + cu / nseg;
-      }
+    ptx::named_bar_sync(1, NCT);
+    const int nout = nb * 8 * BT;
+    for (int idx = threadIdx.x; idx < nout; idx += NCT) {
+      const int gi = idx / (8 * BT), r = (idx / BT) & 7, b = idx % BT;
+      const int cl = (g0 + gi) * 8 + r;                         // column index inside the slice
+      if (cl >= ncols || !row_valid[b]) continue;
       float a = 0.f;
 #pragma unroll
-      for (int bb = 0; bb < BT; ++bb)
-        if (lane == bb) a = acc[g][bb];
+      for (int w = 0; w < NCW; ++w)
+        a += (BT == 1) ? red[(gi * NCW + w) * 8 + r] : red[((gi * NCW + w) * 8 + r) * 8 + b];
+      const int c = col0 + cl;
+      const int rr = p.round_bf16;
       if (EPI == 0) {
-        float v = rnd(a + bias_ph[c - col0], r);
+        float v = rnd(a + bias_ph[cl], rr);
         if (c < D) {
           p.qg[(size_t)b * D + c] = v;
         } else {
@@ -375,20 +361,19 @@ __device__ __forceinline__ void gemv_phase(const GptParams& p, const Smem<BT>& s
         }
       } else if (EPI == 1 || EPI == 3) {
         // the residual stream is fp32 even on the bf16 path (trap P12): only the branch is rounded
-        float o = rnd(a + bias_ph[c - col0], r);
+        float o = rnd(a + bias_ph[cl], rr);
         float xn = sm.xres[b * p.ocap + (c - o0)] + o;
         sm.xres[b * p.ocap + (c - o0)] = xn;
         p.xg[(size_t)b * D + c] = xn;
       } else if (EPI == 2) {
-        float f = rnd(a + bias_ph[c - col0], r);
-        p.fg[(size_t)b * (4 * D) + c] = __float2bfloat16_rn(gelu_new(f, r));
+        float f = rnd(a + bias_ph[cl], rr);
+        p.fg[(size_t)b * FFc + c] = __float2bfloat16_rn(gelu_new(f, rr));
       } else {
-        p.logits[(size_t)b * p.V + c] = rnd(a + bias_ph[c - col0], r);
+        p.logits[(size_t)b * p.V + c] = rnd(a + bias_ph[cl], rr);
       }
     }
+    ptx::named_bar_sync(1, NCT);   // red is reused by the next batch of groups
   }
-  FINE();
-#undef FINE
 }
 
 #define PROF_STAMP()                                                        \
@@ -465,30 +450,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
       const __nv_bfloat16* base = p.wstream + (size_t)p.stream_off[cta] * D;
       unsigned prod_idx = 0;
       bool stop = false;
-      const int phase_units[4] = {nq, no, nf, no * nseg_proj};
+      const int phase_cols[4] = {nq, no, nf, no};
+      const int phase_nseg[4] = {1, 1, 1, nseg_proj};
       for (int step = 0; step < p.nsteps && !stop; ++step) {
         size_t uoff = 0;
         for (int l = 0; l <= L && !stop; ++l) {
           const int nph = (l < L) ? 4 : 1;
           for (int ph = 0; ph < nph && !stop; ++ph) {
-            const int nu = (l < L) ? phase_units[ph] : units_head;
-            for (int u = 0; u < nu; u += UPC) {
-              const int n = min(UPC, nu - u);
-              const int stage = prod_idx % p.nst;
-              const unsigned parity = ((prod_idx / p.nst) & 1u) ^ 1u;
-              unsigned spins = 0;
-              while (!ptx::mbar_try_wait(&sm.empty[stage], parity)) {
-                if (*((volatile int*)&sm.flags[0])) { stop = true; break; }
-                if (++spins > (1u << 26)) __trap();
+            const int ncol = (l < L) ? phase_cols[ph] : units_head;
+            const int nsg = (l < L) ? phase_nseg[ph] : 1;
+            for (int c0 = 0; c0 < ncol && !stop; c0 += 8) {
+              const int rows = min(8, ncol - c0);
+              for (int sgi = 0; sgi < nsg; ++sgi) {
+                const int stage = prod_idx % p.nst;
+                const unsigned parity = ((prod_idx / p.nst) & 1u) ^ 1u;
+                unsigned spins = 0;
+                while (!ptx::mbar_try_wait(&sm.empty[stage], parity)) {
+                  if (*((volatile int*)&sm.flags[0])) { stop = true; break; }
+                  if (++spins > (1u << 26)) __trap();
+                }
+                if (stop) break;
+                const uint32_t bytes = (uint32_t)rows * D * 2;
+                ptx::mbar_arrive_expect_tx(&sm.full[stage], bytes);
+                ptx::bulk_g2s(sm.ring + (size_t)stage * UPC * D, base + uoff * D, bytes, &sm.full[stage], pol);
+                ++prod_idx;
+                uoff += rows;
               }
-              if (stop) break;
-              const uint32_t bytes = (uint32_t)n * D * 2;
-              ptx::mbar_arrive_expect_tx(&sm.full[stage], bytes);
-              ptx::bulk_g2s(sm.ring + (size_t)stage * UPC * D, base + (uoff + u) * D, bytes,
-                            &sm.full[stage], pol);
-              ++prod_idx;
             }
-            uoff += nu;
           }
         }
       }
@@ -572,7 +560,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
             float v[NPL], o[NPL];
             load_row<NPL>(v, p.xg + (size_t)b * D, lane);
             ln_row<NPL>(v, o, lnA, lnA + D, lane);
-            store_row_bf16<NPL>(o, sm.xs + (size_t)b * FF, lane);
+            store_row_bf16<NPL>(o, sm.xs + (size_t)b * FF, b, lane);
           }
         }
         ptx::named_bar_sync(1, NCT);
@@ -719,8 +707,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
               o1v += ob[r3][s] * cc;
             }
             const float inv = (lt > 0.f) ? 1.0f / lt : 0.f;
-            sm.xs[(size_t)b * FF + h * HD + lane] = __float2bfloat16_rn(o0v * inv);
-            sm.xs[(size_t)b * FF + h * HD + 32 + lane] = __float2bfloat16_rn(o1v * inv);
+            sm.xs[(size_t)b * FF + xs_idx(b, h * HD + lane)] = __float2bfloat16_rn(o0v * inv);
+            sm.xs[(size_t)b * FF + xs_idx(b, h * HD + 32 + lane)] = __float2bfloat16_rn(o1v * inv);
           }
         }
         ptx::named_bar_sync(1, NCT);
@@ -749,7 +737,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
             float v[NPL], o[NPL];
             load_row<NPL>(v, p.xg + (size_t)b * D, lane);
             ln_row<NPL>(v, o, lnB, lnB + D, lane);
-            store_row_bf16<NPL>(o, sm.xs + (size_t)b * FF, lane);
+            store_row_bf16<NPL>(o, sm.xs + (size_t)b * FF, b, lane);
           }
         }
         ptx::named_bar_sync(1, NCT);
@@ -763,9 +751,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
         // ---------------- P5: proj + residual ----------------
         if (l + 1 == L && p.mode == 1) prefetch_ln(1, p.fn_w, p.fn_b);  // final_norm for the head
         {
-          const int n16 = BT * FF / 8;
-          for (int idx = tid; idx < n16; idx += NCT)
-            ((uint4*)sm.xs)[idx] = __ldcg(((const uint4*)p.fg) + idx);
+          constexpr int CPR = FF / 8;   // 16-byte chunks per row
+          for (int idx = tid; idx < BT * CPR; idx += NCT) {
+            const int b = idx / CPR, c = idx % CPR;
+            ((uint4*)sm.xs)[b * CPR + (c ^ (b & 7))] = __ldcg(((const uint4*)p.fg) + idx);
+          }
         }
         ptx::named_bar_sync(1, NCT);
         gemv_phase<BT, 3, D>(p, sm, l, o0, no, nseg_proj, cons_idx, row_seq, row_pos,
@@ -793,7 +783,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
             load_row<NPL>(v, p.xg + (size_t)b * D, lane);
             ln_row<NPL>(v, o, lnA, lnA + D, lane);
             ln_row<NPL>(o, v, lnB, lnB + D, lane);
-            store_row_bf16<NPL>(v, sm.xs + (size_t)b * FF, lane);
+            store_row_bf16<NPL>(v, sm.xs + (size_t)b * FF, b, lane);
           }
         }
         ptx::named_bar_sync(1, NCT);
@@ -887,13 +877,17 @@ struct PackUnit {
   const float* src;
   long long base;      // element offset of (k = 0)
   long long kstride;   // element stride along K
+  long long row;       // row of the unit inside its 8-row chunk (swizzle key)
 };
 __global__ void pack_units_kernel(const PackUnit* units, __nv_bfloat16* dst, int D, long long n) {
   long long u = blockIdx.x;
   if (u >= n) return;
   PackUnit pu = units[u];
-  for (int k = threadIdx.x; k < D; k += blockDim.x)
-    dst[u * D + k] = __float2bfloat16_rn(pu.src[pu.base + (long long)k * pu.kstride]);
+  const int r = (int)(pu.row & 7);
+  for (int k = threadIdx.x; k < D; k += blockDim.x) {
+    const int kp = (((k >> 3) ^ r) << 3) | (k & 7);   // 16-byte chunk index XOR row: ldmatrix bank spread
+    dst[u * D + kp] = __float2bfloat16_rn(pu.src[pu.base + (long long)k * pu.kstride]);
+  }
 }
 
 __global__ void round_bf16_kernel(float* x, size_t n) {
@@ -1075,15 +1069,17 @@ extern "C" int idx_gpt_init(idx_engine* e, const idx_gpt_config* cfg) {
       const float* wf = (const float*)e->W(lname(l, "mlp.c_fc.weight")).d;
       const float* wp = (const float*)e->W(lname(l, "mlp.c_proj.weight")).d;
       // HF Conv1D keeps weight as [in, out] (P4): element (k, c) at k*N + c
-      for (int c = q0; c < q1; ++c) units.push_back({wq, c, 3LL * D});
-      for (int c = o0; c < o1; ++c) units.push_back({wo, c, (long long)D});
-      for (int c = f0; c < f1; ++c) units.push_back({wf, c, (long long)FF});
-      for (int c = o0; c < o1; ++c)
+      for (int c = q0; c < q1; ++c) units.push_back({wq, c, 3LL * D, (c - q0) & 7});
+      for (int c = o0; c < o1; ++c) units.push_back({wo, c, (long long)D, (c - o0) & 7});
+      for (int c = f0; c < f1; ++c) units.push_back({wf, c, (long long)FF, (c - f0) & 7});
+      // PROJ: chunks are (8-column group, K-segment): group-major, then segment, then column
+      for (int g0 = o0; g0 < o1; g0 += 8)
         for (int s = 0; s < FF / D; ++s)
-          units.push_back({wp, (long long)s * D * D + c, (long long)D});
+          for (int c = g0; c < std::min(g0 + 8, o1); ++c)
+            units.push_back({wp, (long long)s * D * D + c, (long long)D, (c - g0) & 7});
     }
     // nn.Linear keeps weight as [out, in]
-    for (int c = h0; c < h1; ++c) units.push_back({(const float*)wh.d, (long long)c * D, 1LL});
+    for (int c = h0; c < h1; ++c) units.push_back({(const float*)wh.d, (long long)c * D, 1LL, (c - h0) & 7});
   }
   off[G] = (long long)units.size();
   const long long nunits = (long long)units.size();

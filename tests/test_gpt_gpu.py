@@ -8,7 +8,7 @@ oracle/validate_gpt_vs_hf.py; the 24-layer geometry accumulates ~1.5x that).  Un
 forcing the engine must agree with the oracle per step to rms <= 0.035 and max-abs <= 0.16
 (4.5 sigma of that noise over 8194 logits x 48 steps, plus the final bf16 quantisation of a logit
 of magnitude up to 16) and its greedy pick must equal the oracle's except at near-ties
-(processed-score gap <= 0.07)."""
+(processed-score gap <= 0.13 = 2 bf16 ulps at |logit| in [8,16))."""
 import os
 
 import numpy as np
@@ -21,7 +21,7 @@ from oracle.validate_gpt_vs_hf import small_case
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "gpt_small.npz")
-TOL = dict(max_abs=0.16, max_rms=0.035, tie_tol=0.07)
+TOL = dict(max_abs=0.16, max_rms=0.035, tie_tol=0.13)
 
 
 def test_prepare_inputs_matches_oracle(engine):
