@@ -150,6 +150,31 @@ int idx_gpt_generate(idx_engine* e, const idx_gpt_request* reqs, int nreq,
 int idx_gpt_prepare_inputs(idx_engine* e, const float* style, const float* emo_vec,
                            const int32_t* text_ids, int n_text, int lang, float* out);
 
+/* Emotion-vector path: ConformerEncoder(conv2d2, rel-pos) + PerceiverResampler(1 latent)
+ * + emovec_layer + emo_layer of UnifiedVoice (gpt/model_v2.py:375-392).                              */
+typedef struct {
+  int32_t idim;          /* 1024 (w2v-BERT features)                                            */
+  int32_t odim;          /* emo_condition_module.output_size (512)                              */
+  int32_t linear_units;  /* 1024                                                                */
+  int32_t heads;         /* attention_heads (4)                                                 */
+  int32_t blocks;        /* num_blocks (4)                                                      */
+  int32_t cnn_kernel;    /* 15                                                                  */
+  int32_t p_dim;         /* perceiver dim (1024)                                                */
+  int32_t p_heads;       /* 4                                                                   */
+  int32_t p_dim_head;    /* 64                                                                  */
+  int32_t p_depth;       /* 2                                                                   */
+  int32_t p_ff_mult;     /* perceiver_mult (2)                                                  */
+  int32_t model_dim;     /* 1280                                                                */
+} idx_emo_config;
+int idx_emo_init(idx_engine* e, const idx_emo_config* cfg);
+
+/* base + alpha * (emo - base), each = emo_layer(emovec_layer(perceiver(conformer(feats)))).
+ * spk_feats [Ts, idim], emo_feats [Te, idim] (NULL or the same pointer = same audio) → emo_vec [model_dim].
+ * Replaces UnifiedVoice.merge_emovec (gpt/model_v2.py:833-838), call site infer_v2_5.py:759-765; callers
+ * cache the result per (speaker, emotion, alpha) — the reference recomputes it per segment (trap P11).   */
+int idx_merge_emovec(idx_engine* e, const float* spk_feats, int Ts, const float* emo_feats, int Te,
+                     float alpha, float* emo_vec_out);
+
 /* Timing of the last generate call, measured with CUDA events on the engine stream:
  * out[0] = prefill ms, out[1] = decode ms, out[2] = decode steps,
  * out[3] = fused-step kernel launches.                                               */

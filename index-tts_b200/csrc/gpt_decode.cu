@@ -58,6 +58,9 @@ struct GptParams {
   int max_new;      // decode: max tokens per sequence
   int start_tok, stop_tok, forbid_stop_before;
   float rep_penalty;
+  int do_sample, top_k;       // do_sample: temperature -> top-k -> top-p -> multinomial (HF warper order)
+  float top_p, temperature;
+  unsigned long long seed;
   int round_bf16;   // 1: emulate autocast bf16 rounding points
   int nst;          // ring stages
   int bar_flavor;   // 0: fence after the grid barrier, 1: none (consumers use ld.cg)
@@ -106,6 +109,25 @@ __device__ __forceinline__ long long gtimer() {
   long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
+}
+
+// Philox4x32-10 (Salmon et al.), counter = (step, sequence, 0, 0), key = seed.  The device sampler's
+// RNG contract (documented in DESIGN.md): NOT bit-compatible with torch.multinomial's stream.
+__device__ __forceinline__ void philox4x32_10(unsigned long long seed, unsigned c0, unsigned c1, unsigned (&out)[4]) {
+  unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+  unsigned x0 = c0, x1 = c1, x2 = 0u, x3 = 0u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned long long p0 = (unsigned long long)0xD2511F53u * x0;
+    const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * x2;
+    const unsigned n0 = (unsigned)(p1 >> 32) ^ x1 ^ k0;
+    const unsigned n1 = (unsigned)p1;
+    const unsigned n2 = (unsigned)(p0 >> 32) ^ x3 ^ k1;
+    const unsigned n3 = (unsigned)p0;
+    x0 = n0; x1 = n1; x2 = n2; x3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = x0; out[1] = x1; out[2] = x2; out[3] = x3;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -807,30 +829,94 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
             sm.seen_s[i] = p.seen[(size_t)b * ((V + 31) / 32) + i];
           ptx::named_bar_sync(1, NCT);
           const unsigned* seen = sm.seen_s;
-          float best = -INFINITY;
-          int besti = 0x7fffffff;
-          for (int i = tid; i < V; i += NCT) {
-            float s = __ldcg(lg + i);
-            if ((seen[i >> 5] >> (i & 31)) & 1u)
-              s = (s < 0.f) ? s * p.rep_penalty : s / p.rep_penalty;
-            if (i == p.stop_tok && k < p.forbid_stop_before) s = -INFINITY;
-            if (s > best || (s == best && i < besti)) { best = s; besti = i; }
-          }
+          // processed scores of this thread's slice stay in registers: s = rep_penalty(logit) [/ temperature]
+          constexpr int VPT = 40;   // ceil(V / 256) for V <= 10240
+          float sv[VPT];
+          const float inv_temp = (p.do_sample && p.temperature > 0.f) ? 1.0f / p.temperature : 1.0f;
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const float b2 = __shfl_xor_sync(0xffffffffu, best, o);
-            const int i2 = __shfl_xor_sync(0xffffffffu, besti, o);
-            if (b2 > best || (b2 == best && i2 < besti)) { best = b2; besti = i2; }
+          for (int j = 0; j < VPT; ++j) {
+            const int i = tid + j * NCT;
+            float sc = -INFINITY;
+            if (i < V) {
+              sc = __ldcg(lg + i);
+              if ((seen[i >> 5] >> (i & 31)) & 1u) sc = (sc < 0.f) ? sc * p.rep_penalty : sc / p.rep_penalty;
+              if (i == p.stop_tok && k < p.forbid_stop_before) sc = -INFINITY;
+              if (p.do_sample) sc *= inv_temp;
+            }
+            sv[j] = sc;
           }
           float* red = sm.red;
-          if (lane == 0) { red[warp * 2] = best; ((int*)red)[warp * 2 + 1] = besti; }
-          ptx::named_bar_sync(1, NCT);
-          if (tid == 0) {
-            for (int w = 1; w < NCW; ++w) {
+          // block argmax with lowest-index tie break; `extract` removes the winner from its owner's registers
+          auto block_argmax = [&](float& bestv, int& besti) {
+            float best = -INFINITY;
+            int bi = 0x7fffffff;
+#pragma unroll
+            for (int j = 0; j < VPT; ++j) {
+              const int i = tid + j * NCT;
+              if (sv[j] > best || (sv[j] == best && i < bi && sv[j] > -INFINITY)) { best = sv[j]; bi = i; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const float b2 = __shfl_xor_sync(0xffffffffu, best, o);
+              const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+              if (b2 > best || (b2 == best && i2 < bi)) { best = b2; bi = i2; }
+            }
+            ptx::named_bar_sync(1, NCT);
+            if (lane == 0) { red[warp * 2] = best; ((int*)red)[warp * 2 + 1] = bi; }
+            ptx::named_bar_sync(1, NCT);
+            for (int w = 0; w < NCW; ++w) {
               const float b2 = red[w * 2];
               const int i2 = ((int*)red)[w * 2 + 1];
-              if (b2 > best || (b2 == best && i2 < besti)) { best = b2; besti = i2; }
+              if (w == 0 || b2 > best || (b2 == best && i2 < bi)) { best = b2; bi = i2; }
             }
+            bestv = best; besti = bi;
+          };
+          float best; int besti;
+          block_argmax(best, besti);
+          if (p.do_sample) {
+            // top-k: extract candidates in descending order (ties at the k-th value are all kept, like
+            // TopKLogitsWarper's `scores < kth` test), at most 64
+            float* cv = red + 32;            // [64] candidate scores
+            int* ci = (int*)(red + 96);      // [64] candidate ids
+            const int kk = (p.top_k > 0) ? min(p.top_k, 64) : 64;
+            int nc = 0;
+            float kth = best;
+            while (nc < 64 && best > -INFINITY && (nc < kk || best == kth)) {
+              if (tid == 0) { cv[nc] = best; ci[nc] = besti; }
+              if (nc < kk) kth = best;
+              ++nc;
+#pragma unroll
+              for (int j = 0; j < VPT; ++j)
+                if (tid + j * NCT == besti) sv[j] = -INFINITY;
+              block_argmax(best, besti);
+            }
+            ptx::named_bar_sync(1, NCT);
+            if (tid == 0) {
+              // softmax over the kept candidates, top-p filter (TopPLogitsWarper: drop while the
+              // ascending cumulative probability <= 1 - top_p, keep at least one), multinomial
+              const float mx = cv[0];
+              float tot = 0.f;
+              for (int i = 0; i < nc; ++i) { cv[i] = expf(cv[i] - mx); tot += cv[i]; }
+              int keep = nc;
+              if (p.top_p < 1.0f) {
+                float tail = 0.f;
+                for (int i = nc - 1; i >= 1; --i) {
+                  tail += cv[i] / tot;
+                  if (tail <= 1.0f - p.top_p) keep = i; else break;
+                }
+              }
+              float kt = 0.f;
+              for (int i = 0; i < keep; ++i) kt += cv[i];
+              unsigned rnd4[4];
+              philox4x32_10(p.seed, (unsigned)k, (unsigned)b, rnd4);
+              const float u = (float)(rnd4[0] >> 8) * (1.0f / 16777216.0f) * kt;
+              float acc = 0.f;
+              int pick = keep - 1;
+              for (int i = 0; i < keep; ++i) { acc += cv[i]; if (u < acc) { pick = i; break; } }
+              besti = ci[pick];
+            }
+          }
+          if (tid == 0) {
             const int fin = p.finished[b];
             if (!fin) {
               p.codes[(size_t)b * p.max_new + k] = besti;
@@ -1184,8 +1270,8 @@ extern "C" int idx_gpt_generate(idx_engine* e, const idx_gpt_request* reqs, int 
   GptState* g = e->gpt;
   const idx_gpt_config& c = g->cfg;
   IDX_CHECK(nreq <= c.max_batch, IDX_ERR_ARG, "nreq exceeds max_batch");
-  IDX_CHECK(sp->do_sample == 0 && sp->num_beams == 1, IDX_ERR_ARG,
-            "only greedy decoding (do_sample=False, num_beams=1) is built in this round");
+  IDX_CHECK(sp->num_beams == 1, IDX_ERR_ARG, "beam-sample (num_beams > 1) is not built in this round");
+  IDX_CHECK(c.number_mel_codes <= 40 * 256, IDX_ERR_ARG, "vocabulary too large for the device sampler");
   IDX_CHECK(sp->max_new_tokens >= 1 && sp->max_new_tokens + 2 <= c.max_mel_positions, IDX_ERR_ARG,
             "max_new_tokens must satisfy k+1 <= mel_pos rows - 1 (SURVEY A.3)");
   IDX_CUDA(cudaSetDevice(e->device));
@@ -1261,6 +1347,8 @@ extern "C" int idx_gpt_generate(idx_engine* e, const idx_gpt_request* reqs, int 
   fill_common(e, g, p);
   p.B = nreq; p.mode = 1; p.max_new = max_new; p.rep_penalty = sp->repetition_penalty;
   p.forbid_stop_before = sp->forbid_stop_before;
+  p.do_sample = sp->do_sample; p.top_k = sp->top_k; p.top_p = sp->top_p; p.temperature = sp->temperature;
+  p.seed = sp->seed;
   p.codes = d_codes; p.forced = d_forced; p.logits_dump = d_ldump;
   const int SPL = 32;  // steps per launch: the host looks at one flag every SPL steps
   int steps_done = 0;

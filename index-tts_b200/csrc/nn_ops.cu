@@ -1,6 +1,8 @@
 // nn_ops.cu — normalisation, pointwise and attention kernels shared by the s2mel / codec paths
 // (channels-last fp32, see ops.h).  Reference semantics cited at each kernel.
 #include "ops.h"
+#include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace {
 
@@ -357,6 +359,195 @@ __global__ void heads_merge_kernel(const float* __restrict__ O, float* __restric
   out[((long long)b * T + t) * H * AD + h * AD + i] = O[(((long long)b * H + h) * T + t) * AD + i];
 }
 
+// ---- fused tensor-core flash attention (mma.sync: QK^T in tf32 m16n8k8, PV in bf16 m16n8k16) ----
+// Inputs are the rotated/split tensors of rope_split_fa_kernel: Qr, Kr fp32 [BH][T][64] (q pre-scaled
+// by 1/8), Vb bf16 [BH][T][64].  One CTA = 64 queries of one (batch, head); 4 warps x 16 query rows.
+// K/V tiles of 64 keys are staged in shared memory (row pitches 272 B / 144 B keep ldmatrix conflict
+// free); scores, softmax statistics and the output accumulator never leave registers.
+__global__ void rope_split_fa_kernel(const float* __restrict__ qkv, const float* __restrict__ rope,
+                                     float* __restrict__ Qr, float* __restrict__ Kr,
+                                     __nv_bfloat16* __restrict__ Vb, int T, int H) {
+  const int t = blockIdx.x, h = blockIdx.y, b = blockIdx.z, i = threadIdx.x;  // 64 threads
+  const int ld = 3 * H * AD;
+  const float* row = qkv + ((long long)b * T + t) * ld;
+  const long long bh = (long long)b * H + h;
+  if (i < AD / 2) {
+    const float cs = rope[((long long)t * (AD / 2) + i) * 2], sn = rope[((long long)t * (AD / 2) + i) * 2 + 1];
+    const float q0 = row[h * AD + 2 * i], q1 = row[h * AD + 2 * i + 1];
+    const float k0 = row[H * AD + h * AD + 2 * i], k1 = row[H * AD + h * AD + 2 * i + 1];
+    float* qo = Qr + (bh * T + t) * AD + 2 * i;
+    float* ko = Kr + (bh * T + t) * AD + 2 * i;
+    qo[0] = (q0 * cs - q1 * sn) * 0.125f;
+    qo[1] = (q1 * cs + q0 * sn) * 0.125f;
+    ko[0] = k0 * cs - k1 * sn;
+    ko[1] = k1 * cs + k0 * sn;
+  }
+  Vb[(bh * T + t) * AD + i] = __float2bfloat16_rn(row[2 * H * AD + h * AD + i]);
+}
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_tf32_1688(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                              uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_bf16_16816_fa(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                  uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *(uint32_t*)&v;
+}
+
+constexpr int FQ = 64, FK = 64;
+constexpr int KPITCH = 68;   // floats per K row in smem (272 B)
+constexpr int VPITCH = 72;   // bf16 per V row in smem (144 B)
+__global__ void __launch_bounds__(128) flash_attn_tc_kernel(const float* __restrict__ Qr, const float* __restrict__ Kr,
+                                                            const __nv_bfloat16* __restrict__ Vb,
+                                                            float* __restrict__ out, int T, int H) {
+  __shared__ __align__(16) float Ks[FK * KPITCH];
+  __shared__ __align__(16) __nv_bfloat16 Vs[FK * VPITCH];
+  const int bh = blockIdx.y, q0 = blockIdx.x * FQ;
+  const int b = bh / H, h = bh % H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const float* Qb = Qr + (long long)bh * T * AD;
+  const float* Kb = Kr + (long long)bh * T * AD;
+  const __nv_bfloat16* Vbb = Vb + (long long)bh * T * AD;
+  // Q fragments of this warp's 16 rows: 8 k-steps x (a0..a3), tf32 (rounded to nearest)
+  uint32_t qa[8][4];
+  {
+    const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const int d0 = ks * 8 + t4, d1 = d0 + 4;
+      qa[ks][0] = tf32_rn(r0 < T ? Qb[(long long)r0 * AD + d0] : 0.f);
+      qa[ks][1] = tf32_rn(r1 < T ? Qb[(long long)r1 * AD + d0] : 0.f);
+      qa[ks][2] = tf32_rn(r0 < T ? Qb[(long long)r0 * AD + d1] : 0.f);
+      qa[ks][3] = tf32_rn(r1 < T ? Qb[(long long)r1 * AD + d1] : 0.f);
+    }
+  }
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const uint32_t ks_base = (uint32_t)__cvta_generic_to_shared(Ks);
+  const uint32_t vs_base = (uint32_t)__cvta_generic_to_shared(Vs);
+
+  for (int k0 = 0; k0 < T; k0 += FK) {
+    __syncthreads();
+    // stage K (tf32-rounded fp32) and V (bf16) tiles; rows beyond T are zero
+    for (int i = tid; i < FK * (AD / 4); i += 128) {
+      const int r = i / (AD / 4), c4 = (i % (AD / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + r < T) v = *(const float4*)(Kb + (long long)(k0 + r) * AD + c4);
+      uint4 tv = make_uint4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+      *(uint4*)(Ks + r * KPITCH + c4) = tv;
+    }
+    for (int i = tid; i < FK * (AD / 8); i += 128) {
+      const int r = i / (AD / 8), c8 = (i % (AD / 8)) * 8;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (k0 + r < T) v = *(const uint4*)(Vbb + (long long)(k0 + r) * AD + c8);
+      *(uint4*)(Vs + r * VPITCH + c8) = v;
+    }
+    __syncthreads();
+    // S = Q K^T : 8 key tiles (n = 8 keys) x 8 k-steps
+    float sc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int kp = 0; kp < 4; ++kp) {
+        // one ldmatrix.x4 = B fragments (b0,b1) of k-steps 2kp and 2kp+1 for keys 8j..8j+7:
+        // matrix i covers d = 16kp + 4i .. +3 ; lane supplies the address of key (lane&7), matrix lane>>3
+        uint32_t b0, b1, b2, b3;
+        const uint32_t addr = ks_base + (uint32_t)(((j * 8 + (lane & 7)) * KPITCH + kp * 16 + (lane >> 3) * 4) * 4);
+        ldsm_x4(addr, b0, b1, b2, b3);
+        mma_tf32_1688(sc[j], qa[2 * kp][0], qa[2 * kp][1], qa[2 * kp][2], qa[2 * kp][3], b0, b1);
+        mma_tf32_1688(sc[j], qa[2 * kp + 1][0], qa[2 * kp + 1][1], qa[2 * kp + 1][2], qa[2 * kp + 1][3], b2, b3);
+      }
+    }
+    // mask keys beyond T, online softmax for rows g (c0,c1) and g+8 (c2,c3)
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int key = k0 + j * 8 + 2 * t4;
+      if (key >= T) { sc[j][0] = -INFINITY; sc[j][2] = -INFINITY; }
+      if (key + 1 >= T) { sc[j][1] = -INFINITY; sc[j][3] = -INFINITY; }
+      mx0 = fmaxf(mx0, fmaxf(sc[j][0], sc[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(sc[j][2], sc[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float c0 = (m0 == -INFINITY) ? 0.f : __expf(m0 - mn0);
+    const float c1 = (m1 == -INFINITY) ? 0.f : __expf(m1 - mn1);
+    float rs0 = 0.f, rs1 = 0.f;
+    uint32_t pa[8][2];   // P as bf16 pairs: [tile j][rows g / g+8]
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float p0 = __expf(sc[j][0] - mn0), p1 = __expf(sc[j][1] - mn0);
+      const float p2 = __expf(sc[j][2] - mn1), p3 = __expf(sc[j][3] - mn1);
+      rs0 += p0 + p1;
+      rs1 += p2 + p3;
+      pa[j][0] = pack_bf16(p0, p1);
+      pa[j][1] = pack_bf16(p2, p3);
+    }
+    rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1);
+    rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
+    rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1);
+    rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
+    l0 = l0 * c0 + rs0;
+    l1 = l1 * c1 + rs1;
+    m0 = mn0;
+    m1 = mn1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1; }
+    // O += P V : 4 key blocks of 16 x 8 dim tiles of 8
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) {
+      const uint32_t a0 = pa[2 * kb][0], a1 = pa[2 * kb][1], a2 = pa[2 * kb + 1][0], a3 = pa[2 * kb + 1][1];
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        // ldmatrix.x4.trans: matrices (keys 16kb..+7, d 16dp..+7), (keys +8.., same d), (keys 16kb.., d +8), (keys +8, d +8)
+        uint32_t v0, v1, v2, v3;
+        const int mi = lane >> 3;
+        const uint32_t addr = vs_base + (uint32_t)(((kb * 16 + (mi & 1) * 8 + (lane & 7)) * VPITCH + dp * 16 + (mi >> 1) * 8) * 2);
+        ldsm_x4_trans(addr, v0, v1, v2, v3);
+        mma_bf16_16816_fa(o[2 * dp], a0, a1, a2, a3, v0, v1);
+        mma_bf16_16816_fa(o[2 * dp + 1], a0, a1, a2, a3, v2, v3);
+      }
+    }
+  }
+  const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
+  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int d = j * 8 + 2 * t4;
+    if (r0 < T) *(float2*)(out + ((long long)b * T + r0) * H * AD + h * AD + d) = make_float2(o[j][0] * i0, o[j][1] * i0);
+    if (r1 < T) *(float2*)(out + ((long long)b * T + r1) * H * AD + h * AD + d) = make_float2(o[j][2] * i1, o[j][3] * i1);
+  }
+}
+
 }  // namespace
 
 #define LAUNCH_CHECK(e)            \
@@ -441,6 +632,21 @@ void rope_table(idx_engine* e, float* tab, int T, int hd) {
 }
 void attention_rope(idx_engine* e, const float* qkv, float* out, int B, int T, int H, const float* rope,
                     const int* lens) {
+  static const bool unfused = getenv("IDX_ATTN_UNFUSED") != nullptr;
+  if (gemm_default_backend() == 0 && lens == nullptr && !unfused) {
+    // fused tensor-core flash attention: rotate/split once, then one kernel per layer
+    const size_t mark = e->arena.off;
+    const long long BH = (long long)B * H;
+    float* Qr = e->arena.get<float>((size_t)BH * T * AD);
+    float* Kr = e->arena.get<float>((size_t)BH * T * AD);
+    __nv_bfloat16* Vb = (__nv_bfloat16*)e->arena.alloc((size_t)BH * T * AD * 2);
+    rope_split_fa_kernel<<<dim3(T, H, B), AD, 0, e->stream>>>(qkv, rope, Qr, Kr, Vb, T, H);
+    LAUNCH_CHECK(e);
+    flash_attn_tc_kernel<<<dim3((T + FQ - 1) / FQ, (unsigned)BH), 128, 0, e->stream>>>(Qr, Kr, Vb, out, T, H);
+    LAUNCH_CHECK(e);
+    e->arena.off = mark;
+    return;
+  }
   if (gemm_default_backend() == 0 && lens == nullptr && T >= 128) {
     // tensor-core path: rotate/split -> S = Q K^T (tcgen05) -> row softmax -> O = P V (tcgen05) -> merge
     const size_t mark = e->arena.off;

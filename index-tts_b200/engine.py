@@ -66,6 +66,11 @@ class CodecConfig(C.Structure):
                                          "vocos_intermediate_dim", "vocos_num_layers")]
 
 
+class EmoConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("idim", "odim", "linear_units", "heads", "blocks", "cnn_kernel", "p_dim",
+                                         "p_heads", "p_dim_head", "p_depth", "p_ff_mult", "model_dim")]
+
+
 class VocodeRequest(C.Structure):
     _fields_ = [("codes", C.c_void_p), ("n_codes", C.c_int32), ("prompt_condition", C.c_void_p),
                 ("ref_mel", C.c_void_p), ("P", C.c_int32), ("style", C.c_void_p), ("z", C.c_void_p),
@@ -146,6 +151,8 @@ def load_library(path: str = None):
     lib.idx_cfm_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_float, C.c_void_p]
     lib.idx_s2mel_last_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    lib.idx_emo_init.argtypes = [C.c_void_p, C.POINTER(EmoConfig)]
+    lib.idx_merge_emovec.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p]
     lib.idx_codes_to_wav.argtypes = [C.c_void_p, C.POINTER(VocodeRequest), C.c_int, C.c_float]
     _lib = lib
     return lib
@@ -460,4 +467,21 @@ class Engine:
                                                  biasN, act, _ptr(r_), int(accum), float(scale), int(out_off), ldo,
                                                  int(out_valid), int(per), int(backend), _ptr(out)),
                     "idx_debug_conv_gemm")
+        return out
+
+    # ------------------------------------------------------------------- emotion --
+    def emo_init(self, c: dict):
+        cfg = EmoConfig(*[c[k] for k in ("idim", "odim", "linear_units", "heads", "blocks", "cnn_kernel", "p_dim",
+                                         "p_heads", "p_dim_head", "p_depth", "p_ff_mult", "model_dim")])
+        self._check(self.lib.idx_emo_init(self.h, C.byref(cfg)), "idx_emo_init")
+        self.emo_cfg = cfg
+
+    def merge_emovec(self, spk_feats, emo_feats=None, alpha=1.0):
+        """UnifiedVoice.merge_emovec (gpt/model_v2.py:833-838): feats [T, 1024] → emo_vec [model_dim]."""
+        sf = _as_f32(spk_feats)
+        ef = None if emo_feats is None else _as_f32(emo_feats)
+        out = np.empty(self.emo_cfg.model_dim, dtype=np.float32)
+        self._check(self.lib.idx_merge_emovec(self.h, _ptr(sf), int(sf.shape[0]), _ptr(ef),
+                                              0 if ef is None else int(ef.shape[0]), float(alpha), _ptr(out)),
+                    "idx_merge_emovec")
         return out

@@ -284,3 +284,72 @@ def make_codec_weights(c, seed=4321):
         w[nm + ".weight"] = t(Hs, Hs, 3, std=1.0 / math.sqrt(3 * Hs))
         w[nm + ".bias"] = t(Hs, std=0.05)
     return w
+
+
+EMO_CFG = dict(idim=1024, odim=512, linear_units=1024, heads=4, blocks=4, cnn_kernel=15,
+               p_dim=1024, p_heads=4, p_dim_head=64, p_depth=2, p_ff_mult=2, model_dim=1280)
+
+
+def small_emo_cfg():
+    return dict(idim=40, odim=32, linear_units=48, heads=2, blocks=2, cnn_kernel=15,
+                p_dim=64, p_heads=2, p_dim_head=64, p_depth=2, p_ff_mult=2, model_dim=256)
+
+
+def make_emo_weights(c, seed=777):
+    """Emotion path of UnifiedVoice (gpt/model_v2.py:375-392): emo_conditioning_encoder (Conformer),
+    emo_perceiver_encoder (1 latent), emovec_layer, emo_layer — reference state-dict names."""
+    g = torch.Generator().manual_seed(seed)
+    w = {}
+
+    def t(*shape, std):
+        return torch.randn(*shape, generator=g) * std
+
+    def lin(name, co, ci, bias=True, gain=1.0):
+        w[name + ".weight"] = t(co, ci, std=gain / math.sqrt(ci))
+        if bias:
+            w[name + ".bias"] = t(co, std=0.05)
+
+    def ln(name, d):
+        w[name + ".weight"] = 1.0 + t(d, std=0.1)
+        w[name + ".bias"] = t(d, std=0.05)
+
+    od, H = c["odim"], c["heads"]
+    e = "emo_conditioning_encoder."
+    w[e + "embed.conv.0.weight"] = t(od, 1, 3, 3, std=1.0 / 3.0)
+    w[e + "embed.conv.0.bias"] = t(od, std=0.05)
+    fsub = (c["idim"] - 1) // 2
+    lin(e + "embed.out.0", od, od * fsub, gain=1.5)
+    for i in range(c["blocks"]):
+        p = e + f"encoders.{i}."
+        for nm in ("linear_q", "linear_k", "linear_v", "linear_out"):
+            lin(p + "self_attn." + nm, od, od)
+        lin(p + "self_attn.linear_pos", od, od, bias=False)
+        w[p + "self_attn.pos_bias_u"] = t(H, od // H, std=0.1)
+        w[p + "self_attn.pos_bias_v"] = t(H, od // H, std=0.1)
+        lin(p + "feed_forward.w_1", c["linear_units"], od)
+        lin(p + "feed_forward.w_2", od, c["linear_units"], gain=0.5)
+        w[p + "conv_module.pointwise_conv1.weight"] = t(2 * od, od, 1, std=1.0 / math.sqrt(od))
+        w[p + "conv_module.pointwise_conv1.bias"] = t(2 * od, std=0.05)
+        w[p + "conv_module.depthwise_conv.weight"] = t(od, 1, c["cnn_kernel"], std=1.0 / math.sqrt(c["cnn_kernel"]))
+        w[p + "conv_module.depthwise_conv.bias"] = t(od, std=0.05)
+        ln(p + "conv_module.norm", od)
+        w[p + "conv_module.pointwise_conv2.weight"] = t(od, od, 1, std=0.5 / math.sqrt(od))
+        w[p + "conv_module.pointwise_conv2.bias"] = t(od, std=0.05)
+        for nm in ("norm_ff", "norm_mha", "norm_conv", "norm_final"):
+            ln(p + nm, od)
+    ln(e + "after_norm", od)
+    q = "emo_perceiver_encoder."
+    pd, inner = c["p_dim"], c["p_heads"] * c["p_dim_head"]
+    lin(q + "proj_context", pd, od)
+    w[q + "latents"] = t(1, pd, std=0.02)
+    di = int(pd * c["p_ff_mult"] * 2 / 3)
+    for i in range(c["p_depth"]):
+        lin(q + f"layers.{i}.0.to_q", inner, pd, bias=False)
+        lin(q + f"layers.{i}.0.to_kv", 2 * inner, pd, bias=False)
+        lin(q + f"layers.{i}.0.to_out", pd, inner, bias=False, gain=0.5)
+        lin(q + f"layers.{i}.1.0", 2 * di, pd)
+        lin(q + f"layers.{i}.1.2", pd, di, gain=0.5)
+    w[q + "norm.gamma"] = 1.0 + t(pd, std=0.1)
+    lin("emovec_layer", c["model_dim"], pd)
+    lin("emo_layer", c["model_dim"], c["model_dim"])
+    return w

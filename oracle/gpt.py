@@ -81,6 +81,65 @@ def _ln(x, w, b):
     return torch.nn.functional.layer_norm(x, (x.shape[-1],), w, b, 1e-5)
 
 
+def philox4x32_10(seed, c0, c1):
+    """Philox4x32-10 with counter (c0, c1, 0, 0) and 64-bit key `seed` — the device sampler's RNG."""
+    M0, M1 = 0xD2511F53, 0xCD9E8D57
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    x0, x1, x2, x3 = c0 & 0xFFFFFFFF, c1 & 0xFFFFFFFF, 0, 0
+    for _ in range(10):
+        p0, p1 = M0 * x0, M1 * x2
+        x0, x1, x2, x3 = ((p1 >> 32) ^ x1 ^ k0) & 0xFFFFFFFF, p1 & 0xFFFFFFFF, ((p0 >> 32) ^ x3 ^ k1) & 0xFFFFFFFF, p0 & 0xFFFFFFFF
+        k0, k1 = (k0 + 0x9E3779B9) & 0xFFFFFFFF, (k1 + 0xBB67AE85) & 0xFFFFFFFF
+    return x0, x1, x2, x3
+
+
+def sample_token(scores, top_k, top_p, seed, step, seq):
+    """Temperature is already applied.  TopK (ties at the k-th value kept, at most 64) → TopP → multinomial by
+    inverse CDF over the descending candidates with one Philox draw (transformers logits_process order,
+    transformers_generation_utils.py:1035-1047; RNG contract of the device sampler)."""
+    s = np.asarray(scores, dtype=np.float32)
+    order = np.lexsort((np.arange(len(s)), -s))            # descending, lowest index first among ties
+    kk = min(top_k, 64) if top_k > 0 else 64
+    cand = []
+    kth = None
+    for idx in order:
+        if not np.isfinite(s[idx]) or len(cand) >= 64:
+            break
+        if len(cand) < kk:
+            cand.append(int(idx))
+            kth = s[idx]
+        elif s[idx] == kth:
+            cand.append(int(idx))
+        else:
+            break
+    cv = np.exp((s[cand] - s[cand[0]]).astype(np.float32)).astype(np.float32)
+    tot = np.float32(0)
+    for v in cv:
+        tot = np.float32(tot + v)
+    keep = len(cand)
+    if top_p < 1.0:
+        tail = np.float32(0)
+        for i in range(len(cand) - 1, 0, -1):
+            tail = np.float32(tail + np.float32(cv[i] / tot))
+            if tail <= np.float32(1.0 - top_p):
+                keep = i
+            else:
+                break
+    kt = np.float32(0)
+    for i in range(keep):
+        kt = np.float32(kt + cv[i])
+    r0 = philox4x32_10(seed, step, seq)[0]
+    u = np.float32(np.float32(r0 >> 8) * np.float32(1.0 / 16777216.0) * kt)
+    acc = np.float32(0)
+    pick = keep - 1
+    for i in range(keep):
+        acc = np.float32(acc + cv[i])
+        if u < acc:
+            pick = i
+            break
+    return cand[pick], cand[:keep]
+
+
 class GptOracle:
     def __init__(self, cfg, weights, bf16=True):
         self.cfg, self.w, self.bf16 = cfg, weights, bf16
@@ -132,8 +191,8 @@ class GptOracle:
 
     @torch.no_grad()
     def generate(self, prompt_emb, max_new_tokens, repetition_penalty=10.0, forbid_stop_before=0,
-                 forced=None):
-        """Greedy decode. Returns (codes incl. stop token, raw logits [n, V])."""
+                 forced=None, do_sample=False, top_k=0, top_p=1.0, temperature=1.0, seed=0, seq=0):
+        """Greedy (or sampled) decode. Returns (codes incl. stop token, raw logits [n, V])."""
         cfg, w, rr = self.cfg, self.w, self.rr
         start, stop = cfg["start_mel_token"], cfg["stop_mel_token"]
         self.reset()
@@ -152,7 +211,11 @@ class GptOracle:
             s[idx] = torch.where(sv < 0, sv * repetition_penalty, sv / repetition_penalty)
             if k < forbid_stop_before:
                 s[stop] = float("-inf")
-            tok = int(torch.argmax(s))  # first maximal index on CPU
+            if do_sample:
+                sc = (s.numpy().astype(np.float32) * np.float32(1.0 / temperature)).astype(np.float32)
+                tok, _ = sample_token(sc, top_k, top_p, seed, k, seq)
+            else:
+                tok = int(torch.argmax(s))  # first maximal index on CPU
             codes.append(tok)
             feed = tok if forced is None else int(forced[k])
             if forced is None and tok == stop:

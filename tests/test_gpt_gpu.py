@@ -113,3 +113,29 @@ def test_full_size_v25_decode_vs_oracle(engine):
           f"timing {engine.gpt_last_timing()}")
     if ties == 0:
         assert np.array_equal(f_codes, o_codes)
+
+
+def test_device_sampler_vs_oracle(engine):
+    """do_sample=True, num_beams=1 (temperature → top-k → top-p → multinomial, HF warper order): the device
+    sampler uses a documented Philox stream; with the same seed the oracle reproduces its picks except where a
+    bf16-level logit difference moves a CDF boundary (teacher-forced, >= 90 % identical), every pick lies in
+    the oracle's kept set, top_k=1 is greedy, and the stream is deterministic per seed."""
+    cfg, style, emo, text = small_case()
+    w = make_gpt_weights(cfg, seed=1234, bf16=True)
+    load_gpt(engine, cfg, w)
+    prompt = prepare_gpt_inputs(w, style, r16(emo), text, lang=1, bf16=True).numpy()
+    n = 40
+    kw = dict(do_sample=True, top_k=30, top_p=0.8, temperature=0.8, seed=2024)
+    o_codes, o_logits = GptOracle(cfg, w, bf16=True).generate(prompt, n, 10.0, n, **kw)
+    (e_codes,) = engine.gpt_generate([prompt], n, 10.0, forbid_stop_before=n, forced_codes=[o_codes], **kw)
+    agree = int((e_codes == o_codes).sum())
+    print(f"sampler: {agree}/{n} identical picks under teacher forcing")
+    assert agree >= int(0.9 * n)
+    (a,) = engine.gpt_generate([prompt], n, 10.0, forbid_stop_before=n, **kw)
+    (b,) = engine.gpt_generate([prompt], n, 10.0, forbid_stop_before=n, **kw)
+    assert np.array_equal(a, b)
+    (c,) = engine.gpt_generate([prompt], n, 10.0, forbid_stop_before=n, **dict(kw, seed=99))
+    assert not np.array_equal(a, c)
+    (g1,) = engine.gpt_generate([prompt], n, 10.0, forbid_stop_before=n, do_sample=True, top_k=1, seed=5)
+    (g0,) = engine.gpt_generate([prompt], n, 10.0, forbid_stop_before=n)
+    assert np.array_equal(g1, g0)

@@ -69,3 +69,22 @@ def test_stop_token_ends_generation():
     prompt = prepare_gpt_inputs(w, style, emo, text, lang=0, bf16=False)
     codes, _ = GptOracle(cfg, w, bf16=False).generate(prompt, 10, 10.0, 3)
     assert len(codes) == 4 and codes[-1] == cfg["stop_mel_token"]
+
+
+def test_philox_known_answer_and_sampler_properties():
+    from oracle.gpt import philox4x32_10, sample_token
+    # Random123 known-answer test: counter = 0, key = 0
+    assert philox4x32_10(0, 0, 0) == (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)
+    rng = np.random.default_rng(0)
+    s = rng.standard_normal(500).astype(np.float32) * 3
+    tok, kept = sample_token(s, top_k=1, top_p=1.0, seed=1, step=0, seq=0)
+    assert tok == int(np.argmax(s)) and kept == [tok]
+    tok, kept = sample_token(s, top_k=30, top_p=0.8, seed=7, step=3, seq=0)
+    top30 = set(np.argsort(-s)[:30].tolist())
+    assert tok in top30 and set(kept) <= top30 and 1 <= len(kept) <= 30
+    # frequencies follow the renormalised distribution
+    s2 = np.log(np.array([0.5, 0.3, 0.15, 0.05], dtype=np.float32))
+    cnt = np.zeros(4)
+    for i in range(4000):
+        cnt[sample_token(s2, 0, 1.0, seed=123, step=i, seq=0)[0]] += 1
+    assert np.abs(cnt / 4000 - np.array([0.5, 0.3, 0.15, 0.05])).max() < 0.03
