@@ -164,20 +164,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n = n0 + c0 + lane;
       if (n < p.N) {
         const float bv = p.bias ? __ldg(p.bias + (n % biasN)) : 0.f;
-        const float cs = p.colscale ? __ldg(p.colscale + n) : 1.f;
-#pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) {
-          const int m = mrow0 + rr;
-          if (m >= p.M) break;
-          const long long flat = p.out_off + (long long)m * p.ldo + n;
-          if (flat < 0 || flat >= p.out_valid) continue;
-          float v = tile[rr * 33 + lane] + bv;
-          v = apply_act_tc(v, p.act) * cs;
-          if (p.rowscale) v *= __ldg(p.rowscale + (long long)b * p.M + m);
-          const long long o = (long long)b * obs + flat;
-          if (p.res) v += p.res[o];
-          if (p.accum) v += p.out[o];
-          p.out[o] = v * p.scale;
+        const float cs = (p.colscale ? __ldg(p.colscale + n) : 1.f);
+        const long long flat0 = p.out_off + (long long)mrow0 * p.ldo + n;     // row rr adds rr*ldo
+        const int rows = min(32, p.M - mrow0);
+        // fast path: the 32-row x 32-col chunk lies wholly inside the valid output range
+        const bool interior = rows == 32 && (p.out_off + (long long)mrow0 * p.ldo + n0 + c0) >= 0 &&
+                              (p.out_off + (long long)(mrow0 + 31) * p.ldo + n0 + c0 + 31) < p.out_valid;
+        float* op = p.out + (long long)b * obs + flat0;
+        const float* rp = p.res ? p.res + (long long)b * obs + flat0 : nullptr;
+        if (interior && p.act == ACT_NONE && !p.rowscale) {
+          const float sc = p.scale;
+          if (!rp && !p.accum) {
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) op[(long long)rr * p.ldo] = (tile[rr * 33 + lane] + bv) * cs * sc;
+          } else {
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) {
+              float v = (tile[rr * 33 + lane] + bv) * cs;
+              if (rp) v += rp[(long long)rr * p.ldo];
+              if (p.accum) v += op[(long long)rr * p.ldo];
+              op[(long long)rr * p.ldo] = v * sc;
+            }
+          }
+        } else {
+          for (int rr = 0; rr < rows; ++rr) {
+            const long long flat = flat0 + (long long)rr * p.ldo;
+            if (flat < 0 || flat >= p.out_valid) continue;
+            float v = tile[rr * 33 + lane] + bv;
+            v = apply_act_tc(v, p.act) * cs;
+            if (p.rowscale) v *= __ldg(p.rowscale + (long long)b * p.M + mrow0 + rr);
+            if (rp) v += rp[(long long)rr * p.ldo];
+            if (p.accum) v += op[(long long)rr * p.ldo];
+            op[(long long)rr * p.ldo] = v * p.scale;
+          }
         }
       }
       __syncwarp();
@@ -245,14 +264,15 @@ void launch_bn(idx_engine* e, const ConvGemm& g, const CUtensorMap& tmA, const C
   p.out_valid = g.out_valid ? g.out_valid : (long long)g.M * p.ldo;
   constexpr int STAGE = BM * BK * 4 + BN * BK * 4;
   const int n_iters = p.taps * p.n_kchunks;
-  int stages = (104 * 1024) / STAGE;   // two CTAs per SM: one's epilogue overlaps the other's mainloop
-  if (stages > 6) stages = 6;
+  static const int occ = getenv("IDX_GEMM_OCC") ? atoi(getenv("IDX_GEMM_OCC")) : 2;
+  int stages = ((occ == 1 ? 208 : 104) * 1024) / STAGE;   // two CTAs per SM: one's epilogue overlaps the other's mainloop
+  if (stages > 8) stages = 8;
   if (stages > n_iters) stages = n_iters < 2 ? 2 : n_iters;
   p.stages = stages;
   const size_t smem = (size_t)stages * STAGE + 1024 + (2 * stages + 1) * 8 + 16;
   static bool attr_done = false;
   if (!attr_done) {
-    IDX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    IDX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_done = true;
   }
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.B);
