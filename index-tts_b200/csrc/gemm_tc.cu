@@ -178,13 +178,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 8
             for (int rr = 0; rr < 32; ++rr) op[(long long)rr * p.ldo] = (tile[rr * 33 + lane] + bv) * cs * sc;
           } else {
-#pragma unroll 8
+            // res may alias out (in-place residual): fetch the whole 32-row column into registers first so the
+            // 32 L2 round trips overlap instead of serialising behind the stores
+            float addv[32];
+#pragma unroll
             for (int rr = 0; rr < 32; ++rr) {
-              float v = (tile[rr * 33 + lane] + bv) * cs;
-              if (rp) v += rp[(long long)rr * p.ldo];
-              if (p.accum) v += op[(long long)rr * p.ldo];
-              op[(long long)rr * p.ldo] = v * sc;
+              float a = 0.f;
+              if (rp) a = rp[(long long)rr * p.ldo];
+              if (p.accum) a += op[(long long)rr * p.ldo];
+              addv[rr] = a;
             }
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr)
+              op[(long long)rr * p.ldo] = ((tile[rr * 33 + lane] + bv) * cs + addv[rr]) * sc;
           }
         } else {
           for (int rr = 0; rr < rows; ++rr) {
@@ -310,7 +316,13 @@ void gemm_tc_launch(idx_engine* e, const ConvGemm& g) {
   const long long wbs = g.w_batch_stride ? g.w_batch_stride : (long long)g.N * ldw;
   cuuint64_t bdims[3] = {(cuuint64_t)g.taps * g.K, (cuuint64_t)g.N, (cuuint64_t)(g.w_batch_stride ? g.B : 1)};
   cuuint64_t bstr[2] = {(cuuint64_t)ldw * 4, (cuuint64_t)wbs * 4};
-  const int BN = g.N <= 32 ? 32 : (g.N <= 64 ? 64 : 128);
+  int BN = g.N <= 32 ? 32 : (g.N <= 64 ? 64 : 128);
+  {
+    // fewer 128-wide tiles than SMs: halve the tile so every SM gets work (2 CTAs/SM are resident anyway)
+    static const int bn64 = getenv("IDX_GEMM_BN64") ? atoi(getenv("IDX_GEMM_BN64")) : 1;
+    const long long tiles128 = (long long)((g.N + 127) / 128) * ((g.M + BM - 1) / BM) * g.B;
+    if (bn64 && BN == 128 && tiles128 < 148) BN = 64;
+  }
   cuuint32_t bbox[3] = {BK, (cuuint32_t)BN, 1};
   CUtensorMap tmB = make_map(g.Wk, 3, bdims, bstr, bbox);
   if (BN == 32) launch_bn<32>(e, g, tmA, tmB);

@@ -151,9 +151,27 @@ __device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
 // data is read with ld.global.cg (L2), so no L1 invalidation is needed on the consumer side.
 // Every thread also drains its cp.async prefetches (LayerNorm parameters of the next phase)
 // before the closing CTA barrier, so they are visible to the whole CTA afterwards.
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned& target, int G, int flavor) {
   ptx::named_bar_sync(1, NCT);
-  if (threadIdx.x == 0) {
+  if (flavor == 2) {
+    // flag barrier: one arrival word per CTA (no same-address atomics, which L2 serialises at
+    // ~27 cycles each: 148 arrivals on one counter cost ~2 us), polled by the 32 lanes of warp 0.
+    if (threadIdx.x < 32) {
+      unsigned* flags = ctr + 32;
+      target += 1u;
+      if (threadIdx.x == 0) st_release_gpu(flags + blockIdx.x, target);   // cumulative over the CTA (bar.sync above)
+      unsigned spins = 0;
+      for (int i = threadIdx.x; i < G; i += 32) {
+        while (ld_relaxed_gpu(flags + i) < target) {
+          if (++spins > (1u << 28)) __trap();
+        }
+      }
+      __syncwarp();
+    }
+  } else if (threadIdx.x == 0) {
     target += (unsigned)G;
     __threadfence();                      // release: the CTA's stores of this phase
     atomicAdd(ctr, 1u);
@@ -1068,7 +1086,7 @@ static void launch_fused_t(idx_engine* e, GptState* g, GptParams& p) {
   p.ocap = g->ocap;
   p.bar_flavor = g->bar_flavor;
   size_t smem = smem_bytes(BT, p.D, p.FF, p.nst, g->bias_cap, g->ocap, p.V);
-  IDX_CUDA(cudaMemsetAsync(g->barrier, 0, sizeof(unsigned), e->stream));
+  IDX_CUDA(cudaMemsetAsync(g->barrier, 0, (32 + 256) * sizeof(unsigned), e->stream));
   void* args[] = {(void*)&p};
   IDX_CUDA(cudaLaunchCooperativeKernel((void*)gpt_fused_kernel<BT, NPL>, dim3(g->G), dim3(NTHREADS),
                                        args, smem, e->stream));
@@ -1113,7 +1131,7 @@ extern "C" int idx_gpt_init(idx_engine* e, const idx_gpt_config* cfg) {
   auto cdiv = [](int a, int b) { return (a + b - 1) / b; };
   g->ocap = cdiv(D, G) + 1;
   g->bias_cap = L * (cdiv(3 * D, G) + 1 + 2 * g->ocap + cdiv(FF, G) + 1) + cdiv(V, G) + 1;
-  g->bar_flavor = getenv("IDX_GPT_BAR_FLAVOR") ? atoi(getenv("IDX_GPT_BAR_FLAVOR")) : 1;
+  g->bar_flavor = getenv("IDX_GPT_BAR_FLAVOR") ? atoi(getenv("IDX_GPT_BAR_FLAVOR")) : 1;   // flavor 2 (per-CTA flags) measured slower: 839 vs 683 us/step
   auto pick_nst = [&](int BT) {
     int nst = 2;
     while (nst < 32 && smem_bytes(BT, D, FF, nst + 1, g->bias_cap, g->ocap, V) <= (size_t)dev_smem - 1024) ++nst;
@@ -1233,7 +1251,7 @@ extern "C" int idx_gpt_init(idx_engine* e, const idx_gpt_config* cfg) {
   g->prompt_len = galloc<int>(g, 8);
   g->done = galloc<int>(g, 1);
   g->seen = galloc<unsigned>(g, 8 * (size_t)((V + 31) / 32));
-  g->barrier = galloc<unsigned>(g, 4);
+  g->barrier = galloc<unsigned>(g, 32 + 256);   // [0] counter (flavors 0/1), [32..] per-CTA arrival flags (flavor 2)
   g->prof = galloc<long long>(g, 320);
   IDX_CUDA(cudaEventCreate(&g->ev0));
   IDX_CUDA(cudaEventCreate(&g->ev1));
