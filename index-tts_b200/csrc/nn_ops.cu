@@ -418,8 +418,9 @@ __global__ void __launch_bounds__(128) flash_attn_tc_kernel(const __nv_bfloat16*
                                                             const __nv_bfloat16* __restrict__ Kr,
                                                             const __nv_bfloat16* __restrict__ Vb,
                                                             float* __restrict__ out, int T, int H) {
-  __shared__ __align__(16) __nv_bfloat16 Ks[FK * VPITCH];
-  __shared__ __align__(16) __nv_bfloat16 Vs[FK * VPITCH];
+  // K/V tiles are double buffered: cp.async fills tile i+1 while the tensor cores work on tile i
+  __shared__ __align__(16) __nv_bfloat16 Ks2[2][FK * VPITCH];
+  __shared__ __align__(16) __nv_bfloat16 Vs2[2][FK * VPITCH];
   const int bh = blockIdx.y, q0 = blockIdx.x * FQ;
   const int b = bh / H, h = bh % H;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -444,23 +445,35 @@ __global__ void __launch_bounds__(128) flash_attn_tc_kernel(const __nv_bfloat16*
 #pragma unroll
   for (int j = 0; j < 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-  const uint32_t ks_base = (uint32_t)__cvta_generic_to_shared(Ks);
-  const uint32_t vs_base = (uint32_t)__cvta_generic_to_shared(Vs);
+  const uint32_t ks_base0 = (uint32_t)__cvta_generic_to_shared(&Ks2[0][0]);
+  const uint32_t vs_base0 = (uint32_t)__cvta_generic_to_shared(&Vs2[0][0]);
 
-  for (int k0 = 0; k0 < T; k0 += FK) {
-    __syncthreads();
-    // stage K and V tiles (bf16); rows beyond T are zero
+  auto stage_tile = [&](int buf, int k0) {
+    // rows beyond T are zero-filled (src-size 0), so masked keys never meet NaN garbage
     for (int i = tid; i < FK * (AD / 8); i += 128) {
       const int r = i / (AD / 8), c8 = (i % (AD / 8)) * 8;
-      uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-      if (k0 + r < T) {
-        kv = *(const uint4*)(Kb + (long long)(k0 + r) * AD + c8);
-        vv = *(const uint4*)(Vbb + (long long)(k0 + r) * AD + c8);
-      }
-      *(uint4*)(Ks + r * VPITCH + c8) = kv;
-      *(uint4*)(Vs + r * VPITCH + c8) = vv;
+      const bool ok = k0 + r < T;
+      const long long src = (long long)(ok ? k0 + r : 0) * AD + c8;
+      const uint32_t kd = ks_base0 + (uint32_t)((buf * FK * VPITCH + r * VPITCH + c8) * 2);
+      const uint32_t vd = vs_base0 + (uint32_t)((buf * FK * VPITCH + r * VPITCH + c8) * 2);
+      const int sz = ok ? 16 : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(kd), "l"(Kb + src), "r"(sz) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vd), "l"(Vbb + src), "r"(sz) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage_tile(0, 0);
+  int buf = 0;
+  for (int k0 = 0; k0 < T; k0 += FK, buf ^= 1) {
+    if (k0 + FK < T) {
+      stage_tile(buf ^ 1, k0 + FK);     // buffer buf^1 was released by the barrier that ended the previous tile
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    const uint32_t ks_base = ks_base0 + (uint32_t)(buf * FK * VPITCH * 2);
+    const uint32_t vs_base = vs_base0 + (uint32_t)(buf * FK * VPITCH * 2);
     // S = Q K^T : 8 key tiles (n = 8 keys) x 4 k-steps (16 dims)
     float sc[8][4];
 #pragma unroll
@@ -531,6 +544,7 @@ __global__ void __launch_bounds__(128) flash_attn_tc_kernel(const __nv_bfloat16*
         mma_bf16_16816_fa(o[2 * dp + 1], a0, a1, a2, a3, v2, v3);
       }
     }
+    __syncthreads();   // every warp is done with this tile's buffer
   }
   const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
   const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;

@@ -5,6 +5,7 @@ built by the reference's own constructor, i.e. with its own config/checkpoint lo
 weights of its modules with a B200 engine and rebinds the module-level seams of `infer_generator`
  to the C-ABI:
 
+    tts.gpt.merge_emovec              → idx_merge_emovec                            (model_v2.py:827-838)
     tts.gpt.inference_speech          → idx_gpt_prepare_inputs + idx_gpt_generate   (model_v2.py:716-825)
     tts.semantic_codec.decode         → idx_codec_decode                            (codec/models.py:205-231)
     tts.s2mel.models['length_regulator'](…)  → idx_length_regulate                  (length_regulator.py:90-141)
@@ -42,6 +43,24 @@ def load_reference_weights(engine: Engine, tts, max_batch: int = 1):
                     sd["mel_pos_embedding.emb.weight"].shape[0],
                     max_prompt=sd["text_pos_embedding.emb.weight"].shape[0] + 8, max_batch=max_batch,
                     weights_bf16=True)
+    # emotion conformer + perceiver (model_v2.py:378-398), sized from the tensors; absent on stand-ins without them
+    E, Q = "emo_conditioning_encoder.", "emo_perceiver_encoder."
+    if E + "embed.out.0.weight" in sd:
+        od = sd[E + "embed.out.0.weight"].shape[0]
+        blocks = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith(E + "encoders."))
+        lat = sd[Q + "latents"]
+        inner = sd[Q + "layers.0.0.to_q.weight"].shape[0]
+        heads = sd[E + "encoders.0.self_attn.pos_bias_u"].shape[0]
+        p_heads = int(getattr(getattr(gpt, "emo_perceiver_encoder", None), "heads", 0)) or max(1, inner // 64)
+        # Conv2dSubsampling2 (conformer/subsampling.py:144-160): out Linear takes od * ((idim - 1) // 2) features;
+        # the w2v-BERT feature width is even (1024), hence 2 * fsub + 2
+        fsub = sd[E + "embed.out.0.weight"].shape[1] // od
+        engine.emo_init(dict(idim=int(getattr(gpt, "emo_input_size", 0)) or 2 * fsub + 2, odim=od, linear_units=sd[E + "encoders.0.feed_forward.w_1.weight"].shape[0], heads=heads,
+                             blocks=blocks, cnn_kernel=sd[E + "encoders.0.conv_module.depthwise_conv.weight"].shape[-1],
+                             p_dim=lat.shape[-1], p_heads=p_heads, p_dim_head=inner // p_heads,
+                             p_depth=1 + max(int(k.split(".")[2]) for k in sd if k.startswith(Q + "layers.")),
+                             p_ff_mult=max(1, round(sd[Q + "layers.0.1.0.weight"].shape[0] * 3 / (4 * lat.shape[-1]))),
+                             model_dim=D))
     # s2mel (weight-norm parametrised layers are folded: g * v / ||v||)
     s2 = {k[len("models."):]: v for k, v in _sd(tts.s2mel).items()}
     s2 = fold_weight_norm(s2)
@@ -85,8 +104,12 @@ def attach(tts, engine: Engine = None, device: int = 0):
         # same argument meaning as gpt/model_v2.py:716-825; emo_vec comes from merge_emovec (:833-838)
         if emo_vec is None or campplus_embedding is None:
             raise ValueError("the B200 path needs emo_vec and campplus_embedding (what infer_v2_5.py:759-791 passes)")
-        if hf.get("num_beams", 1) != 1 or hf.get("do_sample", False):
-            raise NotImplementedError("round 1 builds greedy decoding (do_sample=False, num_beams=1)")
+        if hf.get("num_beams", 1) != 1:
+            raise NotImplementedError("beam-sample (num_beams > 1) is not built yet; pass num_beams=1 "
+                                      "(greedy or top-k/top-p sampling run on the device)")
+        sampling = dict(do_sample=bool(hf.get("do_sample", False)), top_k=int(hf.get("top_k", 0) or 0),
+                        top_p=float(hf.get("top_p", 1.0)), temperature=float(hf.get("temperature", 1.0)),
+                        seed=int(torch.initial_seed() & 0x7fffffff))
         lang = int(langs.reshape(-1)[0]) if langs is not None else 0
         outs = []
         for i in range(text_inputs.shape[0]):
@@ -95,7 +118,7 @@ def attach(tts, engine: Engine = None, device: int = 0):
                                                text_inputs[i].cpu().numpy(), lang)
             max_new = max_generate_length if max_generate_length is not None else self.max_mel_tokens - 1
             (codes,) = engine.gpt_generate([prompt], int(max_new),
-                                           repetition_penalty=float(hf.get("repetition_penalty", 1.0)))
+                                           repetition_penalty=float(hf.get("repetition_penalty", 1.0)), **sampling)
             outs.append(torch.from_numpy(codes.astype(np.int64)))
         n = max(len(o) for o in outs)
         pad = torch.full((len(outs), n), self.stop_mel_token, dtype=torch.long)
@@ -104,6 +127,18 @@ def attach(tts, engine: Engine = None, device: int = 0):
         return pad.to(dev), None
 
     gpt.inference_speech = types.MethodType(inference_speech, gpt)
+
+    if getattr(engine, "emo_cfg", None) is not None:
+        def merge_emovec(self, speech_condition, emo_speech_condition, cond_lengths=None, emo_cond_lengths=None, alpha=1.0):
+            # model_v2.py:827-838; features [1, T, 1024] (or [1, 1024, T], transposed like get_emo_conditioning :588-593)
+            def feats(x):
+                x = x[0].float()
+                return (x.t() if x.shape[0] == engine.emo_cfg.idim and x.shape[1] != engine.emo_cfg.idim else x).contiguous()
+            v = engine.merge_emovec(feats(speech_condition).cpu().numpy(), feats(emo_speech_condition).cpu().numpy(),
+                                    float(alpha))
+            return torch.from_numpy(v)[None].to(dev)
+
+        gpt.merge_emovec = types.MethodType(merge_emovec, gpt)
 
     def codec_decode(self, codes):
         c = codes.reshape(-1, codes.shape[-1])

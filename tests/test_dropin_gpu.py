@@ -11,6 +11,7 @@ import torch
 from indextts_b200 import synth
 from indextts_b200.dropin import attach
 from oracle.bigvgan import bigvgan_forward
+from oracle import emo as emo_oracle
 from oracle.gpt import GptOracle, prepare_gpt_inputs
 from oracle.s2mel import cfm_inference, codec_decode, fold_weight_norm, length_regulate
 from oracle.validate_gpt_vs_hf import small_case
@@ -30,10 +31,13 @@ class _Mod:
 def test_attach_rebinds_the_reference_seams(engine):
     cfg, style, emo, text = small_case()
     wg = synth.make_gpt_weights(cfg, seed=1234, bf16=True)
+    ec = dict(synth.small_emo_cfg(), model_dim=cfg["model_dim"])
+    we = synth.make_emo_weights(ec, seed=77)
+    wg_all = dict(wg, **we)
     c, cc, h = synth.small_s2mel_cfg(), synth.small_codec_cfg(), synth.small_config()
     ws, wc, wb = synth.make_s2mel_weights(c, 1234), synth.make_codec_weights(cc, 4321), synth.make_bigvgan_weights(h, 1)
     tts = types.SimpleNamespace()
-    tts.gpt = _Mod(wg, model_dim=cfg["model_dim"], heads=cfg["heads"], number_mel_codes=cfg["number_mel_codes"],
+    tts.gpt = _Mod(wg_all, model_dim=cfg["model_dim"], heads=cfg["heads"], number_mel_codes=cfg["number_mel_codes"],
                    start_mel_token=cfg["start_mel_token"], stop_mel_token=cfg["stop_mel_token"],
                    max_mel_tokens=cfg["max_mel_tokens"], gpt=types.SimpleNamespace(h=[None] * cfg["layers"]))
     cfm = _Mod({}, in_channels=80)
@@ -41,6 +45,14 @@ def test_attach_rebinds_the_reference_seams(engine):
     tts.semantic_codec = _Mod(wc)
     tts.bigvgan = _Mod(wb, h=h)
     attach(tts, engine=engine)
+
+    # --- infer_v2_5.py:759: emotion vector through the rebound merge_emovec
+    ge = torch.Generator().manual_seed(5)
+    spk_f, emo_f = torch.randn(1, 37, ec["idim"], generator=ge), torch.randn(1, 29, ec["idim"], generator=ge)
+    ev = tts.gpt.merge_emovec(spk_f, emo_f, torch.tensor([37]), torch.tensor([29]), alpha=0.6)
+    ev_ref = emo_oracle.merge_emovec(we, ec, spk_f[0], emo_f[0], 0.6)
+    assert ev.shape == (1, cfg["model_dim"])
+    assert np.abs(ev[0].cpu().numpy() - ev_ref.numpy()).max() < 2e-2 * max(1.0, float(ev_ref.abs().max()))
 
     # --- infer_v2_5.py:771-791: speech tokens
     emo16 = synth.r16(emo)
