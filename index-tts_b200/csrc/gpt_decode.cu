@@ -1027,11 +1027,217 @@ __global__ void prepare_inputs_kernel(const float* style, const float* emo_vec,
   }
 }
 
+
+// ============================================================================================
+// Strict fp32 path (idx_gpt_config.weights_bf16 = 0): the reference's default `use_bf16=False`
+// arithmetic (fp32 weights, fp32 activations, fp32 KV cache) as plain per-op kernels, one sequence
+// at a time.  It exists for token-for-token parity against the fp32 oracle; the
+// fused persistent kernel above is the performance path.  Same call sites, same sampler contract.
+// ============================================================================================
+__global__ void strict_embed_kernel(float* x, const float* prompt_row, const float* mel_emb, const float* mel_pos,
+                                    const int* tok, int posidx, int D) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  x[c] = prompt_row ? prompt_row[c] : mel_emb[(size_t)tok[0] * D + c] + mel_pos[(size_t)posidx * D + c];
+}
+
+// LayerNorm(eps 1e-5) of one row, statistics accumulated in double
+__global__ void strict_ln_kernel(const float* x, const float* w, const float* b, float* y, int D) {
+  __shared__ double sh[64];
+  const int tid = threadIdx.x;
+  double s = 0.0;
+  for (int i = tid; i < D; i += blockDim.x) s += (double)x[i];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((tid & 31) == 0) sh[tid >> 5] = s;
+  __syncthreads();
+  double tot = 0.0;
+  for (int q = 0; q < (int)(blockDim.x >> 5); ++q) tot += sh[q];
+  const double mean = tot / D;
+  __syncthreads();
+  double v = 0.0;
+  for (int i = tid; i < D; i += blockDim.x) { const double d = (double)x[i] - mean; v += d * d; }
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((tid & 31) == 0) sh[32 + (tid >> 5)] = v;
+  __syncthreads();
+  double vt = 0.0;
+  for (int q = 0; q < (int)(blockDim.x >> 5); ++q) vt += sh[32 + q];
+  const float rstd = (float)(1.0 / sqrt(vt / D + 1e-5));
+  const float mf = (float)mean;
+  for (int i = tid; i < D; i += blockDim.x) y[i] = (x[i] - mf) * rstd * w[i] + b[i];
+}
+
+// y[c] = act(sum_k x[k] W[k][c] + bias[c]) (+ res[c]);  W is HF Conv1D [K][N] (trap P4).  Block (32, 32):
+// warp ty owns k = ty, ty + 32, ...; a warp reads one 128-byte row segment per k.
+__global__ void strict_gemv_kn_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                      const float* __restrict__ bias, const float* res, float* y, int K, int N, int act) {
+  __shared__ float part[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.x * 32 + tx;
+  float acc = 0.f;
+  if (c < N)
+    for (int k = ty; k < K; k += 32) acc = fmaf(x[k], W[(size_t)k * N + c], acc);
+  part[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && c < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) s += part[q][tx];
+    s += bias[c];
+    if (act == 1) s = gelu_new(s, 0);
+    if (res) s += res[c];
+    y[c] = s;
+  }
+}
+
+// nn.Linear [N][K]: one warp per output row
+__global__ void strict_gemv_nk_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                      const float* __restrict__ bias, float* y, int K, int N) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= N) return;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) acc = fmaf(x[k], W[(size_t)row * K + k], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) y[row] = acc + bias[row];
+}
+
+// one head per block: append (k, v) of this position to the fp32 cache, softmax(q k^T / 8) v over positions 0..pos
+__global__ void strict_attn_kernel(const float* qkv, float* kc, float* vc, int pos, float* out, int D) {
+  extern __shared__ float sc[];           // [pos + 1] scores, then [128] merge buffer
+  __shared__ float redv[8];
+  const int h = blockIdx.x, tid = threadIdx.x;
+  if (tid < HD) {
+    kc[(size_t)pos * D + h * HD + tid] = qkv[D + h * HD + tid];
+    vc[(size_t)pos * D + h * HD + tid] = qkv[2 * D + h * HD + tid];
+  }
+  __syncthreads();
+  const float* q = qkv + h * HD;
+  float mx = -INFINITY;
+  for (int j = tid; j <= pos; j += blockDim.x) {
+    const float* kr = kc + (size_t)j * D + h * HD;
+    float s = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < HD; ++d) s = fmaf(q[d], kr[d], s);
+    s *= 0.125f;
+    sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((tid & 31) == 0) redv[tid >> 5] = mx;
+  __syncthreads();
+  mx = redv[0];
+  for (int q2 = 1; q2 < (int)(blockDim.x >> 5); ++q2) mx = fmaxf(mx, redv[q2]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int j = tid; j <= pos; j += blockDim.x) { const float p = expf(sc[j] - mx); sc[j] = p; sum += p; }
+  sum = warp_sum(sum);
+  if ((tid & 31) == 0) redv[4 + (tid >> 5)] = sum;
+  __syncthreads();
+  float tot = 0.f;
+  for (int q2 = 0; q2 < (int)(blockDim.x >> 5); ++q2) tot += redv[4 + q2];
+  const int d = tid & (HD - 1), half = tid / HD;      // 128 threads: two interleaved halves of the positions
+  float acc = 0.f;
+  for (int j = half; j <= pos; j += 2) acc = fmaf(sc[j], vc[(size_t)j * D + h * HD + d], acc);
+  float* mg = sc + pos + 1;
+  mg[tid] = acc;
+  __syncthreads();
+  if (tid < HD) out[h * HD + tid] = (mg[tid] + mg[tid + HD]) / tot;
+}
+
+// RepetitionPenalty -> (forbid stop) -> [Temperature -> TopK -> TopP -> multinomial | argmax]; same order, tie rules
+// and Philox contract as the sampling phase of the fused kernel.
+__global__ void strict_sample_kernel(const float* logits, unsigned* seen, int V, int k, int seq, float rep_penalty,
+                                     int stop_tok, int forbid_stop_before, int do_sample, int top_k, float top_p,
+                                     float temperature, unsigned long long seed, int* codes, int max_new, int* nout,
+                                     int* finished, int* tok, const int* forced, float* ldump) {
+  extern __shared__ float sv[];            // [V] processed scores
+  __shared__ float rb[16];
+  __shared__ int ri[16];
+  __shared__ float cv[64];
+  __shared__ int ci[64];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const float inv_temp = (do_sample && temperature > 0.f) ? 1.0f / temperature : 1.0f;
+  for (int i = tid; i < V; i += blockDim.x) {
+    float s = logits[i];
+    if (ldump) ldump[i] = s;
+    if ((seen[i >> 5] >> (i & 31)) & 1u) s = (s < 0.f) ? s * rep_penalty : s / rep_penalty;
+    if (i == stop_tok && k < forbid_stop_before) s = -INFINITY;
+    if (do_sample) s *= inv_temp;
+    sv[i] = s;
+  }
+  __syncthreads();
+  auto block_argmax = [&](float& bestv, int& besti) {
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < V; i += blockDim.x)
+      if (sv[i] > best || (sv[i] == best && i < bi && sv[i] > -INFINITY)) { best = sv[i]; bi = i; }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float b2 = __shfl_xor_sync(0xffffffffu, best, o);
+      const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (b2 > best || (b2 == best && i2 < bi)) { best = b2; bi = i2; }
+    }
+    __syncthreads();
+    if (lane == 0) { rb[warp] = best; ri[warp] = bi; }
+    __syncthreads();
+    for (int w = 0; w < nw; ++w)
+      if (w == 0 || rb[w] > best || (rb[w] == best && ri[w] < bi)) { best = rb[w]; bi = ri[w]; }
+    bestv = best; besti = bi;
+  };
+  float best; int besti;
+  block_argmax(best, besti);
+  if (do_sample) {
+    const int kk = (top_k > 0) ? min(top_k, 64) : 64;
+    int nc = 0;
+    float kth = best;
+    while (nc < 64 && best > -INFINITY && (nc < kk || best == kth)) {
+      if (tid == 0) { cv[nc] = best; ci[nc] = besti; sv[besti] = -INFINITY; }
+      if (nc < kk) kth = best;
+      ++nc;
+      __syncthreads();
+      block_argmax(best, besti);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const float mx = cv[0];
+      float tot = 0.f;
+      for (int i = 0; i < nc; ++i) { cv[i] = expf(cv[i] - mx); tot += cv[i]; }
+      int keep = nc;
+      if (top_p < 1.0f) {
+        float tail = 0.f;
+        for (int i = nc - 1; i >= 1; --i) {
+          tail += cv[i] / tot;
+          if (tail <= 1.0f - top_p) keep = i; else break;
+        }
+      }
+      float kt = 0.f;
+      for (int i = 0; i < keep; ++i) kt += cv[i];
+      unsigned rnd4[4];
+      philox4x32_10(seed, (unsigned)k, (unsigned)seq, rnd4);
+      const float u = (float)(rnd4[0] >> 8) * (1.0f / 16777216.0f) * kt;
+      float acc = 0.f;
+      int pick = keep - 1;
+      for (int i = 0; i < keep; ++i) { acc += cv[i]; if (u < acc) { pick = i; break; } }
+      besti = ci[pick];
+    }
+  }
+  if (tid == 0 && !finished[0]) {
+    codes[k] = besti;
+    nout[0] = k + 1;
+    int feed = besti;
+    if (forced) feed = forced[k];
+    else if (besti == stop_tok) finished[0] = 1;
+    if (k + 1 >= max_new) finished[0] = 1;
+    tok[0] = feed;
+    seen[feed >> 5] |= 1u << (feed & 31);
+  }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------ host state --
+struct GptStrict;
 struct GptState {
   idx_gpt_config cfg;
+  GptStrict* strict = nullptr;   // fp32 per-op path (weights_bf16 = 0)
   int G = 0, FF = 0, nst1 = 0, nst8 = 0, bias_cap = 0, ocap = 0, bar_flavor = 0;
   size_t smem1 = 0, smem8 = 0;
   __nv_bfloat16* wstream = nullptr;
@@ -1056,6 +1262,7 @@ struct GptState {
 
 void gpt_destroy(GptState* g) {
   if (!g) return;
+  delete g->strict;
   for (void* p : g->owned) cudaFree(p);
   if (g->ev0) cudaEventDestroy(g->ev0);
   if (g->ev1) cudaEventDestroy(g->ev1);
@@ -1070,6 +1277,146 @@ static T* galloc(GptState* g, size_t n) {
   IDX_CUDA(cudaMemset(p, 0, n * sizeof(T)));
   g->owned.push_back(p);
   return p;
+}
+
+// ------------------------------------------------------------------ strict fp32 host path --
+struct StrictLayer {
+  const float *ln1_w, *ln1_b, *wqkv, *bqkv, *wo, *bo, *ln2_w, *ln2_b, *wfc, *bfc, *wproj, *bproj;
+};
+struct GptStrict {
+  std::vector<StrictLayer> layers;
+  float *kc = nullptr, *vc = nullptr;                 // [L][maxpos][D] fp32, one sequence at a time
+  float *x = nullptr, *h = nullptr, *qkv = nullptr, *att = nullptr, *f = nullptr, *logits = nullptr;
+};
+
+static void strict_init(idx_engine* e, GptState* g) {
+  const idx_gpt_config& c = g->cfg;
+  const int L = c.layers, D = c.model_dim, V = c.number_mel_codes, FF = 4 * D;
+  GptStrict* s = new GptStrict();
+  g->strict = s;
+  auto lname = [&](int l, const char* n) { return "gpt.gpt.h." + std::to_string(l) + "." + n; };
+  for (int l = 0; l < L; ++l) {
+    StrictLayer y;
+    IDX_CHECK(e->W(lname(l, "attn.c_attn.weight")).numel() == (size_t)D * 3 * D, IDX_ERR_ARG, "c_attn.weight shape");
+    IDX_CHECK(e->W(lname(l, "mlp.c_fc.weight")).numel() == (size_t)D * FF, IDX_ERR_ARG, "c_fc.weight shape");
+    y.ln1_w = e->Wf(lname(l, "ln_1.weight")); y.ln1_b = e->Wf(lname(l, "ln_1.bias"));
+    y.wqkv = e->Wf(lname(l, "attn.c_attn.weight")); y.bqkv = e->Wf(lname(l, "attn.c_attn.bias"));
+    y.wo = e->Wf(lname(l, "attn.c_proj.weight")); y.bo = e->Wf(lname(l, "attn.c_proj.bias"));
+    y.ln2_w = e->Wf(lname(l, "ln_2.weight")); y.ln2_b = e->Wf(lname(l, "ln_2.bias"));
+    y.wfc = e->Wf(lname(l, "mlp.c_fc.weight")); y.bfc = e->Wf(lname(l, "mlp.c_fc.bias"));
+    y.wproj = e->Wf(lname(l, "mlp.c_proj.weight")); y.bproj = e->Wf(lname(l, "mlp.c_proj.bias"));
+    s->layers.push_back(y);
+  }
+  IDX_CHECK(e->W("gpt.mel_head.weight").numel() == (size_t)V * D, IDX_ERR_ARG, "mel_head.weight shape");
+  g->maxpos = c.max_prompt + c.max_mel_positions + 8;
+  s->kc = galloc<float>(g, (size_t)L * g->maxpos * D);
+  s->vc = galloc<float>(g, (size_t)L * g->maxpos * D);
+  s->x = galloc<float>(g, D); s->h = galloc<float>(g, D); s->qkv = galloc<float>(g, 3 * (size_t)D);
+  s->att = galloc<float>(g, D); s->f = galloc<float>(g, FF); s->logits = galloc<float>(g, V);
+  g->tok = galloc<int>(g, 8); g->nout = galloc<int>(g, 8); g->finished = galloc<int>(g, 8);
+  g->seen = galloc<unsigned>(g, (size_t)((V + 31) / 32));
+  IDX_CUDA(cudaFuncSetAttribute(strict_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  IDX_CHECK((size_t)(g->maxpos + 129) * 4 <= 96 * 1024, IDX_ERR_ARG, "context too long for the strict attention kernel");
+}
+
+// one position through the 24 blocks (x in s->x, updated in place); pos = its index in the KV cache
+static void strict_layers(idx_engine* e, GptState* g, int pos) {
+  GptStrict* s = g->strict;
+  const int D = g->cfg.model_dim, H = g->cfg.heads, FF = 4 * D;
+  cudaStream_t st = e->stream;
+  const dim3 blk(32, 32);
+  for (int l = 0; l < g->cfg.layers; ++l) {
+    const StrictLayer& y = s->layers[l];
+    float* kc = s->kc + (size_t)l * g->maxpos * D;
+    float* vc = s->vc + (size_t)l * g->maxpos * D;
+    strict_ln_kernel<<<1, 256, 0, st>>>(s->x, y.ln1_w, y.ln1_b, s->h, D);
+    strict_gemv_kn_kernel<<<(3 * D + 31) / 32, blk, 0, st>>>(s->h, y.wqkv, y.bqkv, nullptr, s->qkv, D, 3 * D, 0);
+    strict_attn_kernel<<<H, 128, (size_t)(pos + 1 + 128) * 4, st>>>(s->qkv, kc, vc, pos, s->att, D);
+    strict_gemv_kn_kernel<<<(D + 31) / 32, blk, 0, st>>>(s->att, y.wo, y.bo, s->x, s->x, D, D, 0);
+    strict_ln_kernel<<<1, 256, 0, st>>>(s->x, y.ln2_w, y.ln2_b, s->h, D);
+    strict_gemv_kn_kernel<<<(FF + 31) / 32, blk, 0, st>>>(s->h, y.wfc, y.bfc, nullptr, s->f, D, FF, 1);
+    strict_gemv_kn_kernel<<<(D + 31) / 32, blk, 0, st>>>(s->f, y.wproj, y.bproj, s->x, s->x, FF, D, 0);
+    e->launches += 7;
+    g->last_launches += 7;
+  }
+  IDX_CUDA(cudaGetLastError());
+}
+
+static void strict_generate(idx_engine* e, GptState* g, const idx_gpt_request* reqs, int nreq, const idx_sampling* sp) {
+  GptStrict* s = g->strict;
+  const idx_gpt_config& c = g->cfg;
+  const int D = c.model_dim, V = c.number_mel_codes, max_new = sp->max_new_tokens;
+  cudaStream_t st = e->stream;
+  const size_t wv = (size_t)((V + 31) / 32);
+  const float* mel_emb = e->Wf("gpt.mel_embedding.weight");
+  const float* mel_pos = e->Wf("gpt.mel_pos_embedding.emb.weight");
+  int maxn = 0;
+  IDX_CUDA(cudaEventRecord(g->ev0, st));
+  IDX_CUDA(cudaEventRecord(g->ev1, st));
+  for (int i = 0; i < nreq; ++i) {
+    const int plen = reqs[i].prompt_len;
+    IDX_CHECK(reqs[i].prompt_emb && plen >= 1 && plen <= c.max_prompt, IDX_ERR_ARG, "bad prompt");
+    IDX_CHECK(plen + max_new + 1 <= g->maxpos, IDX_ERR_ARG, "KV cache too small");
+    size_t need = (size_t)plen * D * 4 + 2 * (size_t)max_new * 4 + 4096;
+    if (reqs[i].logits_out) need += (size_t)max_new * V * 4;
+    e->ensure_arena(need + (1 << 20));
+    e->arena.reset();
+    float* d_prompt = e->arena.get<float>((size_t)plen * D);
+    int* d_codes = e->arena.get<int>(max_new);
+    int* d_forced = reqs[i].forced_codes ? e->arena.get<int>(max_new) : nullptr;
+    float* d_ldump = reqs[i].logits_out ? e->arena.get<float>((size_t)max_new * V) : nullptr;
+    idx_to_device(e, d_prompt, reqs[i].prompt_emb, (size_t)plen * D * 4);
+    if (d_forced) idx_to_device(e, d_forced, reqs[i].forced_codes, (size_t)max_new * 4);
+    {
+      std::vector<unsigned> h_seen(wv, 0u);
+      h_seen[1 >> 5] |= 1u << 1;                                            // trap P2: fake ids {1, start_mel}
+      h_seen[c.start_mel_token >> 5] |= 1u << (c.start_mel_token & 31);
+      const int h_tok = c.start_mel_token, zero = 0;
+      IDX_CUDA(cudaMemcpyAsync(g->seen, h_seen.data(), wv * 4, cudaMemcpyHostToDevice, st));
+      IDX_CUDA(cudaMemcpyAsync(g->tok, &h_tok, 4, cudaMemcpyHostToDevice, st));
+      IDX_CUDA(cudaMemcpyAsync(g->nout, &zero, 4, cudaMemcpyHostToDevice, st));
+      IDX_CUDA(cudaMemcpyAsync(g->finished, &zero, 4, cudaMemcpyHostToDevice, st));
+      IDX_CUDA(cudaStreamSynchronize(st));
+    }
+    for (int pos = 0; pos < plen; ++pos) {                                   // prompt positions, one at a time
+      strict_embed_kernel<<<(D + 255) / 256, 256, 0, st>>>(s->x, d_prompt + (size_t)pos * D, nullptr, nullptr, nullptr, 0, D);
+      strict_layers(e, g, pos);
+    }
+    int* h_fin = (int*)e->pinned_buf(64);
+    int k = 0;
+    for (; k < max_new; ++k) {
+      strict_embed_kernel<<<(D + 255) / 256, 256, 0, st>>>(s->x, nullptr, mel_emb, mel_pos, g->tok, k == 0 ? 0 : k + 1, D);   // trap P1
+      strict_layers(e, g, plen + k);
+      strict_ln_kernel<<<1, 256, 0, st>>>(s->x, e->Wf("gpt.gpt.ln_f.weight"), e->Wf("gpt.gpt.ln_f.bias"), s->h, D);
+      strict_ln_kernel<<<1, 256, 0, st>>>(s->h, e->Wf("gpt.final_norm.weight"), e->Wf("gpt.final_norm.bias"), s->att, D);   // trap P3
+      strict_gemv_nk_kernel<<<(V + 7) / 8, 256, 0, st>>>(s->att, e->Wf("gpt.mel_head.weight"), e->Wf("gpt.mel_head.bias"), s->logits, D, V);
+      strict_sample_kernel<<<1, 256, (size_t)V * 4, st>>>(s->logits, g->seen, V, k, i, sp->repetition_penalty, c.stop_mel_token,
+                                                          sp->forbid_stop_before, sp->do_sample, sp->top_k, sp->top_p,
+                                                          sp->temperature, sp->seed, d_codes, max_new, g->nout, g->finished,
+                                                          g->tok, d_forced, d_ldump ? d_ldump + (size_t)k * V : nullptr);
+      IDX_CUDA(cudaGetLastError());
+      e->launches += 5;
+      g->last_launches += 5;
+      IDX_CUDA(cudaMemcpyAsync(h_fin, g->finished, 4, cudaMemcpyDeviceToHost, st));
+      IDX_CUDA(cudaStreamSynchronize(st));
+      if (*h_fin) break;
+    }
+    int h_nout = 0;
+    IDX_CUDA(cudaMemcpyAsync(&h_nout, g->nout, 4, cudaMemcpyDeviceToHost, st));
+    IDX_CUDA(cudaStreamSynchronize(st));
+    maxn = std::max(maxn, h_nout);
+    if (reqs[i].n_codes_out) *reqs[i].n_codes_out = h_nout;
+    if (reqs[i].codes_out) idx_from_device(e, reqs[i].codes_out, d_codes, (size_t)h_nout * 4);
+    if (reqs[i].logits_out) idx_from_device(e, reqs[i].logits_out, d_ldump, (size_t)h_nout * V * 4);
+    IDX_CUDA(cudaStreamSynchronize(st));
+  }
+  IDX_CUDA(cudaEventRecord(g->ev2, st));
+  IDX_CUDA(cudaStreamSynchronize(st));
+  float ms = 0;
+  IDX_CUDA(cudaEventElapsedTime(&ms, g->ev0, g->ev2));
+  g->t_prefill_ms = 0;
+  g->t_decode_ms = ms;
+  g->last_steps = maxn;
 }
 
 static size_t smem_bytes(int BT, int D, int FF, int nst, int bias_cap, int ocap, int V) {
@@ -1121,9 +1468,16 @@ extern "C" int idx_gpt_init(idx_engine* e, const idx_gpt_config* cfg) {
   IDX_CHECK(D == 1280 || D == 256, IDX_ERR_ARG, "model_dim must be 1280 or 256 (instantiated kernel geometries)");
   IDX_CHECK(D == H * HD, IDX_ERR_ARG, "head_dim must be 64");
   IDX_CHECK(cfg->max_batch >= 1 && cfg->max_batch <= 8, IDX_ERR_ARG, "max_batch must be 1..8 (per decode group)");
-  IDX_CHECK(cfg->weights_bf16 == 1, IDX_ERR_ARG, "only the bf16 weight path is built in this round");
   const int G = e->num_sms;
   g->G = G;
+  if (!cfg->weights_bf16) {
+    strict_init(e, g);
+    IDX_CUDA(cudaEventCreate(&g->ev0));
+    IDX_CUDA(cudaEventCreate(&g->ev1));
+    IDX_CUDA(cudaEventCreate(&g->ev2));
+    IDX_CUDA(cudaStreamSynchronize(e->stream));
+    return IDX_OK;
+  }
 
   // ---- ring depth from the shared-memory budget ----
   int dev_smem = 0;
@@ -1296,6 +1650,10 @@ extern "C" int idx_gpt_generate(idx_engine* e, const idx_gpt_request* reqs, int 
   const int D = c.model_dim, V = c.number_mel_codes, max_new = sp->max_new_tokens;
   const int BT = (nreq == 1) ? 1 : 8;
   g->last_launches = 0;
+  if (g->strict) {
+    strict_generate(e, g, reqs, nreq, sp);
+    return IDX_OK;
+  }
 
   // ---- stage prompts ----
   int total_rows = 0;
@@ -1449,7 +1807,7 @@ extern "C" int idx_gpt_profile(idx_engine* e, int enable, int64_t* stamps_out, i
   IDX_CUDA(cudaSetDevice(e->device));
   GptState* g = e->gpt;
   g->prof_on = enable;
-  if (stamps_out && n > 0) {
+  if (stamps_out && n > 0 && g->prof) {
     IDX_CUDA(cudaStreamSynchronize(e->stream));
     IDX_CUDA(cudaMemcpy(stamps_out, g->prof, sizeof(long long) * (size_t)std::min(n, 320), cudaMemcpyDeviceToHost));
   }

@@ -139,3 +139,51 @@ def test_device_sampler_vs_oracle(engine):
     (g1,) = engine.gpt_generate([prompt], n, 10.0, forbid_stop_before=n, do_sample=True, top_k=1, seed=5)
     (g0,) = engine.gpt_generate([prompt], n, 10.0, forbid_stop_before=n)
     assert np.array_equal(g1, g0)
+
+
+def test_strict_fp32_small_vs_oracle(engine):
+    """weights_bf16=False: the reference's default fp32 arithmetic (infer_v2_5.py:77 `use_bf16=False`) through the
+    per-op fp32 kernels.  Teacher-forced logits within 1e-4 of the fp32 oracle (SURVEY section 8c tolerance) and the
+    free-running greedy tokens identical."""
+    cfg, style, emo, text = small_case()
+    w = make_gpt_weights(cfg, seed=1234, bf16=False)
+    load_gpt(engine, cfg, w, max_batch=2, bf16=False)
+    prompt = prepare_gpt_inputs(w, style, emo, text, lang=1, bf16=False).numpy()
+    got_prompt = engine.gpt_prepare_inputs(style.numpy(), emo.numpy(), text.numpy(), 1)
+    assert np.abs(got_prompt - prompt).max() <= 1e-5
+    n = 32
+    o_codes, o_logits = GptOracle(cfg, w, bf16=False).generate(prompt, n, 10.0, n)
+    (e_codes,), (e_logits,) = engine.gpt_generate([prompt], n, 10.0, forbid_stop_before=n,
+                                                  forced_codes=[o_codes], return_logits=True)
+    err = float(np.abs(e_logits - o_logits).max())
+    print(f"strict fp32 small: max |logit err| {err:.2e} at logit std {o_logits.std():.2f}")
+    assert err <= 1e-4
+    assert np.array_equal(e_codes, o_codes)
+    (f_codes,) = engine.gpt_generate([prompt], n, 10.0, forbid_stop_before=n)
+    assert np.array_equal(f_codes, o_codes)
+    # stop handling and sampling run through the same contract as the fused path
+    (s1,) = engine.gpt_generate([prompt], n, 10.0, forbid_stop_before=n, do_sample=True, top_k=1, seed=3)
+    assert np.array_equal(s1, o_codes)
+    two = engine.gpt_generate([prompt, prompt[:-2]], 6, 10.0, forbid_stop_before=6)
+    assert np.array_equal(two[0], o_codes[:6]) and len(two[1]) == 6
+
+
+def test_strict_fp32_full_size_256_tokens_token_for_token(engine):
+    """BASELINE configs[1]: IndexTTS-2.5 geometry, S = 37 prompt rows, 256 greedy speech tokens, fp32 — the engine's
+    free-running tokens equal the fp32 oracle's token for token (north-star parity statement)."""
+    cfg = gpt_config()
+    w = make_gpt_weights(cfg, seed=2025, bf16=False)
+    load_gpt(engine, cfg, w, max_prompt=64, bf16=False)
+    g = torch.Generator().manual_seed(11)
+    style = torch.randn(192, generator=g)
+    emo = torch.randn(cfg["model_dim"], generator=g) * 0.5
+    text = torch.randint(2, 12000, (32,), generator=g)
+    prompt = prepare_gpt_inputs(w, style, emo, text, lang=1, bf16=False).numpy()
+    n = 256
+    o_codes, o_logits = GptOracle(cfg, w, bf16=False).generate(prompt, n, 10.0, n)
+    (e_codes,), (e_logits,) = engine.gpt_generate([prompt], n, 10.0, forbid_stop_before=n, return_logits=True)
+    agree = int((e_codes == o_codes).sum())
+    err = float(np.abs(e_logits - o_logits).max()) if agree == n else float("nan")
+    print(f"strict fp32 full size: {agree}/{n} tokens identical, max |logit err| {err:.2e}, timing {engine.gpt_last_timing()}")
+    assert np.array_equal(e_codes, o_codes)
+    assert err <= 5e-4
