@@ -108,7 +108,9 @@ int idx_gpt_init(idx_engine* e, const idx_gpt_config* cfg);
  * processor order fixed at :900-905,1019-1047.                                      */
 typedef struct {
   int32_t do_sample;            /* 0: greedy argmax                                  */
-  int32_t num_beams;            /* 1 (beam-sample > 1 not in this round)             */
+  int32_t num_beams;            /* 1, or 2..4: beam search (do_sample = 1: beam-sample,
+                                   the reference default num_beams = 3); each request
+                                   then occupies num_beams rows: nreq * num_beams <= 8 */
   int32_t top_k;                /* 0 = off                                           */
   float top_p;                  /* 1.0 = off                                         */
   float temperature;            /* 1.0 = off                                         */
@@ -129,7 +131,8 @@ typedef struct {
   int32_t* codes_out;       /* [max_new_tokens] generated codes, stop token included  */
   int32_t* n_codes_out;     /* number of codes written                                */
   float* logits_out;        /* optional [max_new_tokens, number_mel_codes] f32 of the
-                               processed step logits (tests); NULL to skip            */
+                               raw step logits (tests); NULL to skip.  With
+                               num_beams > 1: [max_new_tokens, num_beams, codes]      */
   const int32_t* forced_codes; /* optional teacher forcing: feed these codes instead of
                                the sampled ones (tests); NULL for free running        */
 } idx_gpt_request;
@@ -174,6 +177,14 @@ int idx_emo_init(idx_engine* e, const idx_emo_config* cfg);
  * cache the result per (speaker, emotion, alpha) — the reference recomputes it per segment (trap P11).   */
 int idx_merge_emovec(idx_engine* e, const float* spk_feats, int Ts, const float* emo_feats, int Te,
                      float alpha, float* emo_vec_out);
+
+/* Beam search trace of the last idx_gpt_generate call with num_beams > 1 (tests, debugging): for every step and
+ * beam slot the (parent beam, token) chosen by BeamSearchScorer.process
+ * (gpt/transformers_beam_search.py:215-320) and the running beam score; the score of the returned hypothesis
+ * (BeamSearchScorer.finalize :322-420).
+ *   parents_tokens [max_steps][num_beams][2] i32, scores [max_steps][num_beams] f32 (either may be NULL)    */
+int idx_gpt_beam_trace(const idx_engine* e, int utterance, int32_t* parents_tokens, float* scores,
+                       int max_steps, int32_t* steps_out, double* final_score);
 
 /* Timing of the last generate call, measured with CUDA events on the engine stream:
  * out[0] = prefill ms, out[1] = decode ms, out[2] = decode steps,

@@ -97,6 +97,11 @@ struct GptParams {
   const float* prompt;  // [rows][D] f32
   const PrefillTile* tiles;
   unsigned* barrier;    // grid barrier counter (zeroed before each launch)
+  // beam search (beam_step_kernel runs between single-step launches)
+  int ext_sample;       // 1: leave the logits in p.logits and skip the sampling phase
+  int beams;            // rows per utterance
+  int phys_stride;
+  const unsigned char* phys;   // [8][phys_stride]: cache slot of generated position t of row b's lineage, or null
   long long* prof;      // optional: globaltimer stamps of CTA 0 for the last step of the launch
 };
 
@@ -633,14 +638,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
             float m = -INFINITY, lsum = 0.f, ov[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) ov[i] = 0.f;
-            const size_t cbase = ((size_t)l * p.nseq + row_seq[b]) * p.maxpos;
+            // beam search: prompt positions live in the utterance's first slot, generated ones where p.phys says
+            const int plen_b = p.phys ? __ldg(p.prompt_len + b) : 0x7fffffff;
+            const int base_seq = p.phys ? (b / p.beams) * p.beams : row_seq[b];
+            const unsigned char* phys_b = p.phys ? p.phys + (size_t)b * p.phys_stride : nullptr;
             for (int j0 = k0 + warp * 4; j0 < k1; j0 += NCW * 4) {
               const int j = j0 + g4;
               const bool valid = j < k1;
               float s = 0.f;
               uint4 vv = make_uint4(0, 0, 0, 0);
               if (valid) {
-                const size_t off = (cbase + j) * D + h * HD + sub * 8;
+                const int sj = (j < plen_b) ? base_seq : (int)phys_b[j - plen_b];
+                const size_t off = ((((size_t)l * p.nseq + sj) * p.maxpos) + j) * D + h * HD + sub * 8;
                 uint4 kk = __ldcg((const uint4*)(p.kc + off));
                 vv = __ldcg((const uint4*)(p.vc + off));
                 s = qv[0] * lo_bf(kk.x) + qv[1] * hi_bf(kk.x) + qv[2] * lo_bf(kk.y) +
@@ -835,7 +844,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
 
         // ---------------- sampling: CTA b handles sequence b ----------------
         prefetch_ln(0, p.ln1_w, p.ln1_b);  // layer 0 of the next step (buffer A is free again)
-        if (cta < p.B) {
+        if (cta < p.B && !p.ext_sample) {
           const int b = cta;
           const int k = p.step0 + step;
           const float* lg = p.logits + (size_t)b * V;
@@ -1231,6 +1240,316 @@ __global__ void strict_sample_kernel(const float* logits, unsigned* seen, int V,
   }
 }
 
+
+// ============================================================================================
+// Beam-sample (the reference's default decoding mode: num_beams = 3, do_sample = True).
+// `GenerationMixin._beam_search` transformers_generation_utils.py:3325-3609 + `BeamSearchScorer.process`
+// transformers_beam_search.py:215-320 + `BeamHypotheses` :930-1010, one CTA per utterance, run between
+// single-step launches of the fused kernel (which then skips its own sampling phase: ext_sample).
+// The beams are rows u*m .. u*m+m-1 of the fused kernel; instead of HF's index_select of the KV cache, row i
+// keeps writing into its own cache slot and `phys[i][t]` names the slot that holds generated position t of its
+// lineage (prompt positions live once, in the utterance's first slot).
+// RNG contract (oracle/beam.py): 2m successive draws without replacement by inverse CDF over the
+// union of the kept candidates (beam-major, descending score), Philox counter (step, 0x10000 + 16 u + draw).
+// ============================================================================================
+struct BeamParams {
+  const float* logits;     // [8][V]
+  int V, m, k, max_new, stop_tok, forbid_stop_before, top_k, hist_stride;
+  float rep_penalty, inv_temp, top_p;
+  double length_penalty;
+  unsigned long long seed;
+  int do_sample;
+  float* beam_scores;                              // [8]
+  const unsigned* seen_cur; unsigned* seen_nxt;    // [8][wv]
+  const int* hist_cur; int* hist_nxt;              // [8][hist_stride]
+  const unsigned char* phys_cur; unsigned char* phys_nxt;   // [8][hist_stride]
+  int* tok;                                        // [8]
+  double* hyp_score;  // [nutt][m+1]
+  int* hyp_len;       // [nutt][m+1]
+  int* hyp_tok;       // [nutt][m+1][hist_stride]
+  int* hyp_order;     // [nutt][m+1] physical slots in list order
+  int* nhyp;          // [nutt]
+  double* worst;      // [nutt]
+  int* done_u;        // [nutt]
+  float* ldump;       // [max_new][8][V] or null
+  int* trace_pt;      // [max_new][8][2] or null
+  float* trace_sc;    // [max_new][8] or null
+};
+
+constexpr int BEAM_MAX = 4;
+
+__global__ void __launch_bounds__(256) beam_step_kernel(const BeamParams p) {
+  constexpr int VPT = 40;
+  __shared__ float red[16];
+  __shared__ int redi[16];
+  __shared__ float cs[BEAM_MAX][64];     // processed score (+ beam score after top-p)
+  __shared__ int ci[BEAM_MAX][64];
+  __shared__ int keepn[BEAM_MAX];
+  __shared__ float nb_score[BEAM_MAX];
+  __shared__ int nb_tok[BEAM_MAX], nb_par[BEAM_MAX];
+  __shared__ int sh_done;
+  const int u = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int V = p.V, m = p.m, k = p.k, wv = (V + 31) / 32, hs = p.hist_stride;
+  const int r0 = u * m;
+
+  if (p.done_u[u]) {
+    // finished utterance: identity reorder, pad token (transformers_beam_search.py:258-266)
+    for (int i = 0; i < m; ++i) {
+      const int r = r0 + i;
+      for (int t = tid; t <= k; t += 256) {
+        p.phys_nxt[r * hs + t] = p.phys_cur[r * hs + t];
+        if (t < k) p.hist_nxt[r * hs + t] = p.hist_cur[r * hs + t];
+      }
+      for (int t = tid; t < wv; t += 256) p.seen_nxt[(size_t)r * wv + t] = p.seen_cur[(size_t)r * wv + t];
+      if (tid == 0) {
+        p.hist_nxt[r * hs + k] = p.stop_tok;
+        p.phys_nxt[r * hs + k + 1] = (unsigned char)r;
+        p.tok[r] = p.stop_tok;
+      }
+    }
+    return;
+  }
+
+  auto block_max = [&](float v) {
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float r = red[0];
+    for (int w = 1; w < 8; ++w) r = fmaxf(r, red[w]);
+    return r;
+  };
+  auto block_sum = [&](float v) {
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float r = 0.f;
+    for (int w = 0; w < 8; ++w) r += red[w];
+    return r;
+  };
+
+  // ---- phase A: per beam, processed scores and the kept candidate list ----
+  for (int j = 0; j < m; ++j) {
+    const int r = r0 + j;
+    const float* lg = p.logits + (size_t)r * V;
+    const unsigned* seen = p.seen_cur + (size_t)r * wv;
+    float sv[VPT];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int q = 0; q < VPT; ++q) {
+      const int i = tid + q * 256;
+      sv[q] = (i < V) ? __ldcg(lg + i) : -INFINITY;
+      mx = fmaxf(mx, sv[q]);
+    }
+    if (p.ldump)
+      for (int q = 0; q < VPT; ++q) {
+        const int i = tid + q * 256;
+        if (i < V) p.ldump[((size_t)k * 8 + r) * V + i] = sv[q];
+      }
+    mx = block_max(mx);
+    float se = 0.f;
+#pragma unroll
+    for (int q = 0; q < VPT; ++q)
+      if (tid + q * 256 < V) se += expf(sv[q] - mx);
+    se = block_sum(se);
+    const float lse = mx + logf(se);
+#pragma unroll
+    for (int q = 0; q < VPT; ++q) {
+      const int i = tid + q * 256;
+      if (i < V) {
+        float s = sv[q] - lse;                                             // log_softmax
+        if ((seen[i >> 5] >> (i & 31)) & 1u) s = (s < 0.f) ? s * p.rep_penalty : s / p.rep_penalty;
+        if (i == p.stop_tok && k < p.forbid_stop_before) s = -INFINITY;
+        sv[q] = s * p.inv_temp;
+      }
+    }
+    auto block_argmax = [&](float& bestv, int& besti) {
+      float best = -INFINITY;
+      int bi = 0x7fffffff;
+#pragma unroll
+      for (int q = 0; q < VPT; ++q) {
+        const int i = tid + q * 256;
+        if (sv[q] > best || (sv[q] == best && i < bi && sv[q] > -INFINITY)) { best = sv[q]; bi = i; }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const float b2 = __shfl_xor_sync(0xffffffffu, best, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (b2 > best || (b2 == best && i2 < bi)) { best = b2; bi = i2; }
+      }
+      __syncthreads();
+      if (lane == 0) { red[warp] = best; redi[warp] = bi; }
+      __syncthreads();
+      for (int w = 0; w < 8; ++w)
+        if (w == 0 || red[w] > best || (red[w] == best && redi[w] < bi)) { best = red[w]; bi = redi[w]; }
+      bestv = best; besti = bi;
+    };
+    float best; int besti;
+    block_argmax(best, besti);
+    const int kk = (p.top_k > 0) ? min(max(p.top_k, 2), 64) : 64;      // min_tokens_to_keep = 2 with beams
+    int nc = 0;
+    float kth = best;
+    while (nc < 64 && best > -INFINITY && (nc < kk || best == kth)) {
+      if (tid == 0) { cs[j][nc] = best; ci[j][nc] = besti; }
+      if (nc < kk) kth = best;
+      ++nc;
+#pragma unroll
+      for (int q = 0; q < VPT; ++q)
+        if (tid + q * 256 == besti) sv[q] = -INFINITY;
+      block_argmax(best, besti);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int keep = nc;
+      if (p.top_p < 1.0f) {
+        float ev[64];
+        const float m0 = cs[j][0];
+        float tot = 0.f;
+        for (int i = 0; i < nc; ++i) { ev[i] = expf(cs[j][i] - m0); tot += ev[i]; }
+        float tail = 0.f;
+        for (int i = nc - 1; i >= 2; --i) {
+          tail += ev[i] / tot;
+          if (tail <= 1.0f - p.top_p) keep = i; else break;
+        }
+      }
+      keepn[j] = keep;
+      const float bsc = p.beam_scores[r];
+      for (int i = 0; i < keep; ++i) cs[j][i] += bsc;
+    }
+    __syncthreads();
+  }
+
+  // ---- phase B (thread 0): union -> 2m draws without replacement -> sort -> scorer.process ----
+  if (tid == 0) {
+    float w[BEAM_MAX * 64];
+    unsigned char used[BEAM_MAX * 64];
+    int ub[BEAM_MAX + 1];
+    ub[0] = 0;
+    for (int j = 0; j < m; ++j) ub[j + 1] = ub[j] + keepn[j];
+    const int nu = ub[m];
+    auto usc = [&](int i) { int j = 0; while (i >= ub[j + 1]) ++j; return cs[j][i - ub[j]]; };
+    auto utok = [&](int i) { int j = 0; while (i >= ub[j + 1]) ++j; return ci[j][i - ub[j]]; };
+    auto upar = [&](int i) { int j = 0; while (i >= ub[j + 1]) ++j; return j; };
+    float umax = -INFINITY;
+    for (int i = 0; i < nu; ++i) umax = fmaxf(umax, usc(i));
+    for (int i = 0; i < nu; ++i) { w[i] = expf(usc(i) - umax); used[i] = 0; }
+    int picks[2 * BEAM_MAX];
+    const int nd = 2 * m;
+    for (int d = 0; d < nd; ++d) {
+      float tot = 0.f;
+      for (int i = 0; i < nu; ++i) if (!used[i]) tot += w[i];
+      int pick = -1;
+      if (tot > 0.f && p.do_sample) {      // do_sample = 0: plain beam search = torch.topk of the union (:3527-3530)
+        unsigned rnd4[4];
+        philox4x32_10(p.seed, (unsigned)k, 0x10000u + 16u * (unsigned)u + (unsigned)d, rnd4);
+        const float uu = (float)(rnd4[0] >> 8) * (1.0f / 16777216.0f) * tot;
+        float acc = 0.f;
+        int last = -1;
+        for (int i = 0; i < nu; ++i) {
+          if (used[i] || w[i] == 0.f) continue;
+          acc += w[i]; last = i;
+          if (uu < acc) { pick = i; break; }
+        }
+        if (pick < 0) pick = last;
+      }
+      if (pick < 0) {       // fewer positive-probability candidates than draws: best remaining score, lowest index
+        for (int i = 0; i < nu; ++i)
+          if (!used[i] && (pick < 0 || usc(i) > usc(pick))) pick = i;
+      }
+      used[pick] = 1;
+      picks[d] = pick;
+    }
+    for (int a = 1; a < nd; ++a) {          // stable insertion sort, descending score
+      const int x = picks[a];
+      int b = a - 1;
+      while (b >= 0 && usc(picks[b]) < usc(x)) { picks[b + 1] = picks[b]; --b; }
+      picks[b + 1] = x;
+    }
+    // scorer.process
+    const int gen_len = k + 1;
+    const double lp_den = pow((double)gen_len, p.length_penalty);
+    double* hs_ = p.hyp_score + (size_t)u * (m + 1);
+    int* hl = p.hyp_len + (size_t)u * (m + 1);
+    int* ho = p.hyp_order + (size_t)u * (m + 1);
+    int nh = p.nhyp[u];
+    double worst = p.worst[u];
+    int nbn = 0;
+    for (int rank = 0; rank < nd && nbn < m; ++rank) {
+      const int i = picks[rank];
+      const int tk = utok(i), par = upar(i);
+      const float sc = usc(i);
+      if (tk == p.stop_tok) {
+        if (rank >= m) continue;
+        const double score = (double)sc / lp_den;
+        if (nh < m || score > worst) {
+          // free physical slot = the one not in the order list
+          bool taken[BEAM_MAX + 1];
+          for (int q = 0; q <= m; ++q) taken[q] = false;
+          for (int q = 0; q < nh; ++q) taken[ho[q]] = true;
+          int slot = 0;
+          while (taken[slot]) ++slot;
+          hs_[slot] = score;
+          hl[slot] = k;
+          const int* src = p.hist_cur + (size_t)(r0 + par) * hs;
+          int* dst = p.hyp_tok + ((size_t)u * (m + 1) + slot) * hs;
+          for (int t = 0; t < k; ++t) dst[t] = src[t];
+          ho[nh++] = slot;
+          if (nh > m) {
+            int lo = 0;                         // smallest (score, list index)
+            for (int q = 1; q < nh; ++q) if (hs_[ho[q]] < hs_[ho[lo]]) lo = q;
+            for (int q = lo; q + 1 < nh; ++q) ho[q] = ho[q + 1];
+            --nh;
+            double w2 = hs_[ho[0]];
+            for (int q = 1; q < nh; ++q) w2 = fmin(w2, hs_[ho[q]]);
+            worst = w2;
+          } else {
+            worst = fmin(score, worst);
+          }
+        }
+      } else {
+        nb_score[nbn] = sc; nb_tok[nbn] = tk; nb_par[nbn] = par;
+        ++nbn;
+      }
+    }
+    // (nbn == m always: every beam keeps >= 2 candidates, so at most m of the 2m draws can be the stop token)
+    p.nhyp[u] = nh;
+    p.worst[u] = worst;
+    int done = 0;
+    if (nh >= m) {
+      const double highest = (double)usc(picks[0]) / lp_den;
+      done = worst >= highest;
+    }
+    sh_done = done;
+    p.done_u[u] = done;
+  }
+  __syncthreads();
+
+  // ---- phase C: reorder histories, cache maps and repetition bitmaps; publish the next inputs ----
+  for (int i = 0; i < m; ++i) {
+    const int r = r0 + i, pr = r0 + nb_par[i], tk = nb_tok[i];
+    for (int t = tid; t <= k; t += 256) {
+      p.phys_nxt[r * hs + t] = p.phys_cur[pr * hs + t];
+      if (t < k) p.hist_nxt[r * hs + t] = p.hist_cur[pr * hs + t];
+    }
+    for (int t = tid; t < wv; t += 256) {
+      unsigned v = p.seen_cur[(size_t)pr * wv + t];
+      if (t == (tk >> 5)) v |= 1u << (tk & 31);
+      p.seen_nxt[(size_t)r * wv + t] = v;
+    }
+    if (tid == 0) {
+      p.hist_nxt[r * hs + k] = tk;
+      p.phys_nxt[r * hs + k + 1] = (unsigned char)r;
+      p.tok[r] = tk;
+      p.beam_scores[r] = nb_score[i];
+      if (p.trace_pt) {
+        p.trace_pt[((size_t)k * 8 + r) * 2] = nb_par[i];
+        p.trace_pt[((size_t)k * 8 + r) * 2 + 1] = tk;
+        p.trace_sc[(size_t)k * 8 + r] = nb_score[i];
+      }
+    }
+  }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------ host state --
@@ -1238,6 +1557,7 @@ struct GptStrict;
 struct GptState {
   idx_gpt_config cfg;
   GptStrict* strict = nullptr;   // fp32 per-op path (weights_bf16 = 0)
+  struct BeamTrace* beam_trace = nullptr;
   int G = 0, FF = 0, nst1 = 0, nst8 = 0, bias_cap = 0, ocap = 0, bar_flavor = 0;
   size_t smem1 = 0, smem8 = 0;
   __nv_bfloat16* wstream = nullptr;
@@ -1260,9 +1580,11 @@ struct GptState {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
 };
 
+static void beam_trace_free(GptState* g);
 void gpt_destroy(GptState* g) {
   if (!g) return;
   delete g->strict;
+  beam_trace_free(g);
   for (void* p : g->owned) cudaFree(p);
   if (g->ev0) cudaEventDestroy(g->ev0);
   if (g->ev1) cudaEventDestroy(g->ev1);
@@ -1634,6 +1956,219 @@ static void fill_common(idx_engine* e, GptState* g, GptParams& p) {
   p.prof = g->prof_on ? g->prof : nullptr;
 }
 
+// ------------------------------------------------------------------ beam-sample host driver --
+struct BeamTrace {
+  int nutt = 0, m = 0, steps = 0, max_new = 0;
+  std::vector<int> pt;        // [steps][8][2] (parent, token)
+  std::vector<float> sc;      // [steps][8]
+  double final_score[8] = {0};
+};
+
+static void beam_trace_free(GptState* g) { delete g->beam_trace; g->beam_trace = nullptr; }
+
+static void beam_generate(idx_engine* e, GptState* g, const idx_gpt_request* reqs, int nreq, const idx_sampling* sp) {
+  const idx_gpt_config& c = g->cfg;
+  const int D = c.model_dim, V = c.number_mel_codes, max_new = sp->max_new_tokens, m = sp->num_beams;
+  IDX_CHECK(m >= 2 && m <= BEAM_MAX, IDX_ERR_ARG, "num_beams must be 1..4");
+  IDX_CHECK(nreq * m <= 8 && nreq * m <= c.max_batch, IDX_ERR_ARG,
+            "beam search needs num_beams rows per request: nreq * num_beams must be <= max_batch (<= 8)");
+  IDX_CHECK(V <= 40 * 256, IDX_ERR_ARG, "vocabulary too large for the device sampler");
+  cudaStream_t st = e->stream;
+  const int rows = nreq * m, wv = (V + 31) / 32, hs = max_new + 2;
+  bool want_logits = false;
+  for (int i = 0; i < nreq; ++i) want_logits |= reqs[i].logits_out != nullptr;
+
+  int total_rows = 0;
+  std::vector<int> plen(8, 0), row0(8, 0), plen_rows(8, 0);
+  for (int i = 0; i < nreq; ++i) {
+    IDX_CHECK(reqs[i].prompt_emb && reqs[i].prompt_len >= 1 && reqs[i].prompt_len <= c.max_prompt, IDX_ERR_ARG, "bad prompt");
+    IDX_CHECK(reqs[i].prompt_len + max_new + 1 <= g->maxpos, IDX_ERR_ARG, "KV cache too small");
+    IDX_CHECK(!reqs[i].forced_codes, IDX_ERR_ARG, "forced_codes is not defined for beam search");
+    plen[i] = reqs[i].prompt_len;
+    row0[i] = total_rows;
+    total_rows += plen[i];
+    for (int j = 0; j < m; ++j) plen_rows[i * m + j] = plen[i];
+  }
+  std::vector<PrefillTile> tiles;
+  for (int i = 0; i < nreq; ++i)
+    for (int p0 = 0; p0 < plen[i]; p0 += 8)
+      tiles.push_back({i * m, p0, std::min(8, plen[i] - p0), row0[i] + p0});     // prompt KV lives in the first beam's slot
+
+  size_t need = (size_t)(total_rows + 8) * D * 4 + tiles.size() * sizeof(PrefillTile) + 2 * 8 * (size_t)wv * 4 +
+                2 * 8 * (size_t)hs * 4 + 2 * 8 * (size_t)hs + (size_t)nreq * (m + 1) * hs * 4 + 8 * (size_t)max_new * 12 + (1 << 16);
+  if (want_logits) need += (size_t)max_new * 8 * V * 4;
+  e->ensure_arena(need + (1 << 20));
+  e->arena.reset();
+  float* d_prompt = e->arena.get<float>((size_t)(total_rows + 8) * D);
+  PrefillTile* d_tiles = e->arena.get<PrefillTile>(tiles.size());
+  unsigned* d_seen[2] = {e->arena.get<unsigned>(8 * (size_t)wv), e->arena.get<unsigned>(8 * (size_t)wv)};
+  int* d_hist[2] = {e->arena.get<int>(8 * (size_t)hs), e->arena.get<int>(8 * (size_t)hs)};
+  unsigned char* d_phys[2] = {e->arena.get<unsigned char>(8 * (size_t)hs + 16), e->arena.get<unsigned char>(8 * (size_t)hs + 16)};
+  float* d_bscore = e->arena.get<float>(8);
+  double* d_hscore = e->arena.get<double>((size_t)nreq * (m + 1) + 2);
+  double* d_worst = e->arena.get<double>(nreq + 2);
+  int* d_hlen = e->arena.get<int>((size_t)nreq * (m + 1));
+  int* d_horder = e->arena.get<int>((size_t)nreq * (m + 1));
+  int* d_nhyp = e->arena.get<int>(nreq);
+  int* d_done = e->arena.get<int>(nreq);
+  int* d_htok = e->arena.get<int>((size_t)nreq * (m + 1) * hs);
+  int* d_trpt = e->arena.get<int>((size_t)max_new * 16);
+  float* d_trsc = e->arena.get<float>((size_t)max_new * 8);
+  float* d_ldump = want_logits ? e->arena.get<float>((size_t)max_new * 8 * V) : nullptr;
+
+  IDX_CUDA(cudaEventRecord(g->ev0, st));
+  for (int i = 0; i < nreq; ++i)
+    idx_to_device(e, d_prompt + (size_t)row0[i] * D, reqs[i].prompt_emb, (size_t)plen[i] * D * 4);
+  IDX_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(PrefillTile), cudaMemcpyHostToDevice, st));
+  {
+    std::vector<int> h_tok(8, c.start_mel_token), zeros(16, 0);
+    std::vector<unsigned> h_seen(8 * (size_t)wv, 0u);
+    std::vector<float> h_bs(8, -1e9f);
+    std::vector<unsigned char> h_phys(8 * (size_t)hs + 16, 0);
+    std::vector<double> h_worst(nreq + 2, 1e9);
+    for (int r = 0; r < rows; ++r) {
+      h_seen[(size_t)r * wv + (1 >> 5)] |= 1u << 1;                                      // trap P2
+      h_seen[(size_t)r * wv + (c.start_mel_token >> 5)] |= 1u << (c.start_mel_token & 31);
+      if (r % m == 0) h_bs[r] = 0.f;          // only the first beam carries probability mass at step 0 (:3408-3410)
+      h_phys[(size_t)r * hs] = (unsigned char)r;
+    }
+    IDX_CUDA(cudaMemcpyAsync(g->tok, h_tok.data(), 32, cudaMemcpyHostToDevice, st));
+    IDX_CUDA(cudaMemcpyAsync(g->finished, zeros.data(), 32, cudaMemcpyHostToDevice, st));
+    IDX_CUDA(cudaMemcpyAsync(g->done, zeros.data(), 4, cudaMemcpyHostToDevice, st));
+    IDX_CUDA(cudaMemcpyAsync(g->prompt_len, plen_rows.data(), 32, cudaMemcpyHostToDevice, st));
+    IDX_CUDA(cudaMemcpyAsync(d_seen[0], h_seen.data(), h_seen.size() * 4, cudaMemcpyHostToDevice, st));
+    IDX_CUDA(cudaMemcpyAsync(d_bscore, h_bs.data(), 32, cudaMemcpyHostToDevice, st));
+    IDX_CUDA(cudaMemcpyAsync(d_phys[0], h_phys.data(), h_phys.size(), cudaMemcpyHostToDevice, st));
+    IDX_CUDA(cudaMemcpyAsync(d_worst, h_worst.data(), h_worst.size() * 8, cudaMemcpyHostToDevice, st));
+    IDX_CUDA(cudaMemsetAsync(d_nhyp, 0, nreq * 4, st));
+    IDX_CUDA(cudaMemsetAsync(d_done, 0, nreq * 4, st));
+    IDX_CUDA(cudaMemsetAsync(d_hlen, 0, (size_t)nreq * (m + 1) * 4, st));
+    IDX_CUDA(cudaStreamSynchronize(st));
+  }
+
+  GptParams p;
+  fill_common(e, g, p);
+  p.B = 8; p.mode = 0; p.nsteps = (int)tiles.size(); p.prompt = d_prompt; p.tiles = d_tiles;
+  p.max_new = max_new; p.rep_penalty = sp->repetition_penalty;
+  launch_fused_bt(e, g, p, 8);
+  IDX_CUDA(cudaEventRecord(g->ev1, st));
+
+  fill_common(e, g, p);
+  p.B = rows; p.mode = 1; p.max_new = max_new; p.ext_sample = 1; p.beams = m; p.phys_stride = hs;
+  BeamParams bp;
+  memset(&bp, 0, sizeof(bp));
+  bp.logits = g->logits; bp.V = V; bp.m = m; bp.max_new = max_new; bp.stop_tok = c.stop_mel_token;
+  bp.forbid_stop_before = sp->forbid_stop_before; bp.hist_stride = hs;
+  bp.rep_penalty = sp->repetition_penalty;
+  bp.do_sample = sp->do_sample;
+  bp.top_k = sp->do_sample ? sp->top_k : 0;
+  bp.top_p = sp->do_sample ? sp->top_p : 1.0f;
+  bp.inv_temp = (sp->do_sample && sp->temperature > 0.f) ? 1.0f / sp->temperature : 1.0f;
+  bp.length_penalty = sp->length_penalty; bp.seed = sp->seed;
+  bp.beam_scores = d_bscore; bp.tok = g->tok;
+  bp.hyp_score = d_hscore; bp.hyp_len = d_hlen; bp.hyp_tok = d_htok; bp.hyp_order = d_horder; bp.nhyp = d_nhyp;
+  bp.worst = d_worst; bp.done_u = d_done; bp.ldump = d_ldump; bp.trace_pt = d_trpt; bp.trace_sc = d_trsc;
+  int* h_done = (int*)e->pinned_buf(64);
+  int steps = 0;
+  for (int k = 0; k < max_new; ++k) {
+    const int cur = k & 1, nxt = cur ^ 1;
+    p.step0 = k; p.nsteps = 1; p.phys = d_phys[cur];
+    launch_fused_bt(e, g, p, 8);
+    bp.k = k;
+    bp.seen_cur = d_seen[cur]; bp.seen_nxt = d_seen[nxt];
+    bp.hist_cur = d_hist[cur]; bp.hist_nxt = d_hist[nxt];
+    bp.phys_cur = d_phys[cur]; bp.phys_nxt = d_phys[nxt];
+    beam_step_kernel<<<nreq, 256, 0, st>>>(bp);
+    IDX_CUDA(cudaGetLastError());
+    e->launches++;
+    g->last_launches++;
+    steps = k + 1;
+    if ((k & 7) == 7 || k + 1 == max_new) {
+      IDX_CUDA(cudaMemcpyAsync(h_done, d_done, nreq * 4, cudaMemcpyDeviceToHost, st));
+      IDX_CUDA(cudaStreamSynchronize(st));
+      bool all = true;
+      for (int i = 0; i < nreq; ++i) all &= h_done[i] != 0;
+      if (all) break;
+    }
+  }
+  IDX_CUDA(cudaEventRecord(g->ev2, st));
+
+  // ---- BeamSearchScorer.finalize (transformers_beam_search.py:322-420) on the host ----
+  const int fin = steps & 1;      // buffers written by the last beam step
+  std::vector<int> h_hist(8 * (size_t)hs), h_hlen((size_t)nreq * (m + 1)), h_horder((size_t)nreq * (m + 1)), h_nhyp(nreq), h_dn(nreq);
+  std::vector<int> h_htok((size_t)nreq * (m + 1) * hs);
+  std::vector<double> h_hscore((size_t)nreq * (m + 1) + 2);
+  std::vector<float> h_bs(8);
+  BeamTrace* tr = g->beam_trace ? g->beam_trace : (g->beam_trace = new BeamTrace());
+  tr->nutt = nreq; tr->m = m; tr->steps = steps; tr->max_new = max_new;
+  tr->pt.assign((size_t)steps * 16, 0); tr->sc.assign((size_t)steps * 8, 0.f);
+  IDX_CUDA(cudaMemcpyAsync(h_hist.data(), d_hist[fin], h_hist.size() * 4, cudaMemcpyDeviceToHost, st));
+  IDX_CUDA(cudaMemcpyAsync(h_hlen.data(), d_hlen, h_hlen.size() * 4, cudaMemcpyDeviceToHost, st));
+  IDX_CUDA(cudaMemcpyAsync(h_horder.data(), d_horder, h_horder.size() * 4, cudaMemcpyDeviceToHost, st));
+  IDX_CUDA(cudaMemcpyAsync(h_nhyp.data(), d_nhyp, nreq * 4, cudaMemcpyDeviceToHost, st));
+  IDX_CUDA(cudaMemcpyAsync(h_dn.data(), d_done, nreq * 4, cudaMemcpyDeviceToHost, st));
+  IDX_CUDA(cudaMemcpyAsync(h_htok.data(), d_htok, h_htok.size() * 4, cudaMemcpyDeviceToHost, st));
+  IDX_CUDA(cudaMemcpyAsync(h_hscore.data(), d_hscore, (size_t)nreq * (m + 1) * 8, cudaMemcpyDeviceToHost, st));
+  IDX_CUDA(cudaMemcpyAsync(h_bs.data(), d_bscore, 32, cudaMemcpyDeviceToHost, st));
+  IDX_CUDA(cudaMemcpyAsync(tr->pt.data(), d_trpt, tr->pt.size() * 4, cudaMemcpyDeviceToHost, st));
+  IDX_CUDA(cudaMemcpyAsync(tr->sc.data(), d_trsc, tr->sc.size() * 4, cudaMemcpyDeviceToHost, st));
+  IDX_CUDA(cudaStreamSynchronize(st));
+  int maxn = 0;
+  for (int u = 0; u < nreq; ++u) {
+    struct Hyp { double score; const int* tok; int len; };
+    std::vector<Hyp> list;
+    for (int q = 0; q < h_nhyp[u]; ++q) {
+      const int slot = h_horder[(size_t)u * (m + 1) + q];
+      list.push_back({h_hscore[(size_t)u * (m + 1) + slot], &h_htok[((size_t)u * (m + 1) + slot) * hs], h_hlen[(size_t)u * (m + 1) + slot]});
+    }
+    double worst = 1e9;
+    for (auto& h : list) worst = std::min(worst, h.score);
+    if (!h_dn[u]) {
+      for (int j = 0; j < m; ++j) {           // add the live beams (:345-356); generated_len = steps
+        const double score = (double)h_bs[u * m + j] / std::pow((double)steps, (double)sp->length_penalty);
+        if ((int)list.size() < m || score > worst) {
+          list.push_back({score, &h_hist[(size_t)(u * m + j) * hs], steps});
+          if ((int)list.size() > m) {
+            size_t lo = 0;
+            for (size_t q = 1; q < list.size(); ++q) if (list[q].score < list[lo].score) lo = q;
+            list.erase(list.begin() + lo);
+            worst = 1e9;
+            for (auto& h : list) worst = std::min(worst, h.score);
+          } else {
+            worst = std::min(worst, score);
+          }
+        }
+      }
+    }
+    // sorted(candidate_beams, key=score).pop(): the LAST of the maximal scores in list order
+    size_t best = 0;
+    for (size_t q = 1; q < list.size(); ++q) if (list[q].score >= list[best].score) best = q;
+    std::vector<int> codes(list[best].tok, list[best].tok + list[best].len);
+    if ((int)codes.size() < max_new) codes.push_back(c.stop_mel_token);
+    tr->final_score[u] = list[best].score;
+    maxn = std::max(maxn, (int)codes.size());
+    if (reqs[u].n_codes_out) *reqs[u].n_codes_out = (int)codes.size();
+    if (reqs[u].codes_out) {
+      IDX_CUDA(cudaMemcpyAsync(d_trpt, codes.data(), codes.size() * 4, cudaMemcpyHostToDevice, st));
+      IDX_CUDA(cudaStreamSynchronize(st));
+      idx_from_device(e, reqs[u].codes_out, d_trpt, codes.size() * 4);
+      IDX_CUDA(cudaStreamSynchronize(st));
+    }
+    if (reqs[u].logits_out) {
+      // [steps][m][V]: the raw logits every beam of this utterance saw at each step
+      for (int k = 0; k < steps; ++k)
+        idx_from_device(e, reqs[u].logits_out + ((size_t)k * m) * V, d_ldump + ((size_t)k * 8 + u * m) * V, (size_t)m * V * 4);
+    }
+  }
+  IDX_CUDA(cudaStreamSynchronize(st));
+  float ms01 = 0, ms12 = 0;
+  IDX_CUDA(cudaEventElapsedTime(&ms01, g->ev0, g->ev1));
+  IDX_CUDA(cudaEventElapsedTime(&ms12, g->ev1, g->ev2));
+  g->t_prefill_ms = ms01;
+  g->t_decode_ms = ms12;
+  g->last_steps = steps;
+}
+
 extern "C" int idx_gpt_generate(idx_engine* e, const idx_gpt_request* reqs, int nreq,
                                 const idx_sampling* sp) {
   IDX_API_BEGIN
@@ -1642,7 +2177,7 @@ extern "C" int idx_gpt_generate(idx_engine* e, const idx_gpt_request* reqs, int 
   GptState* g = e->gpt;
   const idx_gpt_config& c = g->cfg;
   IDX_CHECK(nreq <= c.max_batch, IDX_ERR_ARG, "nreq exceeds max_batch");
-  IDX_CHECK(sp->num_beams == 1, IDX_ERR_ARG, "beam-sample (num_beams > 1) is not built in this round");
+  IDX_CHECK(sp->num_beams >= 1, IDX_ERR_ARG, "num_beams must be >= 1");
   IDX_CHECK(c.number_mel_codes <= 40 * 256, IDX_ERR_ARG, "vocabulary too large for the device sampler");
   IDX_CHECK(sp->max_new_tokens >= 1 && sp->max_new_tokens + 2 <= c.max_mel_positions, IDX_ERR_ARG,
             "max_new_tokens must satisfy k+1 <= mel_pos rows - 1 (SURVEY A.3)");
@@ -1651,7 +2186,12 @@ extern "C" int idx_gpt_generate(idx_engine* e, const idx_gpt_request* reqs, int 
   const int BT = (nreq == 1) ? 1 : 8;
   g->last_launches = 0;
   if (g->strict) {
+    IDX_CHECK(sp->num_beams == 1, IDX_ERR_ARG, "the strict fp32 path decodes one sequence at a time (num_beams = 1)");
     strict_generate(e, g, reqs, nreq, sp);
+    return IDX_OK;
+  }
+  if (sp->num_beams > 1) {
+    beam_generate(e, g, reqs, nreq, sp);
     return IDX_OK;
   }
 
@@ -1812,4 +2352,24 @@ extern "C" int idx_gpt_profile(idx_engine* e, int enable, int64_t* stamps_out, i
     IDX_CUDA(cudaMemcpy(stamps_out, g->prof, sizeof(long long) * (size_t)std::min(n, 320), cudaMemcpyDeviceToHost));
   }
   IDX_API_END(e)
+}
+
+extern "C" int idx_gpt_beam_trace(const idx_engine* e, int utterance, int32_t* parents_tokens, float* scores,
+                                  int max_steps, int32_t* steps_out, double* final_score) {
+  if (!e || !e->gpt || !e->gpt->beam_trace) return IDX_ERR_STATE;
+  const BeamTrace* t = e->gpt->beam_trace;
+  if (utterance < 0 || utterance >= t->nutt) return IDX_ERR_ARG;
+  const int n = std::min(max_steps, t->steps), m = t->m;
+  for (int k = 0; k < n; ++k)
+    for (int j = 0; j < m; ++j) {
+      const int r = utterance * m + j;
+      if (parents_tokens) {
+        parents_tokens[((size_t)k * m + j) * 2] = t->pt[((size_t)k * 8 + r) * 2];
+        parents_tokens[((size_t)k * m + j) * 2 + 1] = t->pt[((size_t)k * 8 + r) * 2 + 1];
+      }
+      if (scores) scores[(size_t)k * m + j] = t->sc[(size_t)k * 8 + r];
+    }
+  if (steps_out) *steps_out = t->steps;
+  if (final_score) *final_score = t->final_score[utterance];
+  return IDX_OK;
 }

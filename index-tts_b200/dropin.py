@@ -93,7 +93,7 @@ def load_reference_weights(engine: Engine, tts, max_batch: int = 1):
 def attach(tts, engine: Engine = None, device: int = 0):
     """Rebind the compute seams of a reference IndexTTS2 instance to the B200 engine (see module doc)."""
     engine = engine or Engine(device)
-    load_reference_weights(engine, tts)
+    load_reference_weights(engine, tts, max_batch=4)      # room for the default 3 beams
     dev = torch.device("cuda", engine.device)
     gpt = tts.gpt
 
@@ -104,12 +104,13 @@ def attach(tts, engine: Engine = None, device: int = 0):
         # same argument meaning as gpt/model_v2.py:716-825; emo_vec comes from merge_emovec (:833-838)
         if emo_vec is None or campplus_embedding is None:
             raise ValueError("the B200 path needs emo_vec and campplus_embedding (what infer_v2_5.py:759-791 passes)")
-        if hf.get("num_beams", 1) != 1:
-            raise NotImplementedError("beam-sample (num_beams > 1) is not built yet; pass num_beams=1 "
-                                      "(greedy or top-k/top-p sampling run on the device)")
+        nb = int(hf.get("num_beams", 1) or 1)
+        if nb > 4:
+            raise NotImplementedError("num_beams <= 4 (the reference default is 3)")
         sampling = dict(do_sample=bool(hf.get("do_sample", False)), top_k=int(hf.get("top_k", 0) or 0),
                         top_p=float(hf.get("top_p", 1.0)), temperature=float(hf.get("temperature", 1.0)),
-                        seed=int(torch.initial_seed() & 0x7fffffff))
+                        seed=int(torch.initial_seed() & 0x7fffffff), num_beams=nb,
+                        length_penalty=float(hf.get("length_penalty", 0.0)))
         lang = int(langs.reshape(-1)[0]) if langs is not None else 0
         outs = []
         for i in range(text_inputs.shape[0]):

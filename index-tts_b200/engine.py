@@ -135,6 +135,7 @@ def load_library(path: str = None):
                                            C.c_int, C.c_int, C.c_void_p]
     lib.idx_gpt_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.idx_gpt_profile.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.idx_gpt_beam_trace.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.idx_bigvgan_init.argtypes = [C.c_void_p, C.POINTER(BigvganConfig)]
     lib.idx_bigvgan_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.idx_antialias_snake.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -272,8 +273,8 @@ class Engine:
         keep = []
         codes = [np.zeros(max_new_tokens, dtype=np.int32) for _ in range(n)]
         ncodes = [np.zeros(1, dtype=np.int32) for _ in range(n)]
-        logits = [np.zeros((max_new_tokens, V), dtype=np.float32) if return_logits else None
-                  for _ in range(n)]
+        lshape = (max_new_tokens, V) if num_beams == 1 else (max_new_tokens, num_beams, V)
+        logits = [np.zeros(lshape, dtype=np.float32) if return_logits else None for _ in range(n)]
         for i, pr in enumerate(prompts):
             pr = _as_f32(pr)
             keep.append(pr)
@@ -294,8 +295,21 @@ class Engine:
         self._check(self.lib.idx_gpt_generate(self.h, reqs, n, C.byref(sp)), "idx_gpt_generate")
         out = [codes[i][: int(ncodes[i][0])].copy() for i in range(n)]
         if return_logits:
+            if num_beams > 1:
+                steps = self.gpt_last_timing()["steps"]
+                return out, [logits[i][:steps] for i in range(n)]
             return out, [logits[i][: int(ncodes[i][0])] for i in range(n)]
         return out
+
+    def gpt_beam_trace(self, utterance=0, max_steps=4096, num_beams=3):
+        """(parents [steps, m], tokens [steps, m], scores [steps, m], final_score) of the last beam-search call."""
+        pt = np.zeros((max_steps, num_beams, 2), dtype=np.int32)
+        sc = np.zeros((max_steps, num_beams), dtype=np.float32)
+        steps, fs = C.c_int32(0), C.c_double(0)
+        self._check(self.lib.idx_gpt_beam_trace(self.h, int(utterance), _ptr(pt), _ptr(sc), max_steps,
+                                                C.byref(steps), C.byref(fs)), "idx_gpt_beam_trace")
+        k = min(steps.value, max_steps)
+        return pt[:k, :, 0].copy(), pt[:k, :, 1].copy(), sc[:k].copy(), fs.value
 
     def gpt_last_timing(self):
         t = (C.c_double * 4)()

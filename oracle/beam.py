@@ -132,7 +132,7 @@ def beam_candidates(logits_row, seen, beam_score, k, p):
     return toks, [F(s[t] + F(beam_score)) for t in toks]
 
 
-def beam_draw(cands, m, V, seed, step, utt):
+def beam_draw(cands, m, V, seed, step, utt, do_sample=True):
     """Union of the beams' candidates → softmax → 2m draws without replacement → sort by score (descending, stable).
     Returns (scores, tokens, parents) of the 2m candidates (transformers_generation_utils.py:3505-3530)."""
     u_sc, u_tok, u_par = [], [], []
@@ -148,7 +148,7 @@ def beam_draw(cands, m, V, seed, step, utt):
             if not used[i]:
                 tot = F(tot + w[i])
         pick = -1
-        if tot > 0:
+        if tot > 0 and do_sample:              # do_sample=False: plain beam search, torch.topk of the union (:3527-3530)
             r0 = philox4x32_10(seed, step, 0x10000 + 16 * utt + d)[0]
             u = F(F(r0 >> 8) * F(1.0 / 16777216.0) * tot)
             acc = F(0)
@@ -184,10 +184,12 @@ def run_beam(logits_fn, p, max_new, utt=0):
     done = False
     trace = []
     steps = 0
+    do_sample = p.get("do_sample", True)
+    pc = p if do_sample else dict(p, temperature=1.0, top_k=0, top_p=1.0)      # warpers exist only when sampling
     for k in range(max_new):
         lg = logits_fn(k, parents, tokens)
-        cands = [beam_candidates(lg[j], seen[j], beam_scores[j], k, p) for j in range(m)]
-        sc, tk, pr = beam_draw(cands, m, lg.shape[-1], p["seed"], k, utt)
+        cands = [beam_candidates(lg[j], seen[j], beam_scores[j], k, pc) for j in range(m)]
+        sc, tk, pr = beam_draw(cands, m, lg.shape[-1], p["seed"], k, utt, do_sample)
         bs, bt, bp, done = scorer_process(hyps, seqs, sc, tk, pr, eos, k + 1)
         seqs = [seqs[q] + [t] for q, t in zip(bp, bt)]
         seen = [set(seen[q]) | {t} for q, t in zip(bp, bt)]

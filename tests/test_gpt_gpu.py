@@ -187,3 +187,86 @@ def test_strict_fp32_full_size_256_tokens_token_for_token(engine):
     print(f"strict fp32 full size: {agree}/{n} tokens identical, max |logit err| {err:.2e}, timing {engine.gpt_last_timing()}")
     assert np.array_equal(e_codes, o_codes)
     assert err <= 5e-4
+
+
+def _beam_params(cfg, **kw):
+    p = dict(num_beams=3, start=cfg["start_mel_token"], stop=cfg["stop_mel_token"], repetition_penalty=10.0,
+             temperature=0.8, top_k=30, top_p=0.8, length_penalty=0.0, seed=7, forbid_stop_before=0, do_sample=True)
+    p.update(kw)
+    return p
+
+
+def _check_beam_run(engine, cfg, prompt, n, p, utt=0, codes=None, lg=None):
+    """Replay the logits the engine's beams saw through the oracle's beam-sample logic: every (parent, token) choice,
+    the running scores, the termination step and the returned hypothesis must be identical."""
+    from oracle import beam
+    par, tok, sc, fs = engine.gpt_beam_trace(utt, num_beams=p["num_beams"])
+    rep = beam.run_beam(lambda k, pa, tk: lg[k], p, n, utt=utt)
+    # the host polls the done flags every 8 steps: after the scorer is done the engine may run a few pad steps
+    assert rep["steps"] <= len(par) < rep["steps"] + 8 or len(par) == n, (rep["steps"], len(par))
+    for k, (bp, bt, bs) in enumerate(rep["trace"]):
+        assert bp == par[k].tolist() and bt == tok[k].tolist(), (k, bp, par[k], bt, tok[k])
+        assert np.allclose(bs, sc[k], rtol=0, atol=2e-4), (k, bs, sc[k])
+    assert rep["codes"].tolist() == codes.tolist()
+    assert abs(rep["score"] - fs) <= 2e-4
+    return par, tok
+
+
+def test_beam_sample_default_mode_vs_oracle(engine):
+    """num_beams=3, do_sample=True — the `.infer()` default (transformers_generation_utils.py:3325-3609).  The engine
+    dumps the raw logits of every beam row at every step; (1) the oracle's restatement of log_softmax → processors →
+    joint multinomial → BeamSearchScorer, fed with those logits and the same Philox stream, reproduces every choice;
+    (2) the logits along the winning lineage equal the model's teacher-forced logits for that token sequence, i.e. the
+    KV-cache lineage map (instead of HF's index_select) is right."""
+    cfg, style, emo, text = small_case()
+    w = make_gpt_weights(cfg, seed=1234, bf16=True)
+    load_gpt(engine, cfg, w, max_batch=8)
+    prompt = prepare_gpt_inputs(w, style, r16(emo), text, lang=1, bf16=True).numpy()
+    n = 28
+    p = _beam_params(cfg)
+    kw = dict(do_sample=True, num_beams=3, top_k=30, top_p=0.8, temperature=0.8, seed=7, length_penalty=0.0)
+    (codes,), (lg,) = engine.gpt_generate([prompt], n, 10.0, return_logits=True, **kw)
+    par, tok = _check_beam_run(engine, cfg, prompt, n, p, 0, codes, lg)
+    # lineage of final beam 0
+    K = min(len(par), len(codes))
+    i = 0
+    toks, rows = [0] * K, [0] * K
+    for k in range(K - 1, -1, -1):
+        toks[k], rows[k] = int(tok[k][i]), int(par[k][i])
+        i = rows[k]
+    (tf_codes,), (tf_logits,) = engine.gpt_generate([prompt], K, 10.0, forbid_stop_before=K, forced_codes=[np.array(toks, np.int32)],
+                                                     return_logits=True)
+    err = max(float(np.abs(lg[k][rows[k]] - tf_logits[k]).max()) for k in range(K))
+    print(f"beam-sample: {K} steps, returned {len(codes)} codes, lineage logits max err vs teacher-forced {err:.3f}")
+    assert err <= 0.13
+    # deterministic per seed; another seed explores differently
+    (again,) = engine.gpt_generate([prompt], n, 10.0, **kw)
+    assert np.array_equal(again, codes)
+    engine.gpt_generate([prompt], n, 10.0, **dict(kw, seed=8))
+    _, tok8, _, _ = engine.gpt_beam_trace(0, num_beams=3)
+    assert not np.array_equal(tok8, tok)          # (the best hypothesis may well coincide; the explored beams do not)
+
+
+def test_beam_search_variants_and_batch(engine):
+    """Plain beam search (do_sample=False: topk of the union), length_penalty, two utterances in one call (rows 0-2 and
+    3-5, ragged prompts) — each replayed through the oracle logic."""
+    cfg, style, emo, text = small_case()
+    w = make_gpt_weights(cfg, seed=1234, bf16=True)
+    load_gpt(engine, cfg, w, max_batch=8)
+    p0 = prepare_gpt_inputs(w, style, r16(emo), text, lang=1, bf16=True).numpy()
+    p1 = prepare_gpt_inputs(w, style * 0.5, r16(emo), text[:-3], lang=0, bf16=True).numpy()
+    n = 16
+    (c,), (lg,) = engine.gpt_generate([p0], n, 10.0, return_logits=True, do_sample=False, num_beams=3, length_penalty=1.0)
+    _check_beam_run(engine, cfg, p0, n, _beam_params(cfg, do_sample=False, length_penalty=1.0), 0, c, lg)
+    (c2,), (lg2,) = engine.gpt_generate([p0], n, 10.0, return_logits=True, do_sample=True, num_beams=2, top_k=5, top_p=0.9,
+                                        temperature=1.2, seed=3)
+    _check_beam_run(engine, cfg, p0, n, _beam_params(cfg, num_beams=2, top_k=5, top_p=0.9, temperature=1.2, seed=3), 0, c2, lg2)
+    kw = dict(do_sample=True, num_beams=3, top_k=30, top_p=0.8, temperature=0.8, seed=21)
+    cs, lgs = engine.gpt_generate([p0, p1], n, 10.0, return_logits=True, **kw)
+    for u, pr in enumerate([p0, p1]):
+        _check_beam_run(engine, cfg, pr, n, _beam_params(cfg, seed=21), u, cs[u], lgs[u])
+    # early termination: a stop token that is easy to sample ends hypotheses; the result still replays exactly
+    (c3,), (lg3,) = engine.gpt_generate([p0], 40, 1.0, return_logits=True, do_sample=True, num_beams=3, top_k=0, top_p=1.0,
+                                        temperature=3.0, seed=5)
+    _check_beam_run(engine, cfg, p0, 40, _beam_params(cfg, repetition_penalty=1.0, top_k=0, top_p=1.0, temperature=3.0, seed=5),
+                    0, c3, lg3)
