@@ -33,6 +33,7 @@
 #include <algorithm>
 #include <cstring>
 #include <cmath>
+#include <type_traits>
 
 namespace {
 
@@ -178,8 +179,13 @@ __device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned& target, int G
     }
   } else if (threadIdx.x == 0) {
     target += (unsigned)G;
-    __threadfence();                      // release: the CTA's stores of this phase
-    atomicAdd(ctr, 1u);
+    if (flavor == 3) {
+      // release-reduction: no returned value to wait for, release ordering instead of a separate fence
+      asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
+    } else {
+      __threadfence();                      // release: the CTA's stores of this phase
+      atomicAdd(ctr, 1u);
+    }
     unsigned spins = 0;
     while (ld_relaxed_gpu(ctr) < target) {
       if (++spins > (1u << 28)) __trap();
@@ -638,40 +644,55 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
             float m = -INFINITY, lsum = 0.f, ov[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) ov[i] = 0.f;
-            // beam search: prompt positions live in the utterance's first slot, generated ones where p.phys says
-            const int plen_b = p.phys ? __ldg(p.prompt_len + b) : 0x7fffffff;
-            const int base_seq = p.phys ? (b / p.beams) * p.beams : row_seq[b];
-            const unsigned char* phys_b = p.phys ? p.phys + (size_t)b * p.phys_stride : nullptr;
-            for (int j0 = k0 + warp * 4; j0 < k1; j0 += NCW * 4) {
-              const int j = j0 + g4;
-              const bool valid = j < k1;
-              float s = 0.f;
-              uint4 vv = make_uint4(0, 0, 0, 0);
-              if (valid) {
-                const int sj = (j < plen_b) ? base_seq : (int)phys_b[j - plen_b];
-                const size_t off = ((((size_t)l * p.nseq + sj) * p.maxpos) + j) * D + h * HD + sub * 8;
-                uint4 kk = __ldcg((const uint4*)(p.kc + off));
-                vv = __ldcg((const uint4*)(p.vc + off));
-                s = qv[0] * lo_bf(kk.x) + qv[1] * hi_bf(kk.x) + qv[2] * lo_bf(kk.y) +
-                    qv[3] * hi_bf(kk.y) + qv[4] * lo_bf(kk.z) + qv[5] * hi_bf(kk.z) +
-                    qv[6] * lo_bf(kk.w) + qv[7] * hi_bf(kk.w);
+            // beam search: prompt positions live in the utterance's first slot, generated ones where p.phys says.
+            // Two instantiations of the key loop so that the plain path keeps its single address stream.
+            const size_t cbase = ((size_t)l * p.nseq + row_seq[b]) * p.maxpos;
+            auto key_loop = [&](auto beamed_tag) {
+              constexpr bool BEAMED = decltype(beamed_tag)::value;
+              int plen_b = 0, base_seq = 0;
+              const unsigned char* phys_b = nullptr;
+              if constexpr (BEAMED) {
+                plen_b = __ldg(p.prompt_len + b);
+                base_seq = (b / p.beams) * p.beams;
+                phys_b = p.phys + (size_t)b * p.phys_stride;
               }
-              s += __shfl_xor_sync(0xffffffffu, s, 1);
-              s += __shfl_xor_sync(0xffffffffu, s, 2);
-              s += __shfl_xor_sync(0xffffffffu, s, 4);
-              if (valid) {
-                s *= 0.125f;
-                const float mn = fmaxf(m, s);
-                const float corr = __expf(m - mn);
-                const float pr = __expf(s - mn);
-                lsum = lsum * corr + pr;
-                const float vf[8] = {lo_bf(vv.x), hi_bf(vv.x), lo_bf(vv.y), hi_bf(vv.y),
-                                     lo_bf(vv.z), hi_bf(vv.z), lo_bf(vv.w), hi_bf(vv.w)};
+              for (int j0 = k0 + warp * 4; j0 < k1; j0 += NCW * 4) {
+                const int j = j0 + g4;
+                const bool valid = j < k1;
+                float s = 0.f;
+                uint4 vv = make_uint4(0, 0, 0, 0);
+                if (valid) {
+                  size_t off;
+                  if constexpr (BEAMED) {
+                    const int sj = (j < plen_b) ? base_seq : (int)phys_b[j - plen_b];
+                    off = ((((size_t)l * p.nseq + sj) * p.maxpos) + j) * D + h * HD + sub * 8;
+                  } else {
+                    off = (cbase + j) * D + h * HD + sub * 8;
+                  }
+                  uint4 kk = __ldcg((const uint4*)(p.kc + off));
+                  vv = __ldcg((const uint4*)(p.vc + off));
+                  s = qv[0] * lo_bf(kk.x) + qv[1] * hi_bf(kk.x) + qv[2] * lo_bf(kk.y) +
+                      qv[3] * hi_bf(kk.y) + qv[4] * lo_bf(kk.z) + qv[5] * hi_bf(kk.z) +
+                      qv[6] * lo_bf(kk.w) + qv[7] * hi_bf(kk.w);
+                }
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                if (valid) {
+                  s *= 0.125f;
+                  const float mn = fmaxf(m, s);
+                  const float corr = __expf(m - mn);
+                  const float pr = __expf(s - mn);
+                  lsum = lsum * corr + pr;
+                  const float vf[8] = {lo_bf(vv.x), hi_bf(vv.x), lo_bf(vv.y), hi_bf(vv.y),
+                                       lo_bf(vv.z), hi_bf(vv.z), lo_bf(vv.w), hi_bf(vv.w)};
 #pragma unroll
-                for (int i = 0; i < 8; ++i) ov[i] = ov[i] * corr + pr * vf[i];
-                m = mn;
+                  for (int i = 0; i < 8; ++i) ov[i] = ov[i] * corr + pr * vf[i];
+                  m = mn;
+                }
               }
-            }
+            };
+            if (p.phys) key_loop(std::true_type{}); else key_loop(std::false_type{});
             // merge the 4 key groups of the warp
 #pragma unroll
             for (int xo = 8; xo <= 16; xo <<= 1) {
