@@ -292,15 +292,18 @@ def main():
     t_dev = e.event_elapsed_ms(0, 1) / 1000.0
     launches = e.launches - l0
     # ---- end to end: host buffers in, pcm16 out, gather on rank 0 ----
+    if dist is not None:
+        from indextts_b200.sharding import gather_wavs
     for _ in range(2):
-        run_utterance(e, host_in, prompt_emb, host=True)
+        _, pcm_w = run_utterance(e, host_in, prompt_emb, host=True)
+        if dist is not None:      # warm the gather too: NCCL sets its point-to-point channels up on first use
+            gather_wavs(dist, torch.from_numpy(pcm_w).to(dev), rank, world, dst=0)
     barrier()
     t0 = time.perf_counter()
     e.event_record(2)
     for _ in range(K):
         codes_h, pcm_h = run_utterance(e, host_in, prompt_emb, host=True)
         if dist is not None:
-            from indextts_b200.sharding import gather_wavs
             gather_wavs(dist, torch.from_numpy(pcm_h).to(dev), rank, world, dst=0)
     e.event_record(3)
     barrier()
