@@ -26,6 +26,16 @@ void idx_engine::ensure_arena(size_t bytes) {
   arena.off = 0;
 }
 
+void idx_engine::check_flag(const char* what) {
+  int v = 0;
+  IDX_CUDA(cudaMemcpyAsync(&v, dev_flag, 4, cudaMemcpyDeviceToHost, stream));
+  IDX_CUDA(cudaStreamSynchronize(stream));
+  if (v) {
+    IDX_CUDA(cudaMemsetAsync(dev_flag, 0, 4, stream));
+    throw IdxError(IDX_ERR_ARG, std::string(what) + " (first offending position " + std::to_string(v - 1) + ")");
+  }
+}
+
 void* idx_engine::pinned_buf(size_t bytes) {
   if (pinned_cap < bytes) {
     if (pinned) cudaFreeHost(pinned);
@@ -95,6 +105,8 @@ int idx_create(int device, idx_engine** out) {
     e->device = device;
     e->num_sms = prop.multiProcessorCount;
     IDX_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    IDX_CUDA(cudaMalloc((void**)&e->dev_flag, 4));
+    IDX_CUDA(cudaMemset(e->dev_flag, 0, 4));
     *out = e;
   } catch (const IdxError& ex) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -117,6 +129,7 @@ void idx_destroy(idx_engine* e) {
   for (auto ev : e->events) if (ev) cudaEventDestroy(ev);
   if (e->arena.base) cudaFree(e->arena.base);
   if (e->pinned) cudaFreeHost(e->pinned);
+  if (e->dev_flag) cudaFree(e->dev_flag);
   cudaStreamDestroy(e->stream);
   delete e;
 }

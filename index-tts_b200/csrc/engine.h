@@ -84,6 +84,7 @@ struct idx_engine {
   void* pinned = nullptr;
   size_t pinned_cap = 0;
   cudaEvent_t events[16] = {};
+  int* dev_flag = nullptr;      // device word set by kernels that meet invalid input (index out of range)
   GptState* gpt = nullptr;
   BigvganState* bigvgan = nullptr;
   S2melState* s2mel = nullptr;
@@ -102,6 +103,8 @@ struct idx_engine {
   }
   void ensure_arena(size_t bytes);
   void* pinned_buf(size_t bytes);
+  // read-and-clear dev_flag after the stream is idle; throws IdxError(IDX_ERR_ARG, what) when it was set
+  void check_flag(const char* what);
 };
 
 // true if p is a device (or managed) pointer

@@ -1039,7 +1039,7 @@ __global__ void prepare_inputs_kernel(const float* style, const float* emo_vec,
                                       const int* text_ids, int n_text, int lang,
                                       const float* spk_w, const float* spk_b,
                                       const float* text_emb, const float* text_pos,
-                                      const float* lang_emb, int D, int r, float* out) {
+                                      const float* lang_emb, int D, int r, float* out, int text_rows, int* bad) {
   const int row = blockIdx.x;
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
     float v = 0.f;
@@ -1050,6 +1050,10 @@ __global__ void prepare_inputs_kernel(const float* style, const float* emo_vec,
     } else if (row >= 3) {
       const int j = row - 3;
       int id = (j == 0) ? 0 : (j == n_text + 1 ? 1 : text_ids[j - 1]);
+      if (id < 0 || id >= text_rows) {      // nn.Embedding raises IndexError here; flagged, never dereferenced
+        if (c == 0) atomicCAS(bad, 0, j);
+        id = 0;
+      }
       v = rnd(text_emb[(size_t)id * D + c] + text_pos[(size_t)j * D + c], r);
       if (lang_emb) v = rnd(v + lang_emb[(size_t)lang * D + c], r);
     }
@@ -2354,11 +2358,13 @@ extern "C" int idx_gpt_prepare_inputs(idx_engine* e, const float* style, const f
   const float* lang_emb = e->has("gpt.lang_embedding.weight") ? e->Wf("gpt.lang_embedding.weight") : nullptr;
   prepare_inputs_kernel<<<rows, 256, 0, e->stream>>>(
       d_style, d_emo, d_ids, n_text, lang, e->Wf("gpt.spk_emb_proj.weight"), e->Wf("gpt.spk_emb_proj.bias"),
-      e->Wf("gpt.text_embedding.weight"), (const float*)tpos.d, lang_emb, D, g->cfg.weights_bf16, d_out);
+      e->Wf("gpt.text_embedding.weight"), (const float*)tpos.d, lang_emb, D, g->cfg.weights_bf16, d_out,
+      (int)e->W("gpt.text_embedding.weight").shape[0], e->dev_flag);
   IDX_CUDA(cudaGetLastError());
   e->launches++;
   idx_from_device(e, out, d_out, (size_t)rows * D * 4);
   IDX_CUDA(cudaStreamSynchronize(e->stream));
+  e->check_flag("text token id outside text_embedding");
   IDX_API_END(e)
 }
 

@@ -108,10 +108,16 @@ __global__ void nearest_kernel(const float* __restrict__ x, float* __restrict__ 
   y[((long long)bi * Tout + t) * C + c] = x[((long long)bi * Tin + src) * C + c];
 }
 
-__global__ void embedding_kernel(const float* __restrict__ table, const int* __restrict__ ids, float* out, int C) {
+// ids outside [0, nrows) never index the table: the row is zero-filled and the engine flag records the position
+// (torch's F.embedding raises IndexError there; the ABI call returns IDX_ERR_ARG after the stream drains)
+__global__ void embedding_kernel(const float* __restrict__ table, const int* __restrict__ ids, float* out, int C,
+                                 int nrows, int* bad) {
   const int t = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) out[(long long)t * C + c] = table[(long long)ids[t] * C + c];
+  const int id = ids[t];
+  const bool ok = id >= 0 && id < nrows;
+  if (!ok && c == 0) atomicCAS(bad, 0, t + 1);
+  if (c < C) out[(long long)t * C + c] = ok ? table[(long long)id * C + c] : 0.f;
 }
 
 __global__ void swiglu_kernel(const float* __restrict__ ab, float* __restrict__ y, long long rows, int N) {
@@ -597,9 +603,9 @@ void nearest_interp(idx_engine* e, const float* x, float* y, int B, int Tin, int
   nearest_kernel<<<grid, 128, 0, e->stream>>>(x, y, Tin, Tout, C);
   LAUNCH_CHECK(e);
 }
-void embedding_rows(idx_engine* e, const float* table, const int* ids, float* out, int n, int C) {
+void embedding_rows(idx_engine* e, const float* table, const int* ids, float* out, int n, int C, int nrows) {
   dim3 grid((C + 127) / 128, n);
-  embedding_kernel<<<grid, 128, 0, e->stream>>>(table, ids, out, C);
+  embedding_kernel<<<grid, 128, 0, e->stream>>>(table, ids, out, C, nrows, e->dev_flag);
   LAUNCH_CHECK(e);
 }
 void swiglu(idx_engine* e, const float* ab, float* y, long long rows, int N) {

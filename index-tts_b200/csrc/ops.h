@@ -61,7 +61,7 @@ void dwconv1d(idx_engine* e, const float* x, float* y, int B, int T, int C, cons
 // y[b][t][:] = x[b][src(t)][:], src(t) = min(floor(t * Tin/Tout), Tin-1)  (F.interpolate nearest)
 void nearest_interp(idx_engine* e, const float* x, float* y, int B, int Tin, int Tout, int C);
 // out[t][:] = table[ids[t]][:]
-void embedding_rows(idx_engine* e, const float* table, const int* ids, float* out, int n, int C);
+void embedding_rows(idx_engine* e, const float* table, const int* ids, float* out, int n, int C, int nrows);
 // y = silu(a) * b where ab [rows][2*N] holds a | b side by side
 void swiglu(idx_engine* e, const float* ab, float* y, long long rows, int N);
 // y = tanh(a + ga[b]) * sigmoid(c + gc[b]),  xin [B][T][2N] = a | c ; g [B][*] with stride

@@ -84,5 +84,6 @@ extern "C" int idx_codes_to_wav(idx_engine* e, const idx_vocode_request* r, int 
   IDX_CUDA(cudaEventElapsedTime(&m3, e->events[13], e->events[14]));
   s2mel_set_ms(s, m0, m1, m2);
   bigvgan_set_ms(bv, m3);
+  e->check_flag("semantic code outside the codebook (codes must be cut before the stop token, infer_v2_5.py:809-821)");
   IDX_API_END(e)
 }

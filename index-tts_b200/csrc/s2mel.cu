@@ -268,7 +268,7 @@ void codec_decode_dev(idx_engine* e, S2melState* s, const int* d_codes, int n, f
   float* y = e->arena.get<float>((size_t)n * Vd);
   float* hbuf = e->arena.get<float>((size_t)n * Vi);
   float* up = e->arena.get<float>((size_t)2 * n * Hs);
-  embedding_rows(e, s->cd_codebook, d_codes, emb, n, c.codebook_dim);
+  embedding_rows(e, s->cd_codebook, d_codes, emb, n, c.codebook_dim, c.codebook_size);
   conv_gemm(e, gemm_of(s->cd_out_proj, emb, 1, n, q));
   conv_gemm(e, gemm_of(s->cd_embed, q, 1, n, y));
   layernorm(e, y, x, 1, n, Vd, s->cd_norm_w, s->cd_norm_b, 1e-6f, nullptr, nullptr, 0);
@@ -568,6 +568,7 @@ extern "C" int idx_codec_decode(idx_engine* e, const int32_t* codes, int n, floa
   IDX_CUDA(cudaEventRecord(s->ev1, e->stream));
   idx_from_device(e, S_out, d_out, (size_t)2 * n * c.hidden_size * 4);
   IDX_CUDA(cudaStreamSynchronize(e->stream));
+  e->check_flag("semantic code outside the codebook (codes must be cut before the stop token, infer_v2_5.py:809-821)");
   float ms; IDX_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1)); s->ms_codec = ms;
   IDX_API_END(e)
 }
