@@ -348,8 +348,9 @@ def main():
                               "other": (t_dev * 1000 - g_ms - c_ms - v_ms) / K},
         "roofline": {"kernel": "gpt_fused_kernel (decode step)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                      "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": 944.2e6, "traffic_note": "dram read+write per step of the same weight stream, ncu --set full, "
-                                                         "profiles/r01_gpt_fused_ncu.md (prefill instantiation; head phase +21 MB)",
+                     "traffic": 965.2e6, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per decode step of "
+                                                         "gpt_fused_kernel<1,40> (32-step launch / 32), ncu --set full, "
+                                                         "profiles/r01_gpt_fused_ncu.md",
                      "peak_source": which,
                      "us_per_decode_step": step_us,
                      "algorithmic_bytes_per_step": w_bytes + kv_bytes},
