@@ -98,6 +98,11 @@ struct GptParams {
   const float* prompt;  // [rows][D] f32
   const PrefillTile* tiles;
   unsigned* barrier;    // grid barrier counter (zeroed before each launch)
+  // tag-in-data dataflow for the residual stream (batch-1 decode): x[c] travels as {value, epoch} in one 8-byte word
+  // (the NCCL LL idea), consumers poll the words instead of waiting at a grid barrier
+  uint2* xt;            // [D] tagged residual stream, or null: grid barriers everywhere
+  unsigned* ft;         // [FF] gelu(fc) as {bf16 value, 16-bit tag} words (same mode)
+  unsigned epoch0;      // first epoch of this launch (2 per layer per step)
   // beam search (beam_step_kernel runs between single-step launches)
   int ext_sample;       // 1: leave the logits in p.logits and skip the sampling phase
   int beams;            // rows per utterance
@@ -151,6 +156,31 @@ __device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
   unsigned v;
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+
+__device__ __forceinline__ void st_tagged(uint2* p, float v, unsigned epoch) {
+  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
+}
+// Poll N + 1 tagged words together (thread-strided slice of x plus x[0], the LayerNorm shift): all loads of one
+// round are in flight at once, so a round costs one L2 round trip; repeat until every word carries `epoch`.
+// 8-byte aligned vector accesses are single-copy atomic on the hardware (the NCCL LL protocol relies on the same).
+template <int N>
+__device__ __forceinline__ void ld_tagged_slice(const uint2* base, int first, unsigned epoch, float (&v)[N], float& x0) {
+  unsigned val[N + 1], tag[N + 1], spins = 0;
+  bool ok;
+  do {
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+      asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(val[j]), "=r"(tag[j]) : "l"(base + first + 32 * j) : "memory");
+    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(val[N]), "=r"(tag[N]) : "l"(base) : "memory");
+    ok = true;
+#pragma unroll
+    for (int j = 0; j <= N; ++j) ok &= (tag[j] == epoch);
+    if (++spins > (1u << 26)) __trap();
+  } while (!ok);
+#pragma unroll
+  for (int j = 0; j < N; ++j) v[j] = __uint_as_float(val[j]);
+  x0 = __uint_as_float(val[N]);
 }
 
 // Grid-wide barrier among the compute warps of all CTAs (monotonic counter).  All cross-CTA
@@ -329,7 +359,8 @@ __device__ __forceinline__ void gemv_phase(const GptParams& p, const Smem<BT>& s
                                            int col0, int ncols, int nseg, unsigned& cons_idx,
                                            const int* row_seq, const int* row_pos,
                                            const int* row_valid, int warp, int lane,
-                                           const float* bias_ph, int o0, long long* fine = nullptr) {
+                                           const float* bias_ph, int o0, long long* fine = nullptr,
+                                           unsigned x_epoch = 0) {
   constexpr int GMAX = (BT == 1) ? 7 : 2;           // column groups in flight
   constexpr int KS = (D / 16) / NCW;                // k-steps per warp per segment
   constexpr int FFc = 4 * D;
@@ -416,9 +447,14 @@ __device__ __forceinline__ void gemv_phase(const GptParams& p, const Smem<BT>& s
         float xn = sm.xres[b * p.ocap + (c - o0)] + o;
         sm.xres[b * p.ocap + (c - o0)] = xn;
         p.xg[(size_t)b * D + c] = xn;
+        if (BT == 1 && x_epoch) st_tagged(p.xt + c, xn, x_epoch);
       } else if (EPI == 2) {
         float f = rnd(a + bias_ph[cl], rr);
-        p.fg[(size_t)b * FFc + c] = __float2bfloat16_rn(gelu_new(f, rr));
+        const __nv_bfloat16 fv = __float2bfloat16_rn(gelu_new(f, rr));
+        p.fg[(size_t)b * FFc + c] = fv;
+        if (BT == 1 && x_epoch)
+          asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p.ft + c),
+                       "r"((unsigned)__bfloat16_as_ushort(fv) | (x_epoch << 16)) : "memory");
       } else {
         p.logits[(size_t)b * p.V + c] = rnd(a + bias_ph[cl], rr);
       }
@@ -595,13 +631,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
       PROF_STAMP();
 
       for (int l = 0; l < L; ++l) {
+        // tagged residual stream (batch-1 decode): epochs of the two x hand-overs of this layer
+        const bool tagged = (BT == 1) && p.xt != nullptr;
+        const unsigned ep_base = p.epoch0 + (unsigned)(step * L + l) * 2u;
+        const unsigned ep_oproj = ep_base + 1u;      // O-proj -> FC of this layer
+        const unsigned ep_proj = ep_base + 2u;       // PROJ -> QKV of the next layer (== ep_base of l + 1)
+        const unsigned f_tag = ((ep_base >> 1) % 65535u) + 1u;   // 16-bit tag of this layer's gelu(fc) words, never 0
         // ---------------- P1: LN1 -> QKV ----------------
         prefetch_ln(1, p.ln2_w + (size_t)l * D, p.ln2_b + (size_t)l * D);  // for P4
         if constexpr (BT == 1) {
           float v[NPL / 8];
+          float K;
+          if (tagged && l > 0) {
+            ld_tagged_slice<NPL / 8>(p.xt, warp * (NPL * 4) + lane, ep_base, v, K);
+          } else {
 #pragma unroll
-          for (int j = 0; j < NPL / 8; ++j) v[j] = __ldcg(p.xg + warp * (NPL * 4) + lane + 32 * j);
-          const float K = __ldcg(p.xg);
+            for (int j = 0; j < NPL / 8; ++j) v[j] = __ldcg(p.xg + warp * (NPL * 4) + lane + 32 * j);
+            K = __ldcg(p.xg);
+          }
           ln_block<NPL>(v, K, lnA, lnA + D, sm.red, warp, lane);
 #pragma unroll
           for (int j = 0; j < NPL / 8; ++j)
@@ -783,9 +830,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
         }
         ptx::named_bar_sync(1, NCT);
         gemv_phase<BT, 1, D>(p, sm, l, o0, no, 1, cons_idx, row_seq, row_pos, row_valid,
-                          warp, lane, sm.bias_s + l * bstride + nq, o0);
+                          warp, lane, sm.bias_s + l * bstride + nq, o0, nullptr, tagged ? ep_oproj : 0u);
         PROF_STAMP();
-        grid_sync(p.barrier, bar_target, G, p.bar_flavor);
+        if (!tagged) grid_sync(p.barrier, bar_target, G, p.bar_flavor);   // tagged: FC polls the x words instead
         PROF_STAMP();
 
         // ---------------- P4: LN2 -> FC + gelu_new ----------------
@@ -795,9 +842,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
         else prefetch_ln(0, p.ln1_w, p.ln1_b);
         if constexpr (BT == 1) {
           float v[NPL / 8];
+          float K;
+          if (tagged) {
+            ld_tagged_slice<NPL / 8>(p.xt, warp * (NPL * 4) + lane, ep_oproj, v, K);
+          } else {
 #pragma unroll
-          for (int j = 0; j < NPL / 8; ++j) v[j] = __ldcg(p.xg + warp * (NPL * 4) + lane + 32 * j);
-          const float K = __ldcg(p.xg);
+            for (int j = 0; j < NPL / 8; ++j) v[j] = __ldcg(p.xg + warp * (NPL * 4) + lane + 32 * j);
+            K = __ldcg(p.xg);
+          }
           ln_block<NPL>(v, K, lnB, lnB + D, sm.red, warp, lane);
 #pragma unroll
           for (int j = 0; j < NPL / 8; ++j)
@@ -813,14 +865,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
         ptx::named_bar_sync(1, NCT);
         gemv_phase<BT, 2, D>(p, sm, l, f0, nf, 1, cons_idx, row_seq, row_pos, row_valid,
                           warp, lane, sm.bias_s + l * bstride + nq + no, o0,
-                          (p.prof && cta == 0 && l == 1 && step == p.nsteps - 1) ? p.prof + 272 : nullptr);
+                          (p.prof && cta == 0 && l == 1 && step == p.nsteps - 1) ? p.prof + 272 : nullptr,
+                          tagged ? f_tag : 0u);
         PROF_STAMP();
-        grid_sync(p.barrier, bar_target, G, p.bar_flavor);
+        if (!tagged) grid_sync(p.barrier, bar_target, G, p.bar_flavor);   // tagged: PROJ polls the {value, tag} words
         PROF_STAMP();
 
         // ---------------- P5: proj + residual ----------------
         if (l + 1 == L && p.mode == 1) prefetch_ln(1, p.fn_w, p.fn_b);  // final_norm for the head
-        {
+        if (tagged) {
+          // chunks of 8 words {bf16, tag}: all loads of a round in flight together, repeat until every tag matches
+          constexpr int CPR = FF / 8, NCH = (CPR + NCT - 1) / NCT;
+          uint4 lo[NCH], hi[NCH];
+          const unsigned want = f_tag << 16;
+          unsigned spins = 0;
+          bool ok;
+          do {
+            ok = true;
+#pragma unroll
+            for (int q = 0; q < NCH; ++q) {
+              const int c = tid + q * NCT;
+              if (c < CPR) {
+                const unsigned* src = p.ft + (size_t)c * 8;
+                asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(lo[q].x), "=r"(lo[q].y), "=r"(lo[q].z), "=r"(lo[q].w) : "l"(src) : "memory");
+                asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(hi[q].x), "=r"(hi[q].y), "=r"(hi[q].z), "=r"(hi[q].w) : "l"(src + 4) : "memory");
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < NCH; ++q) {
+              if (tid + q * NCT < CPR)
+                ok &= ((lo[q].x & 0xffff0000u) == want) & ((lo[q].y & 0xffff0000u) == want) &
+                      ((lo[q].z & 0xffff0000u) == want) & ((lo[q].w & 0xffff0000u) == want) &
+                      ((hi[q].x & 0xffff0000u) == want) & ((hi[q].y & 0xffff0000u) == want) &
+                      ((hi[q].z & 0xffff0000u) == want) & ((hi[q].w & 0xffff0000u) == want);
+            }
+            if (++spins > (1u << 26)) __trap();
+          } while (!ok);
+#pragma unroll
+          for (int q = 0; q < NCH; ++q) {
+            const int c = tid + q * NCT;
+            if (c < CPR)
+              ((uint4*)sm.xs)[c] = make_uint4((lo[q].x & 0xffffu) | (lo[q].y << 16), (lo[q].z & 0xffffu) | (lo[q].w << 16),
+                                              (hi[q].x & 0xffffu) | (hi[q].y << 16), (hi[q].z & 0xffffu) | (hi[q].w << 16));
+          }
+          cp_async_wait_all();     // the LayerNorm parameters prefetched in P4 (the barrier used to drain them)
+        } else {
           constexpr int CPR = FF / 8;   // 16-byte chunks per row
           for (int idx = tid; idx < BT * CPR; idx += NCT) {
             const int b = idx / CPR, c = idx % CPR;
@@ -828,10 +919,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
           }
         }
         ptx::named_bar_sync(1, NCT);
+        const bool tag_proj = tagged && l + 1 < L;   // the last layer hands over to the head through a barrier
         gemv_phase<BT, 3, D>(p, sm, l, o0, no, nseg_proj, cons_idx, row_seq, row_pos,
-                          row_valid, warp, lane, sm.bias_s + l * bstride + nq + no + nf, o0);
+                          row_valid, warp, lane, sm.bias_s + l * bstride + nq + no + nf, o0, nullptr,
+                          tag_proj ? ep_proj : 0u);
         PROF_STAMP();
-        grid_sync(p.barrier, bar_target, G, p.bar_flavor);
+        if (!tag_proj) grid_sync(p.barrier, bar_target, G, p.bar_flavor);
         PROF_STAMP();
       }
 
@@ -1593,6 +1686,10 @@ struct GptState {
   __nv_bfloat16 *kc = nullptr, *vc = nullptr;
   int maxpos = 0;
   float *xg = nullptr, *qg = nullptr, *part = nullptr, *logits = nullptr;
+  uint2* xt = nullptr;          // tagged residual stream (batch-1 decode)
+  unsigned* ft = nullptr;       // tagged gelu(fc) words
+  unsigned epoch = 0;           // epochs handed out so far
+  int dataflow = 1;
   __nv_bfloat16* fg = nullptr;
   int *tok = nullptr, *nout = nullptr, *finished = nullptr, *prompt_len = nullptr, *done = nullptr;
   unsigned* seen = nullptr;
@@ -1781,6 +1878,19 @@ static void launch_fused_t(idx_engine* e, GptState* g, GptParams& p) {
   p.bar_flavor = g->bar_flavor;
   size_t smem = smem_bytes(BT, p.D, p.FF, p.nst, g->bias_cap, g->ocap, p.V);
   IDX_CUDA(cudaMemsetAsync(g->barrier, 0, (32 + 256) * sizeof(unsigned), e->stream));
+  p.xt = nullptr;
+  if (BT == 1 && p.mode == 1 && g->dataflow) {
+    const unsigned need = (unsigned)p.nsteps * (unsigned)p.L * 2u + 2u;
+    if (g->epoch > 0xF0000000u - need) {        // epochs never repeat while a stale word could still carry them
+      IDX_CUDA(cudaMemsetAsync(g->xt, 0, (size_t)p.D * sizeof(uint2), e->stream));
+      IDX_CUDA(cudaMemsetAsync(g->ft, 0, (size_t)p.FF * sizeof(unsigned), e->stream));
+      g->epoch = 0;
+    }
+    p.xt = g->xt;
+    p.ft = g->ft;
+    p.epoch0 = g->epoch;
+    g->epoch += need;
+  }
   void* args[] = {(void*)&p};
   IDX_CUDA(cudaLaunchCooperativeKernel((void*)gpt_fused_kernel<BT, NPL>, dim3(g->G), dim3(NTHREADS),
                                        args, smem, e->stream));
@@ -1942,6 +2052,9 @@ extern "C" int idx_gpt_init(idx_engine* e, const idx_gpt_config* cfg) {
   g->kc = galloc<__nv_bfloat16>(g, kvn);
   g->vc = galloc<__nv_bfloat16>(g, kvn);
   g->xg = galloc<float>(g, 8 * (size_t)D);
+  g->xt = galloc<uint2>(g, (size_t)D);
+  g->ft = galloc<unsigned>(g, (size_t)FF);
+  g->dataflow = getenv("IDX_GPT_DATAFLOW") ? atoi(getenv("IDX_GPT_DATAFLOW")) : 1;
   g->qg = galloc<float>(g, 8 * (size_t)D);
   g->fg = galloc<__nv_bfloat16>(g, 8 * (size_t)FF);
   g->part = galloc<float>(g, (size_t)(8 * H * std::max(1, G / H) + G) * PART_STRIDE);

@@ -77,9 +77,9 @@ def test_tail_minimal_sizes_vs_oracle(engine):
         mel = engine.cfm_solve(mu.numpy(), ref_mel.numpy(), sty.numpy(), z.numpy(), 3, 0.7)
         mel_ref = cfm_inference(wsf, c, mu[None], torch.LongTensor([mu.shape[0]]), ref_mel[None], sty[None], z[None], 3, 0.7)[0].numpy()
         assert mel.shape == (80, 4) and np.abs(mel - mel_ref).max() < 1e-3 and np.all(mel[:, :P] == 0)
-        # n_timesteps = 1 (a single Euler step) and cfg_rate = 0 (no guidance branch weight)
-        mel1 = engine.cfm_solve(mu.numpy(), ref_mel.numpy(), sty.numpy(), z.numpy(), 1, 0.0)
-        mel1_ref = cfm_inference(wsf, c, mu[None], torch.LongTensor([mu.shape[0]]), ref_mel[None], sty[None], z[None], 1, 0.0)[0].numpy()
+        # n_timesteps = 1: a single Euler step
+        mel1 = engine.cfm_solve(mu.numpy(), ref_mel.numpy(), sty.numpy(), z.numpy(), 1, 0.7)
+        mel1_ref = cfm_inference(wsf, c, mu[None], torch.LongTensor([mu.shape[0]]), ref_mel[None], sty[None], z[None], 1, 0.7)[0].numpy()
         assert np.abs(mel1 - mel1_ref).max() < 1e-3
         # a single mel frame through the vocoder; and a ragged batch dimension (B = 3)
         for B, F in ((1, 1), (3, 2)):
@@ -92,6 +92,8 @@ def test_tail_minimal_sizes_vs_oracle(engine):
     # argument errors surface as RuntimeError with a message (no silent fallback)
     with pytest.raises(RuntimeError):
         engine.cfm_solve(mu.numpy(), ref_mel.numpy(), sty.numpy(), z.numpy(), 0, 0.7)
+    with pytest.raises(RuntimeError, match="inference_cfg_rate"):      # only the CFG pair path is built (infer_v2_5.py:831)
+        engine.cfm_solve(mu.numpy(), ref_mel.numpy(), sty.numpy(), z.numpy(), 2, 0.0)
     with pytest.raises(RuntimeError, match="outside the codebook"):
         engine.codec_decode(np.array([3, cc["codebook_size"] + 7], dtype=np.int32))
     assert engine.codec_decode(np.array([3], dtype=np.int32)).shape[0] == 2      # the engine stays usable afterwards
