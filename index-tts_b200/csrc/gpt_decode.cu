@@ -102,6 +102,8 @@ struct GptParams {
   // (the NCCL LL idea), consumers poll the words instead of waiting at a grid barrier
   uint2* xt;            // [D] tagged residual stream, or null: grid barriers everywhere
   unsigned* ft;         // [FF] gelu(fc) as {bf16 value, 16-bit tag} words (same mode)
+  uint2* qt;            // [D] tagged q of the current layer
+  uint2* kvt;           // [2][D] tagged k, v (bf16-valued) of the position being decoded
   unsigned epoch0;      // first epoch of this launch (2 per layer per step)
   // beam search (beam_step_kernel runs between single-step launches)
   int ext_sample;       // 1: leave the logits in p.logits and skip the sampling phase
@@ -436,10 +438,13 @@ __device__ __forceinline__ void gemv_phase(const GptParams& p, const Smem<BT>& s
         float v = rnd(a + bias_ph[cl], rr);
         if (c < D) {
           p.qg[(size_t)b * D + c] = v;
+          if (BT == 1 && x_epoch) st_tagged(p.qt + c, v, x_epoch);
         } else {
           size_t base = (((size_t)layer * p.nseq + row_seq[b]) * p.maxpos + row_pos[b]) * D;
-          if (c < 2 * D) p.kc[base + (c - D)] = __float2bfloat16_rn(v);
-          else p.vc[base + (c - 2 * D)] = __float2bfloat16_rn(v);
+          const __nv_bfloat16 kvb = __float2bfloat16_rn(v);
+          if (c < 2 * D) p.kc[base + (c - D)] = kvb;
+          else p.vc[base + (c - 2 * D)] = kvb;
+          if (BT == 1 && x_epoch) st_tagged(p.kvt + (c - D), __bfloat162float(kvb), x_epoch);
         }
       } else if (EPI == 1 || EPI == 3) {
         // the residual stream is fp32 even on the bf16 path (trap P12): only the branch is rounded
@@ -664,9 +669,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
         ptx::named_bar_sync(1, NCT);
         gemv_phase<BT, 0, D>(p, sm, l, q0, nq, 1, cons_idx, row_seq, row_pos, row_valid,
                           warp, lane, sm.bias_s + l * bstride, o0,
-                          (p.prof && cta == 0 && l == 1 && step == p.nsteps - 1) ? p.prof + 256 : nullptr);
+                          (p.prof && cta == 0 && l == 1 && step == p.nsteps - 1) ? p.prof + 256 : nullptr,
+                          tagged ? ep_oproj : 0u);
         PROF_STAMP();
-        grid_sync(p.barrier, bar_target, G, p.bar_flavor);
+        if (!tagged) grid_sync(p.barrier, bar_target, G, p.bar_flavor);   // tagged: attention polls q and the new k, v
         PROF_STAMP();
 
         // ---------------- P2: attention over the KV cache ----------------
@@ -683,11 +689,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
             const int k0 = (int)(((long long)ctx * sp) / nsplit);
             const int k1 = (int)(((long long)ctx * (sp + 1)) / nsplit);
             float qv[8];
-            {
+            if (tagged) {
+              const uint2* qp = p.qt + h * HD + sub * 8;
+              unsigned val[8], tg[8], spins = 0;
+              bool ok;
+              do {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(val[i]), "=r"(tg[i]) : "l"(qp + i) : "memory");
+                ok = true;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) ok &= (tg[i] == ep_oproj);
+                if (++spins > (1u << 26)) __trap();
+              } while (!ok);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) qv[i] = __uint_as_float(val[i]);
+            } else {
               const float* qp = p.qg + (size_t)b * D + h * HD + sub * 8;
 #pragma unroll
               for (int i = 0; i < 8; ++i) qv[i] = __ldcg(qp + i);
             }
+            // tagged mode: the position being decoded comes from the tagged words, not from the cache
+            const int kend = tagged ? min(k1, ctx - 1) : k1;
             float m = -INFINITY, lsum = 0.f, ov[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) ov[i] = 0.f;
@@ -703,9 +726,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
                 base_seq = (b / p.beams) * p.beams;
                 phys_b = p.phys + (size_t)b * p.phys_stride;
               }
-              for (int j0 = k0 + warp * 4; j0 < k1; j0 += NCW * 4) {
+              for (int j0 = k0 + warp * 4; j0 < kend; j0 += NCW * 4) {
                 const int j = j0 + g4;
-                const bool valid = j < k1;
+                const bool valid = j < kend;
                 float s = 0.f;
                 uint4 vv = make_uint4(0, 0, 0, 0);
                 if (valid) {
@@ -740,6 +763,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
               }
             };
             if (p.phys) key_loop(std::true_type{}); else key_loop(std::false_type{});
+            if (tagged && k1 == ctx && warp == 0 && g4 == 0) {
+              // the new position (owned by the last key split): k and v straight from the QKV epilogue's tagged words
+              const uint2* kp = p.kvt + h * HD + sub * 8;
+              const uint2* vp = p.kvt + D + h * HD + sub * 8;
+              unsigned kvv[16], tg[16], spins = 0;
+              bool ok;
+              do {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(kvv[i]), "=r"(tg[i]) : "l"(kp + i) : "memory");
+                  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(kvv[8 + i]), "=r"(tg[8 + i]) : "l"(vp + i) : "memory");
+                }
+                ok = true;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) ok &= (tg[i] == ep_oproj);
+                if (++spins > (1u << 26)) __trap();
+              } while (!ok);
+              float s = 0.f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) s += qv[i] * __uint_as_float(kvv[i]);
+              s += __shfl_xor_sync(0xffu, s, 1);
+              s += __shfl_xor_sync(0xffu, s, 2);
+              s += __shfl_xor_sync(0xffu, s, 4);
+              s *= 0.125f;
+              const float mn = fmaxf(m, s);
+              const float corr = __expf(m - mn);
+              const float pr = __expf(s - mn);
+              lsum = lsum * corr + pr;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) ov[i] = ov[i] * corr + pr * __uint_as_float(kvv[8 + i]);
+              m = mn;
+            }
+            __syncwarp();
             // merge the 4 key groups of the warp
 #pragma unroll
             for (int xo = 8; xo <= 16; xo <<= 1) {
@@ -845,6 +901,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
           float K;
           if (tagged) {
             ld_tagged_slice<NPL / 8>(p.xt, warp * (NPL * 4) + lane, ep_oproj, v, K);
+            cp_async_wait_all();   // ln_2 parameters prefetched in P1 (ln_block's own CTA barrier publishes them)
           } else {
 #pragma unroll
             for (int j = 0; j < NPL / 8; ++j) v[j] = __ldcg(p.xg + warp * (NPL * 4) + lane + 32 * j);
@@ -1688,6 +1745,7 @@ struct GptState {
   float *xg = nullptr, *qg = nullptr, *part = nullptr, *logits = nullptr;
   uint2* xt = nullptr;          // tagged residual stream (batch-1 decode)
   unsigned* ft = nullptr;       // tagged gelu(fc) words
+  uint2 *qt = nullptr, *kvt = nullptr;
   unsigned epoch = 0;           // epochs handed out so far
   int dataflow = 1;
   __nv_bfloat16* fg = nullptr;
@@ -1884,10 +1942,14 @@ static void launch_fused_t(idx_engine* e, GptState* g, GptParams& p) {
     if (g->epoch > 0xF0000000u - need) {        // epochs never repeat while a stale word could still carry them
       IDX_CUDA(cudaMemsetAsync(g->xt, 0, (size_t)p.D * sizeof(uint2), e->stream));
       IDX_CUDA(cudaMemsetAsync(g->ft, 0, (size_t)p.FF * sizeof(unsigned), e->stream));
+      IDX_CUDA(cudaMemsetAsync(g->qt, 0, (size_t)p.D * sizeof(uint2), e->stream));
+      IDX_CUDA(cudaMemsetAsync(g->kvt, 0, 2 * (size_t)p.D * sizeof(uint2), e->stream));
       g->epoch = 0;
     }
     p.xt = g->xt;
     p.ft = g->ft;
+    p.qt = g->qt;
+    p.kvt = g->kvt;
     p.epoch0 = g->epoch;
     g->epoch += need;
   }
@@ -2054,6 +2116,8 @@ extern "C" int idx_gpt_init(idx_engine* e, const idx_gpt_config* cfg) {
   g->xg = galloc<float>(g, 8 * (size_t)D);
   g->xt = galloc<uint2>(g, (size_t)D);
   g->ft = galloc<unsigned>(g, (size_t)FF);
+  g->qt = galloc<uint2>(g, (size_t)D);
+  g->kvt = galloc<uint2>(g, 2 * (size_t)D);
   g->dataflow = getenv("IDX_GPT_DATAFLOW") ? atoi(getenv("IDX_GPT_DATAFLOW")) : 1;
   g->qg = galloc<float>(g, 8 * (size_t)D);
   g->fg = galloc<__nv_bfloat16>(g, 8 * (size_t)FF);
