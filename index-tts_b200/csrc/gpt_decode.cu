@@ -102,6 +102,7 @@ struct GptParams {
   // (the NCCL LL idea), consumers poll the words instead of waiting at a grid barrier
   uint2* xt;            // [D] tagged residual stream, or null: grid barriers everywhere
   unsigned* ft;         // [FF] gelu(fc) as {bf16 value, 16-bit tag} words (same mode)
+  unsigned* pflag;      // [B*H*nsplit] epoch of the attention partial of each (row, head, key split)
   uint2* qt;            // [D] tagged q of the current layer
   uint2* kvt;           // [2][D] tagged k, v (bf16-valued) of the position being decoded
   unsigned epoch0;      // first epoch of this launch (2 per layer per step)
@@ -163,26 +164,24 @@ __device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
 __device__ __forceinline__ void st_tagged(uint2* p, float v, unsigned epoch) {
   asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
 }
-// Poll N + 1 tagged words together (thread-strided slice of x plus x[0], the LayerNorm shift): all loads of one
-// round are in flight at once, so a round costs one L2 round trip; repeat until every word carries `epoch`.
+// Poll N tagged words together (thread-strided slice of x): all loads of one round are in flight at once, so a
+// round costs one L2 round trip; repeat until every word carries `epoch`.
 // 8-byte aligned vector accesses are single-copy atomic on the hardware (the NCCL LL protocol relies on the same).
 template <int N>
-__device__ __forceinline__ void ld_tagged_slice(const uint2* base, int first, unsigned epoch, float (&v)[N], float& x0) {
-  unsigned val[N + 1], tag[N + 1], spins = 0;
+__device__ __forceinline__ void ld_tagged_slice(const uint2* base, int first, unsigned epoch, float (&v)[N]) {
+  unsigned val[N], tag[N], spins = 0;
   bool ok;
   do {
 #pragma unroll
     for (int j = 0; j < N; ++j)
       asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(val[j]), "=r"(tag[j]) : "l"(base + first + 32 * j) : "memory");
-    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(val[N]), "=r"(tag[N]) : "l"(base) : "memory");
     ok = true;
 #pragma unroll
-    for (int j = 0; j <= N; ++j) ok &= (tag[j] == epoch);
+    for (int j = 0; j < N; ++j) ok &= (tag[j] == epoch);
     if (++spins > (1u << 26)) __trap();
   } while (!ok);
 #pragma unroll
   for (int j = 0; j < N; ++j) v[j] = __uint_as_float(val[j]);
-  x0 = __uint_as_float(val[N]);
 }
 
 // Grid-wide barrier among the compute warps of all CTAs (monotonic counter).  All cross-CTA
@@ -312,13 +311,17 @@ struct Smem {
 };
 
 // Cooperative LayerNorm of ONE row by all 8 compute warps (batch-1 decode, where a warp-per-row
-// LayerNorm would leave 7 warps idle on the critical path).  Shifted one-pass statistics:
-// S1 = sum(x-K), S2 = sum((x-K)^2) with K = x[0]; thread t owns NPL/8 elements.
+// LayerNorm would leave 7 warps idle on the critical path).  Shifted one-pass statistics with a
+// per-warp shift K_w = the warp's first element (a single global shift x[0] would make every thread of
+// every CTA poll the same word of the tagged stream): S1_w = sum(x-K_w), S2_w = sum((x-K_w)^2);
+// mean = sum_w(S1_w + n K_w) / D,  var = sum_w(S2_w + 2 (K_w-mean) S1_w + n (K_w-mean)^2) / D.
 template <int NPL>
-__device__ __forceinline__ void ln_block(float (&v)[NPL / 8], float K, const float* w, const float* b,
+__device__ __forceinline__ void ln_block(float (&v)[NPL / 8], const float* w, const float* b,
                                          float* red, int warp, int lane) {
   constexpr int NPT = NPL / 8;
   constexpr float invD = 1.0f / (float)(NPL * 32);
+  constexpr float nwarp = (float)(NPT * 32);
+  const float K = __shfl_sync(0xffffffffu, v[0], 0);
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int j = 0; j < NPT; ++j) {
@@ -331,14 +334,19 @@ __device__ __forceinline__ void ln_block(float (&v)[NPL / 8], float K, const flo
     s1 += __shfl_xor_sync(0xffffffffu, s1, o);
     s2 += __shfl_xor_sync(0xffffffffu, s2, o);
   }
-  if (lane == 0) { red[2 * warp] = s1; red[2 * warp + 1] = s2; }
+  if (lane == 0) { red[3 * warp] = s1; red[3 * warp + 1] = s2; red[3 * warp + 2] = K; }
   ptx::named_bar_sync(1, NCT);
-  float S1 = 0.f, S2 = 0.f;
+  float tot = 0.f;
 #pragma unroll
-  for (int q = 0; q < NCW; ++q) { S1 += red[2 * q]; S2 += red[2 * q + 1]; }
-  const float m1 = S1 * invD;
-  const float mean = K + m1;
-  const float var = fmaxf(S2 * invD - m1 * m1, 0.f);
+  for (int q = 0; q < NCW; ++q) tot += red[3 * q] + nwarp * red[3 * q + 2];
+  const float mean = tot * invD;
+  float va = 0.f;
+#pragma unroll
+  for (int q = 0; q < NCW; ++q) {
+    const float d = red[3 * q + 2] - mean;
+    va += red[3 * q + 1] + 2.f * d * red[3 * q] + nwarp * d * d;
+  }
+  const float var = fmaxf(va * invD, 0.f);
   const float rstd = rsqrtf(var + 1e-5f);
 #pragma unroll
   for (int j = 0; j < NPT; ++j) {
@@ -646,15 +654,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
         prefetch_ln(1, p.ln2_w + (size_t)l * D, p.ln2_b + (size_t)l * D);  // for P4
         if constexpr (BT == 1) {
           float v[NPL / 8];
-          float K;
           if (tagged && l > 0) {
-            ld_tagged_slice<NPL / 8>(p.xt, warp * (NPL * 4) + lane, ep_base, v, K);
+            ld_tagged_slice<NPL / 8>(p.xt, warp * (NPL * 4) + lane, ep_base, v);
           } else {
 #pragma unroll
             for (int j = 0; j < NPL / 8; ++j) v[j] = __ldcg(p.xg + warp * (NPL * 4) + lane + 32 * j);
-            K = __ldcg(p.xg);
           }
-          ln_block<NPL>(v, K, lnA, lnA + D, sm.red, warp, lane);
+          ln_block<NPL>(v, lnA, lnA + D, sm.red, warp, lane);
 #pragma unroll
           for (int j = 0; j < NPL / 8; ++j)
             sm.xs[warp * (NPL * 4) + lane + 32 * j] = __float2bfloat16_rn(v[j]);
@@ -836,17 +842,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
               if (lane == 0) { pout[0] = mm; pout[1] = lt; }
               pout[2 + lane] = oa;
               pout[2 + 32 + lane] = ob;
+              if (tagged) {
+                // publish the partial: the release is cumulative over the warp's stores ordered by __syncwarp
+                __syncwarp();
+                if (lane == 0) st_release_gpu(p.pflag + (size_t)it * 32, ep_oproj);   // one 128-byte line per flag: no hot line
+              }
             }
           }
         }
         PROF_STAMP();
-        grid_sync(p.barrier, bar_target, G, p.bar_flavor);
+        if (!tagged) grid_sync(p.barrier, bar_target, G, p.bar_flavor);   // tagged: O-proj polls the partials' flags
         PROF_STAMP();
 
         // ---------------- P3: merge attention splits -> O-proj + residual ----------------
         // one warp per (row, head): the nsplit partials of a head are contiguous (66 floats
         // each); every load below is independent so they all fly together (one L2 round trip)
         for (int bh0 = warp; bh0 < BT * H; bh0 += 3 * NCW) {
+          if (tagged) {
+            // lanes 0..23 poll the flags of (head r3 = lane / 8, split lane % 8) of this round together
+            const int r3f = lane >> 3, sf = lane & 7;
+            const int bhf = bh0 + r3f * NCW;
+            const bool onf = r3f < 3 && bhf < BT * H && sf < nsplit && row_valid[bhf / H];
+            const unsigned* fp = p.pflag + ((size_t)bhf * nsplit + sf) * 32;
+            unsigned spins = 0;
+            for (;;) {
+              unsigned fv = ep_oproj;
+              if (onf) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(fv) : "l"(fp) : "memory");
+              if (__all_sync(0xffffffffu, fv == ep_oproj)) break;
+              if (++spins > (1u << 26)) __trap();
+            }
+          }
           float ms[3][8], ls[3][8], oa[3][8], ob[3][8];
 #pragma unroll
           for (int r3 = 0; r3 < 3; ++r3) {
@@ -898,16 +923,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
         else prefetch_ln(0, p.ln1_w, p.ln1_b);
         if constexpr (BT == 1) {
           float v[NPL / 8];
-          float K;
           if (tagged) {
-            ld_tagged_slice<NPL / 8>(p.xt, warp * (NPL * 4) + lane, ep_oproj, v, K);
+            ld_tagged_slice<NPL / 8>(p.xt, warp * (NPL * 4) + lane, ep_oproj, v);
             cp_async_wait_all();   // ln_2 parameters prefetched in P1 (ln_block's own CTA barrier publishes them)
           } else {
 #pragma unroll
             for (int j = 0; j < NPL / 8; ++j) v[j] = __ldcg(p.xg + warp * (NPL * 4) + lane + 32 * j);
-            K = __ldcg(p.xg);
           }
-          ln_block<NPL>(v, K, lnB, lnB + D, sm.red, warp, lane);
+          ln_block<NPL>(v, lnB, lnB + D, sm.red, warp, lane);
 #pragma unroll
           for (int j = 0; j < NPL / 8; ++j)
             sm.xs[warp * (NPL * 4) + lane + 32 * j] = __float2bfloat16_rn(v[j]);
@@ -991,9 +1014,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
           float v[NPL / 8];
 #pragma unroll
           for (int j = 0; j < NPL / 8; ++j) v[j] = __ldcg(p.xg + warp * (NPL * 4) + lane + 32 * j);
-          const float K = __ldcg(p.xg);
-          ln_block<NPL>(v, K, lnA, lnA + D, sm.red, warp, lane);
-          ln_block<NPL>(v, 0.f, lnB, lnB + D, sm.red + 2 * NCW, warp, lane);
+          ln_block<NPL>(v, lnA, lnA + D, sm.red, warp, lane);
+          ln_block<NPL>(v, lnB, lnB + D, sm.red + 3 * NCW, warp, lane);
 #pragma unroll
           for (int j = 0; j < NPL / 8; ++j)
             sm.xs[warp * (NPL * 4) + lane + 32 * j] = __float2bfloat16_rn(v[j]);
@@ -1746,6 +1768,7 @@ struct GptState {
   uint2* xt = nullptr;          // tagged residual stream (batch-1 decode)
   unsigned* ft = nullptr;       // tagged gelu(fc) words
   uint2 *qt = nullptr, *kvt = nullptr;
+  unsigned* pflag = nullptr;
   unsigned epoch = 0;           // epochs handed out so far
   int dataflow = 1;
   __nv_bfloat16* fg = nullptr;
@@ -1943,12 +1966,14 @@ static void launch_fused_t(idx_engine* e, GptState* g, GptParams& p) {
       IDX_CUDA(cudaMemsetAsync(g->xt, 0, (size_t)p.D * sizeof(uint2), e->stream));
       IDX_CUDA(cudaMemsetAsync(g->ft, 0, (size_t)p.FF * sizeof(unsigned), e->stream));
       IDX_CUDA(cudaMemsetAsync(g->qt, 0, (size_t)p.D * sizeof(uint2), e->stream));
+      IDX_CUDA(cudaMemsetAsync(g->pflag, 0, 32 * (size_t)(8 * p.H * std::max(1, p.G / p.H) + p.G) * sizeof(unsigned), e->stream));
       IDX_CUDA(cudaMemsetAsync(g->kvt, 0, 2 * (size_t)p.D * sizeof(uint2), e->stream));
       g->epoch = 0;
     }
     p.xt = g->xt;
     p.ft = g->ft;
     p.qt = g->qt;
+    p.pflag = g->pflag;
     p.kvt = g->kvt;
     p.epoch0 = g->epoch;
     g->epoch += need;
@@ -2117,6 +2142,7 @@ extern "C" int idx_gpt_init(idx_engine* e, const idx_gpt_config* cfg) {
   g->xt = galloc<uint2>(g, (size_t)D);
   g->ft = galloc<unsigned>(g, (size_t)FF);
   g->qt = galloc<uint2>(g, (size_t)D);
+  g->pflag = galloc<unsigned>(g, 32 * (size_t)(8 * H * std::max(1, G / H) + G));
   g->kvt = galloc<uint2>(g, 2 * (size_t)D);
   g->dataflow = getenv("IDX_GPT_DATAFLOW") ? atoi(getenv("IDX_GPT_DATAFLOW")) : 1;
   g->qg = galloc<float>(g, 8 * (size_t)D);
