@@ -644,6 +644,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
       PROF_STAMP();
 
       for (int l = 0; l < L; ++l) {
+        // Data-flow hand-overs (batch-1 decode): no grid barrier inside a layer.  Epochs are unique per (step, layer).
+        // Write-after-read safety without extra synchronisation — the next writer of every buffer transitively depends on
+        // data that all CTAs produce only after their own reads of it (program order + CTA barriers inside a CTA):
+        //   xt  (O-proj -> FC, PROJ -> next QKV): PROJ(l) starts on a CTA once it holds every ft word of FC(l), which each
+        //        CTA writes after its FC(l) read of xt; O-proj(l+1) needs the attention partials of all heads, hence
+        //        q/k/v columns from every CTA's QKV(l+1), each written after that CTA's read of xt;
+        //   ft  (FC -> PROJ): FC(l+1) needs every xt word of O-proj(l+1), which follows each CTA's PROJ(l) read of ft;
+        //   qt, kvt (QKV -> attention) and part/pflag (attention -> O-proj): QKV(l+1) needs every xt word of PROJ(l),
+        //        which follows each CTA's attention(l) and O-proj(l) reads.
+        // Steps are separated by the grid barriers around the head and the sampling phase.
         // tagged residual stream (batch-1 decode): epochs of the two x hand-overs of this layer
         const bool tagged = (BT == 1) && p.xt != nullptr;
         const unsigned ep_base = p.epoch0 + (unsigned)(step * L + l) * 2u;
