@@ -1058,22 +1058,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
           for (int i = tid; i < (V + 31) / 32; i += NCT)
             sm.seen_s[i] = p.seen[(size_t)b * ((V + 31) / 32) + i];
           ptx::named_bar_sync(1, NCT);
+#define FINE_STAMP(n) do { if (p.prof && cta == 0 && tid == 0 && step == p.nsteps - 1) p.prof[256 + (n)] = gtimer(); } while (0)
+          FINE_STAMP(32);
           const unsigned* seen = sm.seen_s;
           // processed scores of this thread's slice stay in registers: s = rep_penalty(logit) [/ temperature]
           constexpr int VPT = 40;   // ceil(V / 256) for V <= 10240
           float sv[VPT];
           const float inv_temp = (p.do_sample && p.temperature > 0.f) ? 1.0f / p.temperature : 1.0f;
+          // two passes: all loads first (they then fly together: one L2 round trip instead of one per element —
+          // fused into one loop the compiler serialised load -> test -> next load, 10.8 us of the 14 us of this phase)
 #pragma unroll
           for (int j = 0; j < VPT; ++j) {
             const int i = tid + j * NCT;
-            float sc = -INFINITY;
+            sv[j] = (i < V) ? __ldcg(lg + i) : -INFINITY;
+          }
+#pragma unroll
+          for (int j = 0; j < VPT; ++j) {
+            const int i = tid + j * NCT;
             if (i < V) {
-              sc = __ldcg(lg + i);
+              float sc = sv[j];
               if ((seen[i >> 5] >> (i & 31)) & 1u) sc = (sc < 0.f) ? sc * p.rep_penalty : sc / p.rep_penalty;
               if (i == p.stop_tok && k < p.forbid_stop_before) sc = -INFINITY;
               if (p.do_sample) sc *= inv_temp;
+              sv[j] = sc;
             }
-            sv[j] = sc;
           }
           float* red = sm.red;
           // block argmax with lowest-index tie break; `extract` removes the winner from its owner's registers
@@ -1101,8 +1109,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
             }
             bestv = best; besti = bi;
           };
+          FINE_STAMP(33);
           float best; int besti;
           block_argmax(best, besti);
+          FINE_STAMP(34);
           if (p.do_sample) {
             // top-k: extract candidates in descending order (ties at the k-th value are all kept, like
             // TopKLogitsWarper's `scores < kth` test), at most 64
@@ -1159,6 +1169,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
               p.seen[(size_t)b * ((V + 31) / 32) + (feed >> 5)] |= 1u << (feed & 31);
             }
           }
+          FINE_STAMP(35);
           ptx::named_bar_sync(1, NCT);
         }
         PROF_STAMP();

@@ -34,6 +34,10 @@ def main():
     fine = st_all[256:]
     print('fine QKV (ns deltas):', np.diff(fine[:12][fine[:12] > 0]).tolist())
     print('fine FC  (ns deltas):', np.diff(fine[16:28][fine[16:28] > 0]).tolist())
+    fs = fine[32:36]
+    if (fs > 0).all():
+        print('sampling phase (us): seen copy+sync -> logits/penalty', (fs[1] - fs[0]) / 1000, '-> argmax', (fs[2] - fs[1]) / 1000,
+              '-> bookkeeping', (fs[3] - fs[2]) / 1000)
     st = st_all[:256]
     st = st[st > 0]
     d = np.diff(st)
