@@ -171,13 +171,12 @@ static EmoState* g_emo_of(idx_engine* e);
     (e)->launches++;               \
   } while (0)
 
-static std::unordered_map<idx_engine*, EmoState*>& emo_map() {
-  static std::unordered_map<idx_engine*, EmoState*> m;
-  return m;
-}
-static EmoState* g_emo_of(idx_engine* e) {
-  auto it = emo_map().find(e);
-  return it == emo_map().end() ? nullptr : it->second;
+static EmoState* g_emo_of(idx_engine* e) { return e->emo; }
+
+void emo_destroy(EmoState* s) {
+  if (!s) return;
+  s->pool.release();
+  delete s;
 }
 
 // stack q,k,v linears into one [3*od][od] packed weight
@@ -207,10 +206,10 @@ extern "C" int idx_emo_init(idx_engine* e, const idx_emo_config* cfg) {
   IDX_API_BEGIN
   IDX_CHECK(e && cfg, IDX_ERR_ARG, "null argument");
   IDX_CUDA(cudaSetDevice(e->device));
-  EmoState* s = g_emo_of(e);
-  if (s) { s->pool.release(); delete s; }
-  s = new EmoState();
-  emo_map()[e] = s;
+  emo_destroy(e->emo);
+  e->emo = nullptr;
+  EmoState* s = new EmoState();
+  e->emo = s;
   s->cfg = *cfg;
   const std::string E = "gpt.emo_conditioning_encoder.", Q = "gpt.emo_perceiver_encoder.";
   s->conv_w = e->Wf(E + "embed.conv.0.weight");

@@ -51,6 +51,7 @@ static inline size_t idx_dtype_size(int dt) {
 }
 
 struct GptState;      // gpt_decode.cu
+struct EmoState;      // emo.cu
 struct BigvganState;  // bigvgan.cu
 struct S2melState;    // s2mel.cu
 
@@ -88,6 +89,7 @@ struct idx_engine {
   GptState* gpt = nullptr;
   BigvganState* bigvgan = nullptr;
   S2melState* s2mel = nullptr;
+  EmoState* emo = nullptr;
 
   const DevTensor& W(const std::string& name) const {
     auto it = weights.find(name);
@@ -118,6 +120,7 @@ void idx_from_device(idx_engine* e, void* dst, const void* src_dev, size_t bytes
 void gpt_destroy(GptState*);
 void bigvgan_destroy(BigvganState*);
 void s2mel_destroy(S2melState*);
+void emo_destroy(EmoState*);
 
 #define IDX_API_BEGIN try {
 #define IDX_API_END(e)                                     \
