@@ -3,11 +3,15 @@
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs.  The product path (index-tts_b200/) never imports it.
 
-Parity status: the reference's own tests pin no numbers for this path (SURVEY.md §4, §8c —
-"parity unpinned" by the reference).  This restatement is pinned instead against stock
-`transformers.GPT2Model` (the block arithmetic the reference executes, gpt/model_v2.py:263)
-run in this container — fp32 and CPU-autocast bf16 — by oracle/validate_gpt_vs_hf.py, and the
-golden vectors in tests/golden/gpt_*.npz were minted from that HF path.
+Parity status: PINNED against the reference itself.  The reference's own tests pin no numbers for
+this path, so the restatement is checked against outputs of the reference's own
+`UnifiedVoice.inference_speech` (gpt/model_v2.py:716-825: its prepare_gpt_inputs, vendored GPT2 blocks,
+vendored generate()/_beam_search and BeamSearchScorer) run on CPU in this container with the same
+seeded weights — oracle/make_goldens_gpt_ref.py → tests/golden/gpt_ref_wrapper.npz: prompt embeddings,
+greedy tokens and logits (6.4e-6), plain beam search, beam-sample with the RNG contract substituted.
+In addition the blocks are checked against stock `transformers.GPT2Model` in fp32 and under CPU
+autocast bf16 (oracle/validate_gpt_vs_hf.py → tests/golden/gpt_small.npz), which is what anchors the
+bf16 rounding-point model.
 
 What is restated (reference file:line):
   prepare_gpt_inputs                       indextts/gpt/model_v2.py:648-714 (+ :754-768 conds)

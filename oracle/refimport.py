@@ -120,3 +120,95 @@ def codec_module(**kw):
     m = EnhancedCodec(**kw)
     m.eval()
     return m
+
+
+def gpt_module(cfg, weights):
+    """The reference's own `UnifiedVoice` (indextts/gpt/model_v2.py:305-493, spk_cond_mode="campplus" = IndexTTS-2.5)
+    with its vendored GPT2 blocks and generate() loop, running on CPU under transformers 5.x.
+
+    `indextts/gpt/transformers_generation_utils.py` was vendored from transformers 4.52 and imports ~25 names that
+    5.x removed.  None of them is on the executed path of greedy / beam decoding: missing classes and constants are
+    stubbed with empty types, `isin_mps_friendly` is given its definition (torch.isin), the removed
+    `transformers.generation.beam_search` module is replaced by the reference's own vendored
+    `indextts/gpt/transformers_beam_search.py`, and three legacy GenerationConfig attributes default to None.
+    `weights` (reference state-dict names, oracle.gpt.make_gpt_weights) are loaded into the module."""
+    import importlib
+    import importlib.util
+    import re
+
+    import torch
+    import transformers  # noqa: F401  (before setup(): its optional-dependency probe must not meet the librosa stub)
+    from transformers import GenerationConfig, PretrainedConfig
+    import transformers.generation  # noqa: F401
+    setup()
+
+    def dummy(name):
+        return type(name, (), {"__init__": lambda self, *a, **k: None})
+
+    def stub_module(name):
+        mod = types.ModuleType(name)
+        mod.__path__ = []
+
+        def _ga(n):
+            if n.startswith("__"):
+                raise AttributeError(n)
+            return dummy(n)
+        mod.__getattr__ = _ga
+        sys.modules[name] = mod
+        parent, _, child = name.rpartition(".")
+        if parent in sys.modules:
+            setattr(sys.modules[parent], child, mod)
+        return mod
+
+    # the reference's own BeamSearchScorer stands in for the module transformers 5.x dropped
+    if "transformers.generation.beam_constraints" not in sys.modules:
+        stub_module("transformers.generation.beam_constraints")
+    if "transformers.generation.beam_search" not in sys.modules:
+        spec = importlib.util.spec_from_file_location("transformers.generation.beam_search",
+                                                      os.path.join(REF, "indextts", "gpt", "transformers_beam_search.py"))
+        bs = importlib.util.module_from_spec(spec)
+        sys.modules["transformers.generation.beam_search"] = bs
+        spec.loader.exec_module(bs)
+        setattr(sys.modules["transformers.generation"], "beam_search", bs)
+    m = None
+    for _ in range(100):
+        for k in [k for k in sys.modules if k.startswith("indextts.gpt")]:
+            del sys.modules[k]
+        try:
+            m = importlib.import_module("indextts.gpt.model_v2")
+            break
+        except ModuleNotFoundError as e:
+            stub_module(e.name)
+        except ImportError as e:
+            mm = re.search(r"cannot import name '(\w+)' from '([\w\.]+)'", str(e))
+            if not mm:
+                raise
+            setattr(sys.modules[mm.group(2)], mm.group(1), dummy(mm.group(1)))
+    assert m is not None, "could not import indextts.gpt.model_v2"
+    tgu = sys.modules["indextts.gpt.transformers_generation_utils"]
+    tgu.isin_mps_friendly = lambda elements, test_elements: torch.isin(elements, test_elements)
+    if not hasattr(PretrainedConfig, "_get_non_default_generation_parameters"):
+        PretrainedConfig._get_non_default_generation_parameters = lambda self: {}
+    names = set(re.findall(r"generation_config\.(\w+)", open(os.path.join(REF, "indextts", "gpt", "transformers_generation_utils.py")).read()))
+    probe = GenerationConfig()
+    for n in sorted(names):
+        if not n.startswith("_") and not hasattr(probe, n):
+            setattr(GenerationConfig, n, None)
+
+    tiny = dict(output_size=32, linear_units=48, attention_heads=2, num_blocks=1, input_layer="conv2d2", perceiver_mult=2)
+    g = m.UnifiedVoice(layers=cfg["layers"], model_dim=cfg["model_dim"], heads=cfg["heads"],
+                       max_text_tokens=cfg["max_text_tokens"], max_mel_tokens=cfg["max_mel_tokens"],
+                       number_text_tokens=cfg["number_text_tokens"], number_mel_codes=cfg["number_mel_codes"],
+                       start_mel_token=cfg["start_mel_token"], stop_mel_token=cfg["stop_mel_token"],
+                       condition_type="conformer_perceiver", condition_module=dict(tiny), emo_condition_module=dict(tiny),
+                       spk_cond_mode="campplus")
+    sd = g.state_dict()
+    own = {k: v for k, v in weights.items() if k in sd}
+    missing = [k for k in weights if k not in sd]
+    assert not missing, f"oracle weight names unknown to the reference module: {missing}"
+    for k, v in own.items():
+        assert tuple(sd[k].shape) == tuple(v.shape), (k, tuple(sd[k].shape), tuple(v.shape))
+    g.load_state_dict(own, strict=False)
+    g.eval()
+    g.post_init_gpt2_config(use_deepspeed=False, kv_cache=True, half=False)
+    return g

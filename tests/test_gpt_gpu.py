@@ -286,3 +286,21 @@ def test_beam_search_variants_and_batch(engine):
                                         temperature=3.0, seed=5)
     _check_beam_run(engine, cfg, p0, 40, _beam_params(cfg, repetition_penalty=1.0, top_k=0, top_p=1.0, temperature=3.0, seed=5),
                     0, c3, lg3)
+
+
+def test_strict_fp32_engine_vs_reference_unifiedvoice_golden(engine):
+    """The CUDA path (strict fp32) against outputs of the reference's own `UnifiedVoice.inference_speech`
+    (tests/golden/gpt_ref_wrapper.npz, oracle/make_goldens_gpt_ref.py): prompt assembly, 24 greedy tokens, logits."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "gpt_ref_wrapper.npz"))
+    cfg, _, _, _ = small_case()
+    cfg = dict(cfg, n_langs=106)
+    w = make_gpt_weights(cfg, seed=int(g["seed"]), bf16=False)
+    load_gpt(engine, cfg, w, bf16=False)
+    prompt = engine.gpt_prepare_inputs(g["style"], g["emo"], g["text"], int(g["lang"]))
+    assert prompt.shape == g["prompt"].shape and np.abs(prompt - g["prompt"]).max() <= 1e-5
+    n = int(g["n_steps"])
+    (codes,), (logits,) = engine.gpt_generate([prompt], n, 10.0, return_logits=True)
+    assert codes.tolist() == g["greedy_codes"][: len(codes)].tolist()
+    err = float(np.abs(logits - g["greedy_logits"][: len(codes)]).max())
+    print(f"strict fp32 engine vs reference UnifiedVoice: {len(codes)} tokens identical, max |logit diff| {err:.2e}")
+    assert err <= 1e-4

@@ -88,3 +88,59 @@ def test_philox_known_answer_and_sampler_properties():
     for i in range(4000):
         cnt[sample_token(s2, 0, 1.0, seed=123, step=i, seq=0)[0]] += 1
     assert np.abs(cnt / 4000 - np.array([0.5, 0.3, 0.15, 0.05])).max() < 0.03
+
+
+REF_GOLD = os.path.join(os.path.dirname(__file__), "golden", "gpt_ref_wrapper.npz")
+
+
+def _ref_case():
+    g = np.load(REF_GOLD)
+    cfg, _, _, _ = small_case()
+    cfg = dict(cfg, n_langs=106)
+    w = make_gpt_weights(cfg, seed=int(g["seed"]), bf16=False)
+    return g, cfg, w
+
+
+def test_oracle_matches_reference_unifiedvoice_wrapper():
+    """Golden minted from the reference's own `UnifiedVoice.inference_speech` (model_v2.py:716-825: its
+    prepare_gpt_inputs, its vendored GPT2 blocks, its vendored generate loop) run on CPU in fp32 with these seeded
+    weights (oracle/make_goldens_gpt_ref.py): the restated wrapper logic — prompt assembly, the P1 position rule, the
+    fake prompt ids in the repetition penalty (P2), the double LayerNorm head (P3) — reproduces it."""
+    g, cfg, w = _ref_case()
+    style, emo, text = torch.from_numpy(g["style"]), torch.from_numpy(g["emo"]), torch.from_numpy(g["text"])
+    prompt = prepare_gpt_inputs(w, style, emo, text, lang=int(g["lang"]), bf16=False).numpy()
+    assert prompt.shape == g["prompt"].shape and np.abs(prompt - g["prompt"]).max() < 1e-6
+    n = int(g["n_steps"])
+    codes, logits = GptOracle(cfg, w, bf16=False).generate(prompt, n, 10.0, 0)
+    assert codes.tolist() == g["greedy_codes"][: len(codes)].tolist()
+    assert np.abs(logits - g["greedy_logits"][: len(codes)]).max() < 1e-4
+
+
+def test_oracle_beam_search_matches_reference_beam_search():
+    """The reference's `_beam_search` + its own BeamSearchScorer (num_beams=3, do_sample=False) produced
+    `beam_codes`; the restated beam logic driven by the restated model returns the same hypothesis."""
+    from oracle import beam
+    g, cfg, w = _ref_case()
+    n = int(g["n_steps"])
+    p = dict(num_beams=3, start=cfg["start_mel_token"], stop=cfg["stop_mel_token"], repetition_penalty=10.0,
+             temperature=0.8, top_k=30, top_p=0.8, length_penalty=0.0, seed=0, forbid_stop_before=0, do_sample=False)
+    out = beam.generate_beam(lambda: GptOracle(cfg, w, bf16=False), g["prompt"], p, n)
+    assert out["codes"].tolist() == g["beam_codes"][: len(out["codes"])].tolist()
+
+
+def test_oracle_beam_sample_matches_reference_beam_sample_with_substituted_rng():
+    """Beam-sample (num_beams=3, do_sample=True, the `.infer()` default).  The goldens come from the reference's own
+    `_beam_search` + HF logits processors + BeamSearchScorer, with `torch.multinomial` replaced by the documented Philox
+    draw applied to the scores the reference computed (oracle/make_goldens_gpt_ref.py): every step's (parent, token)
+    choices and the returned hypothesis — two sampling configurations, one sharp, one flat."""
+    from oracle import beam
+    g, cfg, w = _ref_case()
+    n = int(g["n_steps"])
+    for tag, kw in (("a", dict(top_p=0.8, top_k=30, temperature=0.8)), ("b", dict(top_p=0.95, top_k=12, temperature=2.5))):
+        p = dict(num_beams=3, start=cfg["start_mel_token"], stop=cfg["stop_mel_token"], repetition_penalty=10.0,
+                 length_penalty=0.0, seed=int(g["beam_sample_seed"]), forbid_stop_before=0, do_sample=True, **kw)
+        out = beam.generate_beam(lambda: GptOracle(cfg, w, bf16=False), g["prompt"], p, n)
+        assert out["codes"].tolist() == g[f"beam_sample_{tag}_codes"][: len(out["codes"])].tolist()
+        assert [t[0] for t in out["trace"]] == g[f"beam_sample_{tag}_parents"].tolist()
+        assert [t[1] for t in out["trace"]] == g[f"beam_sample_{tag}_tokens"].tolist()
+    assert g["beam_sample_b_codes"].tolist() != g["beam_codes"].tolist()      # the flat configuration really samples
