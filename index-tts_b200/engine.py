@@ -436,9 +436,9 @@ class Engine:
         """infer_v2_5.py:827-856 for one segment.  Host or device (torch.cuda) buffers.
         Returns dict(wav=[F*256] f32, pcm16=..., mel=[80,F])."""
         on_dev = torch is not None and isinstance(z, torch.Tensor) and z.is_cuda
-        if on_dev:
+        if on_dev and isinstance(codes, torch.Tensor):
             codes_t = codes.to(torch.int32).contiguous()
-        else:
+        else:      # host codes are fine next to device buffers: every ABI pointer may be host or device
             codes_t = np.ascontiguousarray(np.asarray(codes, dtype=np.int32).reshape(-1))
         pc, rm, st, zz = (_as_f32(a) for a in (prompt_condition, ref_mel, style, z))
         P = int(rm.shape[-1])
