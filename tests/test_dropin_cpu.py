@@ -1,0 +1,88 @@
+"""CPU (build container only: needs /root/reference): `dropin.load_reference_weights` against the REAL reference
+modules.  The reference's own classes are instantiated (random init, small dims) through oracle/refimport.py, a
+recording stand-in replaces the engine, and the test checks that every hyper-parameter the drop-in derives from the
+modules' state dicts equals what the modules were constructed with, and that every tensor name the engine will ask for
+(`gpt.…`, `s2mel.…`, `codec.…`, `bigvgan.…`) is present.  Skipped where the reference tree is absent (GPU box)."""
+import types
+
+import pytest
+import torch
+
+from oracle import refimport
+
+pytestmark = pytest.mark.skipif(not refimport.available(), reason="/root/reference not present")
+
+
+class RecordingEngine:
+    device = 0
+
+    def __init__(self):
+        self.weights, self.calls = {}, {}
+
+    def load_state_dict(self, prefix, sd):
+        for k, v in sd.items():
+            self.weights[prefix + k] = tuple(v.shape)
+
+    def gpt_init(self, *a, **k):
+        self.calls["gpt_init"] = (a, k)
+
+    def emo_init(self, c):
+        self.calls["emo_init"] = dict(c)
+        self.emo_cfg = types.SimpleNamespace(**c)
+
+    def s2mel_init(self, c):
+        self.calls["s2mel_init"] = dict(c)
+
+    def codec_init(self, c):
+        self.calls["codec_init"] = dict(c)
+
+    def bigvgan_init(self, h):
+        self.calls["bigvgan_init"] = dict(h)
+
+
+def test_config_derivation_from_real_reference_modules():
+    from indextts_b200 import synth
+    from indextts_b200.dropin import load_reference_weights
+    from oracle.gpt import make_gpt_weights
+    from oracle.validate_gpt_vs_hf import small_case
+
+    cfg, _, _, _ = small_case()
+    cfg = dict(cfg, n_langs=106)
+    gpt = refimport.gpt_module(cfg, make_gpt_weights(cfg, seed=1, bf16=False))
+    s2 = refimport.s2mel_module(refimport.s2mel_args(hidden=64, heads=1, depth=3, wn_hidden=64, wn_layers=2,
+                                                     content_dim=64, lr_in=96, style_dim=24))
+    codec = refimport.codec_module(codebook_size=64, hidden_size=96, codebook_dim=8, vocos_dim=48,
+                                   vocos_intermediate_dim=64, vocos_num_layers=2)
+    h = synth.small_config()
+    bv = refimport.bigvgan_module(h)
+    tts = types.SimpleNamespace(gpt=gpt, s2mel=s2, semantic_codec=codec, bigvgan=bv)
+    eng = RecordingEngine()
+    load_reference_weights(eng, tts, max_batch=4)
+
+    a, k = eng.calls["gpt_init"]
+    assert a[:6] == (cfg["layers"], cfg["model_dim"], cfg["heads"], cfg["number_mel_codes"], cfg["start_mel_token"],
+                     cfg["stop_mel_token"])
+    assert a[6] == cfg["max_mel_tokens"] + 2 + 1            # mel_pos rows (model_v2.py:398-400)
+    assert k["max_batch"] == 4 and k["weights_bf16"] is True
+    emo = eng.calls["emo_init"]
+    assert (emo["idim"], emo["odim"], emo["linear_units"], emo["heads"], emo["blocks"]) == (1024, 32, 48, 2, 1)
+    assert emo["model_dim"] == cfg["model_dim"] and emo["p_dim"] == gpt.emo_perceiver_encoder.latents.shape[-1]
+    s = eng.calls["s2mel_init"]
+    assert (s["hidden"], s["heads"], s["depth"], s["wn_hidden"], s["wn_layers"], s["wn_kernel"]) == (64, 1, 3, 64, 2, 5)
+    assert (s["in_channels"], s["content_dim"], s["style_dim"], s["lr_in"], s["lr_convs"]) == (80, 64, 24, 96, 4)
+    c = eng.calls["codec_init"]
+    assert c == dict(codebook_size=64, hidden_size=96, codebook_dim=8, vocos_dim=48, vocos_intermediate_dim=64,
+                     vocos_num_layers=2)
+    assert eng.calls["bigvgan_init"]["upsample_rates"] == list(h["upsample_rates"])
+    # the tensors the C++ side looks up by name exist under the names the reference uses
+    need = ["gpt.gpt.h.0.attn.c_attn.weight", "gpt.mel_head.weight", "gpt.final_norm.weight", "gpt.spk_emb_proj.weight",
+            "gpt.lang_embedding.weight", "gpt.text_pos_embedding.emb.weight", "gpt.emovec_layer.weight",
+            "gpt.emo_conditioning_encoder.embed.out.0.weight", "gpt.emo_perceiver_encoder.latents",
+            "s2mel.cfm.estimator.cond_projection.weight", "s2mel.cfm.estimator.wavenet.in_layers.0.conv.conv.weight",
+            "s2mel.length_regulator.content_in_proj.weight", "codec.quantizer.quantizers.0.codebook.weight",
+            "codec.decoder.1.weight", "bigvgan.conv_pre.weight", "bigvgan.ups.0.0.weight",
+            "bigvgan.resblocks.0.convs1.0.weight", "bigvgan.conv_post.weight"]
+    missing = [n for n in need if n not in eng.weights]
+    assert not missing, missing
+    assert not any(".weight_g" in n or ".weight_v" in n or "parametrizations" in n for n in eng.weights), \
+        "weight-norm pairs must be folded before they reach the engine"
