@@ -86,3 +86,61 @@ def test_config_derivation_from_real_reference_modules():
     assert not missing, missing
     assert not any(".weight_g" in n or ".weight_v" in n or "parametrizations" in n for n in eng.weights), \
         "weight-norm pairs must be folded before they reach the engine"
+
+
+def _reference_call_sites():
+    """(positional count, keyword names) of the calls `infer_generator` makes at the six seams (infer_v2_5.py:749-864),
+    read from the reference source with ast."""
+    import ast
+    import os
+    src = open(os.path.join(refimport.REF, "indextts", "infer_v2_5.py")).read()
+    tree = ast.parse(src)
+    want = {"self.gpt.merge_emovec": "merge_emovec", "self.gpt.inference_speech": "inference_speech",
+            "self.semantic_codec.decode": "codec_decode", "self.s2mel.models['length_regulator']": "length_regulator",
+            "self.s2mel.models['cfm'].inference": "cfm_inference", "self.bigvgan": "bigvgan"}
+    found = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Call):
+            name = ast.unparse(node.func)
+            if name in want:
+                kws = [k.arg for k in node.keywords if k.arg is not None]
+                star = any(k.arg is None for k in node.keywords)
+                found.setdefault(want[name], []).append((len(node.args), kws, star))
+    return found
+
+
+def test_rebound_seams_accept_the_reference_call_sites():
+    """Every call `infer_v2_5.py` makes at a seam binds to the callable `attach` installs there (same positional
+    arity, same keyword names) — the drop-in claim of INTEGRATION.md, checked against the reference source."""
+    import inspect
+
+    from indextts_b200 import synth
+    from indextts_b200.dropin import attach
+    from oracle.gpt import make_gpt_weights
+    from oracle.validate_gpt_vs_hf import small_case
+
+    cfg, _, _, _ = small_case()
+    cfg = dict(cfg, n_langs=106)
+    gpt = refimport.gpt_module(cfg, make_gpt_weights(cfg, seed=1, bf16=False))
+    s2 = refimport.s2mel_module(refimport.s2mel_args(hidden=64, heads=1, depth=3, wn_hidden=64, wn_layers=2,
+                                                     content_dim=64, lr_in=96, style_dim=24))
+    codec = refimport.codec_module(codebook_size=64, hidden_size=96, codebook_dim=8, vocos_dim=48,
+                                   vocos_intermediate_dim=64, vocos_num_layers=2)
+    bv = refimport.bigvgan_module(synth.small_config())
+    tts = types.SimpleNamespace(gpt=gpt, s2mel=s2, semantic_codec=codec, bigvgan=bv)
+    eng = RecordingEngine()
+    attach(tts, engine=eng)
+    seams = {"merge_emovec": tts.gpt.merge_emovec, "inference_speech": tts.gpt.inference_speech,
+             "codec_decode": tts.semantic_codec.decode, "length_regulator": tts.s2mel.models["length_regulator"].forward,
+             "cfm_inference": tts.s2mel.models["cfm"].inference, "bigvgan": tts.bigvgan.forward}
+    sites = _reference_call_sites()
+    assert set(sites) == set(seams), (sorted(sites), sorted(seams))
+    for name, calls in sites.items():
+        sig = inspect.signature(seams[name])
+        for npos, kws, star in calls:
+            try:
+                sig.bind(*([None] * npos), **{k: None for k in kws})
+            except TypeError as e:
+                raise AssertionError(f"{name}: reference call ({npos} positional, keywords {kws}) does not bind to {sig}: {e}")
+    # the rebound objects are the reference's own module objects: infer_generator reaches them unchanged
+    assert tts.gpt is gpt and tts.bigvgan is bv and tts._b200_engine is eng
