@@ -67,7 +67,8 @@ int idx_event_record(idx_engine* e, int slot);
 int idx_event_elapsed_ms(idx_engine* e, int slot_a, int slot_b, double* ms);
 
 /* Engine options.  "gemm_backend": 0 = automatic (tcgen05 tf32 implicit GEMM wherever the shape
- * allows — the default), 1 = SIMT fp32 everywhere (strict-fp32 parity runs).                */
+ * allows — the default), 1 = SIMT fp32 everywhere (strict-fp32 parity runs).  Options belong to the
+ * handle: another engine (another GPU, another thread) keeps its own.                             */
 int idx_set_option(idx_engine* e, const char* name, int value);
 
 /* -------------------------------------------------------------------- weights -- */

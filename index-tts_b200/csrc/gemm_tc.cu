@@ -19,6 +19,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <map>
+#include <mutex>
 #include <tuple>
 #include <cstdlib>
 
@@ -239,6 +240,9 @@ CUtensorMap make_map(const void* ptr, int rank, const cuuint64_t* dims, const cu
   static const bool plain_f32 = getenv("IDX_TMA_F32") != nullptr;
   MapKey key(ptr, (long long)dims[0], (long long)dims[1], rank > 2 ? (long long)dims[2] : 0,
              (long long)strides_bytes[0] ^ ((rank > 2 ? (long long)strides_bytes[1] : 0) << 20), (int)box[1], rank);
+  // process-wide cache (keys carry the unique UVA address): engines may be driven from different threads
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
   auto& cache = map_cache();
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
@@ -276,10 +280,10 @@ void launch_bn(idx_engine* e, const ConvGemm& g, const CUtensorMap& tmA, const C
   if (stages > n_iters) stages = n_iters < 2 ? 2 : n_iters;
   p.stages = stages;
   const size_t smem = (size_t)stages * STAGE + 1024 + (2 * stages + 1) * 8 + 16;
-  static bool attr_done = false;
-  if (!attr_done) {
+  const unsigned bit = BN == 32 ? 1u : (BN == 64 ? 2u : 4u);
+  if (!(e->attr_done & bit)) {     // per engine = per device: function attributes live in the device's context
     IDX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_done = true;
+    e->attr_done |= bit;
   }
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.B);
   gemm_tc_kernel<BN><<<grid, 192, smem, e->stream>>>(tmA, tmB, p);

@@ -647,7 +647,7 @@ void rope_table(idx_engine* e, float* tab, int T, int hd) {
 void attention_rope(idx_engine* e, const float* qkv, float* out, int B, int T, int H, const float* rope,
                     const int* lens) {
   static const bool unfused = getenv("IDX_ATTN_UNFUSED") != nullptr;
-  if (gemm_default_backend() == 0 && lens == nullptr && !unfused) {
+  if (gemm_default_backend(e) == 0 && lens == nullptr && !unfused) {
     // fused tensor-core flash attention: rotate/split once, then one kernel per layer
     const size_t mark = e->arena.off;
     const long long BH = (long long)B * H;
@@ -661,7 +661,7 @@ void attention_rope(idx_engine* e, const float* qkv, float* out, int B, int T, i
     e->arena.off = mark;
     return;
   }
-  if (gemm_default_backend() == 0 && lens == nullptr && T >= 128) {
+  if (gemm_default_backend(e) == 0 && lens == nullptr && T >= 128) {
     // tensor-core path: rotate/split -> S = Q K^T (tcgen05) -> row softmax -> O = P V (tcgen05) -> merge
     const size_t mark = e->arena.off;
     const int Tp = (T + 3) & ~3;
@@ -689,11 +689,10 @@ void attention_rope(idx_engine* e, const float* qkv, float* out, int B, int T, i
     e->arena.off = mark;
     return;
   }
-  static bool attr_set = false;
   const int smem = 4 * AQ * AD * sizeof(float);
-  if (!attr_set) {
+  if (!(e->attr_done & 8u)) {      // per engine = per device: function attributes live in the device's context
     IDX_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    e->attr_done |= 8u;
   }
   dim3 grid((T + AQ - 1) / AQ, H, B);
   attention_kernel<<<grid, 256, smem, e->stream>>>(qkv, out, T, H, rope, lens);

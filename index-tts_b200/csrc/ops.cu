@@ -146,9 +146,6 @@ __global__ void transpose_kernel(const float* in, float* out, int R, int Cc) {
 
 }  // namespace
 
-static int g_force_backend = 0;  // 0 auto, 1 SIMT, 2 tensor core (diagnostics)
-static int g_default_backend = 0; // set through idx_set_option("gemm_backend")
-int gemm_default_backend() { return g_default_backend; }
 
 extern "C" int idx_set_option(idx_engine* e, const char* name, int value) {
   IDX_API_BEGIN
@@ -156,7 +153,7 @@ extern "C" int idx_set_option(idx_engine* e, const char* name, int value) {
   const std::string n(name);
   if (n == "gemm_backend") {
     IDX_CHECK(value >= 0 && value <= 1, IDX_ERR_ARG, "gemm_backend: 0 = auto (tcgen05 tf32 where applicable), 1 = SIMT fp32");
-    g_default_backend = value;
+    e->gemm_backend = value;       // per engine: another handle (another GPU, another thread) keeps its own
   } else {
     throw IdxError(IDX_ERR_ARG, "unknown option: " + n);
   }
@@ -166,12 +163,12 @@ extern "C" int idx_set_option(idx_engine* e, const char* name, int value) {
 void conv_gemm(idx_engine* e, const ConvGemm& g) {
   IDX_CHECK(g.A && g.out && g.M > 0 && g.N > 0 && g.K > 0, IDX_ERR_ARG, "conv_gemm: bad arguments");
   static const bool force_simt = getenv("IDX_FORCE_SIMT") != nullptr;
-  if (g_force_backend == 2) {
+  if (e->force_backend == 2) {
     IDX_CHECK(g.Wk && !g.reflect, IDX_ERR_ARG, "conv_gemm: tensor-core path not applicable");
     gemm_tc_launch(e, g);
     return;
   }
-  if (!force_simt && g_force_backend != 1 && !(g_force_backend == 0 && g_default_backend == 1) && g.Wk &&
+  if (!force_simt && e->force_backend != 1 && !(e->force_backend == 0 && e->gemm_backend == 1) && g.Wk &&
       gemm_tc_supported(g)) {
     gemm_tc_launch(e, g);
     return;
@@ -304,7 +301,7 @@ extern "C" int idx_debug_conv_gemm(idx_engine* e, const float* A, int B, int Tin
   g.A = dA; g.B = B; g.Tin = Tin; g.K = K; g.W = dWs; g.Wk = dWk; g.taps = taps; g.dil = dil; g.pad = pad;
   g.M = M; g.N = N; g.bias = dBias; g.biasN = biasN; g.act = act; g.res = dRes; g.accum = accum; g.scale = scale;
   g.out = dOut; g.out_off = out_off; g.ldo = ldo; g.out_valid = out_valid; g.out_batch_stride = out_elems_per_batch;
-  g_force_backend = backend;
+  e->force_backend = backend;
   try {
     conv_gemm(e, g);
     // timing loop (diagnostics): env IDX_GEMM_REPS=n repeats the launch between CUDA events
@@ -322,10 +319,10 @@ extern "C" int idx_debug_conv_gemm(idx_engine* e, const float* A, int B, int Tin
       cudaEventDestroy(a); cudaEventDestroy(b2);
     }
   } catch (...) {
-    g_force_backend = 0;
+    e->force_backend = 0;
     throw;
   }
-  g_force_backend = 0;
+  e->force_backend = 0;
   idx_from_device(e, out, dOut, no * 4);
   IDX_CUDA(cudaStreamSynchronize(e->stream));
   IDX_API_END(e)

@@ -39,7 +39,7 @@ struct ConvGemm {
 };
 
 void conv_gemm(idx_engine* e, const ConvGemm& g);
-int gemm_default_backend();   // 0 auto (tcgen05 where applicable), 1 SIMT fp32
+inline int gemm_default_backend(const idx_engine* e) { return e->gemm_backend; }   // 0 auto (tcgen05), 1 SIMT fp32
 
 // [B][C][T] <-> [B][T][C]
 void transpose_bct_to_btc(idx_engine* e, const float* in, float* out, int B, int C, int T);
