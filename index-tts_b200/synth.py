@@ -353,3 +353,70 @@ def make_emo_weights(c, seed=777):
     lin("emovec_layer", c["model_dim"], pd)
     lin("emo_layer", c["model_dim"], c["model_dim"])
     return w
+
+
+# ------------------------------------------------------------------ IndexTTS v1 / v1.5 vocoder (row a13) --
+def small_v1_config():
+    """A tiny latent-conditioned BigVGAN (indextts/BigVGAN/models.py:129-199) for tests; the ECAPA-TDNN speaker encoder
+    inside it is always the full 512/1536-channel network (ECAPA_TDNN.py:470-541 defaults)."""
+    return dict(gpt_dim=32, upsample_rates=[4, 2], upsample_kernel_sizes=[8, 4], upsample_initial_channel=32,
+                resblock="1", resblock_kernel_sizes=[3, 7], resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5]],
+                activation="snakebeta", snake_logscale=True, feat_upsample=False,
+                cond_d_vector_in_each_upsampling_layer=True, speaker_embedding_dim=24, num_mels=20)
+
+
+def make_ecapa_weights(n_mels, emb_dim, seed=99, prefix="speaker_encoder.", channels=(512, 512, 512, 512, 1536),
+                       kernel_sizes=(5, 3, 3, 3, 1), scale=8, se_channels=128, attention_channels=128):
+    """Seeded ECAPA-TDNN weights under the reference state-dict names (ECAPA_TDNN.py:470-541), BatchNorm running
+    statistics included (eval mode)."""
+    g = torch.Generator().manual_seed(seed)
+    w = {}
+
+    def conv(name, co, ci, k, gain=1.0):
+        w[name + ".weight"] = torch.randn(co, ci, k, generator=g) * (gain / math.sqrt(ci * k))
+        w[name + ".bias"] = torch.randn(co, generator=g) * 0.05
+
+    def bn(name, c):
+        w[name + ".weight"] = 1.0 + torch.randn(c, generator=g) * 0.1
+        w[name + ".bias"] = torch.randn(c, generator=g) * 0.05
+        w[name + ".running_mean"] = torch.randn(c, generator=g) * 0.1
+        w[name + ".running_var"] = 0.6 + torch.rand(c, generator=g) * 0.8
+
+    def tdnn(name, ci, co, k):
+        conv(name + ".conv.conv", co, ci, k, gain=1.4)      # ReLU halves the power
+        bn(name + ".norm.norm", co)
+
+    q = prefix
+    tdnn(q + "blocks.0", n_mels, channels[0], kernel_sizes[0])
+    for i in range(1, len(channels) - 1):
+        p = q + f"blocks.{i}"
+        if channels[i - 1] != channels[i]:
+            conv(p + ".shortcut.conv", channels[i], channels[i - 1], 1)
+        tdnn(p + ".tdnn1", channels[i - 1], channels[i], 1)
+        for j in range(scale - 1):
+            tdnn(p + f".res2net_block.blocks.{j}", channels[i] // scale, channels[i] // scale, kernel_sizes[i])
+        tdnn(p + ".tdnn2", channels[i], channels[i], 1)
+        conv(p + ".se_block.conv1.conv", se_channels, channels[i], 1)
+        conv(p + ".se_block.conv2.conv", channels[i], se_channels, 1)
+    tdnn(q + "mfa", channels[-2] * (len(channels) - 2), channels[-1], kernel_sizes[-1])
+    tdnn(q + "asp.tdnn", channels[-1] * 3, attention_channels, 1)
+    conv(q + "asp.conv.conv", channels[-1], attention_channels, 1)
+    bn(q + "asp_bn.norm", channels[-1] * 2)
+    conv(q + "fc.conv", emb_dim, channels[-1] * 2, 1)
+    return w
+
+
+def make_bigvgan_v1_weights(h, seed=4321):
+    """Seeded weights of the latent-conditioned v1 BigVGAN under the reference state-dict names (weight norm removed)."""
+    h2 = dict(h, num_mels=h["gpt_dim"], use_bias_at_final=True)
+    w = make_bigvgan_weights(h2, seed=seed)                 # same generator layout: conv_pre takes gpt_dim channels
+    g = torch.Generator().manual_seed(seed + 1)
+    E, ch = h["speaker_embedding_dim"], h["upsample_initial_channel"]
+    w["cond_layer.weight"] = torch.randn(ch, E, 1, generator=g) * (0.5 / math.sqrt(E))
+    w["cond_layer.bias"] = torch.randn(ch, generator=g) * 0.05
+    for i in range(len(h["upsample_rates"])):
+        ch //= 2
+        w[f"conds.{i}.weight"] = torch.randn(ch, E, 1, generator=g) * (0.5 / math.sqrt(E))
+        w[f"conds.{i}.bias"] = torch.randn(ch, generator=g) * 0.05
+    w.update(make_ecapa_weights(h["num_mels"], E, seed=seed + 2))
+    return w
