@@ -134,12 +134,31 @@ def main():
         print(f"[{tag}] every (parent, token, score) of {len(trace)} steps identical; {explored} distinct beam-token triples explored")
         results[tag] = (scodes, np.array([t[0] for t in trace], np.int32), np.array([t[1] for t in trace], np.int32))
 
+    # ---- row a7 at the wrapper level: UnifiedVoice.merge_emovec (model_v2.py:827-838, :588-593) ----
+    from oracle.emo import make_emo_weights, merge_emovec
+    ecfg = dict(idim=1024, odim=32, linear_units=48, heads=2, blocks=1, cnn_kernel=15, p_dim=1024, p_heads=2, p_dim_head=64,
+                p_depth=2, p_ff_mult=2, model_dim=cfg["model_dim"])
+    we = make_emo_weights(ecfg, seed=31)
+    sd = g.state_dict()
+    unknown = [k for k in we if k not in sd]
+    assert not unknown, unknown
+    g.load_state_dict(we, strict=False)
+    ge = torch.Generator().manual_seed(9)
+    spk_f, emo_f = torch.randn(1, 23, 1024, generator=ge), torch.randn(1, 31, 1024, generator=ge)
+    with torch.no_grad():
+        ev_ref = g.merge_emovec(spk_f, emo_f, torch.tensor([23]), torch.tensor([31]), alpha=0.6)[0]
+    ev = merge_emovec(we, ecfg, spk_f[0], emo_f[0], 0.6)
+    eerr = float((ev - ev_ref).abs().max())
+    print(f"merge_emovec: oracle vs the reference wrapper max |diff| {eerr:.2e} (std {float(ev_ref.std()):.2f})")
+    assert eerr < 5e-4
+
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "gpt_ref_wrapper.npz")
     np.savez_compressed(out, seed=seed, n_steps=n, style=style.numpy(), emo=emo.numpy(), text=text.numpy(), lang=1,
                         prompt=prompt_ref.astype(np.float32), greedy_codes=codes, greedy_logits=logits.astype(np.float32),
                         beam_codes=bcodes, beam_sample_seed=bseed,
                         beam_sample_a_codes=results['a'][0], beam_sample_a_parents=results['a'][1], beam_sample_a_tokens=results['a'][2],
-                        beam_sample_b_codes=results['b'][0], beam_sample_b_parents=results['b'][1], beam_sample_b_tokens=results['b'][2])
+                        beam_sample_b_codes=results['b'][0], beam_sample_b_parents=results['b'][1], beam_sample_b_tokens=results['b'][2],
+                        emo_vec=ev_ref.numpy(), emo_seed=31, emo_feats_seed=9)   # features: torch.Generator(9) -> randn(1,23,1024), randn(1,31,1024)
     print("wrote", out)
 
 

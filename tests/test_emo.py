@@ -45,3 +45,43 @@ def test_engine_emovec_vs_golden_and_merge(engine, name, cfg):
     ref = merge_emovec(w, cfg, torch.from_numpy(g["feats"]), emo_feats, alpha=0.6).numpy()
     got = engine.merge_emovec(g["feats"], emo_feats.numpy(), alpha=0.6)
     assert np.abs(got - ref).max() < 2e-2
+
+
+REF_WRAPPER_GOLD = os.path.join(GOLD, "gpt_ref_wrapper.npz")
+
+
+def _ref_emo_feats(g):
+    ge = torch.Generator().manual_seed(int(g["emo_feats_seed"]))
+    return torch.randn(1, 23, 1024, generator=ge)[0], torch.randn(1, 31, 1024, generator=ge)[0]
+
+
+REF_ECFG = dict(idim=1024, odim=32, linear_units=48, heads=2, blocks=1, cnn_kernel=15, p_dim=1024, p_heads=2, p_dim_head=64,
+                p_depth=2, p_ff_mult=2, model_dim=256)
+
+
+def test_oracle_merge_emovec_vs_reference_wrapper_golden():
+    """`UnifiedVoice.merge_emovec` of the reference itself (model_v2.py:827-838 through get_emo_conditioning :588-593),
+    run by oracle/make_goldens_gpt_ref.py with these seeded weights."""
+    g = np.load(REF_WRAPPER_GOLD)
+    w = make_emo_weights(REF_ECFG, seed=int(g["emo_seed"]))
+    spk_f, emo_f = _ref_emo_feats(g)
+    ev = merge_emovec(w, REF_ECFG, spk_f, emo_f, 0.6).numpy()
+    assert np.abs(ev - g["emo_vec"]).max() < 1e-5
+
+
+@pytest.mark.gpu
+def test_engine_merge_emovec_vs_reference_wrapper_golden(engine):
+    g = np.load(REF_WRAPPER_GOLD)
+    w = make_emo_weights(REF_ECFG, seed=int(g["emo_seed"]))
+    engine.load_state_dict("gpt.", w)
+    engine.emo_init(REF_ECFG)
+    spk_f, emo_f = (t.numpy() for t in _ref_emo_feats(g))
+    engine.set_option("gemm_backend", 1)
+    try:
+        ev32 = engine.merge_emovec(spk_f, emo_f, alpha=0.6)
+    finally:
+        engine.set_option("gemm_backend", 0)
+    ev = engine.merge_emovec(spk_f, emo_f, alpha=0.6)
+    e32, e = float(np.abs(ev32 - g["emo_vec"]).max()), float(np.abs(ev - g["emo_vec"]).max())
+    print(f"merge_emovec vs the reference wrapper: fp32 back end {e32:.2e}, tf32 {e:.2e}")
+    assert e32 < 2e-3 and e < 2e-2
