@@ -295,7 +295,8 @@ def small_emo_cfg():
                 p_dim=64, p_heads=2, p_dim_head=64, p_depth=2, p_ff_mult=2, model_dim=256)
 
 
-def make_emo_weights(c, seed=777):
+def make_emo_weights(c, seed=777, enc_prefix="emo_conditioning_encoder.", per_prefix="emo_perceiver_encoder.", n_latents=1,
+                     heads_out=True):
     """Emotion path of UnifiedVoice (gpt/model_v2.py:375-392): emo_conditioning_encoder (Conformer),
     emo_perceiver_encoder (1 latent), emovec_layer, emo_layer — reference state-dict names."""
     g = torch.Generator().manual_seed(seed)
@@ -314,7 +315,7 @@ def make_emo_weights(c, seed=777):
         w[name + ".bias"] = t(d, std=0.05)
 
     od, H = c["odim"], c["heads"]
-    e = "emo_conditioning_encoder."
+    e = enc_prefix
     w[e + "embed.conv.0.weight"] = t(od, 1, 3, 3, std=1.0 / 3.0)
     w[e + "embed.conv.0.bias"] = t(od, std=0.05)
     fsub = (c["idim"] - 1) // 2
@@ -338,10 +339,10 @@ def make_emo_weights(c, seed=777):
         for nm in ("norm_ff", "norm_mha", "norm_conv", "norm_final"):
             ln(p + nm, od)
     ln(e + "after_norm", od)
-    q = "emo_perceiver_encoder."
+    q = per_prefix
     pd, inner = c["p_dim"], c["p_heads"] * c["p_dim_head"]
     lin(q + "proj_context", pd, od)
-    w[q + "latents"] = t(1, pd, std=0.02)
+    w[q + "latents"] = t(n_latents, pd, std=0.02 if n_latents == 1 else 1.0)
     di = int(pd * c["p_ff_mult"] * 2 / 3)
     for i in range(c["p_depth"]):
         lin(q + f"layers.{i}.0.to_q", inner, pd, bias=False)
@@ -350,8 +351,9 @@ def make_emo_weights(c, seed=777):
         lin(q + f"layers.{i}.1.0", 2 * di, pd)
         lin(q + f"layers.{i}.1.2", pd, di, gain=0.5)
     w[q + "norm.gamma"] = 1.0 + t(pd, std=0.1)
-    lin("emovec_layer", c["model_dim"], pd)
-    lin("emo_layer", c["model_dim"], c["model_dim"])
+    if heads_out:
+        lin("emovec_layer", c["model_dim"], pd)
+        lin("emo_layer", c["model_dim"], c["model_dim"])
     return w
 
 
@@ -419,4 +421,21 @@ def make_bigvgan_v1_weights(h, seed=4321):
         w[f"conds.{i}.weight"] = torch.randn(ch, E, 1, generator=g) * (0.5 / math.sqrt(E))
         w[f"conds.{i}.bias"] = torch.randn(ch, generator=g) * 0.05
     w.update(make_ecapa_weights(h["num_mels"], E, seed=seed + 2))
+    return w
+
+
+def small_v1_cond_cfg(model_dim=256):
+    """v1 conditioning encoder (gpt/model.py:352-363) at test size: conformer over a 100-bin mel + 32-latent perceiver."""
+    return dict(idim=100, odim=32, linear_units=48, heads=2, blocks=2, cnn_kernel=15, p_dim=model_dim, p_heads=2,
+                p_dim_head=64, p_depth=2, p_ff_mult=2, model_dim=model_dim)
+
+
+def make_gpt_v1_weights(cfg, ccfg, seed=1234):
+    """Seeded v1 UnifiedVoice weights (reference state-dict names): the GPT stack of make_gpt_weights without the v2-only
+    tensors, plus conditioning_encoder.* / perceiver_encoder.* (32 latents)."""
+    w = make_gpt_weights(cfg, seed=seed, bf16=False)
+    for k in ("spk_emb_proj.weight", "spk_emb_proj.bias", "lang_embedding.weight"):
+        w.pop(k, None)
+    w.update(make_emo_weights(ccfg, seed=seed + 7, enc_prefix="conditioning_encoder.", per_prefix="perceiver_encoder.",
+                              n_latents=32, heads_out=False))
     return w

@@ -39,9 +39,9 @@ def pos_table(T, d):
 
 
 @torch.no_grad()
-def conformer_encode(w, c, x):
+def conformer_encode(w, c, x, prefix="emo_conditioning_encoder."):
     """x [T, idim] → [T', odim]  (ConformerEncoder with conv2d2 front-end, rel-pos attention)."""
-    e = "emo_conditioning_encoder."
+    e = prefix
     od, H = c["odim"], c["heads"]
     dk = od // H
     y = F.relu(F.conv2d(x[None, None], w[e + "embed.conv.0.weight"], w[e + "embed.conv.0.bias"], stride=2))
@@ -76,27 +76,29 @@ def conformer_encode(w, c, x):
 
 
 @torch.no_grad()
-def perceiver_resample(w, c, ctx):
-    """ctx [T', odim] → [p_dim] (1 latent)."""
-    q = "emo_perceiver_encoder."
+def perceiver_resample(w, c, ctx, prefix="emo_perceiver_encoder.", squeeze=True):
+    """ctx [T', odim] → [p_dim] (1 latent; `squeeze=False`: [n_latents, p_dim], the v1 32-latent prompt)."""
+    q = prefix
     hh, dh = c["p_heads"], c["p_dim_head"]
     x = _lin(ctx, w, q + "proj_context")
     lat = w[q + "latents"].clone()
     for i in range(c["p_depth"]):
         a = q + f"layers.{i}.0."
         context = torch.cat([lat, x], 0)
-        qq = F.linear(lat, w[a + "to_q.weight"]).view(1, hh, dh).transpose(0, 1)
+        nl = lat.shape[0]
+        qq = F.linear(lat, w[a + "to_q.weight"]).view(nl, hh, dh).transpose(0, 1)
         kv = F.linear(context, w[a + "to_kv.weight"])
         k, v = kv.chunk(2, -1)
         k = k.view(-1, hh, dh).transpose(0, 1)
         v = v.view(-1, hh, dh).transpose(0, 1)
         att = torch.softmax(qq @ k.transpose(1, 2) * dh ** -0.5, -1) @ v
-        lat = F.linear(att.transpose(0, 1).reshape(1, hh * dh), w[a + "to_out.weight"]) + lat
+        lat = F.linear(att.transpose(0, 1).reshape(nl, hh * dh), w[a + "to_out.weight"]) + lat
         f = q + f"layers.{i}.1."
         h = _lin(lat, w, f + "0")
         xg, gate = h.chunk(2, -1)
         lat = _lin(F.gelu(gate) * xg, w, f + "2") + lat
-    return (F.normalize(lat, dim=-1) * (c["p_dim"] ** 0.5) * w[q + "norm.gamma"])[0]
+    out = F.normalize(lat, dim=-1) * (c["p_dim"] ** 0.5) * w[q + "norm.gamma"]
+    return out[0] if squeeze else out
 
 
 @torch.no_grad()

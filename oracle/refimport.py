@@ -18,7 +18,9 @@ def available():
 def _stub(name, **attrs):
     if name in sys.modules:
         return sys.modules[name]
+    import importlib.machinery
     m = types.ModuleType(name)
+    m.__spec__ = importlib.machinery.ModuleSpec(name, loader=None)     # importlib.util.find_spec(name) must not raise
     m.__dict__.update(attrs)
     sys.modules[name] = m
     return m
@@ -122,24 +124,22 @@ def codec_module(**kw):
     return m
 
 
-def gpt_module(cfg, weights):
-    """The reference's own `UnifiedVoice` (indextts/gpt/model_v2.py:305-493, spk_cond_mode="campplus" = IndexTTS-2.5)
-    with its vendored GPT2 blocks and generate() loop, running on CPU under transformers 5.x.
-
-    `indextts/gpt/transformers_generation_utils.py` was vendored from transformers 4.52 and imports ~25 names that
-    5.x removed.  None of them is on the executed path of greedy / beam decoding: missing classes and constants are
-    stubbed with empty types, `isin_mps_friendly` is given its definition (torch.isin), the removed
-    `transformers.generation.beam_search` module is replaced by the reference's own vendored
-    `indextts/gpt/transformers_beam_search.py`, and three legacy GenerationConfig attributes default to None.
-    `weights` (reference state-dict names, oracle.gpt.make_gpt_weights) are loaded into the module."""
+def _import_gpt(modname):
+    """Import `indextts.gpt.<modname>` under transformers 5.x (see gpt_module).  Returns the module."""
     import importlib
     import importlib.util
     import re
 
     import torch
-    import transformers  # noqa: F401  (before setup(): its optional-dependency probe must not meet the librosa stub)
+    # transformers probes optional dependencies at import: it must not meet the librosa stub of setup() (it would then
+    # import soxr); park the stubs while its modules load
+    parked = {k: sys.modules.pop(k) for k in list(sys.modules)
+              if k.split(".")[0] == "librosa" and getattr(sys.modules[k], "__file__", None) is None}
+    import transformers  # noqa: F401
     from transformers import GenerationConfig, PretrainedConfig
+    from transformers import GPT2Config, GPT2Model  # noqa: F401  (the v1 model builds on the stock classes, model.py:262)
     import transformers.generation  # noqa: F401
+    sys.modules.update(parked)
     setup()
 
     def dummy(name):
@@ -175,7 +175,7 @@ def gpt_module(cfg, weights):
         for k in [k for k in sys.modules if k.startswith("indextts.gpt")]:
             del sys.modules[k]
         try:
-            m = importlib.import_module("indextts.gpt.model_v2")
+            m = importlib.import_module("indextts.gpt." + modname)
             break
         except ModuleNotFoundError as e:
             stub_module(e.name)
@@ -184,7 +184,7 @@ def gpt_module(cfg, weights):
             if not mm:
                 raise
             setattr(sys.modules[mm.group(2)], mm.group(1), dummy(mm.group(1)))
-    assert m is not None, "could not import indextts.gpt.model_v2"
+    assert m is not None, "could not import indextts.gpt." + modname
     tgu = sys.modules["indextts.gpt.transformers_generation_utils"]
     tgu.isin_mps_friendly = lambda elements, test_elements: torch.isin(elements, test_elements)
     if not hasattr(PretrainedConfig, "_get_non_default_generation_parameters"):
@@ -194,7 +194,31 @@ def gpt_module(cfg, weights):
     for n in sorted(names):
         if not n.startswith("_") and not hasattr(probe, n):
             setattr(GenerationConfig, n, None)
+    return m
 
+
+def _load(g, weights):
+    sd = g.state_dict()
+    unknown = [k for k in weights if k not in sd]
+    assert not unknown, f"oracle weight names unknown to the reference module: {unknown}"
+    for k, v in weights.items():
+        assert tuple(sd[k].shape) == tuple(v.shape), (k, tuple(sd[k].shape), tuple(v.shape))
+    g.load_state_dict(weights, strict=False)
+    g.eval()
+    return g
+
+
+def gpt_module(cfg, weights):
+    """The reference's own `UnifiedVoice` (indextts/gpt/model_v2.py:305-493, spk_cond_mode="campplus" = IndexTTS-2.5)
+    with its vendored GPT2 blocks and generate() loop, running on CPU under transformers 5.x.
+
+    `indextts/gpt/transformers_generation_utils.py` was vendored from transformers 4.52 and imports ~25 names that
+    5.x removed.  None of them is on the executed path of greedy / beam decoding: missing classes and constants are
+    stubbed with empty types, `isin_mps_friendly` is given its definition (torch.isin), the removed
+    `transformers.generation.beam_search` module is replaced by the reference's own vendored
+    `indextts/gpt/transformers_beam_search.py`, and three legacy GenerationConfig attributes default to None.
+    `weights` (reference state-dict names, oracle.gpt.make_gpt_weights) are loaded into the module."""
+    m = _import_gpt("model_v2")
     tiny = dict(output_size=32, linear_units=48, attention_heads=2, num_blocks=1, input_layer="conv2d2", perceiver_mult=2)
     g = m.UnifiedVoice(layers=cfg["layers"], model_dim=cfg["model_dim"], heads=cfg["heads"],
                        max_text_tokens=cfg["max_text_tokens"], max_mel_tokens=cfg["max_mel_tokens"],
@@ -202,13 +226,23 @@ def gpt_module(cfg, weights):
                        start_mel_token=cfg["start_mel_token"], stop_mel_token=cfg["stop_mel_token"],
                        condition_type="conformer_perceiver", condition_module=dict(tiny), emo_condition_module=dict(tiny),
                        spk_cond_mode="campplus")
-    sd = g.state_dict()
-    own = {k: v for k, v in weights.items() if k in sd}
-    missing = [k for k in weights if k not in sd]
-    assert not missing, f"oracle weight names unknown to the reference module: {missing}"
-    for k, v in own.items():
-        assert tuple(sd[k].shape) == tuple(v.shape), (k, tuple(sd[k].shape), tuple(v.shape))
-    g.load_state_dict(own, strict=False)
-    g.eval()
+    _load(g, weights)
     g.post_init_gpt2_config(use_deepspeed=False, kv_cache=True, half=False)
+    return g
+
+
+def gpt_module_v1(cfg, ccfg, weights, kv_cache=False):
+    """The reference's v1 / v1.5 `UnifiedVoice` (indextts/gpt/model.py:305-440): 32-latent conformer-perceiver prompt
+    from a 100-bin mel; `kv_cache=False` is what `infer.py:101` uses on CPU."""
+    m = _import_gpt("model")
+    g = m.UnifiedVoice(layers=cfg["layers"], model_dim=cfg["model_dim"], heads=cfg["heads"],
+                       max_text_tokens=cfg["max_text_tokens"], max_mel_tokens=cfg["max_mel_tokens"],
+                       number_text_tokens=cfg["number_text_tokens"], number_mel_codes=cfg["number_mel_codes"],
+                       start_mel_token=cfg["start_mel_token"], stop_mel_token=cfg["stop_mel_token"],
+                       condition_type="conformer_perceiver",
+                       condition_module=dict(output_size=ccfg["odim"], linear_units=ccfg["linear_units"],
+                                             attention_heads=ccfg["heads"], num_blocks=ccfg["blocks"], input_layer="conv2d2",
+                                             perceiver_mult=ccfg["p_ff_mult"]))
+    _load(g, weights)
+    g.post_init_gpt2_config(use_deepspeed=False, kv_cache=kv_cache, half=False)
     return g

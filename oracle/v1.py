@@ -15,6 +15,7 @@ BASELINE config 1): the ECAPA-TDNN speaker encoder and the latent-conditioned Bi
 Pinned against the reference's own `indextts.BigVGAN.models.BigVGAN` (which owns the ECAPA encoder) by
 oracle/make_goldens_v1.py -> tests/golden/v1_vocoder_small.npz.  The CUDA side of row a13 is NOT built yet
 (DESIGN.md section 1): this file and its goldens are the checker it will be built against."""
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -124,3 +125,80 @@ def bigvgan_v1_forward(h, w, latent, mel_ref):
     x = act("activation_post", x)
     x = F.conv1d(x, w["conv_post.weight"], w["conv_post.bias"], padding=3)
     return torch.tanh(x)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPT side of v1 / v1.5 (indextts/gpt/model.py).  Same GPT-2 stack and head as v2 (oracle/gpt.py); what differs:
+#   get_conditioning ("conformer_perceiver")  model.py:493-503: ConformerEncoder(100-bin mel, conv2d2) -> PerceiverResampler
+#                                             with 32 latents -> conds [32, D]
+#   prepare_gpt_inputs                         model.py:597-660: [conds(32)][text_emb(start, text, stop) + text_pos(arange)]
+#   decode positions                           model.py:139-161: with the KV cache step k>=1 sits at mel position k+1
+#                                              (trap P1); WITHOUT it (infer.py:101, the CPU default) the whole suffix
+#                                              [start, t1..tk] is re-embedded at positions 0..k every step
+#   latents for the vocoder                    model.py:526-589 (return_latent=True): one teacher-forced pass over
+#                                              [conds][start_text, text, stop_text][start_mel, codes, stop_mel],
+#                                              final_norm(ln_f hidden) of the mel part, last two positions dropped
+# Pinned against the reference's own v1 UnifiedVoice by oracle/make_goldens_v1.py (tests/golden/v1_gpt_small.npz).
+def get_conditioning_v1(w, ccfg, mel):
+    """mel [T, 100] -> conds [32, D]."""
+    from oracle.emo import conformer_encode, perceiver_resample
+    ctx = conformer_encode(w, ccfg, mel, prefix="conditioning_encoder.")
+    return perceiver_resample(w, ccfg, ctx, prefix="perceiver_encoder.", squeeze=False)
+
+
+def prepare_inputs_v1(w, conds, text_ids):
+    """[conds][text_embedding(start, text.., stop) + text_pos_embedding(0..L+1)]  (model.py:597-660, batch 1, no padding)."""
+    ids = torch.as_tensor(text_ids, dtype=torch.long)
+    ids = ids[(ids != 0) & (ids != 1)]
+    ids = F.pad(F.pad(ids, (1, 0), value=0), (0, 1), value=1)
+    emb = w["text_embedding.weight"][ids] + w["text_pos_embedding.emb.weight"][: ids.shape[0]]
+    return torch.cat([conds, emb], dim=0)
+
+
+@torch.no_grad()
+def generate_v1(oracle, prompt, max_new, repetition_penalty=10.0, kv_cache=False):
+    """Greedy decode of the v1 model.  `oracle` is an oracle.gpt.GptOracle (fp32).  kv_cache=False reproduces the CPU
+    default of infer.py:101: every step re-runs the whole sequence with mel positions 0..k."""
+    if kv_cache:
+        return oracle.generate(prompt, max_new, repetition_penalty, 0)
+    w, cfg = oracle.w, oracle.cfg
+    start, stop = cfg["start_mel_token"], cfg["stop_mel_token"]
+    prompt = torch.as_tensor(prompt, dtype=torch.float32)
+    toks, codes, logits = [start], [], []
+    seen = {1, start}
+    for k in range(max_new):
+        oracle.reset()
+        t = torch.tensor(toks)
+        emb = w["mel_embedding.weight"][t] + w["mel_pos_embedding.emb.weight"][: len(toks)]
+        hidden = oracle.forward_rows(torch.cat([prompt, emb], 0))[-1:]
+        lg = oracle.logits(hidden)[0]
+        logits.append(lg.clone())
+        s = lg.clone()
+        idx = torch.tensor(sorted(seen))
+        sv = s[idx]
+        s[idx] = torch.where(sv < 0, sv * repetition_penalty, sv / repetition_penalty)
+        tok = int(torch.argmax(s))
+        codes.append(tok)
+        if tok == stop:
+            break
+        toks.append(tok)
+        seen.add(tok)
+    return np.array(codes, dtype=np.int32), torch.stack(logits).numpy()
+
+
+@torch.no_grad()
+def latents_v1(oracle, conds, text_ids, codes):
+    """UnifiedVoice.forward(..., return_latent=True) (model.py:526-589) for one utterance: final_norm(ln_f(hidden)) at the
+    mel positions [start_mel, codes..., stop_mel] minus the last two -> [len(codes), D]  (what BigVGAN v1 consumes)."""
+    w, cfg = oracle.w, oracle.cfg
+    ids = torch.as_tensor(text_ids, dtype=torch.long)
+    ids = F.pad(F.pad(ids, (0, 1), value=1), (1, 0), value=0)            # stop appended, then start prepended (:565-569)
+    text_emb = w["text_embedding.weight"][ids] + w["text_pos_embedding.emb.weight"][: ids.shape[0]]
+    mel = torch.as_tensor(np.asarray(codes), dtype=torch.long)
+    mel = F.pad(F.pad(mel, (0, 1), value=cfg["stop_mel_token"]), (1, 0), value=cfg["start_mel_token"])
+    mel_emb = w["mel_embedding.weight"][mel] + w["mel_pos_embedding.emb.weight"][: mel.shape[0]]
+    oracle.reset()
+    hidden = oracle.forward_rows(torch.cat([conds, text_emb, mel_emb], 0))
+    h = F.layer_norm(hidden, (hidden.shape[-1],), w["gpt.ln_f.weight"], w["gpt.ln_f.bias"], 1e-5)
+    h = F.layer_norm(h, (h.shape[-1],), w["final_norm.weight"], w["final_norm.bias"], 1e-5)
+    return h[-mel.shape[0]:][:-2]
