@@ -148,6 +148,11 @@ def stage_breakdown(e):
     return g, s
 
 
+WORKLOAD = ("IndexTTS-2.5 infer_v2_5 batch=1 per GPU: 10 s reference (P=861), 32 text tokens, "
+            "256 greedy speech tokens, codec->length-regulator->CFM 25 steps CFG 0.7 (T=1741)->BigVGAN "
+            "(225280 samples); speaker/emotion conditioning cached per speaker as in the reference")
+
+
 # -------------------------------------------------------------------------- cpu arm --
 def cpu_reference_sample(threads):
     """The oracle port of the same per-segment path on the host cores, on a bounded sample:
@@ -207,7 +212,8 @@ def run_reference(args, rank):
             "steps": steps, "warmup": 1, "ms_per_step": t * 1000, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16(gpt)+f32(s2mel,vocoder)", "data": "synthetic",
             "rtf": t / (ntok * AUDIO_S_PER_TOKEN),
-            "config": {"workload": "IndexTTS-2.5 per-segment pipeline, bounded CPU sample: " + sample},
+            "config": {"workload": WORKLOAD, "utterances_per_gpu_per_step": 1, "parallelism": "host cores",
+                       "sample": "each step is a bounded sample of that workload: " + sample},
             "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -339,9 +345,7 @@ def main():
         "ms_per_step": t_dev / K * 1000.0, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16(gpt weights, fp32 accumulate)+f32(s2mel, vocoder)", "data": "synthetic",
         "rtf": (t_dev / K) / audio_s, "e2e_rtf": (t_e2e / K) / audio_s,
-        "config": {"workload": "IndexTTS-2.5 infer_v2_5 batch=1 per GPU: 10 s reference (P=861), 32 text tokens, "
-                               "256 greedy speech tokens, codec->length-regulator->CFM 25 steps CFG 0.7 (T=1741)->BigVGAN "
-                               "(225280 samples); speaker/emotion conditioning cached per speaker as in the reference",
+        "config": {"workload": WORKLOAD,
                    "utterances_per_gpu_per_step": 1, "parallelism": f"dp{world} (utterance sharding)",
                    "l2": "working set >> L2 (0.97 GB of GPT weights streamed per token, 112 M vocoder weights)"},
         "stage_ms_per_step": {"gpt": g_ms / K, "cfm": c_ms / K, "bigvgan": v_ms / K,
