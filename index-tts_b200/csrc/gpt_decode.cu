@@ -106,6 +106,7 @@ struct GptParams {
   uint2* qt;            // [D] tagged q of the current layer
   uint2* kvt;           // [2][D] tagged k, v (bf16-valued) of the position being decoded
   unsigned epoch0;      // first epoch of this launch (2 per layer per step)
+  int seq_base;         // global index of row 0 (requests beyond one decode group run as consecutive groups)
   // beam search (beam_step_kernel runs between single-step launches)
   int ext_sample;       // 1: leave the logits in p.logits and skip the sampling phase
   int beams;            // rows per utterance
@@ -1148,7 +1149,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
               float kt = 0.f;
               for (int i = 0; i < keep; ++i) kt += cv[i];
               unsigned rnd4[4];
-              philox4x32_10(p.seed, (unsigned)k, (unsigned)b, rnd4);
+              philox4x32_10(p.seed, (unsigned)k, (unsigned)(b + p.seq_base), rnd4);
               const float u = (float)(rnd4[0] >> 8) * (1.0f / 16777216.0f) * kt;
               float acc = 0.f;
               int pick = keep - 1;
@@ -1472,7 +1473,7 @@ __global__ void strict_sample_kernel(const float* logits, unsigned* seen, int V,
 // ============================================================================================
 struct BeamParams {
   const float* logits;     // [8][V]
-  int V, m, k, max_new, stop_tok, forbid_stop_before, top_k, hist_stride;
+  int V, m, k, max_new, stop_tok, forbid_stop_before, top_k, hist_stride, utt_base;
   float rep_penalty, inv_temp, top_p;
   double length_penalty;
   unsigned long long seed;
@@ -1659,7 +1660,7 @@ __global__ void __launch_bounds__(256) beam_step_kernel(const BeamParams p) {
       int pick = -1;
       if (tot > 0.f && p.do_sample) {      // do_sample = 0: plain beam search = torch.topk of the union (:3527-3530)
         unsigned rnd4[4];
-        philox4x32_10(p.seed, (unsigned)k, 0x10000u + 16u * (unsigned)u + (unsigned)d, rnd4);
+        philox4x32_10(p.seed, (unsigned)k, 0x10000u + 16u * (unsigned)(u + p.utt_base) + (unsigned)d, rnd4);
         const float uu = (float)(rnd4[0] >> 8) * (1.0f / 16777216.0f) * tot;
         float acc = 0.f;
         int last = -1;
@@ -1776,6 +1777,7 @@ struct GptState {
   idx_gpt_config cfg;
   GptStrict* strict = nullptr;   // fp32 per-op path (weights_bf16 = 0)
   struct BeamTrace* beam_trace = nullptr;
+  int seq_base = 0;             // first request of the decode group being run (idx_gpt_generate splits large calls)
   int G = 0, FF = 0, nst1 = 0, nst8 = 0, bias_cap = 0, ocap = 0, bar_flavor = 0;
   size_t smem1 = 0, smem8 = 0;
   __nv_bfloat16* wstream = nullptr;
@@ -1936,7 +1938,7 @@ static void strict_generate(idx_engine* e, GptState* g, const idx_gpt_request* r
       strict_ln_kernel<<<1, 256, 0, st>>>(s->x, e->Wf("gpt.gpt.ln_f.weight"), e->Wf("gpt.gpt.ln_f.bias"), s->h, D);
       strict_ln_kernel<<<1, 256, 0, st>>>(s->h, e->Wf("gpt.final_norm.weight"), e->Wf("gpt.final_norm.bias"), s->att, D);   // trap P3
       strict_gemv_nk_kernel<<<(V + 7) / 8, 256, 0, st>>>(s->att, e->Wf("gpt.mel_head.weight"), e->Wf("gpt.mel_head.bias"), s->logits, D, V);
-      strict_sample_kernel<<<1, 256, (size_t)V * 4, st>>>(s->logits, g->seen, V, k, i, sp->repetition_penalty, c.stop_mel_token,
+      strict_sample_kernel<<<1, 256, (size_t)V * 4, st>>>(s->logits, g->seen, V, k, i + g->seq_base, sp->repetition_penalty, c.stop_mel_token,
                                                           sp->forbid_stop_before, sp->do_sample, sp->top_k, sp->top_p,
                                                           sp->temperature, sp->seed, d_codes, max_new, g->nout, g->finished,
                                                           g->tok, d_forced, d_ldump ? d_ldump + (size_t)k * V : nullptr);
@@ -2313,7 +2315,7 @@ static void beam_generate(idx_engine* e, GptState* g, const idx_gpt_request* req
   bp.top_k = sp->do_sample ? sp->top_k : 0;
   bp.top_p = sp->do_sample ? sp->top_p : 1.0f;
   bp.inv_temp = (sp->do_sample && sp->temperature > 0.f) ? 1.0f / sp->temperature : 1.0f;
-  bp.length_penalty = sp->length_penalty; bp.seed = sp->seed;
+  bp.length_penalty = sp->length_penalty; bp.seed = sp->seed; bp.utt_base = g->seq_base;
   bp.beam_scores = d_bscore; bp.tok = g->tok;
   bp.hyp_score = d_hscore; bp.hyp_len = d_hlen; bp.hyp_tok = d_htok; bp.hyp_order = d_horder; bp.nhyp = d_nhyp;
   bp.worst = d_worst; bp.done_u = d_done; bp.ldump = d_ldump; bp.trace_pt = d_trpt; bp.trace_sc = d_trsc;
@@ -2425,8 +2427,27 @@ extern "C" int idx_gpt_generate(idx_engine* e, const idx_gpt_request* reqs, int 
   IDX_CHECK(reqs && sp && nreq >= 1, IDX_ERR_ARG, "bad request");
   GptState* g = e->gpt;
   const idx_gpt_config& c = g->cfg;
-  IDX_CHECK(nreq <= c.max_batch, IDX_ERR_ARG, "nreq exceeds max_batch");
   IDX_CHECK(sp->num_beams >= 1, IDX_ERR_ARG, "num_beams must be >= 1");
+  {
+    // more requests than one decode group holds (max_batch rows, num_beams rows per request): run consecutive groups;
+    // the sampler's sequence index stays the request's global index, so the result does not depend on the grouping
+    const int cap = g->strict ? nreq : std::max(0, c.max_batch / sp->num_beams);
+    IDX_CHECK(cap >= 1, IDX_ERR_ARG, "max_batch is smaller than num_beams (every request needs num_beams rows)");
+    if (nreq > cap) {
+      double tp = 0, td = 0;
+      int steps = 0, launches = 0, rc = IDX_OK;
+      const int base0 = g->seq_base;
+      for (int i0 = 0; i0 < nreq && rc == IDX_OK; i0 += cap) {
+        g->seq_base = base0 + i0;
+        rc = idx_gpt_generate(e, reqs + i0, std::min(cap, nreq - i0), sp);
+        tp += g->t_prefill_ms; td += g->t_decode_ms;
+        steps = std::max(steps, g->last_steps); launches += g->last_launches;
+      }
+      g->seq_base = base0;
+      g->t_prefill_ms = tp; g->t_decode_ms = td; g->last_steps = steps; g->last_launches = launches;
+      return rc;
+    }
+  }
   IDX_CHECK(c.number_mel_codes <= 40 * 256, IDX_ERR_ARG, "vocabulary too large for the device sampler");
   IDX_CHECK(sp->max_new_tokens >= 1 && sp->max_new_tokens + 2 <= c.max_mel_positions, IDX_ERR_ARG,
             "max_new_tokens must satisfy k+1 <= mel_pos rows - 1 (SURVEY A.3)");
@@ -2514,6 +2535,7 @@ extern "C" int idx_gpt_generate(idx_engine* e, const idx_gpt_request* reqs, int 
   p.forbid_stop_before = sp->forbid_stop_before;
   p.do_sample = sp->do_sample; p.top_k = sp->top_k; p.top_p = sp->top_p; p.temperature = sp->temperature;
   p.seed = sp->seed;
+  p.seq_base = g->seq_base;
   p.codes = d_codes; p.forced = d_forced; p.logits_dump = d_ldump;
   const int SPL = 32;  // steps per launch: the host looks at one flag every SPL steps
   int steps_done = 0;

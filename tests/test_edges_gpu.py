@@ -35,8 +35,18 @@ def test_gpt_minimal_prompt_and_limits(engine):
     # a prompt longer than max_prompt, an unsupported beam width
     with pytest.raises(RuntimeError):
         engine.gpt_generate([got], cfg["max_mel_positions"], 10.0)
-    with pytest.raises(RuntimeError):
-        engine.gpt_generate([got, got, got], 4, 10.0)
+    # more requests than max_batch run as consecutive decode groups: same tokens as one request at a time
+    three = engine.gpt_generate([got, ref[:4], got], 6, 10.0, forbid_stop_before=6)
+    (alone,) = engine.gpt_generate([ref[:4]], 6, 10.0, forbid_stop_before=6)
+    assert np.array_equal(three[0], codes) and np.array_equal(three[2], codes) and np.array_equal(three[1], alone)
+    # ... and the sampler's stream follows the request's global index, not its place in a group
+    kw = dict(do_sample=True, top_k=20, top_p=0.9, temperature=1.3, seed=17, forbid_stop_before=6)
+    grouped = engine.gpt_generate([got] * 5, 6, 10.0, **kw)
+    load_gpt(engine, cfg, w, max_batch=8)
+    whole = engine.gpt_generate([got] * 5, 6, 10.0, **kw)
+    load_gpt(engine, cfg, w, max_batch=2)
+    assert all(np.array_equal(a, b) for a, b in zip(grouped, whole))
+    assert any(not np.array_equal(grouped[0], g) for g in grouped[1:])
     with pytest.raises(RuntimeError):
         engine.gpt_generate([np.zeros((129 + 64, cfg["model_dim"]), np.float32)], 4, 10.0)
     with pytest.raises(RuntimeError):
