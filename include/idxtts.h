@@ -231,6 +231,18 @@ int idx_bigvgan_forward(idx_engine* e, const float* mel, int B, int F, float* wa
 int idx_antialias_snake(idx_engine* e, const float* x, const float* alpha,
                         const float* beta, int B, int C, int T, int logscale, float* y);
 
+/* ---- IndexTTS v1 / v1.5 vocoder -------------------------------------------------------
+ * Latent-conditioned BigVGAN with its ECAPA-TDNN speaker encoder (indextts/BigVGAN/models.py:129-249,
+ * indextts/BigVGAN/ECAPA_TDNN.py:429-582), tensors registered under "bigvgan_v1." (weight norm removed as after
+ * BigVGAN.remove_weight_norm(), models.py:251-262).  gen_cfg->num_mels = gpt_dim (the latent width).              */
+int idx_v1_vocoder_init(idx_engine* e, const idx_bigvgan_config* gen_cfg, int n_mels, int speaker_embedding_dim,
+                        int cond_in_each_up_layer);
+/* ECAPA_TDNN.forward for one full-length utterance: mel_ref [Tm, n_mels] f32 -> emb [speaker_embedding_dim].      */
+int idx_v1_speaker_embedding(idx_engine* e, const float* mel_ref, int Tm, float* emb_out);
+/* BigVGAN.forward(x, mel_ref) (models.py:201-249; call site infer.py:~660): latent [T, gpt_dim] f32 and the
+ * reference mel [Tm, n_mels] f32 -> wav [T * prod(rates)] f32 in [-1, 1] (tanh).                                   */
+int idx_v1_vocode(idx_engine* e, const float* latent, int T, const float* mel_ref, int Tm, float* wav_out);
+
 /* Device time of the last idx_bigvgan_forward in ms (CUDA events).                   */
 int idx_bigvgan_last_ms(const idx_engine* e, double* ms);
 

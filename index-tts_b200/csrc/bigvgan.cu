@@ -263,16 +263,16 @@ static void kaiser_sinc_taps(float* out) {
   for (int n = 0; n < K; ++n) out[n] = (float)(f[n] / sum);
 }
 
-extern "C" int idx_bigvgan_init(idx_engine* e, const idx_bigvgan_config* cfg) {
-  IDX_API_BEGIN
-  IDX_CHECK(e && cfg, IDX_ERR_ARG, "null argument");
-  IDX_CUDA(cudaSetDevice(e->device));
-  if (e->bigvgan) { bigvgan_destroy(e->bigvgan); e->bigvgan = nullptr; }
+static void kaiser_sinc_taps(float* out);
+
+// builds a generator from the registered tensors `prefix + conv_pre.weight`, ...; *slot owns it (freed on failure by the
+// engine teardown, like every module state)
+static void bigvgan_build(idx_engine* e, const idx_bigvgan_config* cfg, const std::string& P, BigvganState** slot) {
+  if (*slot) { bigvgan_destroy(*slot); *slot = nullptr; }
   BigvganState* s = new BigvganState();
-  e->bigvgan = s;
+  *slot = s;
   s->cfg = *cfg;
   IDX_CHECK(cfg->num_upsamples >= 1 && cfg->num_upsamples <= 8 && cfg->num_kernels >= 1 && cfg->num_kernels <= 4, IDX_ERR_ARG, "bad bigvgan config");
-  const std::string P = "bigvgan.";
   s->conv_pre = pack_conv(e, s, P + "conv_pre", 1);
   IDX_CHECK(s->conv_pre.k == 7 && s->conv_pre.Ci == cfg->num_mels && s->conv_pre.Co == cfg->upsample_initial_channel, IDX_ERR_ARG, "conv_pre shape");
   int ch = cfg->upsample_initial_channel;
@@ -331,6 +331,13 @@ extern "C" int idx_bigvgan_init(idx_engine* e, const idx_bigvgan_config* cfg) {
   IDX_CUDA(cudaEventCreate(&s->ev0));
   IDX_CUDA(cudaEventCreate(&s->ev1));
   IDX_CUDA(cudaStreamSynchronize(e->stream));
+}
+
+extern "C" int idx_bigvgan_init(idx_engine* e, const idx_bigvgan_config* cfg) {
+  IDX_API_BEGIN
+  IDX_CHECK(e && cfg, IDX_ERR_ARG, "null argument");
+  IDX_CUDA(cudaSetDevice(e->device));
+  bigvgan_build(e, cfg, "bigvgan.", &e->bigvgan);
   IDX_API_END(e)
 }
 
@@ -388,24 +395,36 @@ size_t bigvgan_arena_bytes(const BigvganState* s, int B, int F) {
 int bigvgan_total_up(const BigvganState* s) { return s->total_up; }
 void bigvgan_set_ms(BigvganState* s, double ms) { s->last_ms = ms; }
 
-void bigvgan_forward_dev(idx_engine* e, BigvganState* s, const float* d_mel, int B, int F, float* d_wav) {
+// channels_last_in: d_mel is already [B][F][num_mels] (the v1 latents); pre_bias / up_bias[i]: per-call replacements of the
+// conv_pre / ups[i] biases (the speaker conditioning of the v1 generator, BigVGAN/models.py:230-240, folded into biases)
+static void bigvgan_forward_impl(idx_engine* e, BigvganState* s, const float* d_mel, int B, int F, float* d_wav,
+                                 bool channels_last_in, const float* pre_bias, const float* const* up_bias) {
   const idx_bigvgan_config& cfg = s->cfg;
   const int nm = cfg.num_mels;
   const size_t bufel = (size_t)B * bigvgan_maxel(s, F);
   float* d_melT = e->arena.get<float>((size_t)B * nm * F);
   float* buf[6];
   for (int i = 0; i < 6; ++i) buf[i] = e->arena.get<float>(bufel);
-  transpose_bct_to_btc(e, d_mel, d_melT, B, nm, F);
+  if (channels_last_in) IDX_CUDA(cudaMemcpyAsync(d_melT, d_mel, (size_t)B * nm * F * 4, cudaMemcpyDeviceToDevice, e->stream));
+  else transpose_bct_to_btc(e, d_mel, d_melT, B, nm, F);
   // P: stage input, and — once the transposed conv has consumed it — the accumulator of the
   // resblock outputs (= next stage's input).  Q: the upsampled stage signal read by all blocks.
   float *P = buf[0], *Q = buf[1], *xb0 = buf[2], *xb1 = buf[3], *ta = buf[4], *tc = buf[5];
-  run_conv(e, s->conv_pre, d_melT, P, B, F, nullptr, 0, 1.f);
+  {
+    ConvW pre = s->conv_pre;
+    if (pre_bias) pre.bias = pre_bias;
+    run_conv(e, pre, d_melT, P, B, F, nullptr, 0, 1.f);
+  }
   int T = F;
   for (int i = 0; i < cfg.num_upsamples; ++i) {
     const int u = cfg.upsample_rates[i];
     float* xst = Q;
     float* xsum = P;
-    run_convT(e, s->ups[i], u, P, xst, B, T);
+    {
+      ConvW up = s->ups[i];
+      if (up_bias && up_bias[i]) up.bias = up_bias[i];
+      run_convT(e, up, u, P, xst, B, T);
+    }
     T *= u;
     for (int j = 0; j < cfg.num_kernels; ++j) {
       const int rb = i * cfg.num_kernels + j;
@@ -437,6 +456,127 @@ void bigvgan_forward_dev(idx_engine* e, BigvganState* s, const float* d_mel, int
     IDX_CUDA(cudaGetLastError());
     e->launches++;
   }
+}
+
+void bigvgan_forward_dev(idx_engine* e, BigvganState* s, const float* d_mel, int B, int F, float* d_wav) {
+  bigvgan_forward_impl(e, s, d_mel, B, F, d_wav, false, nullptr, nullptr);
+}
+
+// ------------------------------------------------------------------ v1 / v1.5 vocoder --
+// indextts/BigVGAN/models.py:129-249: ECAPA-TDNN(mel_ref) -> speaker embedding -> cond_layer / conds[i] (1x1 convs)
+// added after conv_pre / ups[i]; GPT latents [T][gpt_dim] in, tanh(wav) out.
+struct V1VocoderState {
+  BigvganState* gen = nullptr;
+  EcapaState* ecapa = nullptr;
+  WeightPool pool;
+  PackedW cond_layer;
+  std::vector<PackedW> conds;
+  int n_mels = 0, emb = 0, cond_each = 1;
+};
+void v1voc_destroy(V1VocoderState* s) {
+  if (!s) return;
+  if (s->gen) bigvgan_destroy(s->gen);
+  ecapa_destroy(s->ecapa);
+  s->pool.release();
+  delete s;
+}
+
+extern "C" int idx_v1_vocoder_init(idx_engine* e, const idx_bigvgan_config* gen_cfg, int n_mels, int speaker_embedding_dim,
+                                   int cond_in_each_up_layer) {
+  IDX_API_BEGIN
+  IDX_CHECK(e && gen_cfg && n_mels >= 1 && speaker_embedding_dim >= 1, IDX_ERR_ARG, "bad arguments");
+  IDX_CUDA(cudaSetDevice(e->device));
+  if (e->v1voc) { v1voc_destroy(e->v1voc); e->v1voc = nullptr; }
+  V1VocoderState* s = new V1VocoderState();
+  e->v1voc = s;
+  s->n_mels = n_mels; s->emb = speaker_embedding_dim; s->cond_each = cond_in_each_up_layer;
+  const std::string P = "bigvgan_v1.";
+  idx_bigvgan_config cfg = *gen_cfg;       // num_mels = gpt_dim (the latent width), tanh at the end (models.py:247)
+  cfg.use_tanh_at_final = 1;
+  bigvgan_build(e, &cfg, P, &s->gen);
+  s->ecapa = ecapa_build(e, P + "speaker_encoder.", n_mels, speaker_embedding_dim);
+  s->cond_layer = pack_conv1d(e, s->pool, P + "cond_layer", 1);
+  IDX_CHECK(s->cond_layer.K == speaker_embedding_dim && s->cond_layer.N == cfg.upsample_initial_channel, IDX_ERR_ARG, "cond_layer shape");
+  if (cond_in_each_up_layer)
+    for (int i = 0; i < cfg.num_upsamples; ++i) s->conds.push_back(pack_conv1d(e, s->pool, P + "conds." + std::to_string(i), 1));
+  IDX_CUDA(cudaStreamSynchronize(e->stream));
+  IDX_API_END(e)
+}
+
+extern "C" int idx_v1_speaker_embedding(idx_engine* e, const float* mel_ref, int Tm, float* emb_out) {
+  IDX_API_BEGIN
+  IDX_CHECK(e && e->v1voc, IDX_ERR_STATE, "idx_v1_vocoder_init has not been called");
+  IDX_CHECK(mel_ref && emb_out && Tm >= 5, IDX_ERR_ARG, "bad arguments (the reference mel needs at least 5 frames)");
+  IDX_CUDA(cudaSetDevice(e->device));
+  V1VocoderState* s = e->v1voc;
+  e->ensure_arena(ecapa_arena_bytes(s->ecapa, Tm) + (size_t)Tm * s->n_mels * 4 + (1 << 16));
+  e->arena.reset();
+  float* d_mel = e->arena.get<float>((size_t)Tm * s->n_mels);
+  float* d_emb = e->arena.get<float>(s->emb);
+  idx_to_device(e, d_mel, mel_ref, (size_t)Tm * s->n_mels * 4);
+  ecapa_forward_dev(e, s->ecapa, d_mel, Tm, d_emb);
+  idx_from_device(e, emb_out, d_emb, (size_t)s->emb * 4);
+  IDX_CUDA(cudaStreamSynchronize(e->stream));
+  IDX_API_END(e)
+}
+
+namespace {
+__global__ void add_vec_kernel(const float* a, const float* b, float* y, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = (a ? a[i] : 0.f) + b[i];
+}
+}  // namespace
+
+extern "C" int idx_v1_vocode(idx_engine* e, const float* latent, int T, const float* mel_ref, int Tm, float* wav_out) {
+  IDX_API_BEGIN
+  IDX_CHECK(e && e->v1voc, IDX_ERR_STATE, "idx_v1_vocoder_init has not been called");
+  IDX_CHECK(latent && mel_ref && wav_out && T >= 1 && Tm >= 5, IDX_ERR_ARG, "bad arguments");
+  IDX_CUDA(cudaSetDevice(e->device));
+  V1VocoderState* s = e->v1voc;
+  BigvganState* g = s->gen;
+  const idx_bigvgan_config& cfg = g->cfg;
+  const int gd = cfg.num_mels, nup = cfg.num_upsamples;
+  const size_t out_n = (size_t)T * g->total_up;
+  e->ensure_arena(bigvgan_arena_bytes(g, 1, T) + ecapa_arena_bytes(s->ecapa, Tm) + (size_t)(Tm * s->n_mels + T * gd) * 4 +
+                  16 * (size_t)cfg.upsample_initial_channel * 4 + (1 << 16));
+  e->arena.reset();
+  float* d_lat = e->arena.get<float>((size_t)T * gd);
+  float* d_mel = e->arena.get<float>((size_t)Tm * s->n_mels);
+  float* d_emb = e->arena.get<float>(s->emb);
+  float* d_wav = e->arena.get<float>(out_n);
+  float* d_bias = e->arena.get<float>(4 * (size_t)cfg.upsample_initial_channel);
+  idx_to_device(e, d_lat, latent, (size_t)T * gd * 4);
+  idx_to_device(e, d_mel, mel_ref, (size_t)Tm * s->n_mels * 4);
+  IDX_CUDA(cudaEventRecord(g->ev0, e->stream));
+  ecapa_forward_dev(e, s->ecapa, d_mel, Tm, d_emb);
+  // speaker conditioning as bias vectors: bias' = bias + cond(spk)
+  const float* up_bias[8] = {nullptr};
+  float* bp = d_bias;
+  float* pre_bias = bp;
+  {
+    const int C0 = cfg.upsample_initial_channel;
+    conv_gemm(e, gemm_of(s->cond_layer, d_emb, 1, 1, bp));
+    add_vec_kernel<<<(C0 + 127) / 128, 128, 0, e->stream>>>(g->conv_pre.bias, bp, bp, C0);
+    IDX_CUDA(cudaGetLastError()); e->launches++;
+    bp += C0;
+    int ch = C0;
+    for (int i = 0; i < nup && s->cond_each; ++i) {
+      ch /= 2;
+      conv_gemm(e, gemm_of(s->conds[i], d_emb, 1, 1, bp));
+      add_vec_kernel<<<(ch + 127) / 128, 128, 0, e->stream>>>(g->ups[i].bias, bp, bp, ch);
+      IDX_CUDA(cudaGetLastError()); e->launches++;
+      up_bias[i] = bp;
+      bp += ch;
+    }
+  }
+  bigvgan_forward_impl(e, g, d_lat, 1, T, d_wav, true, pre_bias, up_bias);
+  IDX_CUDA(cudaEventRecord(g->ev1, e->stream));
+  idx_from_device(e, wav_out, d_wav, out_n * 4);
+  IDX_CUDA(cudaStreamSynchronize(e->stream));
+  float ms = 0;
+  IDX_CUDA(cudaEventElapsedTime(&ms, g->ev0, g->ev1));
+  g->last_ms = ms;
+  IDX_API_END(e)
 }
 
 extern "C" int idx_bigvgan_forward(idx_engine* e, const float* mel, int B, int F, float* wav) {

@@ -52,6 +52,7 @@ static inline size_t idx_dtype_size(int dt) {
 
 struct GptState;      // gpt_decode.cu
 struct EmoState;      // emo.cu
+struct V1VocoderState; // bigvgan.cu (latent-conditioned BigVGAN + ECAPA-TDNN, row a13)
 struct BigvganState;  // bigvgan.cu
 struct S2melState;    // s2mel.cu
 
@@ -93,6 +94,7 @@ struct idx_engine {
   BigvganState* bigvgan = nullptr;
   S2melState* s2mel = nullptr;
   EmoState* emo = nullptr;
+  V1VocoderState* v1voc = nullptr;
 
   const DevTensor& W(const std::string& name) const {
     auto it = weights.find(name);
@@ -124,6 +126,7 @@ void gpt_destroy(GptState*);
 void bigvgan_destroy(BigvganState*);
 void s2mel_destroy(S2melState*);
 void emo_destroy(EmoState*);
+void v1voc_destroy(V1VocoderState*);
 
 #define IDX_API_BEGIN try {
 #define IDX_API_END(e)                                     \

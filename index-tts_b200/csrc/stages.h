@@ -23,3 +23,11 @@ int bigvgan_total_up(const BigvganState* s);
 void bigvgan_forward_dev(idx_engine* e, BigvganState* s, const float* d_mel, int B, int F, float* d_wav);
 void s2mel_set_ms(S2melState* s, double codec, double lr, double cfm);
 void bigvgan_set_ms(BigvganState* s, double ms);
+
+// v1 / v1.5 vocoder side (row a13): ECAPA-TDNN speaker encoder (ecapa.cu)
+struct EcapaState;
+EcapaState* ecapa_build(idx_engine* e, const std::string& prefix, int n_mels, int emb);
+void ecapa_destroy(EcapaState* s);
+size_t ecapa_arena_bytes(const EcapaState* s, int T);
+// d_mel [T][n_mels] -> d_emb [emb]
+void ecapa_forward_dev(idx_engine* e, EcapaState* s, const float* d_mel, int T, float* d_emb);

@@ -135,6 +135,9 @@ def load_library(path: str = None):
                                            C.c_int, C.c_int, C.c_void_p]
     lib.idx_gpt_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.idx_gpt_profile.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.idx_v1_vocoder_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib.idx_v1_speaker_embedding.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.idx_v1_vocode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     lib.idx_gpt_beam_trace.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.idx_bigvgan_init.argtypes = [C.c_void_p, C.POINTER(BigvganConfig)]
     lib.idx_bigvgan_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -324,9 +327,10 @@ class Engine:
         return buf
 
     # ------------------------------------------------------------------ BigVGAN --
-    def bigvgan_init(self, h: dict):
+    @staticmethod
+    def _bigvgan_cfg(h: dict, num_mels):
         cfg = BigvganConfig()
-        cfg.num_mels = h.get("num_mels", 80)
+        cfg.num_mels = num_mels
         cfg.upsample_initial_channel = h["upsample_initial_channel"]
         rates, ks = h["upsample_rates"], h["upsample_kernel_sizes"]
         cfg.num_upsamples = len(rates)
@@ -342,9 +346,37 @@ class Engine:
         cfg.use_tanh_at_final = int(h.get("use_tanh_at_final", True))
         cfg.use_bias_at_final = int(h.get("use_bias_at_final", True))
         cfg.snake_logscale = int(h.get("snake_logscale", True))
+        return cfg
+
+    def bigvgan_init(self, h: dict):
+        cfg = self._bigvgan_cfg(h, h.get("num_mels", 80))
         self._check(self.lib.idx_bigvgan_init(self.h, C.byref(cfg)), "idx_bigvgan_init")
         self.bigvgan_cfg = cfg
-        self._bigvgan_up = int(np.prod(rates))
+        self._bigvgan_up = int(np.prod(h["upsample_rates"]))
+
+    # ------------------------------------------------------- v1 / v1.5 vocoder (row a13) --
+    def v1_vocoder_init(self, h: dict):
+        """indextts/BigVGAN/models.py:129-199 — tensors registered under "bigvgan_v1."."""
+        cfg = self._bigvgan_cfg(dict(h, use_tanh_at_final=True), h["gpt_dim"])
+        self._check(self.lib.idx_v1_vocoder_init(self.h, C.byref(cfg), int(h["num_mels"]), int(h["speaker_embedding_dim"]),
+                                                 int(h.get("cond_d_vector_in_each_upsampling_layer", True))),
+                    "idx_v1_vocoder_init")
+        self.v1_cfg = dict(h)
+        self._v1_up = int(np.prod(h["upsample_rates"]))
+
+    def v1_speaker_embedding(self, mel_ref):
+        """ECAPA_TDNN.forward (ECAPA_TDNN.py:543-582): mel_ref [Tm, n_mels] → [speaker_embedding_dim]."""
+        m = _as_f32(mel_ref)
+        out = np.empty(self.v1_cfg["speaker_embedding_dim"], dtype=np.float32)
+        self._check(self.lib.idx_v1_speaker_embedding(self.h, _ptr(m), int(m.shape[0]), _ptr(out)), "idx_v1_speaker_embedding")
+        return out
+
+    def v1_vocode(self, latent, mel_ref):
+        """BigVGAN.forward(latent, mel_ref) (BigVGAN/models.py:201-249): latent [T, gpt_dim], mel_ref [Tm, n_mels] → wav [T*up]."""
+        x, m = _as_f32(latent), _as_f32(mel_ref)
+        out = np.empty(x.shape[0] * self._v1_up, dtype=np.float32)
+        self._check(self.lib.idx_v1_vocode(self.h, _ptr(x), int(x.shape[0]), _ptr(m), int(m.shape[0]), _ptr(out)), "idx_v1_vocode")
+        return out
 
     def bigvgan_forward(self, mel, out=None):
         """BigVGAN.forward (s2mel/modules/bigvgan/bigvgan.py:360-386): mel [B,80,F] f32 →

@@ -1,0 +1,48 @@
+"""GPU: the v1 / v1.5 vocoder side (ECAPA-TDNN speaker encoder + latent-conditioned BigVGAN)
+through the C-ABI against the golden minted from the reference's own `indextts.BigVGAN.models.BigVGAN`
+(tests/golden/v1_vocoder_small.npz) and against the oracle on a second input."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from indextts_b200 import synth
+from oracle import v1
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "v1_vocoder_small.npz")
+
+
+def test_v1_vocoder_vs_reference_golden(engine):
+    g = np.load(GOLD)
+    h = synth.small_v1_config()
+    w = synth.make_bigvgan_v1_weights(h, seed=int(g["seed"]))
+    engine.load_state_dict("bigvgan_v1.", {k: v for k, v in w.items() if v.is_floating_point()})
+    engine.v1_vocoder_init(h)
+    scale = float(np.abs(g["spk"]).max())
+    for backend, tol_e, tol_w in ((1, 1e-4, 2e-4), (0, 5e-3, 5e-3)):
+        engine.set_option("gemm_backend", backend)
+        try:
+            emb = engine.v1_speaker_embedding(g["mel_ref"][0])
+            wav = engine.v1_vocode(g["latent"][0], g["mel_ref"][0])
+        finally:
+            engine.set_option("gemm_backend", 0)
+        e1 = float(np.abs(emb - g["spk"][0, 0]).max()) / scale
+        e2 = float(np.abs(wav - g["wav"][0, 0]).max())
+        print(f"[backend {backend}] ECAPA embedding rel err {e1:.2e}, wav max err {e2:.2e}")
+        assert e1 < tol_e and e2 < tol_w
+    assert np.abs(wav).max() <= 1.0
+    # a longer, different utterance against the oracle (strict back end)
+    gen = torch.Generator().manual_seed(21)
+    latent = torch.randn(1, 41, h["gpt_dim"], generator=gen)
+    mel_ref = torch.randn(1, 203, h["num_mels"], generator=gen) * 1.5 - 4.0
+    ref = v1.bigvgan_v1_forward(h, w, latent, mel_ref)[0, 0].numpy()
+    engine.set_option("gemm_backend", 1)
+    try:
+        got = engine.v1_vocode(latent[0].numpy(), mel_ref[0].numpy())
+    finally:
+        engine.set_option("gemm_backend", 0)
+    assert got.shape == ref.shape and np.abs(got - ref).max() < 2e-4
+    with pytest.raises(RuntimeError):
+        engine.v1_speaker_embedding(mel_ref[0, :3].numpy())
