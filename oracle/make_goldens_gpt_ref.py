@@ -134,6 +134,37 @@ def main():
         print(f"[{tag}] every (parent, token, score) of {len(trace)} steps identical; {explored} distinct beam-token triples explored")
         results[tag] = (scodes, np.array([t[0] for t in trace], np.int32), np.array([t[1] for t in trace], np.int32))
 
+    # ---- multinomial sampling (num_beams=1, do_sample=True): the reference's _sample + HF warpers, RNG substituted ----
+    from oracle.gpt import sample_token
+    sseed = 55
+    sstate = {"scores": None, "step": 0}
+
+    def softmax_spy1(x, dim=-1, **kw):
+        if x.dim() == 2 and x.shape[-1] == V:
+            sstate["scores"] = x.detach().clone()
+        return real_softmax(x, dim=dim, **kw)
+
+    def philox_multinomial1(probs, num_samples, **kw):
+        sc = sstate["scores"][0].numpy().astype(np.float32)
+        # the warpers already filtered: kept candidates are the finite scores; the draw contract is oracle.gpt.sample_token
+        tok, _ = sample_token(sc, 0, 1.0, sseed, sstate["step"], 0)
+        sstate["step"] += 1
+        return torch.tensor([[tok]], dtype=torch.long)
+
+    skw = dict(top_p=0.9, top_k=20, temperature=1.3)
+    F.softmax, torch.multinomial = softmax_spy1, philox_multinomial1
+    try:
+        with torch.no_grad():
+            scodes1, _ = g.inference_speech(torch.zeros(1, 8, 1024), text[None], do_sample=True, num_beams=1, **dict(common, **skw))
+    finally:
+        F.softmax, torch.multinomial = real_softmax, real_multinomial
+    scodes1 = scodes1[0].numpy().astype(np.int32)
+    o_s, _ = GptOracle(cfg, w, bf16=False).generate(prompt, n, 10.0, 0, do_sample=True, seed=sseed, seq=0, **skw)
+    print("reference sampling (Philox draws):", scodes1.tolist())
+    print("oracle    sampling               :", o_s.tolist())
+    assert o_s.tolist() == scodes1[: len(o_s)].tolist()
+    assert scodes1.tolist() != codes.tolist()
+
     # ---- row a7 at the wrapper level: UnifiedVoice.merge_emovec (model_v2.py:827-838, :588-593) ----
     from oracle.emo import make_emo_weights, merge_emovec
     ecfg = dict(idim=1024, odim=32, linear_units=48, heads=2, blocks=1, cnn_kernel=15, p_dim=1024, p_heads=2, p_dim_head=64,
@@ -158,7 +189,8 @@ def main():
                         beam_codes=bcodes, beam_sample_seed=bseed,
                         beam_sample_a_codes=results['a'][0], beam_sample_a_parents=results['a'][1], beam_sample_a_tokens=results['a'][2],
                         beam_sample_b_codes=results['b'][0], beam_sample_b_parents=results['b'][1], beam_sample_b_tokens=results['b'][2],
-                        emo_vec=ev_ref.numpy(), emo_seed=31, emo_feats_seed=9)   # features: torch.Generator(9) -> randn(1,23,1024), randn(1,31,1024)
+                        emo_vec=ev_ref.numpy(), emo_seed=31, emo_feats_seed=9,
+                        sample_codes=scodes1, sample_seed=sseed)   # features: torch.Generator(9) -> randn(1,23,1024), randn(1,31,1024)
     print("wrote", out)
 
 

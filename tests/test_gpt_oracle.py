@@ -144,3 +144,14 @@ def test_oracle_beam_sample_matches_reference_beam_sample_with_substituted_rng()
         assert [t[0] for t in out["trace"]] == g[f"beam_sample_{tag}_parents"].tolist()
         assert [t[1] for t in out["trace"]] == g[f"beam_sample_{tag}_tokens"].tolist()
     assert g["beam_sample_b_codes"].tolist() != g["beam_codes"].tolist()      # the flat configuration really samples
+
+
+def test_oracle_sampling_matches_reference_sample_loop_with_substituted_rng():
+    """num_beams=1, do_sample=True: the reference's `_sample` loop with HF's RepetitionPenalty / Temperature / TopK / TopP
+    processors, `torch.multinomial` replaced by the documented Philox draw (oracle/make_goldens_gpt_ref.py)."""
+    g, cfg, w = _ref_case()
+    n = int(g["n_steps"])
+    codes, _ = GptOracle(cfg, w, bf16=False).generate(g["prompt"], n, 10.0, 0, do_sample=True, seed=int(g["sample_seed"]), seq=0,
+                                                      top_p=0.9, top_k=20, temperature=1.3)
+    assert codes.tolist() == g["sample_codes"][: len(codes)].tolist()
+    assert g["sample_codes"].tolist() != g["greedy_codes"].tolist()
