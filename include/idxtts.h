@@ -316,7 +316,7 @@ typedef struct {
   const float* prompt_condition;  /* [P, content_dim] length-regulated reference features (:651-656)  */
   const float* ref_mel;           /* [80, P] reference mel (:640)                                     */
   int32_t P;
-  const float* style;             /* [192] campplus style vector (:644-649)                           */
+  const float* style;             /* [style_dim] campplus style vector, 192 in IndexTTS-2.5 (:644-649)   */
   const float* z;                 /* [80, P + F] the torch.randn noise of cfm.inference (trap P6)     */
   int32_t F;                      /* int(2 * n_codes * 1.72 * duration_factor) (:833)                 */
   float* wav_out;                 /* optional [F * 256] f32 in [-1, 1]                                */

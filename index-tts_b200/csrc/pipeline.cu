@@ -31,9 +31,10 @@ extern "C" int idx_codes_to_wav(idx_engine* e, const idx_vocode_request* r, int 
   BigvganState* bv = e->bigvgan;
   const int n = r->n_codes, F = r->F, P = r->P, T = P + F;
   const int Cd = s2mel_content_dim(s), Hs = s2mel_codec_hidden(s), C = 80, up = bigvgan_total_up(bv);
+  const int Sd = s2mel_style_dim(s);        // 192 for IndexTTS-2.5 (infer_v2_5.py:218); the caller's buffer holds exactly this many
   const size_t need = codec_arena_bytes(s, n) + lr_arena_bytes(s, 2 * n, F) + cfm_arena_bytes(s, T, n_steps) +
                       bigvgan_arena_bytes(bv, 1, F) +
-                      4 * ((size_t)2 * n * Hs + (size_t)T * Cd + (size_t)C * (2 * T + P + F) + 192 + (size_t)F * up * 2) +
+                      4 * ((size_t)2 * n * Hs + (size_t)T * Cd + (size_t)C * (2 * T + P + F) + Sd + (size_t)F * up * 2) +
                       (8 << 20);
   e->ensure_arena(need);
   e->arena.reset();
@@ -41,7 +42,7 @@ extern "C" int idx_codes_to_wav(idx_engine* e, const idx_vocode_request* r, int 
   float* d_S = e->arena.get<float>((size_t)2 * n * Hs);
   float* d_mu = e->arena.get<float>((size_t)T * Cd);
   float* d_prompt = e->arena.get<float>((size_t)C * std::max(P, 1));
-  float* d_style = e->arena.get<float>(192);
+  float* d_style = e->arena.get<float>(Sd);
   float* d_z = e->arena.get<float>((size_t)C * T);
   float* d_mel = e->arena.get<float>((size_t)C * T);
   float* d_melF = e->arena.get<float>((size_t)C * F);
@@ -52,7 +53,7 @@ extern "C" int idx_codes_to_wav(idx_engine* e, const idx_vocode_request* r, int 
     idx_to_device(e, d_mu, r->prompt_condition, (size_t)P * Cd * 4);
     idx_to_device(e, d_prompt, r->ref_mel, (size_t)C * P * 4);
   }
-  idx_to_device(e, d_style, r->style, 192 * 4);
+  idx_to_device(e, d_style, r->style, (size_t)Sd * 4);
   idx_to_device(e, d_z, r->z, (size_t)C * T * 4);
   auto stamp = [&](int slot) {
     if (!e->events[slot]) IDX_CUDA(cudaEventCreate(&e->events[slot]));

@@ -545,6 +545,7 @@ size_t cfm_arena_bytes(const S2melState* s, int T, int n_steps) {
   return dit_arena_bytes(s, 2, T) + 4 * (size_t)T * (8 * c.in_channels + 3 * c.content_dim + 6 * c.hidden + 2 * c.style_dim) +
          4 * (size_t)n_steps * (s->mod_width + 2 * c.wn_hidden * (c.wn_layers + 1) + 6 * c.hidden + 512) + (4 << 20);
 }
+int s2mel_style_dim(const S2melState* s) { return s->cfg.style_dim; }
 int s2mel_content_dim(const S2melState* s) { return s->cfg.content_dim; }
 int s2mel_codec_hidden(const S2melState* s) { return s->ccfg.hidden_size; }
 bool s2mel_ready(const S2melState* s) { return s && s->has_s2mel && s->has_codec; }

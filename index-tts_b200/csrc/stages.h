@@ -14,6 +14,7 @@ size_t cfm_arena_bytes(const S2melState* s, int T, int n_steps);
 void cfm_solve_dev(idx_engine* e, S2melState* s, const float* d_mu, int T, const float* d_prompt, int P,
                    const float* d_style, const float* d_z, int n_steps, float rate, float* d_mel);
 int s2mel_content_dim(const S2melState* s);
+int s2mel_style_dim(const S2melState* s);
 int s2mel_codec_hidden(const S2melState* s);
 bool s2mel_ready(const S2melState* s);
 
