@@ -157,7 +157,7 @@ WORKLOAD = ("IndexTTS-2.5 infer_v2_5 batch=1 per GPU: 10 s reference (P=861), 32
 def cpu_reference_sample(threads):
     """The oracle port of the same per-segment path on the host cores, on a bounded sample:
     8 speech tokens with a 0.5 s reference (P = 43): GPT prefill + 8 cached steps (full 24x1280
-    geometry, bf16 policy), codec decode, length regulator, CFM 25 steps at T = 43 + 27, BigVGAN
+    geometry, fp32 like the reference on a CPU: use_bf16 needs CUDA autocast), codec decode, length regulator, CFM 25 steps at T = 43 + 27, BigVGAN
     F = 27.  Returns (tokens, callable) — the callable runs the sample once and returns seconds."""
     from indextts_b200 import synth
     from oracle.gpt import GptOracle, prepare_gpt_inputs
@@ -165,7 +165,7 @@ def cpu_reference_sample(threads):
     from oracle.bigvgan import bigvgan_forward
     torch.set_num_threads(threads)
     cfg = synth.gpt_config()
-    wg = synth.make_gpt_weights(cfg, seed=2025, bf16=True)
+    wg = synth.make_gpt_weights(cfg, seed=2025, bf16=False)
     c, cc, h = dict(synth.S2MEL_CFG), dict(synth.CODEC_CFG), dict(synth.BIGVGAN_V2_22K)
     ws = fold_weight_norm(synth.make_s2mel_weights(c, seed=1234))
     wc = fold_weight_norm(synth.make_codec_weights(cc, seed=4321))
@@ -173,9 +173,9 @@ def cpu_reference_sample(threads):
     g = torch.Generator().manual_seed(0)
     ntok, P = 8, 43
     style = torch.randn(192, generator=g)
-    emo = synth.r16(torch.randn(cfg["model_dim"], generator=g) * 0.5)
+    emo = torch.randn(cfg["model_dim"], generator=g) * 0.5
     text = torch.randint(2, 12000, (N_TEXT,), generator=g)
-    prompt = prepare_gpt_inputs(wg, style, emo, text, lang=1, bf16=True)
+    prompt = prepare_gpt_inputs(wg, style, emo, text, lang=1, bf16=False)
     F = int(2 * ntok * 1.72)
     pc = torch.randn(1, P, 512, generator=g)
     ref_mel = torch.randn(1, 80, P, generator=g) * 1.5 - 4.0
@@ -183,7 +183,7 @@ def cpu_reference_sample(threads):
 
     def once():
         t0 = time.perf_counter()
-        codes, _ = GptOracle(cfg, wg, bf16=True).generate(prompt, ntok, 10.0, ntok)
+        codes, _ = GptOracle(cfg, wg, bf16=False).generate(prompt, ntok, 10.0, ntok)
         S = codec_decode(wc, torch.from_numpy(codes.astype(np.int64))[None])
         cond = length_regulate(ws, S, F)
         mu = torch.cat([pc, cond], 1)
@@ -210,7 +210,7 @@ def run_reference(args, rank):
               f"(of {os.cpu_count()} host cores; more threads are slower for these small ops)")
     line = {"impl": "reference", "metric": "speech_tokens_per_s", "value": val, "unit": "tokens/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": 1, "ms_per_step": t * 1000, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16(gpt)+f32(s2mel,vocoder)", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "rtf": t / (ntok * AUDIO_S_PER_TOKEN),
             "config": {"workload": WORKLOAD, "utterances_per_gpu_per_step": 1, "parallelism": "host cores",
                        "sample": "each step is a bounded sample of that workload: " + sample},
