@@ -28,6 +28,7 @@
 // zeros of null_position_embeddings promote it, model_v2.py:23-24 — trap P12); logits are bf16
 // values upcast to fp32 (P5).  See DESIGN.md "GPT numerics".
 #include "engine.h"
+#include "ops.h"
 #include "ptx.cuh"
 #include <cooperative_groups.h>
 #include <algorithm>
@@ -96,6 +97,7 @@ struct GptParams {
   int* done;            // [1] all sequences finished
   // prefill
   const float* prompt;  // [rows][D] f32
+  float* hidden_out;    // prefill only, optional: [rows][D] residual stream after the last block (v1 latent pass)
   const PrefillTile* tiles;
   unsigned* barrier;    // grid barrier counter (zeroed before each launch)
   // tag-in-data dataflow for the residual stream (batch-1 decode): x[c] travels as {value, epoch} in one 8-byte word
@@ -1020,6 +1022,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
         PROF_STAMP();
       }
 
+      if (p.mode == 0 && p.hidden_out) {
+        // v1 latent pass: every CTA writes its own column slice of the final residual stream (kept in xres by the
+        // PROJ epilogue), so no other CTA's data is touched and the next tile may start at once
+        for (int idx = tid; idx < BT * (o1 - o0); idx += NCT) {
+          const int b = idx / (o1 - o0), c = o0 + idx % (o1 - o0);
+          if (row_valid[b]) p.hidden_out[(size_t)row_posidx[b] * D + c] = sm.xres[b * p.ocap + (c - o0)];
+        }
+        ptx::named_bar_sync(1, NCT);
+      }
       if (p.mode == 1) {
         // ---------------- head: ln_f -> final_norm -> mel_head ----------------
         if constexpr (BT == 1) {
@@ -2725,12 +2736,12 @@ extern "C" int idx_gpt_latents_v1(idx_engine* e, const float* conds, int n_laten
   IDX_CHECK(conds && codes && latents_out && n_latents >= 1 && n_text >= 0 && n_codes >= 1, IDX_ERR_ARG, "bad arguments");
   IDX_CUDA(cudaSetDevice(e->device));
   GptState* g = e->gpt;
-  IDX_CHECK(g->strict, IDX_ERR_STATE, "the latent pass is built on the strict fp32 path only (idx_gpt_init with weights_bf16 = 0)");
   GptStrict* s = g->strict;
   const int D = g->cfg.model_dim, R = n_latents + n_text + 2 + n_codes + 2;
   IDX_CHECK(R <= g->maxpos, IDX_ERR_ARG, "sequence longer than the KV cache");
   for (int i = 0; i < n_codes; ++i) (void)i;
-  e->ensure_arena(4 * ((size_t)(R + n_latents + n_codes + 2) * D + (size_t)n_text + n_codes + 32) + (1 << 16));
+  e->ensure_arena(4 * ((size_t)(2 * R + n_latents + 2 * n_codes + 2) * D + (size_t)n_text + n_codes + 32) +
+                  (size_t)(R / 8 + 2) * sizeof(PrefillTile) + (1 << 16));
   e->arena.reset();
   float* d_c = e->arena.get<float>((size_t)n_latents * D);
   int* d_ids = e->arena.get<int>(n_text + 1);
@@ -2741,10 +2752,32 @@ extern "C" int idx_gpt_latents_v1(idx_engine* e, const float* conds, int n_laten
   if (n_text) idx_to_device(e, d_ids, text_ids, (size_t)n_text * 4);
   idx_to_device(e, d_codes, codes, (size_t)n_codes * 4);
   v1_rows(e, g, d_c, n_latents, d_ids, n_text, d_codes, n_codes, d_rows);
-  // one teacher-forced sweep, position by position (causal: the KV cache of the strict path is the attention mask)
   const int first = R - (n_codes + 2);                 // first mel row; latents = rows first .. first + n_codes - 1
   cudaStream_t st = e->stream;
   g->last_launches = 0;
+  if (!s) {
+    // bf16 path: one prefill sweep of the fused kernel (tiles of 8 rows, sequence slot 0) that dumps the residual stream
+    std::vector<PrefillTile> tiles;
+    for (int p0 = 0; p0 < R - 2; p0 += 8) tiles.push_back({0, p0, std::min(8, R - 2 - p0), p0});
+    PrefillTile* d_tiles = e->arena.get<PrefillTile>(tiles.size());
+    float* d_hid = e->arena.get<float>((size_t)R * D);
+    float* d_tmp = e->arena.get<float>((size_t)n_codes * D);
+    IDX_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(PrefillTile), cudaMemcpyHostToDevice, st));
+    IDX_CUDA(cudaStreamSynchronize(st));
+    GptParams p;
+    fill_common(e, g, p);
+    p.B = 8; p.mode = 0; p.nsteps = (int)tiles.size(); p.prompt = d_rows; p.tiles = d_tiles; p.hidden_out = d_hid;
+    p.max_new = 1; p.rep_penalty = 1.f;
+    launch_fused_bt(e, g, p, 8);
+    layernorm(e, d_hid + (size_t)first * D, d_tmp, 1, n_codes, D, e->Wf("gpt.gpt.ln_f.weight"), e->Wf("gpt.gpt.ln_f.bias"), 1e-5f,
+              nullptr, nullptr, 0);
+    layernorm(e, d_tmp, d_lat, 1, n_codes, D, e->Wf("gpt.final_norm.weight"), e->Wf("gpt.final_norm.bias"), 1e-5f, nullptr, nullptr, 0);
+    idx_from_device(e, latents_out, d_lat, (size_t)n_codes * D * 4);
+    IDX_CUDA(cudaStreamSynchronize(e->stream));
+    e->check_flag("text token id or speech code outside its embedding table");
+    return IDX_OK;
+  }
+  // strict fp32: one teacher-forced sweep, position by position (the KV cache of the strict path is the causal mask)
   for (int pos = 0; pos < R - 2; ++pos) {              // the last two rows are dropped by the caller of get_logits (:583)
     strict_embed_kernel<<<(D + 255) / 256, 256, 0, st>>>(s->x, d_rows + (size_t)pos * D, nullptr, nullptr, nullptr, 0, D);
     strict_layers(e, g, pos);

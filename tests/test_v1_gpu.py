@@ -81,3 +81,22 @@ def test_v1_gpt_side_vs_reference_golden(engine):
     e2 = float(np.abs(lat - g["latents"]).max())
     print(f"v1 latents max err {e2:.2e}")
     assert lat.shape == g["latents"].shape and e2 < 1e-3
+
+
+def test_v1_latents_fused_bf16_path_close_to_reference(engine):
+    """The latent pass on the fused bf16 kernel (prefill sweep with the residual-stream dump): within bf16 noise of the fp32
+    reference latents."""
+    from oracle.validate_gpt_vs_hf import small_case
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "v1_gpt_small.npz"))
+    cfg, _, _, _ = small_case()
+    ccfg = synth.small_v1_cond_cfg(cfg["model_dim"])
+    w = synth.make_gpt_v1_weights(cfg, ccfg, seed=int(g["seed"]))
+    engine.load_state_dict("gpt.", w)
+    engine.gpt_init(cfg["layers"], cfg["model_dim"], cfg["heads"], cfg["number_mel_codes"], cfg["start_mel_token"],
+                    cfg["stop_mel_token"], cfg["max_mel_positions"], max_prompt=128, max_batch=1, weights_bf16=True)
+    toks = g["codes"][g["codes"] != cfg["stop_mel_token"]]
+    lat = engine.gpt_latents_v1(g["conds"], g["text"], toks)
+    ref = g["latents"]
+    rel = float(np.sqrt(((lat - ref) ** 2).mean()) / ref.std())
+    print(f"v1 latents on the fused bf16 path: relative rms error {rel:.3f}")
+    assert lat.shape == ref.shape and rel < 0.05
