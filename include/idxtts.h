@@ -121,6 +121,10 @@ typedef struct {
   uint64_t seed;                /* Philox seed of the device sampler                 */
   int32_t forbid_stop_before;   /* mask stop_mel_token for the first n steps (bench:
                                    length-deterministic runs); 0 = off   */
+  int32_t mel_pos_mode;         /* 0: KV-cache rule — step k >= 1 sits at mel position k+1
+                                   (trap P1, gpt/model_v2.py:158-161); 1: the rule of decoding
+                                   WITHOUT a cache, the v1 CPU default (infer.py:101,
+                                   gpt/model.py:139-156): position k                      */
 } idx_sampling;
 
 /* One utterance (= one text segment) of a generate call.                            */
@@ -178,6 +182,23 @@ int idx_emo_init(idx_engine* e, const idx_emo_config* cfg);
  * cache the result per (speaker, emotion, alpha) — the reference recomputes it per segment (trap P11).   */
 int idx_merge_emovec(idx_engine* e, const float* spk_feats, int Ts, const float* emo_feats, int Te,
                      float alpha, float* emo_vec_out);
+
+/* ---- IndexTTS v1 / v1.5 GPT side (indextts/gpt/model.py) ------------------------------
+ * Prompt encoder: ConformerEncoder(100-bin mel, conv2d2) + PerceiverResampler(n_latents = 32) -> conds
+ * (get_conditioning, model.py:493-503); tensors "gpt.conditioning_encoder.*", "gpt.perceiver_encoder.*".           */
+int idx_v1_cond_init(idx_engine* e, const idx_emo_config* cfg, int n_latents);
+/* mel [T, idim] f32 -> conds [n_latents, model_dim] f32                                                           */
+int idx_v1_get_conditioning(idx_engine* e, const float* mel, int T, float* conds_out);
+/* prepare_gpt_inputs of v1 (model.py:597-660): [conds][text_embedding(start, text.., stop) + text_pos(0..)]
+ *   out [n_latents + n_text + 2, model_dim] f32 — the prompt rows for idx_gpt_generate                             */
+int idx_gpt_prepare_inputs_v1(idx_engine* e, const float* conds, int n_latents, const int32_t* text_ids, int n_text,
+                              float* out);
+/* UnifiedVoice.forward(..., return_latent=True) (model.py:526-589) for one utterance: one teacher-forced pass over
+ * [conds][start_text, text, stop_text][start_mel, codes.., stop_mel]; final_norm(ln_f(hidden)) at the mel
+ * positions without the last two -> latents [n_codes, model_dim] f32, the input of idx_v1_vocode.                  */
+int idx_gpt_latents_v1(idx_engine* e, const float* conds, int n_latents, const int32_t* text_ids, int n_text,
+                       const int32_t* codes, int n_codes, float* latents_out);
+
 
 /* Beam search trace of the last idx_gpt_generate call with num_beams > 1 (tests, debugging): for every step and
  * beam slot the (parent beam, token) chosen by BeamSearchScorer.process

@@ -98,6 +98,8 @@ __global__ void latent_attn_kernel(const float* __restrict__ q, const float* __r
                                    int n, int H, int dh) {
   extern __shared__ float sc[];
   const int h = blockIdx.x, inner = H * dh;
+  q += (long long)blockIdx.y * inner;          // one latent per blockIdx.y (32 of them in the v1 prompt encoder)
+  out += (long long)blockIdx.y * inner;
   const float scale = rsqrtf((float)dh);
   float lmax = -INFINITY;
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
@@ -162,6 +164,8 @@ struct EmoState {
   std::vector<EmoBlock> blocks;
   std::vector<EmoPLayer> pl;
   const float *after_w, *after_b, *latents, *gamma;
+  int n_latents = 1;
+  bool has_heads = true;        // emovec_layer / emo_layer (v2.5 emotion path); the v1 prompt encoder has none
 };
 static EmoState* g_emo_of(idx_engine* e);
 
@@ -202,16 +206,19 @@ static PackedW pack3(idx_engine* e, WeightPool& pool, const std::string& a, cons
   return p;
 }
 
-extern "C" int idx_emo_init(idx_engine* e, const idx_emo_config* cfg) {
-  IDX_API_BEGIN
-  IDX_CHECK(e && cfg, IDX_ERR_ARG, "null argument");
-  IDX_CUDA(cudaSetDevice(e->device));
-  emo_destroy(e->emo);
-  e->emo = nullptr;
+static size_t emo_arena_bytes(const EmoState* s, int T);
+static void cond_encode_dev(idx_engine* e, EmoState* s, const float* d_x, int T, float* d_lat_out);
+
+// conformer + perceiver from the tensors under E / Q; *slot owns the state
+static void cond_build(idx_engine* e, const idx_emo_config* cfg, const std::string& E, const std::string& Q, int n_latents,
+                       bool has_heads, EmoState** slot) {
+  emo_destroy(*slot);
+  *slot = nullptr;
   EmoState* s = new EmoState();
-  e->emo = s;
+  *slot = s;
   s->cfg = *cfg;
-  const std::string E = "gpt.emo_conditioning_encoder.", Q = "gpt.emo_perceiver_encoder.";
+  s->n_latents = n_latents;
+  s->has_heads = has_heads;
   s->conv_w = e->Wf(E + "embed.conv.0.weight");
   s->conv_b = e->Wf(E + "embed.conv.0.bias");
   s->embed_out = pack_linear(e, s->pool, E + "embed.out.0");
@@ -237,6 +244,7 @@ extern "C" int idx_emo_init(idx_engine* e, const idx_emo_config* cfg) {
   s->after_w = e->Wf(E + "after_norm.weight"); s->after_b = e->Wf(E + "after_norm.bias");
   s->proj_ctx = pack_linear(e, s->pool, Q + "proj_context");
   s->latents = e->Wf(Q + "latents");
+  IDX_CHECK((int)e->W(Q + "latents").numel() == n_latents * cfg->p_dim, IDX_ERR_ARG, Q + "latents: unexpected size");
   for (int i = 0; i < cfg->p_depth; ++i) {
     const std::string p = Q + "layers." + std::to_string(i) + ".";
     EmoPLayer l;
@@ -248,14 +256,52 @@ extern "C" int idx_emo_init(idx_engine* e, const idx_emo_config* cfg) {
     s->pl.push_back(l);
   }
   s->gamma = e->Wf(Q + "norm.gamma");
-  s->emovec = pack_linear(e, s->pool, "gpt.emovec_layer");
-  s->emol = pack_linear(e, s->pool, "gpt.emo_layer");
+  if (has_heads) {
+    s->emovec = pack_linear(e, s->pool, "gpt.emovec_layer");
+    s->emol = pack_linear(e, s->pool, "gpt.emo_layer");
+  }
+  IDX_CUDA(cudaStreamSynchronize(e->stream));
+}
+
+extern "C" int idx_emo_init(idx_engine* e, const idx_emo_config* cfg) {
+  IDX_API_BEGIN
+  IDX_CHECK(e && cfg, IDX_ERR_ARG, "null argument");
+  IDX_CUDA(cudaSetDevice(e->device));
+  cond_build(e, cfg, "gpt.emo_conditioning_encoder.", "gpt.emo_perceiver_encoder.", 1, true, &e->emo);
+  IDX_API_END(e)
+}
+
+// ---- v1 / v1.5 prompt encoder (gpt/model.py:352-363, get_conditioning :493-503): conformer over the 100-bin mel +
+// perceiver with 32 latents -> conds [32][model_dim] that open the GPT prompt
+extern "C" int idx_v1_cond_init(idx_engine* e, const idx_emo_config* cfg, int n_latents) {
+  IDX_API_BEGIN
+  IDX_CHECK(e && cfg && n_latents >= 1 && n_latents <= 64, IDX_ERR_ARG, "bad arguments");
+  IDX_CHECK(cfg->p_dim == cfg->model_dim, IDX_ERR_ARG, "the v1 perceiver works at model_dim");
+  IDX_CUDA(cudaSetDevice(e->device));
+  cond_build(e, cfg, "gpt.conditioning_encoder.", "gpt.perceiver_encoder.", n_latents, false, &e->v1cond);
+  IDX_API_END(e)
+}
+
+extern "C" int idx_v1_get_conditioning(idx_engine* e, const float* mel, int T, float* conds_out) {
+  IDX_API_BEGIN
+  EmoState* s = e ? e->v1cond : nullptr;
+  IDX_CHECK(s, IDX_ERR_STATE, "idx_v1_cond_init has not been called");
+  IDX_CHECK(mel && conds_out && T >= 3, IDX_ERR_ARG, "bad arguments");
+  IDX_CUDA(cudaSetDevice(e->device));
+  const idx_emo_config& c = s->cfg;
+  e->ensure_arena(emo_arena_bytes(s, T) + 4 * ((size_t)T * c.idim + (size_t)s->n_latents * c.p_dim) + (1 << 16));
+  e->arena.reset();
+  float* d_x = e->arena.get<float>((size_t)T * c.idim);
+  float* d_o = e->arena.get<float>((size_t)s->n_latents * c.p_dim);
+  idx_to_device(e, d_x, mel, (size_t)T * c.idim * 4);
+  cond_encode_dev(e, s, d_x, T, d_o);
+  idx_from_device(e, conds_out, d_o, (size_t)s->n_latents * c.p_dim * 4);
   IDX_CUDA(cudaStreamSynchronize(e->stream));
   IDX_API_END(e)
 }
 
-// feats (device [T][idim]) -> emovec (device [model_dim])
-static void emovec_dev(idx_engine* e, EmoState* s, const float* d_x, int T, float* d_out) {
+// feats (device [T][idim]) -> normalised perceiver latents (device [n_latents][p_dim])
+static void cond_encode_dev(idx_engine* e, EmoState* s, const float* d_x, int T, float* d_lat_out) {
   const idx_emo_config& c = s->cfg;
   const int od = c.odim, H = c.heads, dk = od / H;
   const int T2 = (T - 3) / 2 + 1, Fs = (c.idim - 3) / 2 + 1;
@@ -322,30 +368,41 @@ static void emovec_dev(idx_engine* e, EmoState* s, const float* d_x, int T, floa
   // perceiver resampler with one latent (perceiver.py:224-274)
   const int pd = c.p_dim, inner = c.p_heads * c.p_dim_head;
   const int di = (int)(pd * c.p_ff_mult * 2 / 3);
-  float* ctx = e->arena.get<float>((size_t)(1 + T2) * pd);     // row 0 = latent (cross_attn_include_queries)
-  float* kv = e->arena.get<float>((size_t)(1 + T2) * 2 * inner);
-  float* q = e->arena.get<float>(inner);
-  float* ao = e->arena.get<float>(inner);
-  float* ff = e->arena.get<float>((size_t)2 * di);
-  float* fg = e->arena.get<float>(di);
-  float* lat = ctx;                                             // the latent lives in row 0 of ctx
-  conv_gemm(e, gemm_of(s->proj_ctx, y, 1, T2, ctx + pd));
-  IDX_CUDA(cudaMemcpyAsync(lat, s->latents, (size_t)pd * 4, cudaMemcpyDeviceToDevice, e->stream));
+  const int nl = s->n_latents;
+  float* ctx = e->arena.get<float>((size_t)(nl + T2) * pd);    // rows 0..nl-1 = the latents (cross_attn_include_queries)
+  float* kv = e->arena.get<float>((size_t)(nl + T2) * 2 * inner);
+  float* q = e->arena.get<float>((size_t)nl * inner);
+  float* ao = e->arena.get<float>((size_t)nl * inner);
+  float* ff = e->arena.get<float>((size_t)nl * 2 * di);
+  float* fg = e->arena.get<float>((size_t)nl * di);
+  float* lat = ctx;                                             // the latents live in the first rows of ctx
+  conv_gemm(e, gemm_of(s->proj_ctx, y, 1, T2, ctx + (size_t)nl * pd));
+  IDX_CUDA(cudaMemcpyAsync(lat, s->latents, (size_t)nl * pd * 4, cudaMemcpyDeviceToDevice, e->stream));
   for (auto& l : s->pl) {
-    conv_gemm(e, gemm_of(l.to_q, lat, 1, 1, q));
-    conv_gemm(e, gemm_of(l.to_kv, ctx, 1, 1 + T2, kv));
-    latent_attn_kernel<<<c.p_heads, 128, (size_t)(1 + T2) * 4, e->stream>>>(q, kv, ao, 1 + T2, c.p_heads, c.p_dim_head);
+    conv_gemm(e, gemm_of(l.to_q, lat, 1, nl, q));
+    conv_gemm(e, gemm_of(l.to_kv, ctx, 1, nl + T2, kv));
+    latent_attn_kernel<<<dim3(c.p_heads, nl), 128, (size_t)(nl + T2) * 4, e->stream>>>(q, kv, ao, nl + T2, c.p_heads, c.p_dim_head);
     KCHECK(e);
-    { ConvGemm g = gemm_of(l.to_out, ao, 1, 1, lat); g.res = lat; conv_gemm(e, g); }
-    conv_gemm(e, gemm_of(l.ff0, lat, 1, 1, ff));
-    geglu_kernel<<<(di + 127) / 128, 128, 0, e->stream>>>(ff, fg, di);
-    KCHECK(e);
-    { ConvGemm g = gemm_of(l.ff2, fg, 1, 1, lat); g.res = lat; conv_gemm(e, g); }
+    { ConvGemm g = gemm_of(l.to_out, ao, 1, nl, lat); g.res = lat; conv_gemm(e, g); }
+    conv_gemm(e, gemm_of(l.ff0, lat, 1, nl, ff));
+    for (int r = 0; r < nl; ++r) {
+      geglu_kernel<<<(di + 127) / 128, 128, 0, e->stream>>>(ff + (size_t)r * 2 * di, fg + (size_t)r * di, di);
+      KCHECK(e);
+    }
+    { ConvGemm g = gemm_of(l.ff2, fg, 1, nl, lat); g.res = lat; conv_gemm(e, g); }
   }
-  float* ln = e->arena.get<float>(pd);
+  for (int r = 0; r < nl; ++r) {
+    l2norm_scale_kernel<<<1, 256, 0, e->stream>>>(lat + (size_t)r * pd, s->gamma, d_lat_out + (size_t)r * pd, pd);
+    KCHECK(e);
+  }
+}
+
+// feats (device [T][idim]) -> emovec (device [model_dim])
+static void emovec_dev(idx_engine* e, EmoState* s, const float* d_x, int T, float* d_out) {
+  const idx_emo_config& c = s->cfg;
+  float* ln = e->arena.get<float>(c.p_dim);
   float* ev = e->arena.get<float>(c.model_dim);
-  l2norm_scale_kernel<<<1, 256, 0, e->stream>>>(lat, s->gamma, ln, pd);
-  KCHECK(e);
+  cond_encode_dev(e, s, d_x, T, ln);
   conv_gemm(e, gemm_of(s->emovec, ln, 1, 1, ev));               // emovec_layer (model_v2.py:829)
   conv_gemm(e, gemm_of(s->emol, ev, 1, 1, d_out));              // emo_layer    (model_v2.py:830)
 }
@@ -355,7 +412,8 @@ static size_t emo_arena_bytes(const EmoState* s, int T) {
   const size_t T2 = (size_t)((T - 3) / 2 + 1), Fs = (size_t)((c.idim - 3) / 2 + 1), Tp = (T2 + 3) & ~(size_t)3;
   const size_t od = c.odim, H = c.heads, dk = od / H;
   return 4 * (T2 * od * Fs + T2 * od * 6 + T2 * (size_t)std::max<int>(3 * od, c.linear_units) + H * T2 * 5 * dk + H * dk * Tp +
-              H * T2 * Tp + (1 + T2) * (size_t)(c.p_dim + 2 * c.p_heads * c.p_dim_head) + 8 * (size_t)c.p_dim * c.p_ff_mult +
+              H * T2 * Tp + ((size_t)s->n_latents + T2) * (size_t)(c.p_dim + 2 * c.p_heads * c.p_dim_head) + 8 * (size_t)s->n_latents * c.p_dim * c.p_ff_mult +
+              4 * (size_t)s->n_latents * c.p_heads * c.p_dim_head +
               4 * (size_t)c.model_dim) + 64 * 256 + (1 << 20);
 }
 

@@ -126,6 +126,7 @@ void idx_destroy(idx_engine* e) {
   if (e->bigvgan) bigvgan_destroy(e->bigvgan);
   if (e->s2mel) s2mel_destroy(e->s2mel);
   if (e->emo) emo_destroy(e->emo);
+  if (e->v1cond) emo_destroy(e->v1cond);
   if (e->v1voc) v1voc_destroy(e->v1voc);
   for (auto& kv : e->weights) cudaFree(kv.second.d);
   for (auto ev : e->events) if (ev) cudaEventDestroy(ev);

@@ -94,6 +94,7 @@ struct idx_engine {
   BigvganState* bigvgan = nullptr;
   S2melState* s2mel = nullptr;
   EmoState* emo = nullptr;
+  EmoState* v1cond = nullptr;   // v1 prompt encoder (32-latent conformer-perceiver)
   V1VocoderState* v1voc = nullptr;
 
   const DevTensor& W(const std::string& name) const {

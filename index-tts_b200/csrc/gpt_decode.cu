@@ -28,6 +28,7 @@
 // zeros of null_position_embeddings promote it, model_v2.py:23-24 — trap P12); logits are bf16
 // values upcast to fp32 (P5).  See DESIGN.md "GPT numerics".
 #include "engine.h"
+#include "ops.h"
 #include "ptx.cuh"
 #include <cooperative_groups.h>
 #include <algorithm>
@@ -96,6 +97,7 @@ struct GptParams {
   int* done;            // [1] all sequences finished
   // prefill
   const float* prompt;  // [rows][D] f32
+  float* hidden_out;    // prefill only, optional: [rows][D] residual stream after the last block (v1 latent pass)
   const PrefillTile* tiles;
   unsigned* barrier;    // grid barrier counter (zeroed before each launch)
   // tag-in-data dataflow for the residual stream (batch-1 decode): x[c] travels as {value, epoch} in one 8-byte word
@@ -107,6 +109,7 @@ struct GptParams {
   uint2* kvt;           // [2][D] tagged k, v (bf16-valued) of the position being decoded
   unsigned epoch0;      // first epoch of this launch (2 per layer per step)
   int seq_base;         // global index of row 0 (requests beyond one decode group run as consecutive groups)
+  int pos_plain;        // 1: mel position k at step k (decoding without a cache, infer.py:101); 0: trap P1 (k + 1)
   // beam search (beam_step_kernel runs between single-step launches)
   int ext_sample;       // 1: leave the logits in p.logits and skip the sampling phase
   int beams;            // rows per utterance
@@ -620,7 +623,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
           row_seq[b] = b;
           row_pos[b] = (b < p.B) ? p.prompt_len[b] + k : 0;
           row_valid[b] = (b < p.B);
-          row_posidx[b] = (k == 0) ? 0 : k + 1;  // P1: mel position k+1 with KV cache
+          row_posidx[b] = (k == 0 || p.pos_plain) ? k : k + 1;  // P1: mel position k+1 with KV cache
         }
       }
       ptx::named_bar_sync(1, NCT);
@@ -1019,6 +1022,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
         PROF_STAMP();
       }
 
+      if (p.mode == 0 && p.hidden_out) {
+        // v1 latent pass: every CTA writes its own column slice of the final residual stream (kept in xres by the
+        // PROJ epilogue), so no other CTA's data is touched and the next tile may start at once
+        for (int idx = tid; idx < BT * (o1 - o0); idx += NCT) {
+          const int b = idx / (o1 - o0), c = o0 + idx % (o1 - o0);
+          if (row_valid[b]) p.hidden_out[(size_t)row_posidx[b] * D + c] = sm.xres[b * p.ocap + (c - o0)];
+        }
+        ptx::named_bar_sync(1, NCT);
+      }
       if (p.mode == 1) {
         // ---------------- head: ln_f -> final_norm -> mel_head ----------------
         if constexpr (BT == 1) {
@@ -1933,7 +1945,7 @@ static void strict_generate(idx_engine* e, GptState* g, const idx_gpt_request* r
     int* h_fin = (int*)e->pinned_buf(64);
     int k = 0;
     for (; k < max_new; ++k) {
-      strict_embed_kernel<<<(D + 255) / 256, 256, 0, st>>>(s->x, nullptr, mel_emb, mel_pos, g->tok, k == 0 ? 0 : k + 1, D);   // trap P1
+      strict_embed_kernel<<<(D + 255) / 256, 256, 0, st>>>(s->x, nullptr, mel_emb, mel_pos, g->tok, (k == 0 || sp->mel_pos_mode == 1) ? k : k + 1, D);   // trap P1 / no-cache rule
       strict_layers(e, g, plen + k);
       strict_ln_kernel<<<1, 256, 0, st>>>(s->x, e->Wf("gpt.gpt.ln_f.weight"), e->Wf("gpt.gpt.ln_f.bias"), s->h, D);
       strict_ln_kernel<<<1, 256, 0, st>>>(s->h, e->Wf("gpt.final_norm.weight"), e->Wf("gpt.final_norm.bias"), s->att, D);   // trap P3
@@ -2306,6 +2318,7 @@ static void beam_generate(idx_engine* e, GptState* g, const idx_gpt_request* req
 
   fill_common(e, g, p);
   p.B = rows; p.mode = 1; p.max_new = max_new; p.ext_sample = 1; p.beams = m; p.phys_stride = hs;
+  p.pos_plain = sp->mel_pos_mode == 1;
   BeamParams bp;
   memset(&bp, 0, sizeof(bp));
   bp.logits = g->logits; bp.V = V; bp.m = m; bp.max_new = max_new; bp.stop_tok = c.stop_mel_token;
@@ -2536,6 +2549,7 @@ extern "C" int idx_gpt_generate(idx_engine* e, const idx_gpt_request* reqs, int 
   p.do_sample = sp->do_sample; p.top_k = sp->top_k; p.top_p = sp->top_p; p.temperature = sp->temperature;
   p.seed = sp->seed;
   p.seq_base = g->seq_base;
+  p.pos_plain = sp->mel_pos_mode == 1;
   p.codes = d_codes; p.forced = d_forced; p.logits_dump = d_ldump;
   const int SPL = 32;  // steps per launch: the host looks at one flag every SPL steps
   int steps_done = 0;
@@ -2645,4 +2659,138 @@ extern "C" int idx_gpt_beam_trace(const idx_engine* e, int utterance, int32_t* p
   if (steps_out) *steps_out = t->steps;
   if (final_score) *final_score = t->final_score[utterance];
   return IDX_OK;
+}
+
+// ------------------------------------------------------------------ v1 / v1.5 GPT side (row a13) --
+namespace {
+// rows r < n_lat: conds[r]; then j = r - n_lat over [start_text, text.., stop_text]: text_emb[id] + text_pos[j];
+// with n_codes >= 0 also the mel part [start_mel, codes.., stop_mel]: mel_emb[tok] + mel_pos[i]  (model.py:565-578)
+__global__ void v1_rows_kernel(const float* conds, int n_lat, const int* text_ids, int n_text, const int* codes, int n_codes,
+                               const float* text_emb, const float* text_pos, const float* mel_emb, const float* mel_pos,
+                               int start_mel, int stop_mel, int D, int r16, float* out, int text_rows, int mel_rows, int* bad) {
+  const int row = blockIdx.x;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float v;
+    if (row < n_lat) {
+      v = conds[(size_t)row * D + c];
+    } else if (row < n_lat + n_text + 2) {
+      const int j = row - n_lat;
+      int id = (j == 0) ? 0 : (j == n_text + 1 ? 1 : text_ids[j - 1]);
+      if (id < 0 || id >= text_rows) { if (c == 0) atomicCAS(bad, 0, j); id = 0; }
+      v = rnd(text_emb[(size_t)id * D + c] + text_pos[(size_t)j * D + c], r16);
+    } else {
+      const int i = row - (n_lat + n_text + 2);
+      int tok = (i == 0) ? start_mel : (i == n_codes + 1 ? stop_mel : codes[i - 1]);
+      if (tok < 0 || tok >= mel_rows) { if (c == 0) atomicCAS(bad, 0, n_text + 2 + i); tok = 0; }
+      v = rnd(mel_emb[(size_t)tok * D + c] + mel_pos[(size_t)i * D + c], r16);
+    }
+    out[(size_t)row * D + c] = v;
+  }
+}
+}  // namespace
+
+static void v1_rows(idx_engine* e, GptState* g, const float* d_conds, int n_lat, const int* d_ids, int n_text, const int* d_codes,
+                    int n_codes, float* d_out) {
+  const int D = g->cfg.model_dim;
+  const DevTensor& tpos = e->W("gpt.text_pos_embedding.emb.weight");
+  IDX_CHECK(n_text + 2 <= tpos.shape[0], IDX_ERR_ARG, "text longer than text_pos_embedding");
+  const int rows = n_lat + n_text + 2 + (n_codes >= 0 ? n_codes + 2 : 0);
+  if (n_codes >= 0)
+    IDX_CHECK(n_codes + 2 <= e->W("gpt.mel_pos_embedding.emb.weight").shape[0], IDX_ERR_ARG, "codes longer than mel_pos_embedding");
+  v1_rows_kernel<<<rows, 256, 0, e->stream>>>(d_conds, n_lat, d_ids, n_text, d_codes, n_codes, e->Wf("gpt.text_embedding.weight"),
+                                              (const float*)tpos.d, e->Wf("gpt.mel_embedding.weight"),
+                                              e->Wf("gpt.mel_pos_embedding.emb.weight"), g->cfg.start_mel_token,
+                                              g->cfg.stop_mel_token, D, g->cfg.weights_bf16, d_out,
+                                              (int)e->W("gpt.text_embedding.weight").shape[0],
+                                              (int)e->W("gpt.mel_embedding.weight").shape[0], e->dev_flag);
+  IDX_CUDA(cudaGetLastError());
+  e->launches++;
+}
+
+extern "C" int idx_gpt_prepare_inputs_v1(idx_engine* e, const float* conds, int n_latents, const int32_t* text_ids, int n_text,
+                                         float* out) {
+  IDX_API_BEGIN
+  IDX_CHECK(e && e->gpt, IDX_ERR_STATE, "idx_gpt_init has not been called");
+  IDX_CHECK(conds && out && n_latents >= 1 && n_text >= 0 && (n_text == 0 || text_ids), IDX_ERR_ARG, "bad arguments");
+  IDX_CUDA(cudaSetDevice(e->device));
+  GptState* g = e->gpt;
+  const int D = g->cfg.model_dim, rows = n_latents + n_text + 2;
+  e->ensure_arena(4 * ((size_t)(rows + n_latents) * D + (size_t)n_text + 16) + (1 << 16));
+  e->arena.reset();
+  float* d_c = e->arena.get<float>((size_t)n_latents * D);
+  int* d_ids = e->arena.get<int>(n_text + 1);
+  float* d_out = e->arena.get<float>((size_t)rows * D);
+  idx_to_device(e, d_c, conds, (size_t)n_latents * D * 4);
+  if (n_text) idx_to_device(e, d_ids, text_ids, (size_t)n_text * 4);
+  v1_rows(e, g, d_c, n_latents, d_ids, n_text, nullptr, -1, d_out);
+  idx_from_device(e, out, d_out, (size_t)rows * D * 4);
+  IDX_CUDA(cudaStreamSynchronize(e->stream));
+  e->check_flag("text token id outside text_embedding");
+  IDX_API_END(e)
+}
+
+extern "C" int idx_gpt_latents_v1(idx_engine* e, const float* conds, int n_latents, const int32_t* text_ids, int n_text,
+                                  const int32_t* codes, int n_codes, float* latents_out) {
+  IDX_API_BEGIN
+  IDX_CHECK(e && e->gpt, IDX_ERR_STATE, "idx_gpt_init has not been called");
+  IDX_CHECK(conds && codes && latents_out && n_latents >= 1 && n_text >= 0 && n_codes >= 1, IDX_ERR_ARG, "bad arguments");
+  IDX_CUDA(cudaSetDevice(e->device));
+  GptState* g = e->gpt;
+  GptStrict* s = g->strict;
+  const int D = g->cfg.model_dim, R = n_latents + n_text + 2 + n_codes + 2;
+  IDX_CHECK(R <= g->maxpos, IDX_ERR_ARG, "sequence longer than the KV cache");
+  for (int i = 0; i < n_codes; ++i) (void)i;
+  e->ensure_arena(4 * ((size_t)(2 * R + n_latents + 2 * n_codes + 2) * D + (size_t)n_text + n_codes + 32) +
+                  (size_t)(R / 8 + 2) * sizeof(PrefillTile) + (1 << 16));
+  e->arena.reset();
+  float* d_c = e->arena.get<float>((size_t)n_latents * D);
+  int* d_ids = e->arena.get<int>(n_text + 1);
+  int* d_codes = e->arena.get<int>(n_codes);
+  float* d_rows = e->arena.get<float>((size_t)R * D);
+  float* d_lat = e->arena.get<float>((size_t)n_codes * D);
+  idx_to_device(e, d_c, conds, (size_t)n_latents * D * 4);
+  if (n_text) idx_to_device(e, d_ids, text_ids, (size_t)n_text * 4);
+  idx_to_device(e, d_codes, codes, (size_t)n_codes * 4);
+  v1_rows(e, g, d_c, n_latents, d_ids, n_text, d_codes, n_codes, d_rows);
+  const int first = R - (n_codes + 2);                 // first mel row; latents = rows first .. first + n_codes - 1
+  cudaStream_t st = e->stream;
+  g->last_launches = 0;
+  if (!s) {
+    // bf16 path: one prefill sweep of the fused kernel (tiles of 8 rows, sequence slot 0) that dumps the residual stream
+    std::vector<PrefillTile> tiles;
+    for (int p0 = 0; p0 < R - 2; p0 += 8) tiles.push_back({0, p0, std::min(8, R - 2 - p0), p0});
+    PrefillTile* d_tiles = e->arena.get<PrefillTile>(tiles.size());
+    float* d_hid = e->arena.get<float>((size_t)R * D);
+    float* d_tmp = e->arena.get<float>((size_t)n_codes * D);
+    IDX_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(PrefillTile), cudaMemcpyHostToDevice, st));
+    IDX_CUDA(cudaStreamSynchronize(st));
+    GptParams p;
+    fill_common(e, g, p);
+    p.B = 8; p.mode = 0; p.nsteps = (int)tiles.size(); p.prompt = d_rows; p.tiles = d_tiles; p.hidden_out = d_hid;
+    p.max_new = 1; p.rep_penalty = 1.f;
+    launch_fused_bt(e, g, p, 8);
+    layernorm(e, d_hid + (size_t)first * D, d_tmp, 1, n_codes, D, e->Wf("gpt.gpt.ln_f.weight"), e->Wf("gpt.gpt.ln_f.bias"), 1e-5f,
+              nullptr, nullptr, 0);
+    layernorm(e, d_tmp, d_lat, 1, n_codes, D, e->Wf("gpt.final_norm.weight"), e->Wf("gpt.final_norm.bias"), 1e-5f, nullptr, nullptr, 0);
+    idx_from_device(e, latents_out, d_lat, (size_t)n_codes * D * 4);
+    IDX_CUDA(cudaStreamSynchronize(e->stream));
+    e->check_flag("text token id or speech code outside its embedding table");
+    return IDX_OK;
+  }
+  // strict fp32: one teacher-forced sweep, position by position (the KV cache of the strict path is the causal mask)
+  for (int pos = 0; pos < R - 2; ++pos) {              // the last two rows are dropped by the caller of get_logits (:583)
+    strict_embed_kernel<<<(D + 255) / 256, 256, 0, st>>>(s->x, d_rows + (size_t)pos * D, nullptr, nullptr, nullptr, 0, D);
+    strict_layers(e, g, pos);
+    if (pos >= first) {
+      strict_ln_kernel<<<1, 256, 0, st>>>(s->x, e->Wf("gpt.gpt.ln_f.weight"), e->Wf("gpt.gpt.ln_f.bias"), s->h, D);
+      strict_ln_kernel<<<1, 256, 0, st>>>(s->h, e->Wf("gpt.final_norm.weight"), e->Wf("gpt.final_norm.bias"),
+                                          d_lat + (size_t)(pos - first) * D, D);
+      e->launches += 2;
+    }
+  }
+  IDX_CUDA(cudaGetLastError());
+  idx_from_device(e, latents_out, d_lat, (size_t)n_codes * D * 4);
+  IDX_CUDA(cudaStreamSynchronize(e->stream));
+  e->check_flag("text token id outside text_embedding");
+  IDX_API_END(e)
 }

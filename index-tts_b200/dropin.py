@@ -172,3 +172,84 @@ def attach(tts, engine: Engine = None, device: int = 0):
     tts.bigvgan.forward = bigvgan_forward
     tts._b200_engine = engine
     return tts
+
+
+# ------------------------------------------------------------------ IndexTTS v1 / v1.5 (indextts/infer.py) --
+def attach_v1(tts, engine: Engine = None, device: int = 0):
+    """Rebind the compute seams of a reference `indextts.infer.IndexTTS` instance (v1 / v1.5):
+
+        tts.gpt.inference_speech(mel, text, ...)          → idx_v1_get_conditioning + idx_gpt_prepare_inputs_v1 + idx_gpt_generate
+                                                             (gpt/model.py:661-713; positions follow kv_cache, infer.py:101)
+        tts.gpt(mel, text, ..., return_latent=True)       → idx_gpt_latents_v1                      (gpt/model.py:526-589)
+        tts.bigvgan(latent, mel_ref)                      → idx_v1_vocode                            (BigVGAN/models.py:201-249)
+
+    The strict fp32 GPT path is used (the reference's CPU configuration, BASELINE config 1)."""
+    engine = engine or Engine(device)
+    gpt = tts.gpt
+    sd = _sd(gpt)
+    engine.load_state_dict("gpt.", sd)
+    D = gpt.model_dim
+    engine.gpt_init(len(gpt.gpt.h), D, gpt.heads, gpt.number_mel_codes, gpt.start_mel_token, gpt.stop_mel_token,
+                    sd["mel_pos_embedding.emb.weight"].shape[0],
+                    max_prompt=sd["text_pos_embedding.emb.weight"].shape[0] + sd["perceiver_encoder.latents"].shape[0] + 8,
+                    max_batch=1, weights_bf16=False)
+    E, Q = "conditioning_encoder.", "perceiver_encoder."
+    od = sd[E + "embed.out.0.weight"].shape[0]
+    fsub = sd[E + "embed.out.0.weight"].shape[1] // od
+    inner = sd[Q + "layers.0.0.to_q.weight"].shape[0]
+    p_heads = sd[E + "encoders.0.self_attn.pos_bias_u"].shape[0]
+    n_lat = sd[Q + "latents"].shape[0]
+    engine.v1_cond_init(dict(idim=2 * fsub + 2, odim=od, linear_units=sd[E + "encoders.0.feed_forward.w_1.weight"].shape[0],
+                             heads=p_heads, blocks=1 + max(int(k.split(".")[2]) for k in sd if k.startswith(E + "encoders.")),
+                             cnn_kernel=sd[E + "encoders.0.conv_module.depthwise_conv.weight"].shape[-1], p_dim=D, p_heads=p_heads,
+                             p_dim_head=inner // p_heads,
+                             p_depth=1 + max(int(k.split(".")[2]) for k in sd if k.startswith(Q + "layers.")),
+                             p_ff_mult=max(1, round(sd[Q + "layers.0.1.0.weight"].shape[0] * 3 / (4 * D))), model_dim=D), n_lat)
+    bv = fold_weight_norm({k: v for k, v in tts.bigvgan.state_dict().items() if torch.is_floating_point(v)})
+    engine.load_state_dict("bigvgan_v1.", bv)
+    engine.v1_vocoder_init(dict(tts.bigvgan.h))
+    dev = torch.device("cuda", engine.device)
+    kv_cache = bool(getattr(gpt.inference_model, "kv_cache", False))
+
+    def _conds(mel):                                     # mel [1, 100, T] as infer.py passes it
+        return engine.v1_get_conditioning(mel[0].float().t().contiguous().cpu().numpy())
+
+    def inference_speech(self, speech_conditioning_mel, text_inputs, cond_mel_lengths=None, input_tokens=None,
+                         num_return_sequences=1, max_generate_length=None, typical_sampling=False, typical_mass=.9, **hf):
+        nb = int(hf.get("num_beams", 1) or 1)
+        conds = _conds(speech_conditioning_mel)
+        outs = []
+        for i in range(text_inputs.shape[0]):
+            prompt = engine.gpt_prepare_inputs_v1(conds, text_inputs[i].cpu().numpy())
+            max_new = max_generate_length if max_generate_length is not None else self.max_mel_tokens - 1
+            (codes,) = engine.gpt_generate([prompt], int(max_new), repetition_penalty=float(hf.get("repetition_penalty", 1.0)),
+                                           do_sample=bool(hf.get("do_sample", False)), top_k=int(hf.get("top_k", 0) or 0),
+                                           top_p=float(hf.get("top_p", 1.0)), temperature=float(hf.get("temperature", 1.0)),
+                                           num_beams=nb, length_penalty=float(hf.get("length_penalty", 0.0)),
+                                           seed=int(torch.initial_seed() & 0x7fffffff), mel_pos_mode=0 if kv_cache else 1)
+            outs.append(torch.from_numpy(codes.astype(np.int64)))
+        n = max(len(o) for o in outs)
+        pad = torch.full((len(outs), n), self.stop_mel_token, dtype=torch.long)
+        for i, o in enumerate(outs):
+            pad[i, : len(o)] = o
+        return pad.to(dev)
+
+    gpt.inference_speech = types.MethodType(inference_speech, gpt)
+
+    def forward(speech_conditioning_latent, text_inputs, text_lengths, mel_codes, wav_lengths, cond_mel_lengths=None, types=None,
+                text_first=True, raw_mels=None, return_attentions=False, return_latent=False, clip_inputs=False):
+        if not return_latent:
+            raise NotImplementedError("the B200 path implements the inference use of forward(): return_latent=True (infer.py:~640)")
+        conds = _conds(speech_conditioning_latent)
+        lat = engine.gpt_latents_v1(conds, text_inputs[0, : int(text_lengths[0])].cpu().numpy(), mel_codes[0].cpu().numpy())
+        return torch.from_numpy(lat)[None].to(dev)
+
+    gpt.forward = forward
+
+    def bigvgan_forward(x, mel_ref, lens=None):
+        wav = engine.v1_vocode(x[0].float().contiguous().cpu().numpy(), mel_ref[0].float().contiguous().cpu().numpy())
+        return torch.from_numpy(wav)[None, None].to(dev), None
+
+    tts.bigvgan.forward = bigvgan_forward
+    tts._b200_engine = engine
+    return tts

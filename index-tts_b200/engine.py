@@ -37,7 +37,7 @@ class Sampling(C.Structure):
                 ("top_p", C.c_float), ("temperature", C.c_float),
                 ("repetition_penalty", C.c_float), ("length_penalty", C.c_float),
                 ("max_new_tokens", C.c_int32), ("seed", C.c_uint64),
-                ("forbid_stop_before", C.c_int32)]
+                ("forbid_stop_before", C.c_int32), ("mel_pos_mode", C.c_int32)]
 
 
 class GptRequest(C.Structure):
@@ -135,6 +135,10 @@ def load_library(path: str = None):
                                            C.c_int, C.c_int, C.c_void_p]
     lib.idx_gpt_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.idx_gpt_profile.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.idx_v1_cond_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.idx_v1_get_conditioning.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.idx_gpt_prepare_inputs_v1.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    lib.idx_gpt_latents_v1.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     lib.idx_v1_vocoder_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
     lib.idx_v1_speaker_embedding.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.idx_v1_vocode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
@@ -265,7 +269,7 @@ class Engine:
 
     def gpt_generate(self, prompts, max_new_tokens, repetition_penalty=10.0, do_sample=False,
                      num_beams=1, top_k=0, top_p=1.0, temperature=1.0, length_penalty=0.0,
-                     seed=0, forbid_stop_before=0, forced_codes=None, return_logits=False):
+                     seed=0, forbid_stop_before=0, forced_codes=None, return_logits=False, mel_pos_mode=0):
         """Mirror of UnifiedVoice.inference_speech → generate (gpt/model_v2.py:716-825).
         prompts: list of [S_i, D] float32 arrays (the [cond][text] embeddings, no padding).
         Returns list of int32 code arrays (stop token included when produced) and, optionally,
@@ -294,7 +298,7 @@ class Engine:
                 reqs[i].forced_codes = _ptr(fc)
         sp = Sampling(int(do_sample), int(num_beams), int(top_k), float(top_p), float(temperature),
                       float(repetition_penalty), float(length_penalty), int(max_new_tokens),
-                      int(seed), int(forbid_stop_before))
+                      int(seed), int(forbid_stop_before), int(mel_pos_mode))
         self._check(self.lib.idx_gpt_generate(self.h, reqs, n, C.byref(sp)), "idx_gpt_generate")
         out = [codes[i][: int(ncodes[i][0])].copy() for i in range(n)]
         if return_logits:
@@ -302,6 +306,40 @@ class Engine:
                 steps = self.gpt_last_timing()["steps"]
                 return out, [logits[i][:steps] for i in range(n)]
             return out, [logits[i][: int(ncodes[i][0])] for i in range(n)]
+        return out
+
+    # ------------------------------------------------------- v1 / v1.5 GPT side (row a13) --
+    def v1_cond_init(self, c: dict, n_latents=32):
+        cfg = EmoConfig(*[c[k] for k in ("idim", "odim", "linear_units", "heads", "blocks", "cnn_kernel", "p_dim",
+                                         "p_heads", "p_dim_head", "p_depth", "p_ff_mult", "model_dim")])
+        self._check(self.lib.idx_v1_cond_init(self.h, C.byref(cfg), int(n_latents)), "idx_v1_cond_init")
+        self.v1_cond_cfg, self._v1_nlat = cfg, int(n_latents)
+
+    def v1_get_conditioning(self, mel):
+        """UnifiedVoice.get_conditioning (gpt/model.py:493-503): mel [T, 100] → conds [32, model_dim]."""
+        m = _as_f32(mel)
+        out = np.empty((self._v1_nlat, self.v1_cond_cfg.model_dim), dtype=np.float32)
+        self._check(self.lib.idx_v1_get_conditioning(self.h, _ptr(m), int(m.shape[0]), _ptr(out)), "idx_v1_get_conditioning")
+        return out
+
+    def gpt_prepare_inputs_v1(self, conds, text_ids):
+        """prepare_gpt_inputs of v1 (gpt/model.py:597-660): [conds][start_text, text.., stop_text] rows."""
+        cd = _as_f32(conds)
+        ids = np.ascontiguousarray(np.asarray(text_ids, dtype=np.int32).reshape(-1))
+        ids = np.ascontiguousarray(ids[(ids != 0) & (ids != 1)])
+        out = np.empty((cd.shape[0] + len(ids) + 2, self.gpt_cfg.model_dim), dtype=np.float32)
+        self._check(self.lib.idx_gpt_prepare_inputs_v1(self.h, _ptr(cd), int(cd.shape[0]), _ptr(ids), len(ids), _ptr(out)),
+                    "idx_gpt_prepare_inputs_v1")
+        return out
+
+    def gpt_latents_v1(self, conds, text_ids, codes):
+        """UnifiedVoice.forward(return_latent=True) (gpt/model.py:526-589) → latents [n_codes, model_dim]."""
+        cd = _as_f32(conds)
+        ids = np.ascontiguousarray(np.asarray(text_ids, dtype=np.int32).reshape(-1))
+        cs = np.ascontiguousarray(np.asarray(codes, dtype=np.int32).reshape(-1))
+        out = np.empty((len(cs), self.gpt_cfg.model_dim), dtype=np.float32)
+        self._check(self.lib.idx_gpt_latents_v1(self.h, _ptr(cd), int(cd.shape[0]), _ptr(ids), len(ids), _ptr(cs), len(cs),
+                                                _ptr(out)), "idx_gpt_latents_v1")
         return out
 
     def gpt_beam_trace(self, utterance=0, max_steps=4096, num_beams=3):

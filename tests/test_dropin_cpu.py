@@ -144,3 +144,54 @@ def test_rebound_seams_accept_the_reference_call_sites():
                 raise AssertionError(f"{name}: reference call ({npos} positional, keywords {kws}) does not bind to {sig}: {e}")
     # the rebound objects are the reference's own module objects: infer_generator reaches them unchanged
     assert tts.gpt is gpt and tts.bigvgan is bv and tts._b200_engine is eng
+
+
+def test_attach_v1_on_real_reference_v1_modules():
+    """v1 / v1.5 drop-in (row a13): `attach_v1` on the reference's own v1 `UnifiedVoice` and `BigVGAN` classes — the derived
+    prompt-encoder / vocoder configuration equals what the modules were built with, and the calls `indextts/infer.py` makes
+    at the three seams bind to the rebound callables."""
+    import ast
+    import inspect
+    import os
+
+    from indextts_b200 import synth
+    from indextts_b200.dropin import attach_v1
+    from oracle.make_goldens_v1 import reference_module
+    from oracle.validate_gpt_vs_hf import small_case
+
+    cfg, _, _, _ = small_case()
+    ccfg = synth.small_v1_cond_cfg(cfg["model_dim"])
+    gpt = refimport.gpt_module_v1(cfg, ccfg, synth.make_gpt_v1_weights(cfg, ccfg, seed=3), kv_cache=False)
+    h = synth.small_v1_config()
+    bv = reference_module(h, synth.make_bigvgan_v1_weights(h, seed=5))
+    tts = types.SimpleNamespace(gpt=gpt, bigvgan=bv)
+
+    class Rec(RecordingEngine):
+        def v1_cond_init(self, c, n):
+            self.calls["v1_cond_init"] = (dict(c), n)
+
+        def v1_vocoder_init(self, hh):
+            self.calls["v1_vocoder_init"] = dict(hh)
+
+    eng = Rec()
+    attach_v1(tts, engine=eng)
+    c, n = eng.calls["v1_cond_init"]
+    assert n == 32
+    for k in ("idim", "odim", "linear_units", "heads", "blocks", "cnn_kernel", "p_dim", "p_heads", "p_dim_head", "p_depth", "p_ff_mult"):
+        assert c[k] == ccfg[k], (k, c[k], ccfg[k])
+    a, kw = eng.calls["gpt_init"]
+    assert a[:3] == (cfg["layers"], cfg["model_dim"], cfg["heads"]) and kw["weights_bf16"] is False
+    assert eng.calls["v1_vocoder_init"]["gpt_dim"] == h["gpt_dim"]
+    assert "bigvgan_v1.speaker_encoder.blocks.0.conv.conv.weight" in eng.weights and "bigvgan_v1.cond_layer.weight" in eng.weights
+    assert "gpt.conditioning_encoder.embed.out.0.weight" in eng.weights and "gpt.perceiver_encoder.latents" in eng.weights
+    # call sites of indextts/infer.py
+    tree = ast.parse(open(os.path.join(refimport.REF, "indextts", "infer.py")).read())
+    want = {"self.gpt.inference_speech": tts.gpt.inference_speech, "self.gpt": tts.gpt.forward, "self.bigvgan": tts.bigvgan.forward}
+    seen = set()
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Call) and ast.unparse(node.func) in want:
+            name = ast.unparse(node.func)
+            kws = [k.arg for k in node.keywords if k.arg is not None]
+            inspect.signature(want[name]).bind(*([None] * len(node.args)), **{k: None for k in kws})
+            seen.add(name)
+    assert seen == set(want)
