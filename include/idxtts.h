@@ -18,6 +18,12 @@
  *   - one handle = one CUDA device = one caller thread at a time (the reference is
  *     not re-entrant either: infer_v2_5.py:268-275, gpt/model_v2.py:88).
  *   - calls are synchronous with respect to the host unless stated otherwise.
+ *   - STREAM CONTRACT: the engine launches on its own non-blocking stream.  Device buffers handed
+ *     to a call must be complete with respect to that stream: a caller that produced them with
+ *     asynchronous work on another stream (e.g. torch's current stream) calls
+ *     idx_wait_stream(e, that_stream) first — the engine stream then waits (on the device, no host
+ *     block) for everything queued on that stream so far.  The Python shim does this before every
+ *     call.  Outputs need nothing: every call drains the engine stream before it returns.
  */
 #ifndef IDXTTS_H
 #define IDXTTS_H
@@ -61,6 +67,9 @@ const char* idx_version(void);
 int64_t idx_launch_count(const idx_engine* e);
 /* Block until all work queued by this engine has finished.                          */
 int idx_sync(idx_engine* e);
+/* Order the engine stream after all work queued so far on `cuda_stream` (a cudaStream_t passed as
+ * void*; NULL = the legacy default stream): event record + cudaStreamWaitEvent, no host block.  */
+int idx_wait_stream(idx_engine* e, void* cuda_stream);
 /* CUDA events on the engine's own stream (slots 0..15) — what bench.py times with, since the
  * engine does not launch on torch's current stream.                                   */
 int idx_event_record(idx_engine* e, int slot);
@@ -217,6 +226,9 @@ int idx_gpt_last_timing(const idx_engine* e, double* out4);
  * every phase boundary of the last step of each launch (2 stamps per grid barrier: before and
  * after).  Copies up to n (<= 256) stamps of the most recent launch into stamps_out.          */
 int idx_gpt_profile(idx_engine* e, int enable, int64_t* stamps_out, int n);
+/* Diagnostic (profiling enabled as above): %globaltimer stamps of EVERY CTA at the sub-phase boundaries of the middle
+ * layer of the last decode step: stamps_out [num_SMs][64] (0 where a slot is unused).                          */
+int idx_gpt_profile_fine(idx_engine* e, int64_t* stamps_out, int n);
 
 /* ------------------------------------------------------------------- BigVGAN -- */
 

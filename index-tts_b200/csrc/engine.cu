@@ -130,6 +130,7 @@ void idx_destroy(idx_engine* e) {
   if (e->v1voc) v1voc_destroy(e->v1voc);
   for (auto& kv : e->weights) cudaFree(kv.second.d);
   for (auto ev : e->events) if (ev) cudaEventDestroy(ev);
+  if (e->order_ev) cudaEventDestroy(e->order_ev);
   if (e->arena.base) cudaFree(e->arena.base);
   if (e->pinned) cudaFreeHost(e->pinned);
   if (e->dev_flag) cudaFree(e->dev_flag);
@@ -148,6 +149,16 @@ int idx_sync(idx_engine* e) {
   IDX_API_BEGIN
   IDX_CUDA(cudaSetDevice(e->device));
   IDX_CUDA(cudaStreamSynchronize(e->stream));
+  IDX_API_END(e)
+}
+
+int idx_wait_stream(idx_engine* e, void* cuda_stream) {
+  IDX_API_BEGIN
+  IDX_CHECK(e, IDX_ERR_ARG, "null engine");
+  IDX_CUDA(cudaSetDevice(e->device));
+  if (!e->order_ev) IDX_CUDA(cudaEventCreateWithFlags(&e->order_ev, cudaEventDisableTiming));
+  IDX_CUDA(cudaEventRecord(e->order_ev, (cudaStream_t)cuda_stream));
+  IDX_CUDA(cudaStreamWaitEvent(e->stream, e->order_ev, 0));
   IDX_API_END(e)
 }
 

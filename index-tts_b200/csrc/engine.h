@@ -86,6 +86,7 @@ struct idx_engine {
   void* pinned = nullptr;
   size_t pinned_cap = 0;
   cudaEvent_t events[16] = {};
+  cudaEvent_t order_ev = nullptr;   // idx_wait_stream: orders the engine stream after a caller stream
   int gemm_backend = 0;         // idx_set_option("gemm_backend"): 0 auto (tcgen05 tf32 where applicable), 1 SIMT fp32
   int force_backend = 0;        // diagnostics (idx_debug_conv_gemm): 0 none, 1 SIMT, 2 tensor core
   unsigned attr_done = 0;       // bit i: >48 KB dynamic-smem attribute of kernel family i set on this engine's device

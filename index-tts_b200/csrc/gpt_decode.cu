@@ -45,6 +45,7 @@ constexpr int UPC = 8;                      // weight units (one K-segment of D 
 constexpr int MAXPL = 40;                   // max LayerNorm elements per lane (D <= 1280)
 constexpr int HD = 64;                      // head dim (fixed)
 constexpr int PART_STRIDE = 66;             // attention partial: m, l, o[64]
+constexpr int CMAX = 128;                   // candidates the samplers keep after TopK (1 <= top_k <= CMAX, checked by the host)
 #define RED_FLOATS(BT) (((BT) == 1 ? 7 * NCW * 8 : 2 * NCW * 64) > (NCW * PART_STRIDE) ? ((BT) == 1 ? 7 * NCW * 8 : 2 * NCW * 64) : (NCW * PART_STRIDE))
 
 struct PrefillTile {
@@ -116,6 +117,8 @@ struct GptParams {
   int phys_stride;
   const unsigned char* phys;   // [8][phys_stride]: cache slot of generated position t of row b's lineage, or null
   long long* prof;      // optional: globaltimer stamps of CTA 0 for the last step of the launch
+  long long* prof2;     // optional: [G][64] fine globaltimer stamps of every CTA for layer prof2_layer of the last step
+  int prof2_layer;
 };
 
 __device__ __forceinline__ float bf16r(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
@@ -386,7 +389,6 @@ __device__ __forceinline__ void gemv_phase(const GptParams& p, const Smem<BT>& s
   const uint32_t ring_base = ptx::smem_u32(sm.ring);
   const uint32_t xs_base = ptx::smem_u32(sm.xs) + (uint32_t)b_n * FFc * 2;
   const int g = lane >> 2, t4 = lane & 3;
-  (void)fine;
   for (int g0 = 0; g0 < ngroups; g0 += gpb) {
     const int nb = min(gpb, ngroups - g0);
     float acc[GMAX][4];
@@ -399,6 +401,7 @@ __device__ __forceinline__ void gemv_phase(const GptParams& p, const Smem<BT>& s
           const unsigned n = cons_idx + gi * nseg + sgi;
           const int stage = n % p.nst;
           ptx::mbar_wait(&sm.full[stage], (n / p.nst) & 1u);
+          if (fine && threadIdx.x == 0 && g0 == 0 && gi == 0 && sgi == 0) fine[0] = gtimer();
           const uint32_t a_row = ring_base + (uint32_t)((stage * UPC + a_r) * D * 2);
           const uint32_t b_row = xs_base + (uint32_t)(sgi * D * 2);
 #pragma unroll
@@ -415,6 +418,7 @@ __device__ __forceinline__ void gemv_phase(const GptParams& p, const Smem<BT>& s
       }
     }
     // the weights of these chunks are consumed: hand the stages back to the producer
+    if (fine && threadIdx.x == 0 && g0 == 0) fine[1] = gtimer();
     __syncwarp();
     if (lane == 0)
       for (int i = 0; i < nb * nseg; ++i) ptx::mbar_arrive(&sm.empty[(cons_idx + i) % p.nst]);
@@ -435,6 +439,7 @@ __device__ __forceinline__ void gemv_phase(const GptParams& p, const Smem<BT>& s
       }
     }
     ptx::named_bar_sync(1, NCT);
+    if (fine && threadIdx.x == 0 && g0 == 0) fine[2] = gtimer();
     const int nout = nb * 8 * BT;
     for (int idx = threadIdx.x; idx < nout; idx += NCT) {
       const int gi = idx / (8 * BT), r = (idx / BT) & 7, b = idx % BT;
@@ -476,8 +481,10 @@ __device__ __forceinline__ void gemv_phase(const GptParams& p, const Smem<BT>& s
         p.logits[(size_t)b * p.V + c] = rnd(a + bias_ph[cl], rr);
       }
     }
+    if (fine && threadIdx.x == 0 && g0 + gpb >= ngroups) fine[3] = gtimer();
     ptx::named_bar_sync(1, NCT);   // red is reused by the next batch of groups
   }
+  if (fine && threadIdx.x == 0) fine[4] = gtimer();
 }
 
 #define PROF_STAMP()                                                        \
@@ -660,6 +667,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
         // Steps are separated by the grid barriers around the head and the sampling phase.
         // tagged residual stream (batch-1 decode): epochs of the two x hand-overs of this layer
         const bool tagged = (BT == 1) && p.xt != nullptr;
+        long long* f2 = (p.prof2 && l == p.prof2_layer && step == p.nsteps - 1) ? p.prof2 + (size_t)cta * 64 : nullptr;
+#define F2(i) do { if (f2 && tid == 0) f2[(i)] = gtimer(); } while (0)
+        F2(0);
         const unsigned ep_base = p.epoch0 + (unsigned)(step * L + l) * 2u;
         const unsigned ep_oproj = ep_base + 1u;      // O-proj -> FC of this layer
         const unsigned ep_proj = ep_base + 2u;       // PROJ -> QKV of the next layer (== ep_base of l + 1)
@@ -670,11 +680,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
           float v[NPL / 8];
           if (tagged && l > 0) {
             ld_tagged_slice<NPL / 8>(p.xt, warp * (NPL * 4) + lane, ep_base, v);
+            F2(1);
           } else {
 #pragma unroll
             for (int j = 0; j < NPL / 8; ++j) v[j] = __ldcg(p.xg + warp * (NPL * 4) + lane + 32 * j);
           }
           ln_block<NPL>(v, lnA, lnA + D, sm.red, warp, lane);
+          F2(2);
 #pragma unroll
           for (int j = 0; j < NPL / 8; ++j)
             sm.xs[warp * (NPL * 4) + lane + 32 * j] = __float2bfloat16_rn(v[j]);
@@ -687,10 +699,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
           }
         }
         ptx::named_bar_sync(1, NCT);
+        F2(3);
         gemv_phase<BT, 0, D>(p, sm, l, q0, nq, 1, cons_idx, row_seq, row_pos, row_valid,
                           warp, lane, sm.bias_s + l * bstride, o0,
-                          (p.prof && cta == 0 && l == 1 && step == p.nsteps - 1) ? p.prof + 256 : nullptr,
-                          tagged ? ep_oproj : 0u);
+                          f2 ? f2 + 4 : nullptr, tagged ? ep_oproj : 0u);
+        F2(9);
         PROF_STAMP();
         if (!tagged) grid_sync(p.barrier, bar_target, G, p.bar_flavor);   // tagged: attention polls q and the new k, v
         PROF_STAMP();
@@ -722,6 +735,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
                 for (int i = 0; i < 8; ++i) ok &= (tg[i] == ep_oproj);
                 if (++spins > (1u << 26)) __trap();
               } while (!ok);
+              F2(10);
 #pragma unroll
               for (int i = 0; i < 8; ++i) qv[i] = __uint_as_float(val[i]);
             } else {
@@ -783,6 +797,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
               }
             };
             if (p.phys) key_loop(std::true_type{}); else key_loop(std::false_type{});
+            F2(11);
             if (tagged && k1 == ctx && warp == 0 && g4 == 0) {
               // the new position (owned by the last key split): k and v straight from the QKV epilogue's tagged words
               const uint2* kp = p.kvt + h * HD + sub * 8;
@@ -816,6 +831,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
               m = mn;
             }
             __syncwarp();
+            F2(12);
             // merge the 4 key groups of the warp
 #pragma unroll
             for (int xo = 8; xo <= 16; xo <<= 1) {
@@ -842,6 +858,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
               for (int i = 0; i < 8; ++i) rw[2 + lane * 8 + i] = ov[i];
             }
             ptx::named_bar_sync(1, NCT);
+            F2(13);
             if (warp == 0) {
               float mm = -INFINITY;
               for (int w = 0; w < NCW; ++w) mm = fmaxf(mm, red[w * PART_STRIDE]);
@@ -864,6 +881,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
             }
           }
         }
+        F2(14);
         PROF_STAMP();
         if (!tagged) grid_sync(p.barrier, bar_target, G, p.bar_flavor);   // tagged: O-proj polls the partials' flags
         PROF_STAMP();
@@ -885,6 +903,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
               if (__all_sync(0xffffffffu, fv == ep_oproj)) break;
               if (++spins > (1u << 26)) __trap();
             }
+            if (bh0 == warp) F2(16);
           }
           float ms[3][8], ls[3][8], oa[3][8], ob[3][8];
 #pragma unroll
@@ -924,8 +943,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
           }
         }
         ptx::named_bar_sync(1, NCT);
+        F2(17);
         gemv_phase<BT, 1, D>(p, sm, l, o0, no, 1, cons_idx, row_seq, row_pos, row_valid,
-                          warp, lane, sm.bias_s + l * bstride + nq, o0, nullptr, tagged ? ep_oproj : 0u);
+                          warp, lane, sm.bias_s + l * bstride + nq, o0, f2 ? f2 + 18 : nullptr, tagged ? ep_oproj : 0u);
+        F2(23);
         PROF_STAMP();
         if (!tagged) grid_sync(p.barrier, bar_target, G, p.bar_flavor);   // tagged: FC polls the x words instead
         PROF_STAMP();
@@ -939,12 +960,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
           float v[NPL / 8];
           if (tagged) {
             ld_tagged_slice<NPL / 8>(p.xt, warp * (NPL * 4) + lane, ep_oproj, v);
+            F2(24);
             cp_async_wait_all();   // ln_2 parameters prefetched in P1 (ln_block's own CTA barrier publishes them)
           } else {
 #pragma unroll
             for (int j = 0; j < NPL / 8; ++j) v[j] = __ldcg(p.xg + warp * (NPL * 4) + lane + 32 * j);
           }
           ln_block<NPL>(v, lnB, lnB + D, sm.red, warp, lane);
+          F2(25);
 #pragma unroll
           for (int j = 0; j < NPL / 8; ++j)
             sm.xs[warp * (NPL * 4) + lane + 32 * j] = __float2bfloat16_rn(v[j]);
@@ -957,10 +980,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
           }
         }
         ptx::named_bar_sync(1, NCT);
+        F2(26);
         gemv_phase<BT, 2, D>(p, sm, l, f0, nf, 1, cons_idx, row_seq, row_pos, row_valid,
                           warp, lane, sm.bias_s + l * bstride + nq + no, o0,
-                          (p.prof && cta == 0 && l == 1 && step == p.nsteps - 1) ? p.prof + 272 : nullptr,
-                          tagged ? f_tag : 0u);
+                          f2 ? f2 + 27 : nullptr, tagged ? f_tag : 0u);
+        F2(32);
         PROF_STAMP();
         if (!tagged) grid_sync(p.barrier, bar_target, G, p.bar_flavor);   // tagged: PROJ polls the {value, tag} words
         PROF_STAMP();
@@ -997,6 +1021,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
             }
             if (++spins > (1u << 26)) __trap();
           } while (!ok);
+          F2(33);
 #pragma unroll
           for (int q = 0; q < NCH; ++q) {
             const int c = tid + q * NCT;
@@ -1013,10 +1038,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
           }
         }
         ptx::named_bar_sync(1, NCT);
+        F2(34);
         const bool tag_proj = tagged && l + 1 < L;   // the last layer hands over to the head through a barrier
         gemv_phase<BT, 3, D>(p, sm, l, o0, no, nseg_proj, cons_idx, row_seq, row_pos,
-                          row_valid, warp, lane, sm.bias_s + l * bstride + nq + no + nf, o0, nullptr,
+                          row_valid, warp, lane, sm.bias_s + l * bstride + nq + no + nf, o0, f2 ? f2 + 35 : nullptr,
                           tag_proj ? ep_proj : 0u);
+        F2(40);
         PROF_STAMP();
         if (!tag_proj) grid_sync(p.barrier, bar_target, G, p.bar_flavor);
         PROF_STAMP();
@@ -1127,14 +1154,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
           block_argmax(best, besti);
           FINE_STAMP(34);
           if (p.do_sample) {
-            // top-k: extract candidates in descending order (ties at the k-th value are all kept, like
-            // TopKLogitsWarper's `scores < kth` test), at most 64
-            float* cv = red + 32;            // [64] candidate scores
-            int* ci = (int*)(red + 96);      // [64] candidate ids
-            const int kk = (p.top_k > 0) ? min(p.top_k, 64) : 64;
+            // top-k: extract candidates in descending order (ties at the k-th value are kept, like
+            // TopKLogitsWarper's `scores < kth` test, up to the CMAX slots); the host rejects top_k outside 1..CMAX
+            float* cv = red + 32;                    // [CMAX] candidate scores
+            int* ci = (int*)(red + 32 + CMAX);       // [CMAX] candidate ids
+            const int kk = min(max(p.top_k, 1), CMAX);
             int nc = 0;
             float kth = best;
-            while (nc < 64 && best > -INFINITY && (nc < kk || best == kth)) {
+            while (nc < CMAX && best > -INFINITY && (nc < kk || best == kth)) {
               if (tid == 0) { cv[nc] = best; ci[nc] = besti; }
               if (nc < kk) kth = best;
               ++nc;
@@ -1392,8 +1419,8 @@ __global__ void strict_sample_kernel(const float* logits, unsigned* seen, int V,
   extern __shared__ float sv[];            // [V] processed scores
   __shared__ float rb[16];
   __shared__ int ri[16];
-  __shared__ float cv[64];
-  __shared__ int ci[64];
+  __shared__ float cv[CMAX];
+  __shared__ int ci[CMAX];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const float inv_temp = (do_sample && temperature > 0.f) ? 1.0f / temperature : 1.0f;
   for (int i = tid; i < V; i += blockDim.x) {
@@ -1425,10 +1452,10 @@ __global__ void strict_sample_kernel(const float* logits, unsigned* seen, int V,
   float best; int besti;
   block_argmax(best, besti);
   if (do_sample) {
-    const int kk = (top_k > 0) ? min(top_k, 64) : 64;
+    const int kk = min(max(top_k, 1), CMAX);
     int nc = 0;
     float kth = best;
-    while (nc < 64 && best > -INFINITY && (nc < kk || best == kth)) {
+    while (nc < CMAX && best > -INFINITY && (nc < kk || best == kth)) {
       if (tid == 0) { cv[nc] = best; ci[nc] = besti; sv[besti] = -INFINITY; }
       if (nc < kk) kth = best;
       ++nc;
@@ -1513,8 +1540,8 @@ __global__ void __launch_bounds__(256) beam_step_kernel(const BeamParams p) {
   constexpr int VPT = 40;
   __shared__ float red[16];
   __shared__ int redi[16];
-  __shared__ float cs[BEAM_MAX][64];     // processed score (+ beam score after top-p)
-  __shared__ int ci[BEAM_MAX][64];
+  __shared__ float cs[BEAM_MAX][CMAX];   // processed score (+ beam score after top-p)
+  __shared__ int ci[BEAM_MAX][CMAX];
   __shared__ int keepn[BEAM_MAX];
   __shared__ float nb_score[BEAM_MAX];
   __shared__ int nb_tok[BEAM_MAX], nb_par[BEAM_MAX];
@@ -1617,10 +1644,10 @@ __global__ void __launch_bounds__(256) beam_step_kernel(const BeamParams p) {
     };
     float best; int besti;
     block_argmax(best, besti);
-    const int kk = (p.top_k > 0) ? min(max(p.top_k, 2), 64) : 64;      // min_tokens_to_keep = 2 with beams
+    const int kk = (p.top_k > 0) ? min(max(p.top_k, 2), CMAX) : CMAX;  // min_tokens_to_keep = 2 with beams; plain beam search (top_k = 0) keeps CMAX >= 2m candidates per beam
     int nc = 0;
     float kth = best;
-    while (nc < 64 && best > -INFINITY && (nc < kk || best == kth)) {
+    while (nc < CMAX && best > -INFINITY && (nc < kk || best == kth)) {
       if (tid == 0) { cs[j][nc] = best; ci[j][nc] = besti; }
       if (nc < kk) kth = best;
       ++nc;
@@ -1633,7 +1660,7 @@ __global__ void __launch_bounds__(256) beam_step_kernel(const BeamParams p) {
     if (tid == 0) {
       int keep = nc;
       if (p.top_p < 1.0f) {
-        float ev[64];
+        float ev[CMAX];
         const float m0 = cs[j][0];
         float tot = 0.f;
         for (int i = 0; i < nc; ++i) { ev[i] = expf(cs[j][i] - m0); tot += ev[i]; }
@@ -1652,8 +1679,8 @@ __global__ void __launch_bounds__(256) beam_step_kernel(const BeamParams p) {
 
   // ---- phase B (thread 0): union -> 2m draws without replacement -> sort -> scorer.process ----
   if (tid == 0) {
-    float w[BEAM_MAX * 64];
-    unsigned char used[BEAM_MAX * 64];
+    float w[BEAM_MAX * CMAX];
+    unsigned char used[BEAM_MAX * CMAX];
     int ub[BEAM_MAX + 1];
     ub[0] = 0;
     for (int j = 0; j < m; ++j) ub[j + 1] = ub[j] + keepn[j];
@@ -1811,6 +1838,7 @@ struct GptState {
   unsigned* seen = nullptr;
   unsigned* barrier = nullptr;
   long long* prof = nullptr;
+  long long* prof2 = nullptr;
   int prof_on = 0;
   std::vector<void*> owned;
   double t_prefill_ms = 0, t_decode_ms = 0;
@@ -2192,6 +2220,7 @@ extern "C" int idx_gpt_init(idx_engine* e, const idx_gpt_config* cfg) {
   g->seen = galloc<unsigned>(g, 8 * (size_t)((V + 31) / 32));
   g->barrier = galloc<unsigned>(g, 32 + 256);   // [0] counter (flavors 0/1), [32..] per-CTA arrival flags (flavor 2)
   g->prof = galloc<long long>(g, 320);
+  g->prof2 = galloc<long long>(g, (size_t)G * 64);
   IDX_CUDA(cudaEventCreate(&g->ev0));
   IDX_CUDA(cudaEventCreate(&g->ev1));
   IDX_CUDA(cudaEventCreate(&g->ev2));
@@ -2217,6 +2246,8 @@ static void fill_common(idx_engine* e, GptState* g, GptParams& p) {
   p.tok = g->tok; p.nout = g->nout; p.finished = g->finished; p.prompt_len = g->prompt_len;
   p.seen = g->seen; p.done = g->done; p.barrier = g->barrier;
   p.prof = g->prof_on ? g->prof : nullptr;
+  p.prof2 = g->prof_on ? g->prof2 : nullptr;
+  p.prof2_layer = c.layers / 2;
 }
 
 // ------------------------------------------------------------------ beam-sample host driver --
@@ -2441,6 +2472,10 @@ extern "C" int idx_gpt_generate(idx_engine* e, const idx_gpt_request* reqs, int 
   GptState* g = e->gpt;
   const idx_gpt_config& c = g->cfg;
   IDX_CHECK(sp->num_beams >= 1, IDX_ERR_ARG, "num_beams must be >= 1");
+  // HF semantics are kept exactly or refused: top_k = 0 (warper disabled) or top_k > CMAX would need more candidate slots
+  // than the device samplers hold, and capping them silently would change the support of the top-p / multinomial step
+  IDX_CHECK(!sp->do_sample || (sp->top_k >= 1 && sp->top_k <= CMAX), IDX_ERR_ARG,
+            "do_sample needs 1 <= top_k <= 128 (the reference default is 30; top_k = 0 / larger values are not built)");
   {
     // more requests than one decode group holds (max_batch rows, num_beams rows per request): run consecutive groups;
     // the sampler's sequence index stays the request's global index, so the result does not depend on the grouping
@@ -2638,6 +2673,16 @@ extern "C" int idx_gpt_profile(idx_engine* e, int enable, int64_t* stamps_out, i
     IDX_CUDA(cudaStreamSynchronize(e->stream));
     IDX_CUDA(cudaMemcpy(stamps_out, g->prof, sizeof(long long) * (size_t)std::min(n, 320), cudaMemcpyDeviceToHost));
   }
+  IDX_API_END(e)
+}
+
+// diagnostics: [G][64] fine globaltimer stamps of every CTA for the middle layer of the last decode step (see F2 in the kernel)
+extern "C" int idx_gpt_profile_fine(idx_engine* e, int64_t* stamps_out, int n) {
+  IDX_API_BEGIN
+  IDX_CHECK(e && e->gpt && e->gpt->prof2, IDX_ERR_STATE, "idx_gpt_init (bf16 path) has not been called");
+  IDX_CUDA(cudaSetDevice(e->device));
+  IDX_CUDA(cudaStreamSynchronize(e->stream));
+  IDX_CUDA(cudaMemcpy(stamps_out, e->gpt->prof2, sizeof(long long) * (size_t)std::min(n, e->gpt->G * 64), cudaMemcpyDeviceToHost));
   IDX_API_END(e)
 }
 

@@ -1,7 +1,9 @@
 """Drop-in binding for the reference pipeline classes.
 
-`attach(tts)` takes a live reference object — `indextts.infer_v2_5.IndexTTS2` (or `infer_v2.IndexTTS2`)
-built by the reference's own constructor, i.e. with its own config/checkpoint loaders — registers the
+`attach(tts)` takes a live reference object — `indextts.infer_v2_5.IndexTTS2` built by the reference's own
+constructor, i.e. with its own config/checkpoint loaders (`indextts.infer_v2.IndexTTS2` is NOT covered: its
+`inference_speech` call passes no `campplus_embedding` and consumes the returned conditioning latent,
+infer_v2.py:583-662 — `attach` raises for it) — registers the
 weights of its modules with a B200 engine and rebinds the module-level seams of `infer_generator`
  to the C-ABI:
 
@@ -14,8 +16,10 @@ weights of its modules with a B200 engine and rebinds the module-level seams of 
 
 `infer_v2_5.py` itself is not modified: `.infer()` keeps its signature, text front-end, prompt caching,
 segment loop and timing prints, and simply reaches these callables instead of the PyTorch modules.  Tensors
-stay torch tensors (containers); the engine receives raw device pointers.  Nothing here falls back to
-PyTorch compute: if the engine cannot be created the call raises.
+stay torch tensors (containers) ON THE DEVICE: the engine receives their raw device pointers and writes its results into
+torch CUDA tensors (no `.cpu().numpy()` bounce at any seam; only the few dozen text ids and the generated codes cross
+the host).  The engine stream is ordered after torch's current stream before every call (include/idxtts.h, stream
+contract).  Nothing here falls back to PyTorch compute: if the engine cannot be created the call raises.
 """
 import types
 
@@ -90,8 +94,33 @@ def load_reference_weights(engine: Engine, tts, max_batch: int = 1):
     return engine
 
 
+def _fresh_seed():
+    """A new Philox key per generate call, drawn from torch's global generator: `torch.manual_seed(s)` before `.infer()`
+    reproduces a take, and successive calls / segments differ — like the reference's torch.multinomial draws, which
+    advance the global generator on every call (a constant torch.initial_seed() replayed one stream forever)."""
+    return int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+
+
+def _check_hf_kwargs(num_return_sequences, typical_sampling, hf):
+    if typical_sampling:
+        raise NotImplementedError("typical_sampling=True (TypicalLogitsWarper, model_v2.py:798-800) is not built on the B200 path")
+    if int(num_return_sequences or 1) != 1:
+        raise NotImplementedError("num_return_sequences must be 1 (what infer_v2_5.py:771-791 / infer.py pass)")
+    nb = int(hf.get("num_beams", 1) or 1)
+    if nb > 4:
+        raise NotImplementedError("num_beams <= 4 (the reference default is 3)")
+    if hf.get("do_sample", False):
+        tk = int(hf.get("top_k", 0) or 0)
+        if tk <= 0 or tk > 128:
+            raise NotImplementedError("do_sample needs 1 <= top_k <= 128 on the B200 path (the reference default is 30, the "
+                                      "webui allows up to 100); top_k=0 / larger values are rejected, never silently capped")
+    return nb
+
+
 def attach(tts, engine: Engine = None, device: int = 0):
-    """Rebind the compute seams of a reference IndexTTS2 instance to the B200 engine (see module doc)."""
+    """Rebind the compute seams of a reference IndexTTS2 (infer_v2_5) instance to the B200 engine (see module doc)."""
+    if type(tts).__module__.endswith("infer_v2"):
+        raise NotImplementedError("attach() covers indextts.infer_v2_5.IndexTTS2; infer_v2.IndexTTS2 (row f3) is not built")
     engine = engine or Engine(device)
     load_reference_weights(engine, tts, max_batch=4)      # room for the default 3 beams
     dev = torch.device("cuda", engine.device)
@@ -104,19 +133,18 @@ def attach(tts, engine: Engine = None, device: int = 0):
         # same argument meaning as gpt/model_v2.py:716-825; emo_vec comes from merge_emovec (:833-838)
         if emo_vec is None or campplus_embedding is None:
             raise ValueError("the B200 path needs emo_vec and campplus_embedding (what infer_v2_5.py:759-791 passes)")
-        nb = int(hf.get("num_beams", 1) or 1)
-        if nb > 4:
-            raise NotImplementedError("num_beams <= 4 (the reference default is 3)")
+        nb = _check_hf_kwargs(num_return_sequences, typical_sampling, hf)
         sampling = dict(do_sample=bool(hf.get("do_sample", False)), top_k=int(hf.get("top_k", 0) or 0),
                         top_p=float(hf.get("top_p", 1.0)), temperature=float(hf.get("temperature", 1.0)),
-                        seed=int(torch.initial_seed() & 0x7fffffff), num_beams=nb,
+                        seed=_fresh_seed(), num_beams=nb,
                         length_penalty=float(hf.get("length_penalty", 0.0)))
         lang = int(langs.reshape(-1)[0]) if langs is not None else 0
         outs = []
+        styles = campplus_embedding.reshape(-1, 192)
         for i in range(text_inputs.shape[0]):
-            prompt = engine.gpt_prepare_inputs(campplus_embedding.reshape(-1, 192)[min(i, campplus_embedding.reshape(-1, 192).shape[0] - 1)].float().cpu().numpy(),
-                                               emo_vec.reshape(-1, self.model_dim)[0].float().cpu().numpy(),
-                                               text_inputs[i].cpu().numpy(), lang)
+            # device tensors go in as device pointers; the prompt rows stay on the device for idx_gpt_generate
+            prompt = engine.gpt_prepare_inputs(styles[min(i, styles.shape[0] - 1)], emo_vec.reshape(-1, self.model_dim)[0],
+                                               text_inputs[i], lang)
             max_new = max_generate_length if max_generate_length is not None else self.max_mel_tokens - 1
             (codes,) = engine.gpt_generate([prompt], int(max_new),
                                            repetition_penalty=float(hf.get("repetition_penalty", 1.0)), **sampling)
@@ -135,15 +163,14 @@ def attach(tts, engine: Engine = None, device: int = 0):
             def feats(x):
                 x = x[0].float()
                 return (x.t() if x.shape[0] == engine.emo_cfg.idim and x.shape[1] != engine.emo_cfg.idim else x).contiguous()
-            v = engine.merge_emovec(feats(speech_condition).cpu().numpy(), feats(emo_speech_condition).cpu().numpy(),
-                                    float(alpha))
-            return torch.from_numpy(v)[None].to(dev)
+            v = engine.merge_emovec(feats(speech_condition), feats(emo_speech_condition), float(alpha))
+            return torch.as_tensor(v)[None].to(dev)
 
         gpt.merge_emovec = types.MethodType(merge_emovec, gpt)
 
     def codec_decode(self, codes):
         c = codes.reshape(-1, codes.shape[-1])
-        out = [torch.from_numpy(engine.codec_decode(c[i].cpu().numpy())) for i in range(c.shape[0])]
+        out = [torch.as_tensor(engine.codec_decode(c[i])) for i in range(c.shape[0])]
         return torch.stack(out).to(dev)
 
     tts.semantic_codec.decode = types.MethodType(codec_decode, tts.semantic_codec)
@@ -151,7 +178,7 @@ def attach(tts, engine: Engine = None, device: int = 0):
     class _LengthRegulator(torch.nn.Module):
         def forward(self, x, ylens=None, n_quantizers=None, f0=None):
             y = engine.length_regulate(x[0].float().contiguous(), int(ylens.max()))
-            return torch.from_numpy(y)[None].to(dev), ylens, None, None, None
+            return torch.as_tensor(y)[None].to(dev), ylens, None, None, None
 
     tts.s2mel.models["length_regulator"] = _LengthRegulator()
 
@@ -162,7 +189,7 @@ def attach(tts, engine: Engine = None, device: int = 0):
         z = torch.randn([B, self.in_channels, T], device=mu.device) * temperature   # same RNG call (trap P6)
         out = engine.cfm_solve(mu[0].float().contiguous(), prompt[0].float().contiguous(), style[0].float().contiguous(),
                                z[0].contiguous(), n_timesteps, inference_cfg_rate)
-        return torch.from_numpy(out)[None].to(mu.device)
+        return torch.as_tensor(out)[None].to(mu.device)
 
     cfm.inference = types.MethodType(cfm_inference, cfm)
 
@@ -216,7 +243,7 @@ def attach_v1(tts, engine: Engine = None, device: int = 0):
 
     def inference_speech(self, speech_conditioning_mel, text_inputs, cond_mel_lengths=None, input_tokens=None,
                          num_return_sequences=1, max_generate_length=None, typical_sampling=False, typical_mass=.9, **hf):
-        nb = int(hf.get("num_beams", 1) or 1)
+        nb = _check_hf_kwargs(num_return_sequences, typical_sampling, hf)
         conds = _conds(speech_conditioning_mel)
         outs = []
         for i in range(text_inputs.shape[0]):
@@ -226,7 +253,7 @@ def attach_v1(tts, engine: Engine = None, device: int = 0):
                                            do_sample=bool(hf.get("do_sample", False)), top_k=int(hf.get("top_k", 0) or 0),
                                            top_p=float(hf.get("top_p", 1.0)), temperature=float(hf.get("temperature", 1.0)),
                                            num_beams=nb, length_penalty=float(hf.get("length_penalty", 0.0)),
-                                           seed=int(torch.initial_seed() & 0x7fffffff), mel_pos_mode=0 if kv_cache else 1)
+                                           seed=_fresh_seed(), mel_pos_mode=0 if kv_cache else 1)
             outs.append(torch.from_numpy(codes.astype(np.int64)))
         n = max(len(o) for o in outs)
         pad = torch.full((len(outs), n), self.stop_mel_token, dtype=torch.long)

@@ -123,6 +123,7 @@ def load_library(path: str = None):
     lib.idx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     lib.idx_destroy.argtypes = [C.c_void_p]
     lib.idx_sync.argtypes = [C.c_void_p]
+    lib.idx_wait_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.idx_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     lib.idx_event_record.argtypes = [C.c_void_p, C.c_int]
     lib.idx_event_elapsed_ms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
@@ -135,6 +136,7 @@ def load_library(path: str = None):
                                            C.c_int, C.c_int, C.c_void_p]
     lib.idx_gpt_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.idx_gpt_profile.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.idx_gpt_profile_fine.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.idx_v1_cond_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.idx_v1_get_conditioning.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.idx_gpt_prepare_inputs_v1.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
@@ -183,6 +185,40 @@ def _as_f32(x):
     return np.ascontiguousarray(x, dtype=np.float32)
 
 
+def _is_cuda(x):
+    return torch is not None and isinstance(x, torch.Tensor) and x.is_cuda
+
+
+def _empty_like_src(src, shape, np_dtype=np.float32):
+    """Output container that lives where `src` lives: a torch CUDA tensor for a CUDA input (the library then writes
+    device-to-device, nothing bounces through the host), a numpy array otherwise."""
+    if _is_cuda(src):
+        return torch.empty(shape, dtype=getattr(torch, np.dtype(np_dtype).name), device=src.device)
+    return np.empty(shape, dtype=np_dtype)
+
+
+class _OrderedLib:
+    """Proxy over the ctypes library that honours the stream contract of include/idxtts.h: before every call the
+    engine stream is ordered (idx_wait_stream: event + cudaStreamWaitEvent, no host block) after torch's current
+    stream, so device tensors still being produced by pending torch kernels are complete when the engine reads them."""
+    _PLAIN = ("idx_last_error", "idx_destroy", "idx_launch_count", "idx_version", "idx_wait_stream", "idx_create")
+
+    def __init__(self, lib, eng):
+        self._lib, self._eng = lib, eng
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if name in self._PLAIN:
+            return fn
+        eng, raw = self._eng, self._lib
+
+        def call(*a):
+            if torch is not None and torch.cuda.is_available() and torch.cuda.is_initialized():
+                raw.idx_wait_stream(eng.h, C.c_void_p(torch.cuda.current_stream(eng.device).cuda_stream))
+            return fn(*a)
+        return call
+
+
 class Engine:
     """One engine = one CUDA device = one caller thread at a time (include/idxtts.h)."""
 
@@ -195,6 +231,7 @@ class Engine:
         self.h = h
         self.device = device
         self._keep = []
+        self.lib = _OrderedLib(self.lib, self)
 
     def close(self):
         if getattr(self, "h", None):
@@ -255,13 +292,16 @@ class Engine:
 
     def gpt_prepare_inputs(self, style, emo_vec, text_ids, lang: int):
         """prepare_gpt_inputs (gpt/model_v2.py:648-714): returns [3+L+2, D] float32 (numpy)."""
-        style = np.ascontiguousarray(np.asarray(style, dtype=np.float32).reshape(-1))
-        emo_vec = np.ascontiguousarray(np.asarray(emo_vec, dtype=np.float32).reshape(-1))
+        dev_src = style if _is_cuda(style) else (emo_vec if _is_cuda(emo_vec) else None)
+        style = _as_f32(style).reshape(-1)
+        emo_vec = _as_f32(emo_vec).reshape(-1)
+        if torch is not None and isinstance(text_ids, torch.Tensor):
+            text_ids = text_ids.detach().cpu().numpy()       # a few dozen ids: the valid_mask below is host logic
         ids = np.ascontiguousarray(np.asarray(text_ids, dtype=np.int32).reshape(-1))
         # valid_mask of model_v2.py:674: start/stop text tokens inside the padded ids are dropped
         ids = np.ascontiguousarray(ids[(ids != 0) & (ids != 1)])
         D = self.gpt_cfg.model_dim
-        out = np.empty((3 + len(ids) + 2, D), dtype=np.float32)
+        out = _empty_like_src(dev_src, (3 + len(ids) + 2, D))
         self._check(self.lib.idx_gpt_prepare_inputs(self.h, _ptr(style), _ptr(emo_vec), _ptr(ids),
                                                     len(ids), int(lang), _ptr(out)),
                     "idx_gpt_prepare_inputs")
@@ -364,6 +404,12 @@ class Engine:
                     "idx_gpt_profile")
         return buf
 
+    def gpt_profile_fine(self, num_sms=148):
+        """[num_sms][64] sub-phase %globaltimer stamps (ns) of every CTA, middle layer of the last decode step."""
+        buf = np.zeros((num_sms, 64), dtype=np.int64)
+        self._check(self.lib.idx_gpt_profile_fine(self.h, _ptr(buf), buf.size), "idx_gpt_profile_fine")
+        return buf
+
     # ------------------------------------------------------------------ BigVGAN --
     @staticmethod
     def _bigvgan_cfg(h: dict, num_mels):
@@ -464,15 +510,18 @@ class Engine:
 
     def codec_decode(self, codes):
         """EnhancedCodec.decode (codec/models.py:205-231): codes [n] → S_infer [2n, hidden]."""
-        codes = np.ascontiguousarray(np.asarray(codes, dtype=np.int32).reshape(-1))
-        out = np.empty((2 * len(codes), self.codec_cfg.hidden_size), dtype=np.float32)
-        self._check(self.lib.idx_codec_decode(self.h, _ptr(codes), len(codes), _ptr(out)), "idx_codec_decode")
+        if _is_cuda(codes):
+            codes = codes.detach().reshape(-1).to(torch.int32).contiguous()
+        else:
+            codes = np.ascontiguousarray(np.asarray(codes, dtype=np.int32).reshape(-1))
+        out = _empty_like_src(codes, (2 * int(codes.shape[0]), self.codec_cfg.hidden_size))
+        self._check(self.lib.idx_codec_decode(self.h, _ptr(codes), int(codes.shape[0]), _ptr(out)), "idx_codec_decode")
         return out
 
     def length_regulate(self, S, ylen):
         """InterpolateRegulator.forward (length_regulator.py:90-141): S [n, in] → [ylen, C]."""
         S = _as_f32(S)
-        out = np.empty((int(ylen), self.s2mel_cfg.content_dim), dtype=np.float32)
+        out = _empty_like_src(S, (int(ylen), self.s2mel_cfg.content_dim))
         self._check(self.lib.idx_length_regulate(self.h, _ptr(S), int(S.shape[0]), int(ylen), _ptr(out)),
                     "idx_length_regulate")
         return out
@@ -481,7 +530,7 @@ class Engine:
         """DiT.forward (diffusion_transformer.py:186-257) for full-length sequences."""
         x, prompt_x, t, style, cond = (_as_f32(a) for a in (x, prompt_x, t, style, cond))
         B, _, T = x.shape
-        out = np.empty((B, self.s2mel_cfg.in_channels, T), dtype=np.float32)
+        out = _empty_like_src(x, (B, self.s2mel_cfg.in_channels, T))
         self._check(self.lib.idx_dit_forward(self.h, _ptr(x), _ptr(prompt_x), _ptr(t), _ptr(style), _ptr(cond),
                                              B, T, _ptr(out)), "idx_dit_forward")
         return out
@@ -491,7 +540,7 @@ class Engine:
         mu, prompt, style, z = (_as_f32(a) for a in (mu, prompt, style, z))
         T = mu.shape[0]
         P = prompt.shape[-1]
-        out = np.empty((self.s2mel_cfg.in_channels, T), dtype=np.float32)
+        out = _empty_like_src(z, (self.s2mel_cfg.in_channels, T))
         self._check(self.lib.idx_cfm_solve(self.h, _ptr(mu), T, _ptr(prompt), P, _ptr(style), _ptr(z),
                                            int(n_steps), float(cfg_rate), _ptr(out)), "idx_cfm_solve")
         return out
@@ -564,7 +613,7 @@ class Engine:
         """UnifiedVoice.merge_emovec (gpt/model_v2.py:833-838): feats [T, 1024] → emo_vec [model_dim]."""
         sf = _as_f32(spk_feats)
         ef = None if emo_feats is None else _as_f32(emo_feats)
-        out = np.empty(self.emo_cfg.model_dim, dtype=np.float32)
+        out = _empty_like_src(sf, (self.emo_cfg.model_dim,))
         self._check(self.lib.idx_merge_emovec(self.h, _ptr(sf), int(sf.shape[0]), _ptr(ef),
                                               0 if ef is None else int(ef.shape[0]), float(alpha), _ptr(out)),
                     "idx_merge_emovec")

@@ -19,7 +19,7 @@ import math
 
 import numpy as np
 
-from oracle.gpt import philox4x32_10
+from oracle.gpt import CMAX, philox4x32_10
 
 F = np.float32
 
@@ -104,10 +104,10 @@ def beam_candidates(logits_row, seen, beam_score, k, p):
         s[p["stop"]] = -np.inf
     s = (s * F(1.0 / p["temperature"])).astype(F)
     order = np.lexsort((np.arange(len(s)), -s))
-    kk = min(max(p["top_k"], 2), 64) if p["top_k"] > 0 else 64
+    kk = min(max(p["top_k"], 2), CMAX) if p["top_k"] > 0 else CMAX
     cand, kth = [], None
     for i in order:
-        if not np.isfinite(s[i]) or len(cand) >= 64:
+        if not np.isfinite(s[i]) or len(cand) >= CMAX:
             break
         if len(cand) < kk:
             cand.append(int(i)); kth = s[i]

@@ -97,17 +97,20 @@ def philox4x32_10(seed, c0, c1):
     return x0, x1, x2, x3
 
 
+CMAX = 128     # candidate slots of the device samplers (csrc/gpt_decode.cu)
+
+
 def sample_token(scores, top_k, top_p, seed, step, seq):
-    """Temperature is already applied.  TopK (ties at the k-th value kept, at most 64) → TopP → multinomial by
+    """Temperature is already applied.  TopK (1 <= top_k <= CMAX = 128 — the device sampler refuses anything else; ties at the k-th value kept up to CMAX slots) → TopP → multinomial by
     inverse CDF over the descending candidates with one Philox draw (transformers logits_process order,
     transformers_generation_utils.py:1035-1047; RNG contract of the device sampler)."""
     s = np.asarray(scores, dtype=np.float32)
     order = np.lexsort((np.arange(len(s)), -s))            # descending, lowest index first among ties
-    kk = min(top_k, 64) if top_k > 0 else 64
+    kk = min(top_k, CMAX) if top_k > 0 else CMAX      # top_k = 0: warper disabled (the device refuses it; kept for the checker's own tests)
     cand = []
     kth = None
     for idx in order:
-        if not np.isfinite(s[idx]) or len(cand) >= 64:
+        if not np.isfinite(s[idx]) or len(cand) >= CMAX:
             break
         if len(cand) < kk:
             cand.append(int(idx))

@@ -282,10 +282,17 @@ def test_beam_search_variants_and_batch(engine):
     for u, pr in enumerate([p0, p1]):
         _check_beam_run(engine, cfg, pr, n, _beam_params(cfg, seed=21), u, cs[u], lgs[u])
     # early termination: a stop token that is easy to sample ends hypotheses; the result still replays exactly
-    (c3,), (lg3,) = engine.gpt_generate([p0], 40, 1.0, return_logits=True, do_sample=True, num_beams=3, top_k=0, top_p=1.0,
+    # (top_k = 100 is the webui's maximum: more than the 64 candidate slots of round 1)
+    (c3,), (lg3,) = engine.gpt_generate([p0], 40, 1.0, return_logits=True, do_sample=True, num_beams=3, top_k=100, top_p=1.0,
                                         temperature=3.0, seed=5)
-    _check_beam_run(engine, cfg, p0, 40, _beam_params(cfg, repetition_penalty=1.0, top_k=0, top_p=1.0, temperature=3.0, seed=5),
+    _check_beam_run(engine, cfg, p0, 40, _beam_params(cfg, repetition_penalty=1.0, top_k=100, top_p=1.0, temperature=3.0, seed=5),
                     0, c3, lg3)
+    # HF semantics are kept exactly or refused, never silently capped
+    for bad in (0, 129):
+        with pytest.raises(RuntimeError, match="top_k"):
+            engine.gpt_generate([p0], 4, 1.0, do_sample=True, num_beams=3, top_k=bad, seed=1)
+        with pytest.raises(RuntimeError, match="top_k"):
+            engine.gpt_generate([p0], 4, 1.0, do_sample=True, top_k=bad, seed=1)
 
 
 def test_strict_fp32_engine_vs_reference_unifiedvoice_golden(engine):
