@@ -154,11 +154,24 @@ WORKLOAD = ("IndexTTS-2.5 infer_v2_5 batch=1 per GPU: 10 s reference (P=861), 32
 
 
 # -------------------------------------------------------------------------- cpu arm --
-def cpu_reference_sample(threads):
-    """The oracle port of the same per-segment path on the host cores, on a bounded sample:
-    8 speech tokens with a 0.5 s reference (P = 43): GPT prefill + 8 cached steps (full 24x1280
-    geometry, fp32 like the reference on a CPU: use_bf16 needs CUDA autocast), codec decode, length regulator, CFM 25 steps at T = 43 + 27, BigVGAN
-    F = 27.  Returns (tokens, callable) — the callable runs the sample once and returns seconds."""
+DTYPE = ("bf16 GPT (bf16 weights/activations, fp32 accumulate, fp32 residual stream = the reference's use_bf16 autocast) + "
+         "tf32 tensor-core GEMMs over fp32 storage (codec, length regulator, DiT/WaveNet, BigVGAN; fp32 accumulate) + "
+         "bf16 mma.sync attention in the DiT (fp32 softmax)")
+
+
+def config_block(world):
+    """Identical for both arms: the driver compares it to decide `same_config`."""
+    return {"workload": WORKLOAD, "utterances_per_gpu_per_step": 1,
+            "parallelism": f"dp{world} (utterance sharding)" if world > 1 else "dp1",
+            "l2": "working set >> L2 (0.97 GB of GPT weights streamed per token, 112 M vocoder weights)"}
+
+
+def cpu_reference_full(threads):
+    """The reference's per-segment path restated by the oracle port, on the host cores, at the FULL config-2 size
+    (the same WORKLOAD the GPU arm times): fp32 like the reference on a CPU (use_bf16 needs CUDA autocast),
+    GPT prefill + 256 cached greedy steps at 24 x 1280, codec decode, length regulator (F = 880), CFM 25 Euler steps
+    CFG 0.7 at T = 1741, BigVGAN 225 280 samples.  Returns a callable that runs one utterance and returns
+    (seconds, per-stage seconds)."""
     from indextts_b200 import synth
     from oracle.gpt import GptOracle, prepare_gpt_inputs
     from oracle.s2mel import cfm_inference, codec_decode, fold_weight_norm, length_regulate
@@ -170,50 +183,76 @@ def cpu_reference_sample(threads):
     ws = fold_weight_norm(synth.make_s2mel_weights(c, seed=1234))
     wc = fold_weight_norm(synth.make_codec_weights(cc, seed=4321))
     wb = synth.make_bigvgan_weights(h, seed=1234)
-    g = torch.Generator().manual_seed(0)
-    ntok, P = 8, 43
-    style = torch.randn(192, generator=g)
-    emo = torch.randn(cfg["model_dim"], generator=g) * 0.5
-    text = torch.randint(2, 12000, (N_TEXT,), generator=g)
-    prompt = prepare_gpt_inputs(wg, style, emo, text, lang=1, bf16=False)
-    F = int(2 * ntok * 1.72)
-    pc = torch.randn(1, P, 512, generator=g)
-    ref_mel = torch.randn(1, 80, P, generator=g) * 1.5 - 4.0
-    z = torch.randn(1, 80, P + F, generator=g)
+    inp = make_inputs(1000, cfg, wg)
+    prompt = prepare_gpt_inputs(wg, inp["style"], inp["emo"], inp["text"], lang=1, bf16=False)
+    F = inp["F"]
+    pc, ref_mel, z = inp["prompt_condition"][None], inp["ref_mel"][None], inp["z"][None]
+    oracle = GptOracle(cfg, wg, bf16=False)
 
     def once():
         t0 = time.perf_counter()
-        codes, _ = GptOracle(cfg, wg, bf16=False).generate(prompt, ntok, 10.0, ntok)
-        S = codec_decode(wc, torch.from_numpy(codes.astype(np.int64))[None])
-        cond = length_regulate(ws, S, F)
-        mu = torch.cat([pc, cond], 1)
-        mel = cfm_inference(ws, c, mu, torch.LongTensor([P + F]), ref_mel, style[None], z, CFM_STEPS, CFG_RATE)
-        wav = bigvgan_forward(h, wb, mel[:, :, P:])
-        assert wav.shape[-1] == F * 256
-        return time.perf_counter() - t0
-    return ntok, once
+        with torch.no_grad():
+            codes, _ = oracle.generate(prompt, N_TOKENS, 10.0, N_TOKENS)
+            assert len(codes) == N_TOKENS
+            t1 = time.perf_counter()
+            S = codec_decode(wc, torch.from_numpy(np.asarray(codes, dtype=np.int64))[None])
+            cond = length_regulate(ws, S, F)
+            mu = torch.cat([pc, cond], 1)
+            mel = cfm_inference(ws, c, mu, torch.LongTensor([P_FRAMES + F]), ref_mel, inp["style"][None], z, CFM_STEPS, CFG_RATE)
+            t2 = time.perf_counter()
+            wav = bigvgan_forward(h, wb, mel[:, :, P_FRAMES:])
+            assert wav.shape[-1] == F * 256
+        t3 = time.perf_counter()
+        return t3 - t0, {"gpt": t1 - t0, "s2mel": t2 - t1, "bigvgan": t3 - t2}
+    return once
 
 
-def run_reference(args, rank):
+def host_threads():
+    return max(1, min(os.cpu_count() or 1, 64))
+
+
+def run_reference(args, rank, world):
+    """`--impl reference`: the reference's own (CPU, fp32) implementation of the path — the oracle port; the reference
+    itself cannot be built offline — on the box's host cores, SAME config, metric and unit as the
+    B200 arm.  --steps / --warmup are honoured; only if the projected run would exceed IDX_REF_BUDGET_S (default 1500 s,
+    inside the driver's limit) are the timed steps cut, and the line then says how many actually ran."""
     if rank != 0:
         return
-    threads = min(os.cpu_count() or 1, 32)
-    ntok, once = cpu_reference_sample(threads)
-    for _ in range(max(1, min(args.warmup, 1))):
-        once()
-    steps = max(1, min(args.steps, 3))
-    ts = [once() for _ in range(steps)]
+    threads = host_threads()
+    once = cpu_reference_full(threads)
+    budget = float(os.environ.get("IDX_REF_BUDGET_S", "1500"))
+    t_start = time.perf_counter()
+    W, K = max(0, args.warmup), max(1, args.steps)
+    t_first, _ = once()                                   # first warm-up step doubles as the cost probe
+    fit = int((budget - (time.perf_counter() - t_start)) / max(t_first, 1e-3))
+    w_run = 1
+    if W == 0:
+        ts, stages = [t_first], [_]
+        k_run, w_run = 1, 0
+    else:
+        w_left = max(0, min(W - 1, fit - 1))
+        for _i in range(w_left):
+            once()
+        w_run += w_left
+        fit = int((budget - (time.perf_counter() - t_start)) / max(t_first, 1e-3))
+        k_run = max(1, min(K, fit))
+        ts, stages = [], []
+        for _i in range(k_run):
+            t, st = once()
+            ts.append(t)
+            stages.append(st)
     t = float(np.mean(ts))
-    val = ntok / t
-    sample = (f"{ntok} speech tokens, 0.5 s reference (P=43), full 24x1280 GPT / 13x512 DiT / BigVGAN-v2 geometry, "
-              f"CFM {CFM_STEPS} steps at T={43 + int(2 * ntok * 1.72)}; oracle port, torch CPU fp32, {threads} threads "
-              f"(of {os.cpu_count()} host cores; more threads are slower for these small ops)")
+    val = N_TOKENS / t
+    audio_s = N_TOKENS * AUDIO_S_PER_TOKEN
+    sample = (f"the full config-2 utterance per step ({N_TOKENS} speech tokens, P={P_FRAMES}, T={P_FRAMES + int(2 * N_TOKENS * 1.72)}, "
+              f"CFM {CFM_STEPS} steps, {int(2 * N_TOKENS * 1.72) * 256} samples): oracle port, torch CPU fp32, {threads} threads of "
+              f"{os.cpu_count()} host cores; {k_run} timed + {w_run} warm-up steps"
+              + ("" if (k_run == K and w_run == W) else f" (requested {K} + {W}: cut to fit {budget:.0f} s)"))
     line = {"impl": "reference", "metric": "speech_tokens_per_s", "value": val, "unit": "tokens/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": 1, "ms_per_step": t * 1000, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "rtf": t / (ntok * AUDIO_S_PER_TOKEN),
-            "config": {"workload": WORKLOAD, "utterances_per_gpu_per_step": 1, "parallelism": "host cores",
-                       "sample": "each step is a bounded sample of that workload: " + sample},
+            "steps": k_run, "warmup": w_run, "ms_per_step": t * 1000, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "rtf": t / audio_s,
+            "config": config_block(world),
+            "stage_ms_per_step": {k: float(np.mean([st[k] for st in stages])) * 1000 for k in ("gpt", "s2mel", "bigvgan")},
             "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -232,7 +271,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, world)
         return
     W = max(3, args.warmup)
     K = max(1, args.steps)
@@ -343,11 +382,9 @@ def main():
     line = {
         "metric": "speech_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": t_dev / K * 1000.0, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16(gpt weights, fp32 accumulate)+f32(s2mel, vocoder)", "data": "synthetic",
+        "dtype": DTYPE, "data": "synthetic",
         "rtf": (t_dev / K) / audio_s, "e2e_rtf": (t_e2e / K) / audio_s,
-        "config": {"workload": WORKLOAD,
-                   "utterances_per_gpu_per_step": 1, "parallelism": f"dp{world} (utterance sharding)",
-                   "l2": "working set >> L2 (0.97 GB of GPT weights streamed per token, 112 M vocoder weights)"},
+        "config": config_block(world),
         "stage_ms_per_step": {"gpt": g_ms / K, "cfm": c_ms / K, "bigvgan": v_ms / K,
                               "other": (t_dev * 1000 - g_ms - c_ms - v_ms) / K},
         "roofline": {"kernel": "gpt_fused_kernel (decode step)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
@@ -369,13 +406,14 @@ def main():
     }
     if not args.no_cpu_baseline:
         try:
-            threads = min(os.cpu_count() or 1, 32)
-            ntok, once = cpu_reference_sample(threads)
-            tcpu = once()
-            line["cpu_baseline"] = {"value": ntok / tcpu, "unit": "tokens/s", "cores": threads, "kind": "port",
-                                    "sample": f"{ntok} tokens, 0.5 s reference (P=43), full model geometry, same pipeline "
-                                              f"(GPT+codec+length-regulator+CFM 25 steps+BigVGAN), oracle port on torch CPU, "
-                                              f"{tcpu:.1f} s wall, {threads} of {os.cpu_count()} cores"}
+            threads = host_threads()
+            tcpu, st = cpu_reference_full(threads)()
+            line["cpu_baseline"] = {"value": N_TOKENS / tcpu, "unit": "tokens/s", "cores": threads, "kind": "port",
+                                    "rtf": tcpu / audio_s,
+                                    "sample": f"ONE full config-2 utterance (the same workload: {N_TOKENS} tokens, P={P_FRAMES}, "
+                                              f"T={P_FRAMES + mine['F']}, CFM {CFM_STEPS} steps, BigVGAN {mine['F'] * 256} samples), no warm-up, "
+                                              f"oracle port on torch CPU fp32, {tcpu:.1f} s wall (gpt {st['gpt']:.1f}, s2mel {st['s2mel']:.1f}, "
+                                              f"bigvgan {st['bigvgan']:.1f}), {threads} threads of {os.cpu_count()} cores"}
         except Exception as ex:  # the bench line must survive a CPU-leg hiccup
             line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"failed: {ex}"}

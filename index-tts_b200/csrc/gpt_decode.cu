@@ -117,6 +117,15 @@ struct GptParams {
   int phys_stride;
   const unsigned char* phys;   // [8][phys_stride]: cache slot of generated position t of row b's lineage, or null
   long long* prof;      // optional: globaltimer stamps of CTA 0 for the last step of the launch
+  // second-generation batch-1 decode kernel (gpt_decode1.cuh)
+  const __nv_bfloat16* wstream1;  // per-CTA row streams in tile order
+  const long long* stream_off1;   // [G] row offset of CTA i's stream
+  int ring_rows;                  // R: rows of D bf16 in the shared-memory ring
+  int dbg;                        // diagnostics (IDX_GPT_DBG): 1 skip the MMA loops, 2 skip the attention key loop, 4 do not wait in polls
+  uint2* ot;                      // [D] tagged normalised attention output (one CTA per head)
+  uint2* partt;                   // [H * 7][66] tagged (m, l, o) partials (long contexts: key splits)
+  uint2* cand;                    // [G][2] tagged per-CTA argmax candidate (score, index) / sampling flags
+  uint2* tokt;                    // [1] tagged sampled token
   long long* prof2;     // optional: [G][64] fine globaltimer stamps of every CTA for layer prof2_layer of the last step
   int prof2_layer;
 };
@@ -175,7 +184,7 @@ __device__ __forceinline__ void st_tagged(uint2* p, float v, unsigned epoch) {
 // round costs one L2 round trip; repeat until every word carries `epoch`.
 // 8-byte aligned vector accesses are single-copy atomic on the hardware (the NCCL LL protocol relies on the same).
 template <int N>
-__device__ __forceinline__ void ld_tagged_slice(const uint2* base, int first, unsigned epoch, float (&v)[N]) {
+__device__ __forceinline__ void ld_tagged_slice(const uint2* base, int first, unsigned epoch, float (&v)[N], bool nowait = false) {
   unsigned val[N], tag[N], spins = 0;
   bool ok;
   do {
@@ -186,7 +195,7 @@ __device__ __forceinline__ void ld_tagged_slice(const uint2* base, int first, un
 #pragma unroll
     for (int j = 0; j < N; ++j) ok &= (tag[j] == epoch);
     if (++spins > (1u << 26)) __trap();
-  } while (!ok);
+  } while (!ok && !nowait);
 #pragma unroll
   for (int j = 0; j < N; ++j) v[j] = __uint_as_float(val[j]);
 }
@@ -1239,6 +1248,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
   __syncthreads();
 }
 
+#include "gpt_decode1.cuh"
+
 // -------------------------------------------------------------------- packing kernel --
 struct PackUnit {
   const float* src;
@@ -1831,6 +1842,12 @@ struct GptState {
   unsigned* ft = nullptr;       // tagged gelu(fc) words
   uint2 *qt = nullptr, *kvt = nullptr;
   unsigned* pflag = nullptr;
+  // second-generation batch-1 decode kernel
+  int v2 = 0, ring_rows = 0;
+  size_t smem_v2 = 0;
+  __nv_bfloat16* wstream1 = nullptr;
+  long long* stream_off1 = nullptr;
+  uint2 *ot = nullptr, *partt = nullptr, *cand = nullptr, *tokt = nullptr;
   unsigned epoch = 0;           // epochs handed out so far
   int dataflow = 1;
   __nv_bfloat16* fg = nullptr;
@@ -2014,6 +2031,7 @@ static size_t smem_bytes(int BT, int D, int FF, int nst, int bias_cap, int ocap,
          sizeof(float) * 4 * (size_t)D + 64;
 }
 
+static void reset_tagged_fwd(idx_engine* e, GptState* g, const GptParams& p);
 template <int BT, int NPL>
 static void launch_fused_t(idx_engine* e, GptState* g, GptParams& p) {
   p.nst = (BT == 1) ? g->nst1 : g->nst8;
@@ -2025,14 +2043,7 @@ static void launch_fused_t(idx_engine* e, GptState* g, GptParams& p) {
   p.xt = nullptr;
   if (BT == 1 && p.mode == 1 && g->dataflow) {
     const unsigned need = (unsigned)p.nsteps * (unsigned)p.L * 2u + 2u;
-    if (g->epoch > 0xF0000000u - need) {        // epochs never repeat while a stale word could still carry them
-      IDX_CUDA(cudaMemsetAsync(g->xt, 0, (size_t)p.D * sizeof(uint2), e->stream));
-      IDX_CUDA(cudaMemsetAsync(g->ft, 0, (size_t)p.FF * sizeof(unsigned), e->stream));
-      IDX_CUDA(cudaMemsetAsync(g->qt, 0, (size_t)p.D * sizeof(uint2), e->stream));
-      IDX_CUDA(cudaMemsetAsync(g->pflag, 0, 32 * (size_t)(8 * p.H * std::max(1, p.G / p.H) + p.G) * sizeof(unsigned), e->stream));
-      IDX_CUDA(cudaMemsetAsync(g->kvt, 0, 2 * (size_t)p.D * sizeof(uint2), e->stream));
-      g->epoch = 0;
-    }
+    if (g->epoch > 0xF0000000u - need) reset_tagged_fwd(e, g, p);   // epochs never repeat while a stale word could still carry them
     p.xt = g->xt;
     p.ft = g->ft;
     p.qt = g->qt;
@@ -2055,6 +2066,41 @@ static void launch_fused_bt(idx_engine* e, GptState* g, GptParams& p, int BT) {
   else if (npl == 8) { if (BT == 1) launch_fused_t<1, 8>(e, g, p); else launch_fused_t<8, 8>(e, g, p); }
   else throw IdxError(IDX_ERR_ARG, "model_dim must be 1280 or 256 (instantiated kernel geometries)");
 }
+// second-generation batch-1 decode launch (same epoch bookkeeping as the tagged mode of gpt_fused_kernel<1, .>)
+static size_t smem_bytes_v2(int D, int FF, int R, int bias_cap, int ocap, int V) {
+  return (size_t)R * D * 2 + (size_t)FF * 2 + sizeof(float) * (size_t)RED1_FLOATS + 16 * (size_t)NBAR + 16 +
+         4 * (size_t)bias_cap + 4 * (size_t)ocap + 4 * (size_t)((V + 31) / 32) + 16 + sizeof(float) * 4 * (size_t)D + 64;
+}
+static void reset_tagged(idx_engine* e, GptState* g, const GptParams& p) {
+  IDX_CUDA(cudaMemsetAsync(g->xt, 0, (size_t)p.D * sizeof(uint2), e->stream));
+  IDX_CUDA(cudaMemsetAsync(g->ft, 0, (size_t)p.FF * sizeof(unsigned), e->stream));
+  IDX_CUDA(cudaMemsetAsync(g->qt, 0, (size_t)p.D * sizeof(uint2), e->stream));
+  IDX_CUDA(cudaMemsetAsync(g->pflag, 0, 32 * (size_t)(8 * p.H * std::max(1, p.G / p.H) + p.G) * sizeof(unsigned), e->stream));
+  IDX_CUDA(cudaMemsetAsync(g->kvt, 0, 2 * (size_t)p.D * sizeof(uint2), e->stream));
+  if (g->ot) {
+    IDX_CUDA(cudaMemsetAsync(g->ot, 0, (size_t)p.D * sizeof(uint2), e->stream));
+    IDX_CUDA(cudaMemsetAsync(g->partt, 0, (size_t)p.H * 7 * PART_STRIDE * sizeof(uint2), e->stream));
+    IDX_CUDA(cudaMemsetAsync(g->cand, 0, 2 * (size_t)p.G * sizeof(uint2), e->stream));
+    IDX_CUDA(cudaMemsetAsync(g->tokt, 0, sizeof(uint2), e->stream));
+  }
+  g->epoch = 0;
+}
+static void reset_tagged_fwd(idx_engine* e, GptState* g, const GptParams& p) { reset_tagged(e, g, p); }
+static void launch_decode1(idx_engine* e, GptState* g, GptParams& p) {
+  p.bias_cap = g->bias_cap;
+  p.ocap = g->ocap;
+  p.xt = g->xt; p.ft = g->ft; p.qt = g->qt; p.pflag = g->pflag; p.kvt = g->kvt;
+  const unsigned need = (unsigned)p.nsteps * (unsigned)p.L * 2u + 2u;
+  if (g->epoch > 0xF0000000u - need) reset_tagged(e, g, p);   // epochs never repeat while a stale word could still carry them
+  p.epoch0 = g->epoch;
+  g->epoch += need;
+  void* args[] = {(void*)&p};
+  const void* fn = (p.D / 32 == 40) ? (const void*)gpt_decode1_kernel<40> : (const void*)gpt_decode1_kernel<8>;
+  IDX_CUDA(cudaLaunchCooperativeKernel(fn, dim3(g->G), dim3(NTHREADS), args, g->smem_v2, e->stream));
+  e->launches++;
+  g->last_launches++;
+}
+
 template <int BT>
 static void set_smem_attr(int npl, size_t bytes) {
   if (npl == 40) IDX_CUDA(cudaFuncSetAttribute(gpt_fused_kernel<BT, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -2159,6 +2205,68 @@ extern "C" int idx_gpt_init(idx_engine* e, const idx_gpt_config* cfg) {
   IDX_CUDA(cudaStreamSynchronize(e->stream));
   cudaFree(d_units);
 
+  // ---- second-generation batch-1 decode kernel (gpt_decode1.cuh): its own row stream in tile order ----
+  {
+    auto cdiv2 = [](int a, int b) { return (a + b - 1) / b; };
+    const int mq = cdiv2(3 * D, G) + 1, mo = cdiv2(D, G) + 1, mf = cdiv2(FF, G) + 1, mh = cdiv2(V, G) + 1;
+    const bool fits = mo <= TROWS && cdiv2(mq, TROWS) <= MAXIT && cdiv2(mf, TROWS) <= MAXIT && cdiv2(mh, TROWS) <= MAXIT &&
+                      FF / D <= MAXIT && G <= NCT;
+    g->v2 = fits && !(getenv("IDX_GPT_V2") && atoi(getenv("IDX_GPT_V2")) == 0);
+    if (g->v2) {
+      int R = 0;
+      while (smem_bytes_v2(D, FF, R + 1, g->bias_cap, g->ocap, V) <= (size_t)dev_smem - 1024) ++R;
+      if (getenv("IDX_GPT_RING")) R = std::min(R, atoi(getenv("IDX_GPT_RING")));
+      IDX_CHECK(R >= std::max(std::max(mq, mf), std::max((FF / D) * mo, mh)), IDX_ERR_ARG, "shared memory too small for the decode ring");
+      g->ring_rows = R;
+      g->smem_v2 = smem_bytes_v2(D, FF, R, g->bias_cap, g->ocap, V);
+      if (D / 32 == 40) IDX_CUDA(cudaFuncSetAttribute(gpt_decode1_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_v2));
+      else IDX_CUDA(cudaFuncSetAttribute(gpt_decode1_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_v2));
+      std::vector<PackUnit> u1;
+      std::vector<long long> off1(G + 1, 0);
+      auto tile_rows = [&](int c0, int n, int nt, auto&& emit) {     // column tiles of <= TROWS rows; the swizzle key is the row in the tile
+        for (int j = 0; j < nt; ++j) {
+          const int b0 = (n * j) / nt, b1 = (n * (j + 1)) / nt;
+          for (int r = 0; r < b1 - b0; ++r) emit(c0 + b0 + r, r);
+        }
+      };
+      for (int i = 0; i < G; ++i) {
+        off1[i] = (long long)u1.size();
+        const int q0 = (int)(((long long)3 * D * i) / G), q1 = (int)(((long long)3 * D * (i + 1)) / G);
+        const int o0 = (int)(((long long)D * i) / G), o1 = (int)(((long long)D * (i + 1)) / G);
+        const int f0 = (int)(((long long)FF * i) / G), f1 = (int)(((long long)FF * (i + 1)) / G);
+        const int h0 = (int)(((long long)V * i) / G), h1 = (int)(((long long)V * (i + 1)) / G);
+        for (int l = 0; l < L; ++l) {
+          const float* wq = (const float*)e->W(lname(l, "attn.c_attn.weight")).d;
+          const float* wo = (const float*)e->W(lname(l, "attn.c_proj.weight")).d;
+          const float* wf = (const float*)e->W(lname(l, "mlp.c_fc.weight")).d;
+          const float* wp = (const float*)e->W(lname(l, "mlp.c_proj.weight")).d;
+          tile_rows(q0, q1 - q0, cdiv2(q1 - q0, TROWS), [&](int c, int r) { u1.push_back({wq, c, 3LL * D, r}); });
+          tile_rows(o0, o1 - o0, 1, [&](int c, int r) { u1.push_back({wo, c, (long long)D, r}); });
+          tile_rows(f0, f1 - f0, cdiv2(f1 - f0, TROWS), [&](int c, int r) { u1.push_back({wf, c, (long long)FF, r}); });
+          for (int sg = 0; sg < FF / D; ++sg)        // PROJ: one tile per K-segment of D rows of c_proj.weight
+            tile_rows(o0, o1 - o0, 1, [&](int c, int r) { u1.push_back({wp, (long long)sg * D * D + c, (long long)D, r}); });
+        }
+        tile_rows(h0, h1 - h0, cdiv2(h1 - h0, TROWS), [&](int c, int r) { u1.push_back({(const float*)wh.d, (long long)c * D, 1LL, r}); });
+      }
+      off1[G] = (long long)u1.size();
+      const long long n1 = (long long)u1.size();
+      PackUnit* d_u1 = nullptr;
+      IDX_CUDA(cudaMalloc((void**)&d_u1, n1 * sizeof(PackUnit)));
+      IDX_CUDA(cudaMemcpyAsync(d_u1, u1.data(), n1 * sizeof(PackUnit), cudaMemcpyHostToDevice, e->stream));
+      g->wstream1 = galloc<__nv_bfloat16>(g, (size_t)n1 * D + 64);
+      pack_units_kernel<<<(unsigned)n1, 128, 0, e->stream>>>(d_u1, g->wstream1, D, n1);
+      IDX_CUDA(cudaGetLastError());
+      g->stream_off1 = galloc<long long>(g, G + 1);
+      IDX_CUDA(cudaMemcpyAsync(g->stream_off1, off1.data(), (G + 1) * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
+      IDX_CUDA(cudaStreamSynchronize(e->stream));
+      cudaFree(d_u1);
+      g->ot = galloc<uint2>(g, (size_t)D);
+      g->partt = galloc<uint2>(g, (size_t)H * 7 * PART_STRIDE);
+      g->cand = galloc<uint2>(g, 2 * (size_t)G);
+      g->tokt = galloc<uint2>(g, 1);
+    }
+  }
+
   // ---- small parameters gathered into [L][..] arrays ----
   auto gather = [&](const char* suffix, int n) {
     float* dst = galloc<float>(g, (size_t)L * n);
@@ -2245,6 +2353,9 @@ static void fill_common(idx_engine* e, GptState* g, GptParams& p) {
   p.xg = g->xg; p.qg = g->qg; p.fg = g->fg; p.part = g->part; p.logits = g->logits;
   p.tok = g->tok; p.nout = g->nout; p.finished = g->finished; p.prompt_len = g->prompt_len;
   p.seen = g->seen; p.done = g->done; p.barrier = g->barrier;
+  p.wstream1 = g->wstream1; p.stream_off1 = g->stream_off1; p.ring_rows = g->ring_rows;
+  p.dbg = getenv("IDX_GPT_DBG") ? atoi(getenv("IDX_GPT_DBG")) : 0;
+  p.ot = g->ot; p.partt = g->partt; p.cand = g->cand; p.tokt = g->tokt;
   p.prof = g->prof_on ? g->prof : nullptr;
   p.prof2 = g->prof_on ? g->prof2 : nullptr;
   p.prof2_layer = c.layers / 2;
@@ -2586,13 +2697,14 @@ extern "C" int idx_gpt_generate(idx_engine* e, const idx_gpt_request* reqs, int 
   p.seq_base = g->seq_base;
   p.pos_plain = sp->mel_pos_mode == 1;
   p.codes = d_codes; p.forced = d_forced; p.logits_dump = d_ldump;
-  const int SPL = 32;  // steps per launch: the host looks at one flag every SPL steps
+  const int SPL = (BT == 1 && g->v2) ? 64 : 32;  // steps per launch: the host looks at one flag every SPL steps
   int steps_done = 0;
   int* h_done = (int*)e->pinned_buf(64);
   while (steps_done < max_new) {
     p.step0 = steps_done;
     p.nsteps = std::min(SPL, max_new - steps_done);
-    launch_fused_bt(e, g, p, BT);
+    if (BT == 1 && g->v2) launch_decode1(e, g, p);
+    else launch_fused_bt(e, g, p, BT);
     IDX_CUDA(cudaMemcpyAsync(h_done, g->done, 4, cudaMemcpyDeviceToHost, e->stream));
     IDX_CUDA(cudaStreamSynchronize(e->stream));
     steps_done += p.nsteps;

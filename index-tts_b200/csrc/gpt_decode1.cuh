@@ -1,0 +1,903 @@
+// gpt_decode1.cuh — second-generation batch-1 decode kernel (round 2).  Included by gpt_decode.cu inside its
+// anonymous namespace: it reuses GptParams, the tagged-word helpers, ln_block, gelu_new and the Philox sampler.
+//
+// What it replaces: the <1, NPL> instantiation of gpt_fused_kernel for `nreq == 1, num_beams == 1` decode (the
+// BASELINE config-2 hot loop).  Same arithmetic, same rounding points, same sampler contract, same KV-cache layout;
+// prefill, multi-row decode and beam search stay on gpt_fused_kernel<8, NPL>.
+//
+// Why: the per-CTA timeline of round 1 (profiles/r02_gpt_fine_timeline_before.txt; 26 us per layer against 6 us of
+// pure weight streaming) showed where the time of a layer went:
+//   * 6.9 us in the GEMV MMAs: one dependent ldmatrix -> mma chain per 8-row chunk, chunks processed one after
+//     the other, and the 9th column of the 1280-wide phases costing a whole second chain
+//       -> here a tile is 16 REAL weight rows (m16n8k16 with all 16 A rows used), every tile of a phase is in flight
+//          at once (<= 4 independent accumulators per warp, k-steps outermost), so a phase costs KS dependent MMAs;
+//   * 2.2 us in the O-proj merge of the 7 key-splits per head (flag poll -> data loads: two L2 round trips)
+//       -> contexts up to 640 positions use ONE CTA per head which hands over the normalised head output as tagged
+//          words (one round trip, same protocol as the residual stream); longer contexts split the keys and
+//          hand over tagged (m, l, o) partials;
+//   * 1.0 us in the serial cross-warp merge of the attention partials  -> merged by 64 threads in parallel;
+//   * K/V loads only issued after q had arrived  -> first iterations preloaded before the q poll;
+//   * 1.0-1.5 us waiting for weights in PROJ: a ring stage held ONE chunk (a 1-row chunk wasted 17.5 KB)
+//       -> the ring is row-granular (R rows of D bf16), tiles are mbarrier-tracked independently of the rows;
+//   * 22 us per step in embedding / head / sampling with four grid barriers
+//       -> no grid barrier at all: every CTA reduces the per-CTA argmax candidates (tagged words) itself, so
+//          every CTA knows the next token and builds the next input row locally; sampling (do_sample) keeps a
+//          CTA-0 sampler fed by release/acquire flags.
+//
+// Shared-memory ring protocol.  The CTA's weights of one decode step are a fixed sequence of tiles
+// (per layer: QKV column tiles, O-proj, FC column tiles, PROJ K-segments; then the head tiles).  Tile t lands in
+// ring rows [row(t) mod R ...) and completes full[t mod NBAR]; the consumer releases it on empty[t mod NBAR].  The
+// producer may issue tile t when fewer than NBAR tiles are outstanding and its rows fit behind the last released tile.
+
+constexpr int TROWS = 16;       // weight rows per MMA tile
+constexpr int NBAR = 16;        // tile barrier slots
+constexpr int MAXIT = 4;        // (column tile, K segment) items per phase
+constexpr int RED1_MMA = MAXIT * NCW * 16;                 // per-warp partial sums of the phase's tiles
+constexpr int RED1_FLOATS = RED1_MMA + 48 + 64 + NCW * PART_STRIDE;   // + LayerNorm statistics + head scores + attention merge
+
+__device__ __forceinline__ int split_rows(int n, int nt, int j) { return (n * (j + 1)) / nt - (n * j) / nt; }
+__device__ __forceinline__ int split_begin(int n, int nt, int j) { return (n * j) / nt; }
+
+// per-CTA tile schedule of one decode step, in stream order
+struct Sched1 {
+  int L, nseg, nq, no, nf, nh, ntq, ntf, nth;
+  __device__ __forceinline__ int tiles_per_layer() const { return ntq + 1 + ntf + nseg; }
+  __device__ __forceinline__ int tiles_per_step() const { return L * tiles_per_layer() + nth; }
+  __device__ int rows(int i) const {
+    const int tpl = tiles_per_layer();
+    if (i >= L * tpl) return split_rows(nh, nth, i - L * tpl);
+    int j = i % tpl;
+    if (j < ntq) return split_rows(nq, ntq, j);
+    j -= ntq;
+    if (j < 1) return no;
+    j -= 1;
+    if (j < ntf) return split_rows(nf, ntf, j);
+    return no;
+  }
+};
+
+struct Smem1 {
+  __nv_bfloat16* ring;  // [R][D]
+  __nv_bfloat16* xs;    // [FF] GEMV input row (bf16, plain layout)
+  float* red;           // [RED1_MMA] K-split partial sums (disjoint regions: no barrier is needed between the phases' uses)
+  float* red_ln;        // [48] LayerNorm statistics (two sets)
+  float* cs;            // [64] processed scores of this CTA's head columns
+  float* red_att;       // [NCW][66] attention merge / sampler scratch
+  uint64_t* full;       // [NBAR]
+  uint64_t* empty;      // [NBAR]
+  int* flags;           // [4]
+  float* bias_s;
+  float* xres;          // [ocap] this CTA's slice of the fp32 residual stream
+  unsigned* seen_s;     // [(V+31)/32]
+  float* lnp;           // [2][2][D]
+};
+
+// All MMAs of one phase: `nitems` tiles in flight, k-steps outermost.  Item i: `nrows[i]` weight rows starting at
+// stream row `row0[i]` (ring slot = row mod R), multiplied with the activation segment xs[seg[i] * D ...).
+// Leaves the per-warp partial sums in red[(i * NCW + warp) * 16 + row] and synchronises the compute warps.
+template <int D>
+__device__ __forceinline__ void mma_items(const Smem1& sm, int nitems, const int (&row0)[MAXIT], const int (&nrows)[MAXIT],
+                                          const int (&seg)[MAXIT], unsigned tile0, int R, int warp, int lane,
+                                          long long* st = nullptr, int dbg = 0) {
+  constexpr int KS = (D / 16) / NCW;
+  const uint32_t ring_base = ptx::smem_u32(sm.ring);
+  const int g = lane >> 2, t4 = lane & 3;
+  const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, khalf = lane >> 4;
+  uint32_t a_base[MAXIT];
+  int key[MAXIT];
+  float acc[MAXIT][4];
+#pragma unroll
+  for (int i = 0; i < MAXIT; ++i) {
+    acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    a_base[i] = ring_base;
+    key[i] = 0;
+    if (i < nitems) {
+      const int rr = min(lrow, nrows[i] - 1);            // rows beyond the tile read a valid row; their results are unused
+      a_base[i] = ring_base + (uint32_t)(((row0[i] + rr) % R) * (D * 2));
+      key[i] = rr & 7;
+      const unsigned n = tile0 + (unsigned)i;
+      ptx::mbar_wait(&sm.full[n % NBAR], (n / NBAR) & 1u);
+    }
+  }
+  if (st && threadIdx.x == 0) { st[0] = gtimer(); st[32] = clock64(); }
+  const uint32_t* xw = (const uint32_t*)sm.xs;
+  if (!(dbg & 1))
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    const int kk = warp * KS + ks;                        // k-step: k0 = 16 * kk
+#pragma unroll
+    for (int i = 0; i < MAXIT; ++i) {
+      if (i < nitems) {
+        uint32_t a0, a1, a2, a3;
+        ldmatrix_x4(a_base[i] + (uint32_t)(((2 * kk + khalf) ^ key[i]) << 4), a0, a1, a2, a3);
+        const uint32_t* xb = xw + seg[i] * (D / 2) + kk * 8 + t4;
+        mma_bf16_16816(acc[i], a0, a1, a2, a3, xb[0], xb[4]);   // B: the one activation row in every n column
+      }
+    }
+  }
+  __syncwarp();
+  if (st && threadIdx.x == 0) { st[1] = gtimer(); st[33] = clock64(); }
+  if (lane == 0)
+    for (int i = 0; i < nitems; ++i) ptx::mbar_arrive(&sm.empty[(tile0 + (unsigned)i) % NBAR]);
+  if (t4 == 0) {
+#pragma unroll
+    for (int i = 0; i < MAXIT; ++i)
+      if (i < nitems) {
+        sm.red[(i * NCW + warp) * 16 + g] = acc[i][0];
+        sm.red[(i * NCW + warp) * 16 + g + 8] = acc[i][2];
+      }
+  }
+  ptx::named_bar_sync(1, NCT);
+  if (st && threadIdx.x == 0) { st[2] = gtimer(); st[34] = clock64(); }
+}
+
+__device__ __forceinline__ float red_sum(const float* red, int item, int row) {
+  float a = 0.f;
+#pragma unroll
+  for (int w = 0; w < NCW; ++w) a += red[(item * NCW + w) * 16 + row];
+  return a;
+}
+
+__device__ __forceinline__ uint2 ld_tagged_word(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+
+// The sampling phase of gpt_fused_kernel as a function (same processor order, tie rules and Philox contract):
+// RepetitionPenalty -> (forbid stop) -> Temperature -> TopK (ties kept) -> TopP -> multinomial.  Called by the 8 compute
+// warps of ONE CTA; `red` is >= 32 + 2 * CMAX floats of scratch.  The pick is valid in thread 0.
+struct SampleArgs {
+  int V, stop_tok, forbid_stop_before, top_k, seq_base;
+  float rep_penalty, temperature, top_p;
+  unsigned long long seed;
+};
+__device__ __noinline__ int sample_block(const SampleArgs p, float* red, const unsigned* seen, const float* lg, int k, int b,
+                                         int tid, int lane, int warp) {
+  constexpr int VPT = 40;   // ceil(V / 256) for V <= 10240
+  const int V = p.V;
+  float sv[VPT];
+  const float inv_temp = (p.temperature > 0.f) ? 1.0f / p.temperature : 1.0f;
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    const int i = tid + j * NCT;
+    sv[j] = (i < V) ? __ldcg(lg + i) : -INFINITY;
+  }
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    const int i = tid + j * NCT;
+    if (i < V) {
+      float sc = sv[j];
+      if ((seen[i >> 5] >> (i & 31)) & 1u) sc = (sc < 0.f) ? sc * p.rep_penalty : sc / p.rep_penalty;
+      if (i == p.stop_tok && k < p.forbid_stop_before) sc = -INFINITY;
+      sv[j] = sc * inv_temp;
+    }
+  }
+  auto block_argmax = [&](float& bestv, int& besti) {
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      const int i = tid + j * NCT;
+      if (sv[j] > best || (sv[j] == best && i < bi && sv[j] > -INFINITY)) { best = sv[j]; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float b2 = __shfl_xor_sync(0xffffffffu, best, o);
+      const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (b2 > best || (b2 == best && i2 < bi)) { best = b2; bi = i2; }
+    }
+    ptx::named_bar_sync(1, NCT);
+    if (lane == 0) { red[warp * 2] = best; ((int*)red)[warp * 2 + 1] = bi; }
+    ptx::named_bar_sync(1, NCT);
+    for (int w = 0; w < NCW; ++w) {
+      const float b2 = red[w * 2];
+      const int i2 = ((int*)red)[w * 2 + 1];
+      if (w == 0 || b2 > best || (b2 == best && i2 < bi)) { best = b2; bi = i2; }
+    }
+    bestv = best; besti = bi;
+  };
+  float best; int besti;
+  block_argmax(best, besti);
+  float* cv = red + 32;
+  int* ci = (int*)(red + 32 + CMAX);
+  const int kk = min(max(p.top_k, 1), CMAX);
+  int nc = 0;
+  float kth = best;
+  while (nc < CMAX && best > -INFINITY && (nc < kk || best == kth)) {
+    if (tid == 0) { cv[nc] = best; ci[nc] = besti; }
+    if (nc < kk) kth = best;
+    ++nc;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j)
+      if (tid + j * NCT == besti) sv[j] = -INFINITY;
+    block_argmax(best, besti);
+  }
+  ptx::named_bar_sync(1, NCT);
+  if (tid == 0) {
+    const float mx = cv[0];
+    float tot = 0.f;
+    for (int i = 0; i < nc; ++i) { cv[i] = expf(cv[i] - mx); tot += cv[i]; }
+    int keep = nc;
+    if (p.top_p < 1.0f) {
+      float tail = 0.f;
+      for (int i = nc - 1; i >= 1; --i) {
+        tail += cv[i] / tot;
+        if (tail <= 1.0f - p.top_p) keep = i; else break;
+      }
+    }
+    float kt = 0.f;
+    for (int i = 0; i < keep; ++i) kt += cv[i];
+    unsigned rnd4[4];
+    philox4x32_10(p.seed, (unsigned)k, (unsigned)(b + p.seq_base), rnd4);
+    const float u = (float)(rnd4[0] >> 8) * (1.0f / 16777216.0f) * kt;
+    float acc = 0.f;
+    int pick = keep - 1;
+    for (int i = 0; i < keep; ++i) { acc += cv[i]; if (u < acc) { pick = i; break; } }
+    besti = ci[pick];
+  }
+  return besti;
+}
+
+template <int NPL>
+__global__ void __launch_bounds__(NTHREADS, 1) gpt_decode1_kernel(const GptParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int D = NPL * 32, FF = 4 * D, NSEG = FF / D;
+  static_assert(NSEG <= MAXIT, "PROJ K-segments must fit the item slots");
+  const int G = p.G, L = p.L, H = p.H, V = p.V, R = p.ring_rows;
+  const int cta = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  Smem1 sm;
+  {
+    unsigned char* q = smem_raw;
+    sm.ring = (__nv_bfloat16*)q;  q += (size_t)R * D * 2;
+    sm.xs = (__nv_bfloat16*)q;    q += (size_t)FF * 2;
+    sm.red = (float*)q;           q += sizeof(float) * RED1_FLOATS;
+    sm.red_ln = sm.red + RED1_MMA;
+    sm.cs = sm.red_ln + 48;
+    sm.red_att = sm.cs + 64;
+    sm.full = (uint64_t*)q;       q += sizeof(uint64_t) * NBAR;
+    sm.empty = (uint64_t*)q;      q += sizeof(uint64_t) * NBAR;
+    sm.flags = (int*)q;           q += 16;
+    sm.bias_s = (float*)q;        q += sizeof(float) * (size_t)p.bias_cap;
+    sm.xres = (float*)q;          q += sizeof(float) * (size_t)p.ocap;
+    sm.seen_s = (unsigned*)q;     q += sizeof(unsigned) * (size_t)((V + 31) / 32);
+    q = (unsigned char*)(((uintptr_t)q + 15) & ~(uintptr_t)15);
+    sm.lnp = (float*)q;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < NBAR; ++s) {
+      ptx::mbar_init(&sm.full[s], 1);
+      ptx::mbar_init(&sm.empty[s], NCW);
+    }
+    sm.flags[0] = 0;
+    sm.flags[2] = 0;
+    sm.flags[3] = 0;
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+
+  // column slices of this CTA (same ownership as gpt_fused_kernel)
+  const int q0 = col_begin(3 * D, cta, G), q1 = col_begin(3 * D, cta + 1, G);
+  const int o0 = col_begin(D, cta, G), o1 = col_begin(D, cta + 1, G);
+  const int f0 = col_begin(FF, cta, G), f1 = col_begin(FF, cta + 1, G);
+  const int h0 = col_begin(V, cta, G), h1 = col_begin(V, cta + 1, G);
+  const int nq = q1 - q0, no = o1 - o0, nf = f1 - f0, nh = h1 - h0;
+  Sched1 sc;
+  sc.L = L; sc.nseg = NSEG; sc.nq = nq; sc.no = no; sc.nf = nf; sc.nh = nh;
+  sc.ntq = (nq + TROWS - 1) / TROWS; sc.ntf = (nf + TROWS - 1) / TROWS; sc.nth = (nh + TROWS - 1) / TROWS;
+  const int bstride = nq + 2 * no + nf;
+  if (warp < NCW) {
+    for (int i = tid; i < L * bstride; i += NCT) {
+      const int l = i / bstride, j = i % bstride;
+      float v;
+      if (j < nq) v = p.qkv_b[(size_t)l * 3 * D + q0 + j];
+      else if (j < nq + no) v = p.o_b[(size_t)l * D + o0 + (j - nq)];
+      else if (j < nq + no + nf) v = p.fc_b[(size_t)l * FF + f0 + (j - nq - no)];
+      else v = p.proj_b[(size_t)l * D + o0 + (j - nq - no - nf)];
+      sm.bias_s[i] = v;
+    }
+    for (int i = tid; i < nh; i += NCT) sm.bias_s[L * bstride + i] = p.head_b[h0 + i];
+    for (int i = tid; i < (V + 31) / 32; i += NCT) sm.seen_s[i] = p.seen[i];
+  }
+  __syncthreads();
+
+  // =============================================================== producer warp ====
+  if (warp == NCW) {
+    if (lane == 0) {
+      const uint64_t pol = ptx::policy_evict_first();
+      const __nv_bfloat16* base = p.wstream1 + (size_t)p.stream_off1[cta] * D;
+      const int tps = sc.tiles_per_step();
+      unsigned tix = 0, rel = 0;             // tiles issued / known released
+      long long row_issue = 0, row_rel = 0;  // stream rows issued / released (monotonic over the launch)
+      int rel_i = 0;                         // index of tile `rel` inside its step
+      bool stop = false;
+      for (int step = 0; step < p.nsteps && !stop; ++step) {
+        size_t uoff = 0;
+        for (int i = 0; i < tps && !stop; ++i) {
+          const int n = sc.rows(i);
+          while (tix - rel >= (unsigned)NBAR || row_issue + n - row_rel > (long long)R) {
+            unsigned spins = 0;
+            while (!ptx::mbar_try_wait(&sm.empty[rel % NBAR], (rel / NBAR) & 1u)) {
+              if (*((volatile int*)&sm.flags[0])) { stop = true; break; }
+              if (++spins > (1u << 26)) __trap();
+            }
+            if (stop) break;
+            row_rel += sc.rows(rel_i);
+            ++rel;
+            if (++rel_i == tps) rel_i = 0;
+          }
+          if (stop) break;
+          uint64_t* bar = &sm.full[tix % NBAR];
+          const uint32_t bytes = (uint32_t)n * D * 2;
+          ptx::mbar_arrive_expect_tx(bar, bytes);
+          const int s0 = (int)(row_issue % R);
+          const int n1 = min(n, R - s0);
+          ptx::bulk_g2s(sm.ring + (size_t)s0 * D, base + uoff * D, (uint32_t)n1 * D * 2, bar, pol);
+          if (n1 < n) ptx::bulk_g2s(sm.ring, base + (uoff + n1) * D, (uint32_t)(n - n1) * D * 2, bar, pol);
+          ++tix;
+          row_issue += n;
+          uoff += n;
+        }
+      }
+      sm.flags[2] = (int)tix;
+    }
+    __syncwarp();
+  } else {
+    // ============================================================ compute warps ====
+    unsigned cons_tile = 0;
+    int cons_row = 0;                 // stream row (mod R kept small: reduced at every use)
+    const int b = 0;                  // the one sequence
+    const int plen = __ldg(p.prompt_len + b);
+    auto prefetch_ln = [&](int buf, const float* w, const float* bb) {
+      float* dst = sm.lnp + (size_t)buf * 2 * D;
+      const int n4 = D / 4;
+      for (int i = tid; i < 2 * n4; i += NCT) {
+        const int which = i / n4, off = (i % n4) * 4;
+        cp_async16(dst + which * D + off, (which ? bb : w) + off);
+      }
+    };
+    const float* lnA = sm.lnp;
+    const float* lnB = sm.lnp + 2 * D;
+    const int rr = p.round_bf16;
+    const bool nowait = (p.dbg & 4) != 0;      // diagnostics only: polls do not wait (results are garbage, timing = no dependencies)
+    int feed = __ldcg(p.tok + b);
+    const bool already_done = __ldcg(p.finished + b) != 0;
+    int row0[MAXIT], nrw[MAXIT], sg[MAXIT];
+    // one phase worth of tiles: column tiles (nt of them over ncols) x nseg K-segments, in stream order
+    // (either nt column tiles of one K-segment, or one column tile with nseg K-segments; fully unrolled so the item
+    // descriptors stay in registers)
+    auto set_items = [&](int ncols, int nt, int nseg) {
+      const int n = nt * nseg;
+      int r = cons_row;
+#pragma unroll
+      for (int i = 0; i < MAXIT; ++i) {
+        const int rows = (i < n) ? ((nseg > 1) ? ncols : split_rows(ncols, nt, i)) : 0;
+        row0[i] = r; nrw[i] = rows; sg[i] = (nseg > 1) ? i : 0;
+        r += rows;
+      }
+      return n;
+    };
+    auto advance = [&](int nitems) {
+      int r = 0;
+#pragma unroll
+      for (int i = 0; i < MAXIT; ++i) r += nrw[i];
+      cons_row = (cons_row + r) % R;
+      cons_tile += (unsigned)nitems;
+    };
+
+    for (int step = 0; step < p.nsteps && !already_done; ++step) {
+      const int k = p.step0 + step;
+      const int posidx = (k == 0 || p.pos_plain) ? k : k + 1;   // P1: mel position k+1 with the KV cache
+      const int pos = plen + k;                       // position of this token in the cache
+      const int ctx = pos + 1;
+      const int nsplit = (ctx <= 640) ? 1 : min(7, (ctx + 319) / 320);
+      if (step == 0) prefetch_ln(0, p.ln1_w, p.ln1_b);
+      // ---- input row: mel_emb[feed] + mel_pos[posidx], built locally by every CTA (no hand-over) ----
+      float v0[NPL / 8];
+      {
+        const float* er = p.mel_emb + (size_t)feed * D;
+        const float* pr = p.mel_pos + (size_t)posidx * D;
+#pragma unroll
+        for (int j = 0; j < NPL / 8; ++j) {
+          const int i = warp * (NPL * 4) + lane + 32 * j;
+          v0[j] = rnd(__ldg(er + i) + __ldg(pr + i), rr);
+        }
+        if (tid < no) sm.xres[tid] = rnd(__ldg(er + o0 + tid) + __ldg(pr + o0 + tid), rr);
+      }
+
+      for (int l = 0; l < L; ++l) {
+        const unsigned ep_base = p.epoch0 + (unsigned)(step * L + l) * 2u;
+        const unsigned ep_oproj = ep_base + 1u, ep_proj = ep_base + 2u;
+        const unsigned f_tag = ((ep_base >> 1) % 65535u) + 1u;
+        long long* f2 = (p.prof2 && l == p.prof2_layer && step == p.nsteps - 1) ? p.prof2 + (size_t)cta * 64 : nullptr;
+#define G2(i) do { if (f2 && tid == 0) { f2[(i)] = gtimer(); f2[32 + (i)] = clock64(); } } while (0)
+        G2(0);
+        // ---------------- P1: LN1 -> QKV ----------------
+        {
+          float v[NPL / 8];
+          if (l > 0) {
+            ld_tagged_slice<NPL / 8>(p.xt, warp * (NPL * 4) + lane, ep_base, v, nowait);
+          } else {
+#pragma unroll
+            for (int j = 0; j < NPL / 8; ++j) v[j] = v0[j];
+            cp_async_wait_all();          // LN1 parameters of layer 0 (prefetched in the previous step / above)
+          }
+          prefetch_ln(1, p.ln2_w + (size_t)l * D, p.ln2_b + (size_t)l * D);   // for P4 (drained there)
+          G2(1);
+          ln_block<NPL>(v, lnA, lnA + D, sm.red_ln, warp, lane);
+          G2(2);
+#pragma unroll
+          for (int j = 0; j < NPL / 8; ++j) sm.xs[warp * (NPL * 4) + lane + 32 * j] = __float2bfloat16_rn(v[j]);
+        }
+        ptx::named_bar_sync(1, NCT);
+        {
+          const int n = set_items(nq, sc.ntq, 1);
+          mma_items<D>(sm, n, row0, nrw, sg, cons_tile, R, warp, lane, f2 ? f2 + 3 : nullptr, p.dbg);
+          if (tid < nq) {
+            const int cl = tid;
+            int j = 0;
+            while (j + 1 < sc.ntq && cl >= split_begin(nq, sc.ntq, j + 1)) ++j;
+            const float a = red_sum(sm.red, j, cl - split_begin(nq, sc.ntq, j));
+            const float v = rnd(a + sm.bias_s[l * bstride + cl], rr);
+            const int c = q0 + cl;
+            if (c < D) {
+              st_tagged(p.qt + c, v, ep_oproj);
+            } else {
+              const size_t base = (((size_t)l * p.nseq + b) * p.maxpos + pos) * D;
+              const __nv_bfloat16 kvb = __float2bfloat16_rn(v);
+              if (c < 2 * D) p.kc[base + (c - D)] = kvb;
+              else p.vc[base + (c - 2 * D)] = kvb;
+              st_tagged(p.kvt + (c - D), __bfloat162float(kvb), ep_oproj);
+            }
+          }
+          advance(n);
+        }
+        G2(6);
+
+        // ---------------- P2: attention over the KV cache: (head, key split) = CTA ----------------
+        if (cta < H * nsplit) {
+          const int h = cta / nsplit, sp = cta % nsplit;
+          const int k0 = (int)(((long long)ctx * sp) / nsplit);
+          const int k1 = (int)(((long long)ctx * (sp + 1)) / nsplit);
+          const int kend = min(k1, ctx - 1);        // the position being decoded comes from the tagged k, v words
+          const int g4 = lane >> 3, sub = lane & 7;
+          const size_t cbase = ((size_t)l * p.nseq + b) * p.maxpos;
+          const size_t coff = (size_t)h * HD + sub * 8;
+          // software pipeline: the first keys are in flight before q has arrived
+          int j = k0 + warp * 4 + g4;
+          uint4 kk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+          if (j < kend) {
+            kk = __ldcg((const uint4*)(p.kc + (cbase + j) * D + coff));
+            vv = __ldcg((const uint4*)(p.vc + (cbase + j) * D + coff));
+          }
+          float qv[8];
+          {
+            const uint2* qp = p.qt + h * HD + sub * 8;
+            uint2 w[8];
+            unsigned spins = 0;
+            bool ok;
+            do {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) w[i] = ld_tagged_word(qp + i);
+              ok = true;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) ok &= (w[i].y == ep_oproj);
+              if (++spins > (1u << 26)) __trap();
+            } while (!ok && !nowait);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) qv[i] = __uint_as_float(w[i].x);
+          }
+          G2(7);
+          float m = -INFINITY, lsum = 0.f, ov[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ov[i] = 0.f;
+          for (int j0 = k0 + warp * 4; j0 < ((p.dbg & 2) ? k0 : kend); j0 += NCW * 4) {
+            const bool valid = j < kend;
+            const int jn = j + NCW * 4;
+            uint4 kn = make_uint4(0, 0, 0, 0), vn = make_uint4(0, 0, 0, 0);
+            if (jn < kend) {
+              kn = __ldcg((const uint4*)(p.kc + (cbase + jn) * D + coff));
+              vn = __ldcg((const uint4*)(p.vc + (cbase + jn) * D + coff));
+            }
+            float s = qv[0] * lo_bf(kk.x) + qv[1] * hi_bf(kk.x) + qv[2] * lo_bf(kk.y) + qv[3] * hi_bf(kk.y) +
+                      qv[4] * lo_bf(kk.z) + qv[5] * hi_bf(kk.z) + qv[6] * lo_bf(kk.w) + qv[7] * hi_bf(kk.w);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            if (valid) {
+              s *= 0.125f;
+              const float mn = fmaxf(m, s);
+              const float corr = __expf(m - mn);
+              const float pr = __expf(s - mn);
+              lsum = lsum * corr + pr;
+              const float vf[8] = {lo_bf(vv.x), hi_bf(vv.x), lo_bf(vv.y), hi_bf(vv.y),
+                                   lo_bf(vv.z), hi_bf(vv.z), lo_bf(vv.w), hi_bf(vv.w)};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) ov[i] = ov[i] * corr + pr * vf[i];
+              m = mn;
+            }
+            kk = kn; vv = vn; j = jn;
+          }
+          if (k1 == ctx && warp == 0 && g4 == 0) {
+            // the new position (owned by the last key split): k and v straight from the QKV epilogue's tagged words
+            const uint2* kp = p.kvt + h * HD + sub * 8;
+            const uint2* vp = p.kvt + D + h * HD + sub * 8;
+            uint2 wk[8], wv[8];
+            unsigned spins = 0;
+            bool ok;
+            do {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { wk[i] = ld_tagged_word(kp + i); wv[i] = ld_tagged_word(vp + i); }
+              ok = true;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) ok &= (wk[i].y == ep_oproj) & (wv[i].y == ep_oproj);
+              if (++spins > (1u << 26)) __trap();
+            } while (!ok && !nowait);
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s += qv[i] * __uint_as_float(wk[i].x);
+            s += __shfl_xor_sync(0xffu, s, 1);
+            s += __shfl_xor_sync(0xffu, s, 2);
+            s += __shfl_xor_sync(0xffu, s, 4);
+            s *= 0.125f;
+            const float mn = fmaxf(m, s);
+            const float corr = __expf(m - mn);
+            const float pr = __expf(s - mn);
+            lsum = lsum * corr + pr;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ov[i] = ov[i] * corr + pr * __uint_as_float(wv[i].x);
+            m = mn;
+          }
+          __syncwarp();
+          G2(8);
+          // merge the 4 key groups of the warp
+#pragma unroll
+          for (int xo = 8; xo <= 16; xo <<= 1) {
+            const float m2 = __shfl_xor_sync(0xffffffffu, m, xo);
+            const float l2 = __shfl_xor_sync(0xffffffffu, lsum, xo);
+            const float mn = fmaxf(m, m2);
+            const float c1 = (m == -INFINITY) ? 0.f : __expf(m - mn);
+            const float c2 = (m2 == -INFINITY) ? 0.f : __expf(m2 - mn);
+            lsum = lsum * c1 + l2 * c2;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float o2 = __shfl_xor_sync(0xffffffffu, ov[i], xo);
+              ov[i] = ov[i] * c1 + o2 * c2;
+            }
+            m = mn;
+          }
+          // merge the 8 warps: every warp publishes (m, l, o[64]) in shared memory, 64 threads combine them in parallel
+          float* red = sm.red_att;
+          if (lane < 8) {
+            float* rw = red + warp * PART_STRIDE;
+            if (lane == 0) { rw[0] = m; rw[1] = lsum; }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rw[2 + lane * 8 + i] = ov[i];
+          }
+          ptx::named_bar_sync(1, NCT);
+          G2(9);
+          if (tid < HD) {
+            float mm = -INFINITY;
+#pragma unroll
+            for (int w = 0; w < NCW; ++w) mm = fmaxf(mm, red[w * PART_STRIDE]);
+            float lt = 0.f, oa = 0.f;
+#pragma unroll
+            for (int w = 0; w < NCW; ++w) {
+              const float mw = red[w * PART_STRIDE];
+              const float c = (mw == -INFINITY) ? 0.f : __expf(mw - mm);
+              lt += red[w * PART_STRIDE + 1] * c;
+              oa += red[w * PART_STRIDE + 2 + tid] * c;
+            }
+            if (nsplit == 1) {
+              // one CTA saw every key of the head: hand over the normalised output (bf16-rounded like the operand it becomes)
+              const float inv = (lt > 0.f) ? 1.0f / lt : 0.f;
+              st_tagged(p.ot + h * HD + tid, oa * inv, ep_oproj);
+            } else {
+              uint2* pw = p.partt + (size_t)cta * PART_STRIDE;
+              st_tagged(pw + 2 + tid, oa, ep_oproj);
+              if (tid == 0) { st_tagged(pw, mm, ep_oproj); st_tagged(pw + 1, lt, ep_oproj); }
+            }
+          }
+        }
+        G2(10);
+
+        // ---------------- P3: attention output -> O-proj + residual ----------------
+        if (nsplit == 1) {
+          float v[NPL / 8];
+          ld_tagged_slice<NPL / 8>(p.ot, warp * (NPL * 4) + lane, ep_oproj, v, nowait);
+          G2(11);
+#pragma unroll
+          for (int j = 0; j < NPL / 8; ++j) sm.xs[warp * (NPL * 4) + lane + 32 * j] = __float2bfloat16_rn(v[j]);
+        } else {
+          // one warp per head, all loads of a head (nsplit x (m, l, o[lane], o[lane + 32])) in flight together
+          for (int h = warp; h < H; h += NCW) {
+            const uint2* pp = p.partt + (size_t)h * nsplit * PART_STRIDE;
+            uint2 wm[7], wl[7], wa[7], wb[7];
+            unsigned spins = 0;
+            bool ok;
+            do {
+              ok = true;
+#pragma unroll
+              for (int s = 0; s < 7; ++s)
+                if (s < nsplit) {
+                  wm[s] = ld_tagged_word(pp + s * PART_STRIDE);
+                  wl[s] = ld_tagged_word(pp + s * PART_STRIDE + 1);
+                  wa[s] = ld_tagged_word(pp + s * PART_STRIDE + 2 + lane);
+                  wb[s] = ld_tagged_word(pp + s * PART_STRIDE + 34 + lane);
+                }
+#pragma unroll
+              for (int s = 0; s < 7; ++s)
+                if (s < nsplit) ok &= (wm[s].y == ep_oproj) & (wl[s].y == ep_oproj) & (wa[s].y == ep_oproj) & (wb[s].y == ep_oproj);
+              if (++spins > (1u << 26)) __trap();
+            } while (!ok && !nowait);
+            float mm = -INFINITY;
+#pragma unroll
+            for (int s = 0; s < 7; ++s)
+              if (s < nsplit) mm = fmaxf(mm, __uint_as_float(wm[s].x));
+            float lt = 0.f, oa = 0.f, ob = 0.f;
+#pragma unroll
+            for (int s = 0; s < 7; ++s)
+              if (s < nsplit) {
+                const float ms = __uint_as_float(wm[s].x);
+                const float cc = (ms == -INFINITY) ? 0.f : __expf(ms - mm);
+                lt += __uint_as_float(wl[s].x) * cc;
+                oa += __uint_as_float(wa[s].x) * cc;
+                ob += __uint_as_float(wb[s].x) * cc;
+              }
+            const float inv = (lt > 0.f) ? 1.0f / lt : 0.f;
+            sm.xs[h * HD + lane] = __float2bfloat16_rn(oa * inv);
+            sm.xs[h * HD + 32 + lane] = __float2bfloat16_rn(ob * inv);
+          }
+          G2(11);
+        }
+        ptx::named_bar_sync(1, NCT);
+        {
+          const int n = set_items(no, 1, 1);
+          mma_items<D>(sm, n, row0, nrw, sg, cons_tile, R, warp, lane, f2 ? f2 + 12 : nullptr, p.dbg);
+          if (tid < no) {
+            // the residual stream is fp32 even on the bf16 path (trap P12): only the branch is rounded
+            const float o = rnd(red_sum(sm.red, 0, tid) + sm.bias_s[l * bstride + nq + tid], rr);
+            const float xn = sm.xres[tid] + o;
+            sm.xres[tid] = xn;
+            st_tagged(p.xt + o0 + tid, xn, ep_oproj);
+          }
+          advance(n);
+        }
+        G2(15);
+
+        // ---------------- P4: LN2 -> FC + gelu_new ----------------
+        if (l + 1 < L) prefetch_ln(0, p.ln1_w + (size_t)(l + 1) * D, p.ln1_b + (size_t)(l + 1) * D);
+        else prefetch_ln(0, p.lnf_w, p.lnf_b);
+        {
+          float v[NPL / 8];
+          ld_tagged_slice<NPL / 8>(p.xt, warp * (NPL * 4) + lane, ep_oproj, v, nowait);
+          G2(16);
+          cp_async_wait_all();   // ln_2 parameters prefetched in P1 (ln_block's own CTA barrier publishes them)
+          ln_block<NPL>(v, lnB, lnB + D, sm.red_ln, warp, lane);
+          G2(17);
+#pragma unroll
+          for (int j = 0; j < NPL / 8; ++j) sm.xs[warp * (NPL * 4) + lane + 32 * j] = __float2bfloat16_rn(v[j]);
+        }
+        ptx::named_bar_sync(1, NCT);
+        {
+          const int n = set_items(nf, sc.ntf, 1);
+          mma_items<D>(sm, n, row0, nrw, sg, cons_tile, R, warp, lane, f2 ? f2 + 18 : nullptr, p.dbg);
+          if (tid < nf) {
+            const int cl = tid;
+            int j = 0;
+            while (j + 1 < sc.ntf && cl >= split_begin(nf, sc.ntf, j + 1)) ++j;
+            const float a = red_sum(sm.red, j, cl - split_begin(nf, sc.ntf, j));
+            const float f = rnd(a + sm.bias_s[l * bstride + nq + no + cl], rr);
+            const __nv_bfloat16 fv = __float2bfloat16_rn(gelu_new(f, rr));
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p.ft + f0 + cl),
+                         "r"((unsigned)__bfloat16_as_ushort(fv) | (f_tag << 16)) : "memory");
+          }
+          advance(n);
+        }
+        G2(21);
+
+        // ---------------- P5: proj + residual ----------------
+        if (l + 1 == L) prefetch_ln(1, p.fn_w, p.fn_b);   // final_norm for the head
+        {
+          constexpr int CPR = FF / 8, NCH = (CPR + NCT - 1) / NCT;
+          uint4 lo[NCH], hi[NCH];
+          const unsigned want = f_tag << 16;
+          unsigned spins = 0;
+          bool ok;
+          do {
+            ok = true;
+#pragma unroll
+            for (int q = 0; q < NCH; ++q) {
+              const int c = tid + q * NCT;
+              if (c < CPR) {
+                const unsigned* src = p.ft + (size_t)c * 8;
+                asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(lo[q].x), "=r"(lo[q].y), "=r"(lo[q].z), "=r"(lo[q].w) : "l"(src) : "memory");
+                asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(hi[q].x), "=r"(hi[q].y), "=r"(hi[q].z), "=r"(hi[q].w) : "l"(src + 4) : "memory");
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < NCH; ++q) {
+              if (tid + q * NCT < CPR)
+                ok &= ((lo[q].x & 0xffff0000u) == want) & ((lo[q].y & 0xffff0000u) == want) &
+                      ((lo[q].z & 0xffff0000u) == want) & ((lo[q].w & 0xffff0000u) == want) &
+                      ((hi[q].x & 0xffff0000u) == want) & ((hi[q].y & 0xffff0000u) == want) &
+                      ((hi[q].z & 0xffff0000u) == want) & ((hi[q].w & 0xffff0000u) == want);
+            }
+            if (++spins > (1u << 26)) __trap();
+          } while (!ok && !nowait);
+          G2(22);
+#pragma unroll
+          for (int q = 0; q < NCH; ++q) {
+            const int c = tid + q * NCT;
+            if (c < CPR)
+              ((uint4*)sm.xs)[c] = make_uint4((lo[q].x & 0xffffu) | (lo[q].y << 16), (lo[q].z & 0xffffu) | (lo[q].w << 16),
+                                              (hi[q].x & 0xffffu) | (hi[q].y << 16), (hi[q].z & 0xffffu) | (hi[q].w << 16));
+          }
+          cp_async_wait_all();     // the LayerNorm parameters prefetched in P4
+        }
+        ptx::named_bar_sync(1, NCT);
+        {
+          const int n = set_items(no, 1, NSEG);
+          mma_items<D>(sm, n, row0, nrw, sg, cons_tile, R, warp, lane, f2 ? f2 + 23 : nullptr, p.dbg);
+          if (tid < no) {
+            float a = 0.f;
+#pragma unroll
+            for (int s = 0; s < NSEG; ++s) a += red_sum(sm.red, s, tid);
+            const float o = rnd(a + sm.bias_s[l * bstride + nq + no + nf + tid], rr);
+            const float xn = sm.xres[tid] + o;
+            sm.xres[tid] = xn;
+            st_tagged(p.xt + o0 + tid, xn, ep_proj);
+          }
+          advance(n);
+        }
+        G2(26);
+      }
+
+      // ---------------- head: ln_f -> final_norm -> mel_head ----------------
+      const unsigned ep_head = p.epoch0 + (unsigned)(step * L + L - 1) * 2u + 2u;
+      {
+        float v[NPL / 8];
+        ld_tagged_slice<NPL / 8>(p.xt, warp * (NPL * 4) + lane, ep_head, v, nowait);
+        ln_block<NPL>(v, lnA, lnA + D, sm.red_ln, warp, lane);
+        ln_block<NPL>(v, lnB, lnB + D, sm.red_ln + 3 * NCW, warp, lane);
+#pragma unroll
+        for (int j = 0; j < NPL / 8; ++j) sm.xs[warp * (NPL * 4) + lane + 32 * j] = __float2bfloat16_rn(v[j]);
+      }
+      ptx::named_bar_sync(1, NCT);
+      prefetch_ln(0, p.ln1_w, p.ln1_b);      // layer 0 of the next step (buffer A is free: both LNs above are done)
+      int token = 0;
+      {
+        const int n = set_items(nh, sc.nth, 1);
+        mma_items<D>(sm, n, row0, nrw, sg, cons_tile, R, warp, lane);
+        float* cs = sm.cs;
+        if (tid < nh) {
+          const int cl = tid;
+          int j = 0;
+          while (j + 1 < sc.nth && cl >= split_begin(nh, sc.nth, j + 1)) ++j;
+          const float lg = rnd(red_sum(sm.red, j, cl - split_begin(nh, sc.nth, j)) + sm.bias_s[L * bstride + cl], rr);
+          const int i = h0 + cl;
+          if (p.logits_dump) p.logits_dump[((size_t)b * p.max_new + k) * V + i] = lg;
+          if (p.do_sample) {
+            p.logits[(size_t)b * V + i] = lg;
+          } else {
+            float s = lg;
+            if ((sm.seen_s[i >> 5] >> (i & 31)) & 1u) s = (s < 0.f) ? s * p.rep_penalty : s / p.rep_penalty;
+            if (i == p.stop_tok && k < p.forbid_stop_before) s = -INFINITY;
+            cs[cl] = s;
+          }
+        }
+        advance(n);
+        ptx::named_bar_sync(1, NCT);
+        if (!p.do_sample) {
+          // greedy: this CTA's best (score, index), lowest index first among ties -> tagged candidate words;
+          // every CTA then reduces all G candidates itself: no hand-over of the token, no barrier
+          if (warp == 0) {
+            float best = -INFINITY;
+            int bi = 0x7fffffff;
+            for (int c = lane; c < nh; c += 32) {
+              const float s = cs[c];
+              if (s > best) { best = s; bi = h0 + c; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const float b2 = __shfl_xor_sync(0xffffffffu, best, o);
+              const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+              if (b2 > best || (b2 == best && i2 < bi)) { best = b2; bi = i2; }
+            }
+            if (lane == 0) {
+              st_tagged(p.cand + 2 * cta, best, ep_head);
+              st_tagged(p.cand + 2 * cta + 1, __int_as_float(bi), ep_head);
+            }
+          }
+          float best = -INFINITY;
+          int bi = 0x7fffffff;
+          if (tid < G) {
+            uint2 wv, wi;
+            unsigned spins = 0;
+            do {
+              wv = ld_tagged_word(p.cand + 2 * tid);
+              wi = ld_tagged_word(p.cand + 2 * tid + 1);
+              if (++spins > (1u << 26)) __trap();
+            } while ((wv.y != ep_head || wi.y != ep_head) && !nowait);
+            best = __uint_as_float(wv.x);
+            bi = (int)wi.x;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float b2 = __shfl_xor_sync(0xffffffffu, best, o);
+            const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (b2 > best || (b2 == best && i2 < bi)) { best = b2; bi = i2; }
+          }
+          float* rb = sm.red_ln;
+          if (lane == 0) { rb[warp * 2] = best; ((int*)rb)[warp * 2 + 1] = bi; }
+          ptx::named_bar_sync(1, NCT);
+#pragma unroll
+          for (int w = 0; w < NCW; ++w) {
+            const float b2 = rb[w * 2];
+            const int i2 = ((int*)rb)[w * 2 + 1];
+            if (w == 0 || b2 > best || (b2 == best && i2 < bi)) { best = b2; bi = i2; }
+          }
+          token = nowait ? min(max(bi, 0), V - 1) : bi;
+        } else {
+          // sampling: logits -> global, flag with release; CTA 0 samples and publishes the token as a tagged word
+          if (tid == 0) st_release_gpu((unsigned*)(p.cand + 2 * cta) + 1, ep_head);   // cumulative over the CTA (bar.sync above)
+          if (cta == 0) {
+            if (tid < G) {
+              unsigned spins = 0;
+              while (ld_relaxed_gpu((const unsigned*)(p.cand + 2 * tid) + 1) != ep_head)
+                if (++spins > (1u << 26)) __trap();
+            }
+            __threadfence();
+            ptx::named_bar_sync(1, NCT);
+            SampleArgs sa;
+            sa.V = V; sa.stop_tok = p.stop_tok; sa.forbid_stop_before = p.forbid_stop_before; sa.top_k = p.top_k;
+            sa.seq_base = p.seq_base; sa.rep_penalty = p.rep_penalty; sa.temperature = p.temperature; sa.top_p = p.top_p;
+            sa.seed = p.seed;
+            const int tk = sample_block(sa, sm.red_att, sm.seen_s, p.logits + (size_t)b * V, k, b, tid, lane, warp);
+            if (tid == 0) st_tagged(p.tokt, __int_as_float(tk), ep_head);
+            token = tk;
+          }
+          {
+            uint2 w;
+            unsigned spins = 0;
+            do {
+              w = ld_tagged_word(p.tokt);
+              if (++spins > (1u << 26)) __trap();
+            } while (w.y != ep_head);
+            token = (int)w.x;
+          }
+        }
+      }
+      // ---------------- bookkeeping: every CTA knows the token ----------------
+      int nfeed = token;
+      if (p.forced) nfeed = __ldg(p.forced + (size_t)b * p.max_new + k);
+      const bool fin = (!p.forced && token == p.stop_tok) || (k + 1 >= p.max_new);
+      if (tid == 0) {
+        sm.seen_s[nfeed >> 5] |= 1u << (nfeed & 31);
+        if (cta == 0) {
+          p.codes[(size_t)b * p.max_new + k] = token;
+          p.nout[b] = k + 1;
+          p.tok[b] = nfeed;
+          p.seen[nfeed >> 5] |= 1u << (nfeed & 31);
+          if (fin) { p.finished[b] = 1; *p.done = 1; }
+        }
+      }
+      feed = nfeed;
+      ptx::named_bar_sync(1, NCT);      // seen_s / red are reused by the next step
+      if (fin) break;
+    }
+    // tell the producer to stop prefetching
+    if (tid == 0) { *((volatile int*)&sm.flags[0]) = 1; sm.flags[3] = (int)cons_tile; }
+  }
+  __syncthreads();
+  // drain: bulk copies issued beyond what was consumed must land before the CTA exits
+  if (tid == 0) {
+    const unsigned issued = (unsigned)sm.flags[2], consumed = (unsigned)sm.flags[3];
+    for (unsigned n = consumed; n < issued; ++n) ptx::mbar_wait(&sm.full[n % NBAR], (n / NBAR) & 1u);
+  }
+  __syncthreads();
+}

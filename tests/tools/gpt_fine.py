@@ -1,7 +1,9 @@
-"""GPU-box diagnostic: sub-phase timeline of the fused decode kernel for ALL CTAs (middle layer, last step).
+"""GPU-box diagnostic: sub-phase timeline of the batch-1 decode kernel (gpt_decode1_kernel) for ALL CTAs
+(middle layer, last step): %globaltimer for the cross-CTA picture, clock64 deltas for the per-CTA costs.
     python -m tests.tools.gpt_fine [steps]
-Prints, per stamp slot, min / median / max over the CTAs relative to the earliest phase-start stamp, and the per-CTA
-durations between consecutive slots."""
+Environment switches of the library that make sense here: IDX_GPT_DBG (1 skip the MMA loops, 2 skip the attention key
+loop, 4 do not wait in polls), IDX_GPT_RING (ring rows), IDX_GPT_V2=0 (round-1 kernel, old stamp numbering)."""
+import os
 import sys
 
 import numpy as np
@@ -10,15 +12,11 @@ import torch
 from indextts_b200.engine import Engine
 from tests.gpt_common import gpt_config, load_gpt, make_gpt_weights, prepare_gpt_inputs, r16
 
-NAMES = {
-    0: "layer start", 1: "QKV x polled", 2: "QKV LN done", 3: "QKV xs ready", 4: "QKV w0 ready", 5: "QKV mma done",
-    6: "QKV red bar", 7: "QKV epi done", 8: "QKV end", 9: "QKV ret", 10: "ATT q polled", 11: "ATT keys done",
-    12: "ATT syncwarp", 13: "ATT smem merged", 14: "ATT end", 16: "OPJ flags ok", 17: "OPJ xs ready", 18: "OPJ w0 ready",
-    19: "OPJ mma done", 20: "OPJ red bar", 21: "OPJ epi done", 22: "OPJ end", 23: "OPJ ret", 24: "FC x polled",
-    25: "FC LN done", 26: "FC xs ready", 27: "FC w0 ready", 28: "FC mma done(b0)", 29: "FC red bar(b0)", 30: "FC epi done",
-    31: "FC end", 32: "FC ret", 33: "PRJ f polled", 34: "PRJ xs ready", 35: "PRJ w0 ready", 36: "PRJ mma done(b0)",
-    37: "PRJ red bar(b0)", 38: "PRJ epi done", 39: "PRJ end", 40: "PRJ ret",
-}
+NAMES = {0: "layer start", 1: "QKV x polled", 2: "QKV LN done", 3: "QKV weights ready", 4: "QKV mma loop done", 5: "QKV partials synced",
+         6: "QKV epilogue done", 7: "ATT q polled", 8: "ATT keys done", 9: "ATT smem published", 10: "ATT end", 11: "OPJ o polled",
+         12: "OPJ weights ready", 13: "OPJ mma loop done", 14: "OPJ partials synced", 15: "OPJ epilogue done", 16: "FC x polled",
+         17: "FC LN done", 18: "FC weights ready", 19: "FC mma loop done", 20: "FC partials synced", 21: "FC epilogue done",
+         22: "PRJ f polled", 23: "PRJ weights ready", 24: "PRJ mma loop done", 25: "PRJ partials synced", 26: "PRJ epilogue done"}
 
 
 def main():
@@ -33,28 +31,34 @@ def main():
     text = torch.randint(2, 12000, (32,), generator=g)
     prompts = [prepare_gpt_inputs(w, style, emo, text, lang=1, bf16=True).numpy()]
     e.gpt_generate(prompts, 8, 10.0, forbid_stop_before=8)
-    e.gpt_profile(True)
-    for rep in range(2):
+    tag = " ".join(f"{k}={os.environ[k]}" for k in ("IDX_GPT_DBG", "IDX_GPT_RING", "IDX_GPT_V2") if k in os.environ) or "default"
+    for rep in range(3):
         e.gpt_generate(prompts, steps, 10.0, forbid_stop_before=steps)
         t = e.gpt_last_timing()
-        print(f"decode {t['decode_ms'] / t['steps'] * 1000:.1f} us/step")
+        print(f"[{tag}] decode {t['decode_ms'] / max(1, t['steps']) * 1000:.1f} us/step ({t['steps']} steps)")
+    if os.environ.get("IDX_GPT_V2") == "0" or "-q" in sys.argv:
+        e.close()
+        return
+    e.gpt_profile(True)
+    e.gpt_generate(prompts, steps, 10.0, forbid_stop_before=steps)
     f = e.gpt_profile_fine().astype(np.float64)
-    t0 = f[:, 0][f[:, 0] > 0].min()
-    used = [i for i in range(64) if (f[:, i] > 0).any()]
-    print(f"{'slot':>4} {'name':18s} {'n':>4} {'min':>8} {'med':>8} {'max':>8}   (us after the earliest layer start)")
-    for i in used:
-        v = f[:, i][f[:, i] > 0]
-        r = (v - t0) / 1000.0
-        print(f"{i:4d} {NAMES.get(i, ''):18s} {len(v):4d} {r.min():8.2f} {np.median(r):8.2f} {r.max():8.2f}")
-    print("per-CTA deltas between consecutive used slots (us): median / p90 / max")
+    t0 = f[:, 0].min()
+    print(f"{'slot':>4} {'name':22s} {'min':>7} {'med':>7} {'max':>7} us after the earliest layer start | per-CTA clock64 delta to the previous "
+          f"slot: med / p90 / max cycles")
     prev = None
-    for i in used:
+    for i in range(27):
+        r = (f[:, i] - t0) / 1000.0
+        line = f"{i:4d} {NAMES[i]:22s} {r.min():7.2f} {np.median(r):7.2f} {r.max():7.2f}"
         if prev is not None:
-            m = (f[:, i] > 0) & (f[:, prev] > 0)
-            if m.any():
-                d = (f[m, i] - f[m, prev]) / 1000.0
-                print(f"  {prev:2d}->{i:2d} {NAMES.get(i, ''):18s} {np.median(d):7.2f} {np.percentile(d, 90):7.2f} {d.max():7.2f}")
+            d = f[:, 32 + i] - f[:, 32 + prev]
+            if i in (7, 8, 9):               # attention stamps exist only on the CTAs that own a head
+                m = (f[:, i] >= t0) & (f[:, i] < t0 + 1e6)
+                d = d[m] if m.any() else d
+                line = f"{i:4d} {NAMES[i]:22s} {r[m].min():7.2f} {np.median(r[m]):7.2f} {r[m].max():7.2f}" if m.any() else line
+            line += f" | {np.median(d):8.0f} {np.percentile(d, 90):8.0f} {d.max():8.0f}"
+        print(line)
         prev = i
+    os.makedirs("gpurun_out", exist_ok=True)
     np.save("gpurun_out/gpt_fine.npy", f)
     e.close()
 
