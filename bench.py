@@ -107,7 +107,7 @@ def make_inputs(seed, cfg_gpt, w_gpt):
     return dict(style=style, emo=emo, text=text, prompt_condition=prompt_condition, ref_mel=ref_mel, z=z, F=F)
 
 
-def build_engine(device):
+def build_engine(device, max_batch=1):
     from indextts_b200.engine import Engine, fold_weight_norm
     from indextts_b200 import synth
     t0 = time.time()
@@ -116,7 +116,7 @@ def build_engine(device):
     wg = synth.make_gpt_weights(cfg, seed=2025, bf16=True)
     e.load_state_dict("gpt.", wg)
     e.gpt_init(cfg["layers"], cfg["model_dim"], cfg["heads"], cfg["number_mel_codes"], cfg["start_mel_token"],
-               cfg["stop_mel_token"], cfg["max_mel_positions"], max_prompt=64, max_batch=1, weights_bf16=True)
+               cfg["stop_mel_token"], cfg["max_mel_positions"], max_prompt=80 if max_batch > 1 else 64, max_batch=max_batch, weights_bf16=True)
     c, cc = dict(synth.S2MEL_CFG), dict(synth.CODEC_CFG)
     ws = fold_weight_norm(synth.make_s2mel_weights(c, seed=1234))
     e.load_state_dict("s2mel.", {k: v for k, v in ws.items() if v.is_floating_point()})
@@ -258,6 +258,140 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------- batch jobs: BASELINE configs 3 and 5 --
+JOBS = {
+    "config3": ("IndexTTS-2.5 batch=32 on one GPU per rank-share: 32 utterances of one speaker, 512 speech tokens each, full "
+                "gpt->codec->length-regulator->CFM 25 steps (T=861+1761)->BigVGAN pipeline"),
+    "config5": ("IndexTTS-2.5 batch=256 mixed-length utterances (speech tokens U[128,768], seed 0; 4 speakers, 10 s references) "
+                "sharded over the ranks by longest-processing-time-first; NCCL broadcast of the speaker latents, gather of the wavs"),
+}
+
+
+def make_job(name):
+    """The fixed utterance list of a batch workload: (n_tokens, speaker, text_len) per utterance, seeded."""
+    g = torch.Generator().manual_seed(0)
+    if name == "config3":
+        n, toks, spk = 32, [512] * 32, [0] * 32
+    else:
+        n = 256
+        toks = [int(x) for x in torch.randint(128, 769, (n,), generator=g)]
+        spk = [i % 4 for i in range(n)]
+    tl = [int(x) for x in torch.randint(24, 61, (n,), generator=g)]
+    return [dict(idx=i, n=toks[i], spk=spk[i], L=tl[i]) for i in range(n)]
+
+
+def run_job(args, rank, world, local):
+    """`--workload config3|config5`: the whole fixed job once (after a warm-up mini-job), strong scaling over the ranks.
+    GPT decodes up to 8 utterances per group (sorted by length so a group's rows finish together; a row that reached its
+    own length keeps decoding until the group's longest is done — those extra tokens are not counted); the tail runs
+    per utterance.  Reports useful speech-tokens/s and RTF of the whole job, per-stage device time and the per-rank
+    busy time (LPT imbalance)."""
+    import __graft_entry__ as ge
+    from indextts_b200.sharding import broadcast_latents, gather_wavs, lpt_assign
+    if rank == 0:
+        ge.build()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    if rank != 0:
+        ge.build()
+    dev = torch.device("cuda", local)
+    e, cfg, wg, t_load = build_engine(local, max_batch=8)
+    job = make_job(args.workload)
+    nspk = 1 + max(u["spk"] for u in job)
+    # speaker latents: made on rank 0, broadcast once per speaker
+    lats = []
+    for sp in range(nspk):
+        inp = make_inputs(100 + sp, cfg, wg)
+        lat = {k: inp[k].to(dev).contiguous() for k in ("prompt_condition", "ref_mel", "style", "emo")}
+        if dist is not None:
+            broadcast_latents(dist, lat, src=0)
+        lats.append(lat)
+    share = lpt_assign([u["n"] for u in job], world)[rank]
+    mine = sorted((job[i] for i in share), key=lambda u: -u["n"])
+    gtxt = torch.Generator().manual_seed(1234)
+    texts = {u["idx"]: torch.randint(2, 12000, (u["L"],), generator=torch.Generator().manual_seed(5000 + u["idx"])) for u in job}
+    gz = torch.Generator(device=dev).manual_seed(77 + rank)
+
+    def process(utts):
+        t_g = t_c = t_v = 0.0
+        wavs, ntok = [], 0
+        for g0 in range(0, len(utts), 8):
+            grp = utts[g0:g0 + 8]
+            prompts = [e.gpt_prepare_inputs(lats[u["spk"]]["style"], lats[u["spk"]]["emo"], texts[u["idx"]], 1) for u in grp]
+            nmax = max(u["n"] for u in grp)
+            outs = e.gpt_generate(prompts, nmax, 10.0, forbid_stop_before=nmax)
+            t = e.gpt_last_timing()
+            t_g += t["prefill_ms"] + t["decode_ms"]
+            for u, codes in zip(grp, outs):
+                n = u["n"]
+                F = int(2 * n * 1.72)
+                lat = lats[u["spk"]]
+                z = torch.randn(80, P_FRAMES + F, device=dev, generator=gz)          # cfm.inference draws it per utterance (P6)
+                res = e.codes_to_wav(np.minimum(codes[:n], 8191), lat["prompt_condition"], lat["ref_mel"], lat["style"], z, F,
+                                     CFM_STEPS, CFG_RATE, want_wav=False, want_pcm16=True)
+                t_c += e.s2mel_last_ms()["cfm_ms"]
+                t_v += e.bigvgan_last_ms()
+                wavs.append(res["pcm16"])
+                ntok += n
+        return wavs, ntok, (t_g, t_c, t_v)
+
+    def barrier():
+        e.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    process([dict(u, n=64) for u in mine[:3]])                  # warm-up mini-job (allocations, NCCL channels)
+    if dist is not None:
+        gather_wavs(dist, torch.zeros(16, dtype=torch.int16, device=dev), rank, world, dst=0)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = e.launches
+    t0 = time.perf_counter()
+    wavs, ntok, (t_g, t_c, t_v) = process(mine)
+    e.sync()
+    torch.cuda.synchronize()
+    t_busy = time.perf_counter() - t0
+    if dist is not None:
+        gather_wavs(dist, torch.cat([w.reshape(-1) for w in wavs]) if wavs else torch.zeros(0, dtype=torch.int16, device=dev), rank, world, dst=0)
+    barrier()
+    t_job = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = e.launches - l0
+    stats = torch.tensor([t_job, t_busy, t_g, t_c, t_v, float(ntok), float(launches)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        allst = [torch.zeros_like(stats) for _ in range(world)]
+        dist.all_gather(allst, stats)
+    else:
+        allst = [stats]
+    if rank == 0:
+        A = torch.stack(allst).cpu().numpy()
+        t = float(A[:, 0].max())
+        tokens = int(A[:, 5].sum())
+        audio_s = tokens * AUDIO_S_PER_TOKEN
+        line = {"metric": "speech_tokens_per_s", "value": tokens / t, "unit": "tokens/s", "n_gpus": world, "steps": 1, "warmup": 1,
+                "ms_per_step": t * 1000, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": DTYPE,
+                "data": "synthetic", "rtf": t / audio_s,
+                "config": {"workload": JOBS[args.workload], "utterances": len(job), "speech_tokens": tokens, "audio_s": audio_s,
+                           "parallelism": f"dp{world} (LPT utterance sharding)", "gpt_rows_per_group": 8,
+                           "l2": "working set >> L2"},
+                "per_rank": {"busy_s": [float(x) for x in A[:, 1]], "gpt_s": [float(x) / 1000 for x in A[:, 2]],
+                             "cfm_s": [float(x) / 1000 for x in A[:, 3]], "bigvgan_s": [float(x) / 1000 for x in A[:, 4]],
+                             "tokens": [int(x) for x in A[:, 5]]},
+                "lpt_imbalance": float(A[:, 1].max() / max(A[:, 1].mean(), 1e-9)),
+                "e2e": {"value": tokens / t, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                        "note": "device-resident latents; codes cross the host once per group; pcm16 gathered on rank 0 over NCCL"},
+                "gpu_launches": int(A[:, 6].sum()), "clocks": clocks}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 # ---------------------------------------------------------------------------- main --
 def main():
     ap = argparse.ArgumentParser()
@@ -266,12 +400,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config5"],
+                    help="config2 (default): the batch-1 headline; config3 / config5: the fixed batch jobs, run once")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload != "config2":
+        run_job(args, rank, world, local)
         return
     W = max(3, args.warmup)
     K = max(1, args.steps)

@@ -75,9 +75,11 @@ int idx_wait_stream(idx_engine* e, void* cuda_stream);
 int idx_event_record(idx_engine* e, int slot);
 int idx_event_elapsed_ms(idx_engine* e, int slot_a, int slot_b, double* ms);
 
-/* Engine options.  "gemm_backend": 0 = automatic (tcgen05 tf32 implicit GEMM wherever the shape
- * allows — the default), 1 = SIMT fp32 everywhere (strict-fp32 parity runs).  Options belong to the
- * handle: another engine (another GPU, another thread) keeps its own.                             */
+/* Engine options.  "gemm_backend": 0 = automatic (tcgen05 implicit GEMM wherever the shape
+ * allows — the default), 1 = SIMT fp32 everywhere (strict-fp32 parity runs).  "tail_f16" (with gemm_backend 0): 1 = the
+ * DiT / WaveNet / BigVGAN-resblock GEMMs read fp16 operands (kind::f16; activations written as fp16 by the kernel that
+ * produces them, fp32 accumulate and fp32 residual streams — the default), 0 = tf32 over fp32 storage (round 1).
+ * Options belong to the handle: another engine (another GPU, another thread) keeps its own.        */
 int idx_set_option(idx_engine* e, const char* name, int value);
 
 /* -------------------------------------------------------------------- weights -- */

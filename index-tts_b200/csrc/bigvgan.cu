@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256) snake_act_kernel(const float* __restrict_
                                                         float* __restrict__ y,
                                                         const float* __restrict__ ea,
                                                         const float* __restrict__ ib, int T, int C,
-                                                        int CB, Taps taps) {
+                                                        int CB, Taps taps, __half* __restrict__ y16) {
   const int b = blockIdx.z;
   const int lanes_t = 256 / CB;
   const int c = blockIdx.x * CB + threadIdx.x % CB;
@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(256) snake_act_kernel(const float* __restrict_
   const int t0 = (blockIdx.y * lanes_t + tl) * TT;
   if (t0 >= T) return;
   const float* xb = x + (long long)b * T * C + c;
-  float* yb = y + (long long)b * T * C + c;
+  float* yb = y ? y + (long long)b * T * C + c : nullptr;
+  __half* yh = y16 ? y16 + (long long)b * T * C + c : nullptr;
   const float eac = __ldg(ea + c), ibc = __ldg(ib + c);
   const float* f = taps.f;
   auto X = [&](int t) { return __ldg(xb + (long long)min(max(t, 0), T - 1) * C); };
@@ -84,7 +85,8 @@ __global__ void __launch_bounds__(256) snake_act_kernel(const float* __restrict_
     float acc = 0.f;
 #pragma unroll
     for (int k = 0; k < 12; ++k) acc = fmaf(aw[k], f[k], acc);
-    yb[(long long)t * C] = acc;
+    if (yb) yb[(long long)t * C] = acc;
+    if (yh) yh[(long long)t * C] = __float2half_rn(acc);     // operand of the following conv (fp16 tensor-core path)
     // slide: next window is a[clamp(2t-3+k)]
 #pragma unroll
     for (int k = 0; k < 10; ++k) aw[k] = aw[k + 2];
@@ -171,6 +173,7 @@ __global__ void pack_convT_kernel(const float* w, float* wsimt, float* wk, int C
 
 struct ConvW {
   float *wsimt = nullptr, *wk = nullptr;
+  __half* wk16 = nullptr;      // fp16 copy of wk (resblock convs: their input is written as fp16 by the Snake kernel)
   const float* bias = nullptr;
   int Co = 0, Ci = 0, k = 0, dil = 1;
 };
@@ -220,6 +223,10 @@ static ConvW pack_conv(idx_engine* e, BigvganState* s, const std::string& name, 
   c.wk = balloc(s, n);
   pack_conv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>((const float*)w.d, c.wsimt, c.wk, c.Co, c.Ci, c.k);
   IDX_CUDA(cudaGetLastError());
+  if (c.Ci % 8 == 0) {
+    c.wk16 = (__half*)balloc(s, n / 2 + 4);
+    to_half(e, c.wk, c.wk16, (long long)n);
+  }
   c.bias = e->has(name + ".bias") ? e->Wf(name + ".bias") : nullptr;
   return c;
 }
@@ -341,21 +348,23 @@ extern "C" int idx_bigvgan_init(idx_engine* e, const idx_bigvgan_config* cfg) {
   IDX_API_END(e)
 }
 
-static void run_act(idx_engine* e, const BigvganState* s, const ActP& a, const float* x, float* y, int B, int T) {
+static void run_act(idx_engine* e, const BigvganState* s, const ActP& a, const float* x, float* y, int B, int T, __half* y16 = nullptr) {
   const int C = a.C;
   const int CB = C >= 32 ? 32 : C;
   const int lanes_t = 256 / CB;
   constexpr int TT = 32;
   dim3 grid((C + CB - 1) / CB, (T + lanes_t * TT - 1) / (lanes_t * TT), B);
-  snake_act_kernel<TT><<<grid, 256, 0, e->stream>>>(x, y, a.ea, a.ib, T, C, CB, s->taps);
+  snake_act_kernel<TT><<<grid, 256, 0, e->stream>>>(x, y, a.ea, a.ib, T, C, CB, s->taps, y16);
   IDX_CUDA(cudaGetLastError());
   e->launches++;
 }
 
-static void run_conv(idx_engine* e, const ConvW& c, const float* x, float* out, int B, int T, const float* res, int accum, float scale) {
+static void run_conv(idx_engine* e, const ConvW& c, const float* x, float* out, int B, int T, const float* res, int accum, float scale,
+                     const __half* x16 = nullptr) {
   ConvGemm g;
   g.A = x; g.B = B; g.Tin = T; g.K = c.Ci;
   g.W = c.wsimt; g.Wk = c.wk;
+  if (x16) { g.A16 = x16; g.Wk16 = c.wk16; }
   g.taps = c.k; g.dil = c.dil; g.pad = (c.k * c.dil - c.dil) / 2;  // get_padding, bigvgan/utils.py:57-58
   g.M = T; g.N = c.Co; g.bias = c.bias;
   g.res = res; g.accum = accum; g.scale = scale; g.out = out;
@@ -410,6 +419,9 @@ static void bigvgan_forward_impl(idx_engine* e, BigvganState* s, const float* d_
   // P: stage input, and — once the transposed conv has consumed it — the accumulator of the
   // resblock outputs (= next stage's input).  Q: the upsampled stage signal read by all blocks.
   float *P = buf[0], *Q = buf[1], *xb0 = buf[2], *xb1 = buf[3], *ta = buf[4], *tc = buf[5];
+  // fp16 operand mode: the Snake outputs inside the resblocks exist only as fp16 (they are read by a conv and nothing else)
+  const bool hf = tail_half(e);
+  __half* ta16 = (__half*)ta;
   {
     ConvW pre = s->conv_pre;
     if (pre_bias) pre.bias = pre_bias;
@@ -432,18 +444,20 @@ static void bigvgan_forward_impl(idx_engine* e, BigvganState* s, const float* d_
       for (int m = 0; m < 3; ++m) {
         const ActP& a1 = s->acts[rb * 6 + 2 * m];
         const ActP& a2 = s->acts[rb * 6 + 2 * m + 1];
-        run_act(e, s, a1, xcur, ta, B, T);
-        run_conv(e, s->convs1[rb * 3 + m], ta, tc, B, T, nullptr, 0, 1.f);
-        run_act(e, s, a2, tc, ta, B, T);
+        const ConvW &c1 = s->convs1[rb * 3 + m], &c2 = s->convs2[rb * 3 + m];
+        const bool h1 = hf && c1.wk16, h2 = hf && c2.wk16;
+        run_act(e, s, a1, xcur, h1 ? nullptr : ta, B, T, h1 ? ta16 : nullptr);
+        run_conv(e, c1, ta, tc, B, T, nullptr, 0, 1.f, h1 ? ta16 : nullptr);
+        run_act(e, s, a2, tc, h2 ? nullptr : ta, B, T, h2 ? ta16 : nullptr);
         if (m < 2) {
           float* xo = (m == 0) ? xb0 : xb1;
-          run_conv(e, s->convs2[rb * 3 + m], ta, xo, B, T, xcur, 0, 1.f);  // x = xt + x
+          run_conv(e, c2, ta, xo, B, T, xcur, 0, 1.f, h2 ? ta16 : nullptr);  // x = xt + x
           xcur = xo;
         } else {
           // last conv of the block: xs (+)= xt + x ; the /num_kernels average is folded into the
           // last block's epilogue (bigvgan.py:368-376)
           const bool last = (j == cfg.num_kernels - 1);
-          run_conv(e, s->convs2[rb * 3 + m], ta, xsum, B, T, xcur, j > 0, last ? 1.0f / cfg.num_kernels : 1.f);
+          run_conv(e, c2, ta, xsum, B, T, xcur, j > 0, last ? 1.0f / cfg.num_kernels : 1.f, h2 ? ta16 : nullptr);
         }
       }
     }

@@ -13,7 +13,12 @@
 //   warps 2..5  epilogue: tcgen05.ld the accumulator (each warp its 32-lane quarter), apply
 //               bias / activation / layer-scale / residual / accumulate / scale, store with the
 //               generic (out_off, ldo, out_valid) mapping that also serves ConvTranspose1d.
-// Operands are fp32 in HBM; the tensor maps use TFLOAT32 so the TMA unit rounds to tf32 on load.
+// Two operand formats share the kernel (template EB = operand element bytes):
+//   EB = 4: fp32 in HBM, tensor maps TFLOAT32 (the TMA unit rounds to tf32 on load), tcgen05.mma kind::tf32, K = 8 per MMA;
+//   EB = 2: fp16 in HBM (activations written as fp16 by their producing kernel, weights converted once at init),
+//           kind::f16, K = 16 per MMA: the same 10-bit mantissa as tf32 at half the bytes per operand — the tf32 tiles of
+//           this kernel are bound by L2 -> shared-memory operand traffic, so halving the bytes is what counts.
+// A 128-byte swizzle row holds 32 fp32 or 64 fp16 along K; a stage is always A 16 KB + B BN x 128 B.
 #include "ops.h"
 #include "ptx.cuh"
 #include <cuda.h>
@@ -26,7 +31,7 @@
 namespace {
 
 constexpr int BM = 128;
-constexpr int BK = 32;   // fp32 elements = 128 bytes = one SWIZZLE_128B row
+constexpr int BKB = 128; // bytes along K per stage row = one SWIZZLE_128B row (32 tf32 or 64 fp16 elements)
 
 __device__ __forceinline__ float apply_act_tc(float v, int act) {
   switch (act) {
@@ -47,7 +52,7 @@ __device__ __forceinline__ float apply_act_tc(float v, int act) {
 
 struct TcParams {
   int M, N, K, taps, dil, pad, a_bcast, w_batched;
-  int n_kchunks;        // ceil(K / BK)
+  int n_kchunks;        // ceil(K / (BKB / EB))
   const float* bias; int biasN; int act;
   const float* res; const float* rowscale; const float* colscale;
   int accum; float scale;
@@ -67,15 +72,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   return d;
 }
 
-template <int BN>
+template <int BN, int EB>
 __global__ void __launch_bounds__(192, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve: stages x (A 16 KB | B BN*128 B), then barriers
   unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  constexpr int A_BYTES = BM * BK * 4;
-  constexpr int B_BYTES = BN * BK * 4;
+  constexpr int BK = BKB / EB;       // elements along K per stage
+  constexpr int A_BYTES = BM * BKB;
+  constexpr int B_BYTES = BN * BKB;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   uint64_t* full = (uint64_t*)(base + (size_t)p.stages * STAGE_BYTES);
   uint64_t* empty = full + p.stages;
@@ -120,8 +126,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // instruction descriptor: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3, M>>4
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+      // instruction descriptor: D=f32 (1<<4), A=B format (tf32 = 2, f16 = 0) at bits 7 and 10, K-major both, N>>3, M>>4
+      constexpr uint32_t FMT = (EB == 4) ? 2u : 0u;
+      const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(BM >> 4) << 24);
       for (int it = 0; it < n_iters; ++it) {
         const int s = it % p.stages;
@@ -132,10 +139,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t sb = sa + A_BYTES;
         const uint64_t da = make_desc(sa), db = make_desc(sb);
 #pragma unroll
-        for (int k = 0; k < BK / 8; ++k) {
-          // advance 8 tf32 = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
-          ptx::umma_tf32(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                         (it > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < BKB / 32; ++k) {
+          // one MMA consumes 32 bytes of K (8 tf32 / 16 fp16) inside the 128-byte swizzle row: +2 in 16-byte units
+          if (EB == 4) ptx::umma_tf32(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
+          else ptx::umma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
         }
         ptx::umma_commit(&empty[s]);
       }
@@ -236,10 +243,10 @@ std::map<MapKey, CUtensorMap>& map_cache() {
 }
 
 CUtensorMap make_map(const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                     const cuuint32_t* box) {
+                     const cuuint32_t* box, bool half = false) {
   static const bool plain_f32 = getenv("IDX_TMA_F32") != nullptr;
   MapKey key(ptr, (long long)dims[0], (long long)dims[1], rank > 2 ? (long long)dims[2] : 0,
-             (long long)strides_bytes[0] ^ ((rank > 2 ? (long long)strides_bytes[1] : 0) << 20), (int)box[1], rank);
+             (long long)strides_bytes[0] ^ ((rank > 2 ? (long long)strides_bytes[1] : 0) << 20), (int)box[1] | ((int)box[0] << 12), rank | (half ? 16 : 0));
   // process-wide cache (keys carry the unique UVA address): engines may be driven from different threads
   static std::mutex mu;
   std::lock_guard<std::mutex> lock(mu);
@@ -248,7 +255,7 @@ CUtensorMap make_map(const void* ptr, int rank, const cuuint64_t* dims, const cu
   if (it != cache.end()) return it->second;
   CUtensorMap m;
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = get_encode()(&m, plain_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32,
+  CUresult r = get_encode()(&m, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : (plain_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32),
                             (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -259,8 +266,9 @@ CUtensorMap make_map(const void* ptr, int rank, const cuuint64_t* dims, const cu
   return m;
 }
 
-template <int BN>
+template <int BN, int EB>
 void launch_bn(idx_engine* e, const ConvGemm& g, const CUtensorMap& tmA, const CUtensorMap& tmB) {
+  constexpr int BK = BKB / EB;
   TcParams p;
   p.M = g.M; p.N = g.N; p.K = g.K; p.taps = g.taps; p.dil = g.dil; p.pad = g.pad; p.a_bcast = g.a_bcast;
   p.w_batched = g.w_batch_stride != 0;
@@ -272,7 +280,7 @@ void launch_bn(idx_engine* e, const ConvGemm& g, const CUtensorMap& tmA, const C
   p.out_batch_stride = g.out_batch_stride ? g.out_batch_stride : (long long)g.M * g.N;
   p.out_off = g.out_off;
   p.out_valid = g.out_valid ? g.out_valid : (long long)g.M * p.ldo;
-  constexpr int STAGE = BM * BK * 4 + BN * BK * 4;
+  constexpr int STAGE = BM * BKB + BN * BKB;
   const int n_iters = p.taps * p.n_kchunks;
   static const int occ = getenv("IDX_GEMM_OCC") ? atoi(getenv("IDX_GEMM_OCC")) : 2;
   int stages = ((occ == 1 ? 208 : 104) * 1024) / STAGE;   // two CTAs per SM: one's epilogue overlaps the other's mainloop
@@ -280,13 +288,13 @@ void launch_bn(idx_engine* e, const ConvGemm& g, const CUtensorMap& tmA, const C
   if (stages > n_iters) stages = n_iters < 2 ? 2 : n_iters;
   p.stages = stages;
   const size_t smem = (size_t)stages * STAGE + 1024 + (2 * stages + 1) * 8 + 16;
-  const unsigned bit = BN == 32 ? 1u : (BN == 64 ? 2u : 4u);
+  const unsigned bit = (BN == 32 ? 1u : (BN == 64 ? 2u : 4u)) << (EB == 2 ? 8 : 0);
   if (!(e->attr_done & bit)) {     // per engine = per device: function attributes live in the device's context
-    IDX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    IDX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     e->attr_done |= bit;
   }
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.B);
-  gemm_tc_kernel<BN><<<grid, 192, smem, e->stream>>>(tmA, tmB, p);
+  gemm_tc_kernel<BN, EB><<<grid, 192, smem, e->stream>>>(tmA, tmB, p);
   IDX_CUDA(cudaGetLastError());
   e->launches++;
 }
@@ -295,31 +303,35 @@ void launch_bn(idx_engine* e, const ConvGemm& g, const CUtensorMap& tmA, const C
 
 bool gemm_tc_supported(const ConvGemm& g) {
   static const bool off = getenv("IDX_NO_TC") != nullptr;
-  if (off || g.reflect || !g.Wk) return false;
-  if (g.K % 4 != 0) return false;                             // 16-byte global strides
+  const bool half = g.A16 && g.Wk16;
+  if (off || g.reflect || (!g.Wk && !half)) return false;
+  const int al = half ? 8 : 4;                                // 16-byte global strides: 8 fp16 / 4 fp32 elements
+  if (g.K % al != 0) return false;
   const int lda = g.lda ? g.lda : g.K;
-  if (lda % 4 != 0) return false;
-  if (((uintptr_t)g.A & 15) || ((uintptr_t)g.Wk & 15)) return false;
+  if (lda % al != 0) return false;
+  if (half ? (((uintptr_t)g.A16 & 15) || ((uintptr_t)g.Wk16 & 15)) : (((uintptr_t)g.A & 15) || ((uintptr_t)g.Wk & 15))) return false;
   const long long abs_ = g.a_batch_stride ? g.a_batch_stride : (long long)g.Tin * lda;
-  if (abs_ % 4 != 0) return false;
-  if ((g.ldw && g.ldw % 4) || (g.w_batch_stride % 4)) return false;
-  if ((long long)g.M * g.N * g.K * g.taps < (1 << 18)) return false;   // tiny problems: SIMT
+  if (abs_ % al != 0) return false;
+  if ((g.ldw && g.ldw % al) || (g.w_batch_stride % al)) return false;
+  if (!half && (long long)g.M * g.N * g.K * g.taps < (1 << 18)) return false;   // tiny problems: SIMT (fp16 operands have no SIMT twin)
   return true;
 }
 
 void gemm_tc_launch(idx_engine* e, const ConvGemm& g) {
+  const bool half = g.A16 && g.Wk16;
+  const int EBh = half ? 2 : 4;
   const int lda = g.lda ? g.lda : g.K;
   const long long abs_ = g.a_bcast ? (long long)g.Tin * lda : (g.a_batch_stride ? g.a_batch_stride : (long long)g.Tin * lda);
-  // A: [B][Tin][K] fp32, dims (K, Tin, B)
+  // A: [B][Tin][K], dims (K, Tin, B)
   cuuint64_t adims[3] = {(cuuint64_t)g.K, (cuuint64_t)g.Tin, (cuuint64_t)(g.a_bcast ? 1 : g.B)};
-  cuuint64_t astr[2] = {(cuuint64_t)lda * 4, (cuuint64_t)abs_ * 4};
-  cuuint32_t abox[3] = {BK, BM, 1};
-  CUtensorMap tmA = make_map(g.A, 3, adims, astr, abox);
-  // B: Wk [nb][N][taps*K] fp32, dims (taps*K, N, nb)   (nb = 1 for shared weights)
+  cuuint64_t astr[2] = {(cuuint64_t)lda * EBh, (cuuint64_t)abs_ * EBh};
+  cuuint32_t abox[3] = {(cuuint32_t)(BKB / EBh), BM, 1};
+  CUtensorMap tmA = make_map(half ? (const void*)g.A16 : (const void*)g.A, 3, adims, astr, abox, half);
+  // B: Wk [nb][N][taps*K], dims (taps*K, N, nb)   (nb = 1 for shared weights)
   const int ldw = g.ldw ? g.ldw : g.taps * g.K;
   const long long wbs = g.w_batch_stride ? g.w_batch_stride : (long long)g.N * ldw;
   cuuint64_t bdims[3] = {(cuuint64_t)g.taps * g.K, (cuuint64_t)g.N, (cuuint64_t)(g.w_batch_stride ? g.B : 1)};
-  cuuint64_t bstr[2] = {(cuuint64_t)ldw * 4, (cuuint64_t)wbs * 4};
+  cuuint64_t bstr[2] = {(cuuint64_t)ldw * EBh, (cuuint64_t)wbs * EBh};
   int BN = g.N <= 32 ? 32 : (g.N <= 64 ? 64 : 128);
   {
     // fewer 128-wide tiles than SMs: halve the tile so every SM gets work (2 CTAs/SM are resident anyway)
@@ -327,9 +339,15 @@ void gemm_tc_launch(idx_engine* e, const ConvGemm& g) {
     const long long tiles128 = (long long)((g.N + 127) / 128) * ((g.M + BM - 1) / BM) * g.B;
     if (bn64 && BN == 128 && tiles128 < 148) BN = 64;
   }
-  cuuint32_t bbox[3] = {BK, (cuuint32_t)BN, 1};
-  CUtensorMap tmB = make_map(g.Wk, 3, bdims, bstr, bbox);
-  if (BN == 32) launch_bn<32>(e, g, tmA, tmB);
-  else if (BN == 64) launch_bn<64>(e, g, tmA, tmB);
-  else launch_bn<128>(e, g, tmA, tmB);
+  cuuint32_t bbox[3] = {(cuuint32_t)(BKB / EBh), (cuuint32_t)BN, 1};
+  CUtensorMap tmB = make_map(half ? (const void*)g.Wk16 : (const void*)g.Wk, 3, bdims, bstr, bbox, half);
+  if (half) {
+    if (BN == 32) launch_bn<32, 2>(e, g, tmA, tmB);
+    else if (BN == 64) launch_bn<64, 2>(e, g, tmA, tmB);
+    else launch_bn<128, 2>(e, g, tmA, tmB);
+  } else {
+    if (BN == 32) launch_bn<32, 4>(e, g, tmA, tmB);
+    else if (BN == 64) launch_bn<64, 4>(e, g, tmA, tmB);
+    else launch_bn<128, 4>(e, g, tmA, tmB);
+  }
 }

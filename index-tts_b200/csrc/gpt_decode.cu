@@ -2068,7 +2068,7 @@ static void launch_fused_bt(idx_engine* e, GptState* g, GptParams& p, int BT) {
 }
 // second-generation batch-1 decode launch (same epoch bookkeeping as the tagged mode of gpt_fused_kernel<1, .>)
 static size_t smem_bytes_v2(int D, int FF, int R, int bias_cap, int ocap, int V) {
-  return (size_t)R * D * 2 + (size_t)FF * 2 + sizeof(float) * (size_t)RED1_FLOATS + 16 * (size_t)NBAR + 16 +
+  return (size_t)R * D * 2 + (size_t)FF * 2 + sizeof(float) * (size_t)RED1_FLOATS + 8 * (size_t)NBAR + 5 * sizeof(Phase1) + 32 +
          4 * (size_t)bias_cap + 4 * (size_t)ocap + 4 * (size_t)((V + 31) / 32) + 16 + sizeof(float) * 4 * (size_t)D + 64;
 }
 static void reset_tagged(idx_engine* e, GptState* g, const GptParams& p) {
@@ -2096,7 +2096,7 @@ static void launch_decode1(idx_engine* e, GptState* g, GptParams& p) {
   g->epoch += need;
   void* args[] = {(void*)&p};
   const void* fn = (p.D / 32 == 40) ? (const void*)gpt_decode1_kernel<40> : (const void*)gpt_decode1_kernel<8>;
-  IDX_CUDA(cudaLaunchCooperativeKernel(fn, dim3(g->G), dim3(NTHREADS), args, g->smem_v2, e->stream));
+  IDX_CUDA(cudaLaunchCooperativeKernel(fn, dim3(g->G), dim3(NCT), args, g->smem_v2, e->stream));   // 8 warps: no producer warp
   e->launches++;
   g->last_launches++;
 }

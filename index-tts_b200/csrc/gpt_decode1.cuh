@@ -24,13 +24,16 @@
 //          every CTA knows the next token and builds the next input row locally; sampling (do_sample) keeps a
 //          CTA-0 sampler fed by release/acquire flags.
 //
-// Shared-memory ring protocol.  The CTA's weights of one decode step are a fixed sequence of tiles
-// (per layer: QKV column tiles, O-proj, FC column tiles, PROJ K-segments; then the head tiles).  Tile t lands in
-// ring rows [row(t) mod R ...) and completes full[t mod NBAR]; the consumer releases it on empty[t mod NBAR].  The
-// producer may issue tile t when fewer than NBAR tiles are outstanding and its rows fit behind the last released tile.
+// Shared-memory ring protocol.  The CTA's weights of one decode step are a fixed sequence of PHASES
+// (per layer: QKV, O-proj, FC, PROJ; then the head), each a run of consecutive stream rows (its MMA tiles back to back).
+// Phase g lands in ring rows [row(g) mod R ...) with ONE bulk copy (two when it wraps) and completes full[g mod NBAR];
+// There is no producer warp and no "empty" barrier: a phase is free again once all 8 warps have passed the CTA barrier that
+// ends its MMAs, and right there ONE thread (the last one, never an epilogue thread) issues every following phase that
+// now fits (fewer than NBAR outstanding, rows fit behind the consumed ones).  8 warps = 256 threads also lifts the
+// register cap from 168 (288 threads are allocated like 384) to 255 per thread.
 
 constexpr int TROWS = 16;       // weight rows per MMA tile
-constexpr int NBAR = 16;        // tile barrier slots
+constexpr int NBAR = 8;         // phase barrier slots
 constexpr int MAXIT = 4;        // (column tile, K segment) items per phase
 constexpr int RED1_MMA = MAXIT * NCW * 16;                 // per-warp partial sums of the phase's tiles
 constexpr int RED1_FLOATS = RED1_MMA + 48 + 64 + NCW * PART_STRIDE;   // + LayerNorm statistics + head scores + attention merge
@@ -41,19 +44,18 @@ __device__ __forceinline__ int split_begin(int n, int nt, int j) { return (n * j
 // per-CTA tile schedule of one decode step, in stream order
 struct Sched1 {
   int L, nseg, nq, no, nf, nh, ntq, ntf, nth;
-  __device__ __forceinline__ int tiles_per_layer() const { return ntq + 1 + ntf + nseg; }
-  __device__ __forceinline__ int tiles_per_step() const { return L * tiles_per_layer() + nth; }
-  __device__ int rows(int i) const {
-    const int tpl = tiles_per_layer();
-    if (i >= L * tpl) return split_rows(nh, nth, i - L * tpl);
-    int j = i % tpl;
-    if (j < ntq) return split_rows(nq, ntq, j);
-    j -= ntq;
-    if (j < 1) return no;
-    j -= 1;
-    if (j < ntf) return split_rows(nf, ntf, j);
-    return no;
+  __device__ __forceinline__ int phases_per_step() const { return 4 * L + 1; }
+  // stream rows of phase i (0 <= i < phases_per_step): QKV | O | FC | PROJ (nseg K-segments) per layer, then the head
+  __device__ __forceinline__ int rows(int i) const {
+    if (i >= 4 * L) return nh;
+    const int j = i & 3;
+    return j == 0 ? nq : (j == 1 ? no : (j == 2 ? nf : no * nseg));
   }
+};
+
+// MMA tiles of one phase, precomputed once per CTA: item i = rows [off[i], off[i] + nrows[i]) of the phase, K-segment seg[i]
+struct Phase1 {
+  int nitems, total, nrows[MAXIT], off[MAXIT], seg[MAXIT];
 };
 
 struct Smem1 {
@@ -64,71 +66,94 @@ struct Smem1 {
   float* cs;            // [64] processed scores of this CTA's head columns
   float* red_att;       // [NCW][66] attention merge / sampler scratch
   uint64_t* full;       // [NBAR]
-  uint64_t* empty;      // [NBAR]
-  int* flags;           // [4]
+  Phase1* pht;          // [5] MMA tiles of the QKV / O / FC / PROJ / head phases
   float* bias_s;
   float* xres;          // [ocap] this CTA's slice of the fp32 residual stream
   unsigned* seen_s;     // [(V+31)/32]
   float* lnp;           // [2][2][D]
 };
 
-// All MMAs of one phase: `nitems` tiles in flight, k-steps outermost.  Item i: `nrows[i]` weight rows starting at
-// stream row `row0[i]` (ring slot = row mod R), multiplied with the activation segment xs[seg[i] * D ...).
-// Leaves the per-warp partial sums in red[(i * NCW + warp) * 16 + row] and synchronises the compute warps.
-template <int D>
-__device__ __forceinline__ void mma_items(const Smem1& sm, int nitems, const int (&row0)[MAXIT], const int (&nrows)[MAXIT],
-                                          const int (&seg)[MAXIT], unsigned tile0, int R, int warp, int lane,
-                                          long long* st = nullptr, int dbg = 0) {
+// All MMAs of one phase: its tiles in flight together, k-steps outermost, A fragments of k-step ks + 1 loaded (ldmatrix)
+// before the MMAs of k-step ks are issued — with the asm statements volatile the compiler keeps this order, so every
+// HMMA waits only for an LDSM issued a whole k-step earlier.  (Round-2 measurement: with LDSM -> HMMA back to back into
+// one register set the loop cost 55-100 cycles per pair, 100 us of a 505 us step.)
+// Phase rows start at ring row `row0` (< R); leaves the per-warp partial sums in red[(i * NCW + warp) * 16 + row] and
+// synchronises the compute warps.
+// NIT (the number of tiles) is a template parameter: with a run-time bound the compiler kept the fragment arrays in local
+// memory (an STL after every LDSM, an LDL before every HMMA: 5400 cycles for a two-tile phase instead of ~500).
+template <int D, int NIT>
+__device__ __forceinline__ void mma_items_n(const Smem1& sm, const Phase1& ph, int row0, unsigned phase_idx, int R, int warp, int lane,
+                                            long long* st, int dbg) {
   constexpr int KS = (D / 16) / NCW;
   const uint32_t ring_base = ptx::smem_u32(sm.ring);
   const int g = lane >> 2, t4 = lane & 3;
   const int lrow = (lane & 7) + ((lane >> 3) & 1) * 8, khalf = lane >> 4;
-  uint32_t a_base[MAXIT];
-  int key[MAXIT];
-  float acc[MAXIT][4];
+  uint32_t a_base[NIT];
+  int key[NIT], sgo[NIT];
+  float acc[NIT][4];
 #pragma unroll
-  for (int i = 0; i < MAXIT; ++i) {
+  for (int i = 0; i < NIT; ++i) {
     acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-    a_base[i] = ring_base;
-    key[i] = 0;
-    if (i < nitems) {
-      const int rr = min(lrow, nrows[i] - 1);            // rows beyond the tile read a valid row; their results are unused
-      a_base[i] = ring_base + (uint32_t)(((row0[i] + rr) % R) * (D * 2));
-      key[i] = rr & 7;
-      const unsigned n = tile0 + (unsigned)i;
-      ptx::mbar_wait(&sm.full[n % NBAR], (n / NBAR) & 1u);
-    }
+    const int rr = min(lrow, max(ph.nrows[i] - 1, 0));     // rows beyond the tile read a valid row; their results are unused
+    int slot = row0 + ph.off[i] + rr;
+    if (slot >= R) slot -= R;
+    a_base[i] = ring_base + (uint32_t)(slot * (D * 2));
+    key[i] = rr & 7;
+    sgo[i] = ph.seg[i] * (D / 2);
   }
+  ptx::mbar_wait(&sm.full[phase_idx % NBAR], (phase_idx / NBAR) & 1u);
   if (st && threadIdx.x == 0) { st[0] = gtimer(); st[32] = clock64(); }
   const uint32_t* xw = (const uint32_t*)sm.xs;
-  if (!(dbg & 1))
+  if (!(dbg & 1)) {
+    uint32_t a[2][NIT][4];
 #pragma unroll
-  for (int ks = 0; ks < KS; ++ks) {
-    const int kk = warp * KS + ks;                        // k-step: k0 = 16 * kk
+    for (int i = 0; i < NIT; ++i)
+      ldmatrix_x4(a_base[i] + (uint32_t)(((2 * (warp * KS) + khalf) ^ key[i]) << 4), a[0][i][0], a[0][i][1], a[0][i][2], a[0][i][3]);
 #pragma unroll
-    for (int i = 0; i < MAXIT; ++i) {
-      if (i < nitems) {
-        uint32_t a0, a1, a2, a3;
-        ldmatrix_x4(a_base[i] + (uint32_t)(((2 * kk + khalf) ^ key[i]) << 4), a0, a1, a2, a3);
-        const uint32_t* xb = xw + seg[i] * (D / 2) + kk * 8 + t4;
-        mma_bf16_16816(acc[i], a0, a1, a2, a3, xb[0], xb[4]);   // B: the one activation row in every n column
+    for (int ks = 0; ks < KS; ++ks) {
+      const int kk = warp * KS + ks;                        // k-step: k0 = 16 * kk
+      if (ks + 1 < KS) {
+#pragma unroll
+        for (int i = 0; i < NIT; ++i)
+          ldmatrix_x4(a_base[i] + (uint32_t)(((2 * (kk + 1) + khalf) ^ key[i]) << 4), a[(ks + 1) & 1][i][0], a[(ks + 1) & 1][i][1],
+                        a[(ks + 1) & 1][i][2], a[(ks + 1) & 1][i][3]);
       }
+      uint32_t b0[NIT], b1[NIT];
+#pragma unroll
+      for (int i = 0; i < NIT; ++i)
+      {
+        const uint32_t* xb = xw + sgo[i] + kk * 8 + t4;      // B: the one activation row in every n column
+        b0[i] = xb[0];
+        b1[i] = xb[4];
+      }
+#pragma unroll
+      for (int i = 0; i < NIT; ++i)
+        mma_bf16_16816(acc[i], a[ks & 1][i][0], a[ks & 1][i][1], a[ks & 1][i][2], a[ks & 1][i][3], b0[i], b1[i]);
     }
   }
   __syncwarp();
   if (st && threadIdx.x == 0) { st[1] = gtimer(); st[33] = clock64(); }
-  if (lane == 0)
-    for (int i = 0; i < nitems; ++i) ptx::mbar_arrive(&sm.empty[(tile0 + (unsigned)i) % NBAR]);
   if (t4 == 0) {
 #pragma unroll
-    for (int i = 0; i < MAXIT; ++i)
-      if (i < nitems) {
-        sm.red[(i * NCW + warp) * 16 + g] = acc[i][0];
-        sm.red[(i * NCW + warp) * 16 + g + 8] = acc[i][2];
-      }
+    for (int i = 0; i < NIT; ++i)
+    {
+      sm.red[(i * NCW + warp) * 16 + g] = acc[i][0];
+      sm.red[(i * NCW + warp) * 16 + g + 8] = acc[i][2];
+    }
   }
   ptx::named_bar_sync(1, NCT);
   if (st && threadIdx.x == 0) { st[2] = gtimer(); st[34] = clock64(); }
+}
+
+template <int D>
+__device__ __forceinline__ void mma_items(const Smem1& sm, const Phase1& ph, int row0, unsigned phase_idx, int R, int warp, int lane,
+                                          long long* st = nullptr, int dbg = 0) {
+  switch (ph.nitems) {       // CTA-uniform
+    case 1: mma_items_n<D, 1>(sm, ph, row0, phase_idx, R, warp, lane, st, dbg); break;
+    case 2: mma_items_n<D, 2>(sm, ph, row0, phase_idx, R, warp, lane, st, dbg); break;
+    case 3: mma_items_n<D, 3>(sm, ph, row0, phase_idx, R, warp, lane, st, dbg); break;
+    default: mma_items_n<D, 4>(sm, ph, row0, phase_idx, R, warp, lane, st, dbg); break;
+  }
 }
 
 __device__ __forceinline__ float red_sum(const float* red, int item, int row) {
@@ -136,6 +161,23 @@ __device__ __forceinline__ float red_sum(const float* red, int item, int row) {
 #pragma unroll
   for (int w = 0; w < NCW; ++w) a += red[(item * NCW + w) * 16 + row];
   return a;
+}
+
+// Hand-over polls.  Round-2 measurement: the LAST producer's words became visible to the pollers 2-3 us after they were
+// stored when all 256 threads of all 148 CTAs re-read their whole slice in every round — 148 x 4 sector reads per 128-byte
+// line per round queue at the L2 slice that holds the line, in front of the very stores the pollers wait for.  So a warp
+// first spins on ONE word (all lanes the same address = one request per warp per round, the word chosen per (CTA, warp)
+// so the spinners spread over the lines) and only then checks its whole slice.
+template <int N>
+__device__ __forceinline__ void poll_slice(const uint2* base, int first, unsigned epoch, float (&v)[N], int spin_idx, bool nowait) {
+  if (!nowait) {
+    unsigned spins = 0, tag;
+    do {
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(tag) : "l"((const unsigned*)(base + spin_idx) + 1) : "memory");
+      if (++spins > (1u << 26)) __trap();
+    } while (tag != epoch);
+  }
+  ld_tagged_slice<N>(base, first, epoch, v, nowait);
 }
 
 __device__ __forceinline__ uint2 ld_tagged_word(const uint2* p) {
@@ -240,7 +282,7 @@ __device__ __noinline__ int sample_block(const SampleArgs p, float* red, const u
 }
 
 template <int NPL>
-__global__ void __launch_bounds__(NTHREADS, 1) gpt_decode1_kernel(const GptParams p) {
+__global__ void __launch_bounds__(NCT, 1) gpt_decode1_kernel(const GptParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int D = NPL * 32, FF = 4 * D, NSEG = FF / D;
   static_assert(NSEG <= MAXIT, "PROJ K-segments must fit the item slots");
@@ -258,8 +300,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_decode1_kernel(const GptParam
     sm.cs = sm.red_ln + 48;
     sm.red_att = sm.cs + 64;
     sm.full = (uint64_t*)q;       q += sizeof(uint64_t) * NBAR;
-    sm.empty = (uint64_t*)q;      q += sizeof(uint64_t) * NBAR;
-    sm.flags = (int*)q;           q += 16;
+    sm.pht = (Phase1*)q;          q += 5 * sizeof(Phase1);
+    q = (unsigned char*)(((uintptr_t)q + 15) & ~(uintptr_t)15);
     sm.bias_s = (float*)q;        q += sizeof(float) * (size_t)p.bias_cap;
     sm.xres = (float*)q;          q += sizeof(float) * (size_t)p.ocap;
     sm.seen_s = (unsigned*)q;     q += sizeof(unsigned) * (size_t)((V + 31) / 32);
@@ -267,13 +309,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_decode1_kernel(const GptParam
     sm.lnp = (float*)q;
   }
   if (tid == 0) {
-    for (int s = 0; s < NBAR; ++s) {
-      ptx::mbar_init(&sm.full[s], 1);
-      ptx::mbar_init(&sm.empty[s], NCW);
-    }
-    sm.flags[0] = 0;
-    sm.flags[2] = 0;
-    sm.flags[3] = 0;
+    for (int s = 0; s < NBAR; ++s) ptx::mbar_init(&sm.full[s], 1);
     ptx::fence_mbar_init();
   }
   __syncthreads();
@@ -288,7 +324,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_decode1_kernel(const GptParam
   sc.L = L; sc.nseg = NSEG; sc.nq = nq; sc.no = no; sc.nf = nf; sc.nh = nh;
   sc.ntq = (nq + TROWS - 1) / TROWS; sc.ntf = (nf + TROWS - 1) / TROWS; sc.nth = (nh + TROWS - 1) / TROWS;
   const int bstride = nq + 2 * no + nf;
-  if (warp < NCW) {
+  {
     for (int i = tid; i < L * bstride; i += NCT) {
       const int l = i / bstride, j = i % bstride;
       float v;
@@ -303,51 +339,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_decode1_kernel(const GptParam
   }
   __syncthreads();
 
-  // =============================================================== producer warp ====
-  if (warp == NCW) {
-    if (lane == 0) {
-      const uint64_t pol = ptx::policy_evict_first();
-      const __nv_bfloat16* base = p.wstream1 + (size_t)p.stream_off1[cta] * D;
-      const int tps = sc.tiles_per_step();
-      unsigned tix = 0, rel = 0;             // tiles issued / known released
-      long long row_issue = 0, row_rel = 0;  // stream rows issued / released (monotonic over the launch)
-      int rel_i = 0;                         // index of tile `rel` inside its step
-      bool stop = false;
-      for (int step = 0; step < p.nsteps && !stop; ++step) {
-        size_t uoff = 0;
-        for (int i = 0; i < tps && !stop; ++i) {
-          const int n = sc.rows(i);
-          while (tix - rel >= (unsigned)NBAR || row_issue + n - row_rel > (long long)R) {
-            unsigned spins = 0;
-            while (!ptx::mbar_try_wait(&sm.empty[rel % NBAR], (rel / NBAR) & 1u)) {
-              if (*((volatile int*)&sm.flags[0])) { stop = true; break; }
-              if (++spins > (1u << 26)) __trap();
-            }
-            if (stop) break;
-            row_rel += sc.rows(rel_i);
-            ++rel;
-            if (++rel_i == tps) rel_i = 0;
-          }
-          if (stop) break;
-          uint64_t* bar = &sm.full[tix % NBAR];
-          const uint32_t bytes = (uint32_t)n * D * 2;
-          ptx::mbar_arrive_expect_tx(bar, bytes);
-          const int s0 = (int)(row_issue % R);
-          const int n1 = min(n, R - s0);
-          ptx::bulk_g2s(sm.ring + (size_t)s0 * D, base + uoff * D, (uint32_t)n1 * D * 2, bar, pol);
-          if (n1 < n) ptx::bulk_g2s(sm.ring, base + (uoff + n1) * D, (uint32_t)(n - n1) * D * 2, bar, pol);
-          ++tix;
-          row_issue += n;
-          uoff += n;
-        }
+  {
+    // ---- the weight stream: issued by the last thread at the points where ring rows become free ----
+    const bool is_prod = (tid == NCT - 1);
+    const uint64_t pol = ptx::policy_evict_first();
+    const __nv_bfloat16* wbase = p.wstream1 + (size_t)p.stream_off1[cta] * D;
+    const int pps = sc.phases_per_step();
+    unsigned tix = 0;                 // phases issued
+    int fill = 0, wpos = 0;           // ring rows in flight or resident; ring row the next phase lands at
+    int pstep = 0, pidx = 0;          // producer cursor: step, phase inside the step
+    size_t uoff = 0;                  // stream row of that phase inside the step's stream
+    unsigned cons_tile = 0;           // phases consumed
+    int cons_row = 0;                 // ring row of the next phase to consume
+    auto issue_fitting = [&]() {
+      if (!is_prod) return;
+      while (pstep < p.nsteps && tix - cons_tile < (unsigned)NBAR) {
+        const int n = sc.rows(pidx);
+        if (fill + n > R) break;
+        uint64_t* bar = &sm.full[tix % NBAR];
+        ptx::mbar_arrive_expect_tx(bar, (uint32_t)n * D * 2);
+        const int n1 = min(n, R - wpos);
+        ptx::bulk_g2s(sm.ring + (size_t)wpos * D, wbase + uoff * D, (uint32_t)n1 * D * 2, bar, pol);
+        if (n1 < n) ptx::bulk_g2s(sm.ring, wbase + (uoff + n1) * D, (uint32_t)(n - n1) * D * 2, bar, pol);
+        wpos += n;
+        if (wpos >= R) wpos -= R;
+        fill += n;
+        uoff += n;
+        ++tix;
+        if (++pidx == pps) { pidx = 0; uoff = 0; ++pstep; }
       }
-      sm.flags[2] = (int)tix;
-    }
-    __syncwarp();
-  } else {
-    // ============================================================ compute warps ====
-    unsigned cons_tile = 0;
-    int cons_row = 0;                 // stream row (mod R kept small: reduced at every use)
+    };
     const int b = 0;                  // the one sequence
     const int plen = __ldg(p.prompt_len + b);
     auto prefetch_ln = [&](int buf, const float* w, const float* bb) {
@@ -361,31 +382,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_decode1_kernel(const GptParam
     const float* lnA = sm.lnp;
     const float* lnB = sm.lnp + 2 * D;
     const int rr = p.round_bf16;
+    const int spin_x = warp * (NPL * 4) + (cta * 37 + warp * 13) % (NPL * 4);      // the word this warp spins on (inside its own slice)
+    const int spin_f = (cta * 41 + warp * 97) % FF;                                // same for the gelu(fc) words
     const bool nowait = (p.dbg & 4) != 0;      // diagnostics only: polls do not wait (results are garbage, timing = no dependencies)
     int feed = __ldcg(p.tok + b);
     const bool already_done = __ldcg(p.finished + b) != 0;
-    int row0[MAXIT], nrw[MAXIT], sg[MAXIT];
-    // one phase worth of tiles: column tiles (nt of them over ncols) x nseg K-segments, in stream order
-    // (either nt column tiles of one K-segment, or one column tile with nseg K-segments; fully unrolled so the item
-    // descriptors stay in registers)
-    auto set_items = [&](int ncols, int nt, int nseg) {
-      const int n = nt * nseg;
-      int r = cons_row;
-#pragma unroll
-      for (int i = 0; i < MAXIT; ++i) {
-        const int rows = (i < n) ? ((nseg > 1) ? ncols : split_rows(ncols, nt, i)) : 0;
-        row0[i] = r; nrw[i] = rows; sg[i] = (nseg > 1) ? i : 0;
-        r += rows;
-      }
-      return n;
-    };
-    auto advance = [&](int nitems) {
+    // phase descriptors: either nt column tiles of one K-segment, or one column tile with nseg K-segments (computed once;
+    // no division or modulo on the per-phase path)
+    auto make_phase = [&](int ncols, int nt, int nseg) {
+      Phase1 ph;
+      ph.nitems = nt * nseg;
       int r = 0;
 #pragma unroll
-      for (int i = 0; i < MAXIT; ++i) r += nrw[i];
-      cons_row = (cons_row + r) % R;
-      cons_tile += (unsigned)nitems;
+      for (int i = 0; i < MAXIT; ++i) {
+        const int rows = (i < ph.nitems) ? ((nseg > 1) ? ncols : split_rows(ncols, nt, i)) : 0;
+        ph.off[i] = r; ph.nrows[i] = rows; ph.seg[i] = (nseg > 1) ? i : 0;
+        r += rows;
+      }
+      ph.total = r;
+      return ph;
     };
+    if (tid == 0) {
+      sm.pht[0] = make_phase(nq, sc.ntq, 1);
+      sm.pht[1] = make_phase(no, 1, 1);
+      sm.pht[2] = make_phase(nf, sc.ntf, 1);
+      sm.pht[3] = make_phase(no, 1, NSEG);
+      sm.pht[4] = make_phase(nh, sc.nth, 1);
+    }
+    __syncthreads();
+    const Phase1 &ph_q = sm.pht[0], &ph_o = sm.pht[1], &ph_f = sm.pht[2], &ph_p = sm.pht[3], &ph_h = sm.pht[4];
+    // called right after mma_items (which ends with a CTA barrier: every warp is done with the phase's rows)
+    auto advance = [&](const Phase1& ph) {
+      const int tot = ph.total;
+      cons_row += tot;
+      if (cons_row >= R) cons_row -= R;
+      ++cons_tile;
+      fill -= tot;
+      issue_fitting();
+    };
+    issue_fitting();                  // initial fill
 
     for (int step = 0; step < p.nsteps && !already_done; ++step) {
       const int k = p.step0 + step;
@@ -418,7 +453,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_decode1_kernel(const GptParam
         {
           float v[NPL / 8];
           if (l > 0) {
-            ld_tagged_slice<NPL / 8>(p.xt, warp * (NPL * 4) + lane, ep_base, v, nowait);
+            poll_slice<NPL / 8>(p.xt, warp * (NPL * 4) + lane, ep_base, v, spin_x, nowait);
           } else {
 #pragma unroll
             for (int j = 0; j < NPL / 8; ++j) v[j] = v0[j];
@@ -433,8 +468,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_decode1_kernel(const GptParam
         }
         ptx::named_bar_sync(1, NCT);
         {
-          const int n = set_items(nq, sc.ntq, 1);
-          mma_items<D>(sm, n, row0, nrw, sg, cons_tile, R, warp, lane, f2 ? f2 + 3 : nullptr, p.dbg);
+          mma_items<D>(sm, ph_q, cons_row, cons_tile, R, warp, lane, f2 ? f2 + 3 : nullptr, p.dbg);
+          advance(ph_q);
           if (tid < nq) {
             const int cl = tid;
             int j = 0;
@@ -452,7 +487,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_decode1_kernel(const GptParam
               st_tagged(p.kvt + (c - D), __bfloat162float(kvb), ep_oproj);
             }
           }
-          advance(n);
         }
         G2(6);
 
@@ -465,12 +499,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_decode1_kernel(const GptParam
           const int g4 = lane >> 3, sub = lane & 7;
           const size_t cbase = ((size_t)l * p.nseq + b) * p.maxpos;
           const size_t coff = (size_t)h * HD + sub * 8;
-          // software pipeline: the first keys are in flight before q has arrived
-          int j = k0 + warp * 4 + g4;
-          uint4 kk = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-          if (j < kend) {
-            kk = __ldcg((const uint4*)(p.kc + (cbase + j) * D + coff));
-            vv = __ldcg((const uint4*)(p.vc + (cbase + j) * D + coff));
+          // software pipeline, PF iterations deep (a key costs one L2 round trip: with one iteration in flight the loop
+          // ran at ~1200 cycles per 32 keys); the first PF iterations are in flight before q has arrived
+          constexpr int PF = 4;
+          const int jbase = k0 + warp * 4 + g4;          // key of iteration it: jbase + 32 * it
+          uint4 kb[PF], vb[PF];
+#pragma unroll
+          for (int u = 0; u < PF; ++u) {
+            kb[u] = make_uint4(0, 0, 0, 0);
+            vb[u] = make_uint4(0, 0, 0, 0);
+            const int ju = jbase + NCW * 4 * u;
+            if (ju < kend) {
+              kb[u] = __ldcg((const uint4*)(p.kc + (cbase + ju) * D + coff));
+              vb[u] = __ldcg((const uint4*)(p.vc + (cbase + ju) * D + coff));
+            }
           }
           float qv[8];
           {
@@ -493,32 +535,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_decode1_kernel(const GptParam
           float m = -INFINITY, lsum = 0.f, ov[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) ov[i] = 0.f;
-          for (int j0 = k0 + warp * 4; j0 < ((p.dbg & 2) ? k0 : kend); j0 += NCW * 4) {
-            const bool valid = j < kend;
-            const int jn = j + NCW * 4;
-            uint4 kn = make_uint4(0, 0, 0, 0), vn = make_uint4(0, 0, 0, 0);
-            if (jn < kend) {
-              kn = __ldcg((const uint4*)(p.kc + (cbase + jn) * D + coff));
-              vn = __ldcg((const uint4*)(p.vc + (cbase + jn) * D + coff));
-            }
-            float s = qv[0] * lo_bf(kk.x) + qv[1] * hi_bf(kk.x) + qv[2] * lo_bf(kk.y) + qv[3] * hi_bf(kk.y) +
-                      qv[4] * lo_bf(kk.z) + qv[5] * hi_bf(kk.z) + qv[6] * lo_bf(kk.w) + qv[7] * hi_bf(kk.w);
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            s += __shfl_xor_sync(0xffffffffu, s, 4);
-            if (valid) {
-              s *= 0.125f;
-              const float mn = fmaxf(m, s);
-              const float corr = __expf(m - mn);
-              const float pr = __expf(s - mn);
-              lsum = lsum * corr + pr;
-              const float vf[8] = {lo_bf(vv.x), hi_bf(vv.x), lo_bf(vv.y), hi_bf(vv.y),
-                                   lo_bf(vv.z), hi_bf(vv.z), lo_bf(vv.w), hi_bf(vv.w)};
+          const int span = ((p.dbg & 2) ? 0 : kend) - (k0 + warp * 4);
+          const int niter = span > 0 ? (span + NCW * 4 - 1) / (NCW * 4) : 0;        // warp-uniform
+          for (int it0 = 0; it0 < niter; it0 += PF) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) ov[i] = ov[i] * corr + pr * vf[i];
-              m = mn;
+            for (int u = 0; u < PF; ++u) {
+              const int it = it0 + u;
+              if (it < niter) {
+                const int j = jbase + NCW * 4 * it;
+                const bool valid = j < kend;
+                const uint4 kk = kb[u], vv = vb[u];
+                const int jn = j + NCW * 4 * PF;             // refill this slot: in flight for the next PF - 1 iterations
+                kb[u] = make_uint4(0, 0, 0, 0);
+                vb[u] = make_uint4(0, 0, 0, 0);
+                if (jn < kend) {
+                  kb[u] = __ldcg((const uint4*)(p.kc + (cbase + jn) * D + coff));
+                  vb[u] = __ldcg((const uint4*)(p.vc + (cbase + jn) * D + coff));
+                }
+                float s = qv[0] * lo_bf(kk.x) + qv[1] * hi_bf(kk.x) + qv[2] * lo_bf(kk.y) + qv[3] * hi_bf(kk.y) +
+                          qv[4] * lo_bf(kk.z) + qv[5] * hi_bf(kk.z) + qv[6] * lo_bf(kk.w) + qv[7] * hi_bf(kk.w);
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                if (valid) {
+                  s *= 0.125f;
+                  const float mn = fmaxf(m, s);
+                  const float corr = __expf(m - mn);
+                  const float pr = __expf(s - mn);
+                  lsum = lsum * corr + pr;
+                  const float vf[8] = {lo_bf(vv.x), hi_bf(vv.x), lo_bf(vv.y), hi_bf(vv.y),
+                                       lo_bf(vv.z), hi_bf(vv.z), lo_bf(vv.w), hi_bf(vv.w)};
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) ov[i] = ov[i] * corr + pr * vf[i];
+                  m = mn;
+                }
+              }
             }
-            kk = kn; vv = vn; j = jn;
           }
           if (k1 == ctx && warp == 0 && g4 == 0) {
             // the new position (owned by the last key split): k and v straight from the QKV epilogue's tagged words
@@ -606,7 +658,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_decode1_kernel(const GptParam
         // ---------------- P3: attention output -> O-proj + residual ----------------
         if (nsplit == 1) {
           float v[NPL / 8];
-          ld_tagged_slice<NPL / 8>(p.ot, warp * (NPL * 4) + lane, ep_oproj, v, nowait);
+          poll_slice<NPL / 8>(p.ot, warp * (NPL * 4) + lane, ep_oproj, v, spin_x, nowait);
           G2(11);
 #pragma unroll
           for (int j = 0; j < NPL / 8; ++j) sm.xs[warp * (NPL * 4) + lane + 32 * j] = __float2bfloat16_rn(v[j]);
@@ -654,8 +706,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_decode1_kernel(const GptParam
         }
         ptx::named_bar_sync(1, NCT);
         {
-          const int n = set_items(no, 1, 1);
-          mma_items<D>(sm, n, row0, nrw, sg, cons_tile, R, warp, lane, f2 ? f2 + 12 : nullptr, p.dbg);
+          mma_items<D>(sm, ph_o, cons_row, cons_tile, R, warp, lane, f2 ? f2 + 12 : nullptr, p.dbg);
+          advance(ph_o);
           if (tid < no) {
             // the residual stream is fp32 even on the bf16 path (trap P12): only the branch is rounded
             const float o = rnd(red_sum(sm.red, 0, tid) + sm.bias_s[l * bstride + nq + tid], rr);
@@ -663,7 +715,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_decode1_kernel(const GptParam
             sm.xres[tid] = xn;
             st_tagged(p.xt + o0 + tid, xn, ep_oproj);
           }
-          advance(n);
         }
         G2(15);
 
@@ -672,7 +723,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_decode1_kernel(const GptParam
         else prefetch_ln(0, p.lnf_w, p.lnf_b);
         {
           float v[NPL / 8];
-          ld_tagged_slice<NPL / 8>(p.xt, warp * (NPL * 4) + lane, ep_oproj, v, nowait);
+          poll_slice<NPL / 8>(p.xt, warp * (NPL * 4) + lane, ep_oproj, v, spin_x, nowait);
           G2(16);
           cp_async_wait_all();   // ln_2 parameters prefetched in P1 (ln_block's own CTA barrier publishes them)
           ln_block<NPL>(v, lnB, lnB + D, sm.red_ln, warp, lane);
@@ -682,8 +733,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_decode1_kernel(const GptParam
         }
         ptx::named_bar_sync(1, NCT);
         {
-          const int n = set_items(nf, sc.ntf, 1);
-          mma_items<D>(sm, n, row0, nrw, sg, cons_tile, R, warp, lane, f2 ? f2 + 18 : nullptr, p.dbg);
+          mma_items<D>(sm, ph_f, cons_row, cons_tile, R, warp, lane, f2 ? f2 + 18 : nullptr, p.dbg);
+          advance(ph_f);
           if (tid < nf) {
             const int cl = tid;
             int j = 0;
@@ -694,7 +745,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_decode1_kernel(const GptParam
             asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p.ft + f0 + cl),
                          "r"((unsigned)__bfloat16_as_ushort(fv) | (f_tag << 16)) : "memory");
           }
-          advance(n);
         }
         G2(21);
 
@@ -706,6 +756,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_decode1_kernel(const GptParam
           const unsigned want = f_tag << 16;
           unsigned spins = 0;
           bool ok;
+          if (!nowait) {
+            unsigned wv;
+            do {
+              asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(wv) : "l"(p.ft + spin_f) : "memory");
+              if (++spins > (1u << 26)) __trap();
+            } while ((wv & 0xffff0000u) != want);
+          }
           do {
             ok = true;
 #pragma unroll
@@ -741,8 +798,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_decode1_kernel(const GptParam
         }
         ptx::named_bar_sync(1, NCT);
         {
-          const int n = set_items(no, 1, NSEG);
-          mma_items<D>(sm, n, row0, nrw, sg, cons_tile, R, warp, lane, f2 ? f2 + 23 : nullptr, p.dbg);
+          mma_items<D>(sm, ph_p, cons_row, cons_tile, R, warp, lane, f2 ? f2 + 23 : nullptr, p.dbg);
+          advance(ph_p);
           if (tid < no) {
             float a = 0.f;
 #pragma unroll
@@ -752,7 +809,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_decode1_kernel(const GptParam
             sm.xres[tid] = xn;
             st_tagged(p.xt + o0 + tid, xn, ep_proj);
           }
-          advance(n);
         }
         G2(26);
       }
@@ -761,7 +817,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_decode1_kernel(const GptParam
       const unsigned ep_head = p.epoch0 + (unsigned)(step * L + L - 1) * 2u + 2u;
       {
         float v[NPL / 8];
-        ld_tagged_slice<NPL / 8>(p.xt, warp * (NPL * 4) + lane, ep_head, v, nowait);
+        poll_slice<NPL / 8>(p.xt, warp * (NPL * 4) + lane, ep_head, v, spin_x, nowait);
         ln_block<NPL>(v, lnA, lnA + D, sm.red_ln, warp, lane);
         ln_block<NPL>(v, lnB, lnB + D, sm.red_ln + 3 * NCW, warp, lane);
 #pragma unroll
@@ -771,8 +827,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_decode1_kernel(const GptParam
       prefetch_ln(0, p.ln1_w, p.ln1_b);      // layer 0 of the next step (buffer A is free: both LNs above are done)
       int token = 0;
       {
-        const int n = set_items(nh, sc.nth, 1);
-        mma_items<D>(sm, n, row0, nrw, sg, cons_tile, R, warp, lane);
+        mma_items<D>(sm, ph_h, cons_row, cons_tile, R, warp, lane);
+        advance(ph_h);
         float* cs = sm.cs;
         if (tid < nh) {
           const int cl = tid;
@@ -790,7 +846,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_decode1_kernel(const GptParam
             cs[cl] = s;
           }
         }
-        advance(n);
         ptx::named_bar_sync(1, NCT);
         if (!p.do_sample) {
           // greedy: this CTA's best (score, index), lowest index first among ties -> tagged candidate words;
@@ -890,14 +945,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_decode1_kernel(const GptParam
       ptx::named_bar_sync(1, NCT);      // seen_s / red are reused by the next step
       if (fin) break;
     }
-    // tell the producer to stop prefetching
-    if (tid == 0) { *((volatile int*)&sm.flags[0]) = 1; sm.flags[3] = (int)cons_tile; }
-  }
-  __syncthreads();
-  // drain: bulk copies issued beyond what was consumed must land before the CTA exits
-  if (tid == 0) {
-    const unsigned issued = (unsigned)sm.flags[2], consumed = (unsigned)sm.flags[3];
-    for (unsigned n = consumed; n < issued; ++n) ptx::mbar_wait(&sm.full[n % NBAR], (n / NBAR) & 1u);
+    // drain: bulk copies issued beyond what was consumed must land before the CTA exits
+    if (is_prod)
+      for (unsigned n = cons_tile; n < tix; ++n) ptx::mbar_wait(&sm.full[n % NBAR], (n / NBAR) & 1u);
   }
   __syncthreads();
 }

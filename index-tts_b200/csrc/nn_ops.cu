@@ -12,17 +12,24 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// GEMM operands of the fp16 tensor-core path are written by the kernel that produces them: every pointwise kernel
+// below takes an optional fp16 destination next to (or instead of) the fp32 one.
+__device__ __forceinline__ void put(float* __restrict__ y, __half* __restrict__ y16, long long i, float v) {
+  if (y) y[i] = v;
+  if (y16) y16[i] = __float2half_rn(v);
+}
+
 // One warp per row.  MODE 0: LayerNorm (two-pass), MODE 1: RMSNorm (gpt_fast/model.py:317-333).
 template <int MODE>
 __global__ void rownorm_kernel(const float* __restrict__ x, float* __restrict__ y, long long rows, int T,
                                int C, const float* __restrict__ w, const float* __restrict__ b, float eps,
-                               const float* __restrict__ m0, const float* __restrict__ m1, int mod_stride) {
+                               const float* __restrict__ m0, const float* __restrict__ m1, int mod_stride,
+                               __half* __restrict__ y16) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const int bidx = (int)(row / T);
   const float* xr = x + row * C;
-  float* yr = y + row * C;
   float s = 0.f;
   for (int i = lane; i < C; i += 32) s += xr[i];
   float mean = 0.f, q = 0.f;
@@ -44,7 +51,7 @@ __global__ void rownorm_kernel(const float* __restrict__ x, float* __restrict__ 
       // AdaptiveLayerNorm: weight * norm(x) + bias             (gpt_fast/model.py:20-39)
       if (m0) v = m0[(long long)bidx * mod_stride + i] * v + m1[(long long)bidx * mod_stride + i];
     }
-    yr[i] = v;
+    put(y, y16, row * C + i, v);
   }
 }
 
@@ -120,17 +127,17 @@ __global__ void embedding_kernel(const float* __restrict__ table, const int* __r
   if (c < C) out[(long long)t * C + c] = ok ? table[(long long)id * C + c] : 0.f;
 }
 
-__global__ void swiglu_kernel(const float* __restrict__ ab, float* __restrict__ y, long long rows, int N) {
+__global__ void swiglu_kernel(const float* __restrict__ ab, float* __restrict__ y, long long rows, int N, __half* __restrict__ y16) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * N) return;
   const long long r = i / N;
   const int c = (int)(i % N);
   const float a = ab[r * 2 * N + c], b = ab[r * 2 * N + N + c];
-  y[i] = a / (1.f + expf(-a)) * b;   // F.silu(w1 x) * (w3 x)  (gpt_fast/model.py:311-314)
+  put(y, y16, i, a / (1.f + expf(-a)) * b);   // F.silu(w1 x) * (w3 x)  (gpt_fast/model.py:311-314)
 }
 
 __global__ void wn_gate_kernel(const float* __restrict__ xin, const float* __restrict__ g, int g_stride,
-                               float* __restrict__ y, int T, int N) {
+                               float* __restrict__ y, int T, int N, __half* __restrict__ y16) {
   // fused_add_tanh_sigmoid_multiply (s2mel/modules/commons.py:132-141)
   const int bi = blockIdx.z;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -140,16 +147,16 @@ __global__ void wn_gate_kernel(const float* __restrict__ xin, const float* __res
   const float* xr = xin + ((long long)bi * T + t) * 2 * N;
   const float a = xr[c] + g[(long long)bi * g_stride + c];
   const float s = xr[N + c] + g[(long long)bi * g_stride + N + c];
-  y[((long long)bi * T + t) * N + c] = tanhf(a) * (1.f / (1.f + expf(-s)));
+  put(y, y16, ((long long)bi * T + t) * N + c, tanhf(a) * (1.f / (1.f + expf(-s))));
 }
 
 __global__ void copy_cols_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldo,
-                                 int col0, long long rows, int C) {
+                                 int col0, long long rows, int C, __half* __restrict__ dst16) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * C) return;
   const long long r = i / C;
   const int c = (int)(i % C);
-  dst[r * ldo + col0 + c] = src[r * lds + c];
+  put(dst, dst16, r * ldo + col0 + c, src[r * lds + c]);
 }
 __global__ void bcast_cols_kernel(const float* __restrict__ vec, float* __restrict__ dst, int ldo, int col0,
                                   int T, int C) {
@@ -165,14 +172,14 @@ __global__ void silu_kernel(float* x, long long n) {
   if (i < n) { const float v = x[i]; x[i] = v / (1.f + expf(-v)); }
 }
 __global__ void reflect_pad_kernel(const float* __restrict__ x, float* __restrict__ y, int T, int C, int left,
-                                   int Tout) {
+                                   int Tout, __half* __restrict__ y16) {
   const int bi = blockIdx.z, i = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   int t = i - left;
   if (t < 0) t = -t;
   if (t >= T) t = 2 * (T - 1) - t;
-  y[((long long)bi * Tout + i) * C + c] = x[((long long)bi * T + t) * C + c];
+  put(y, y16, ((long long)bi * Tout + i) * C + c, x[((long long)bi * T + t) * C + c]);
 }
 __global__ void zero_kernel(float* x, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -365,14 +372,15 @@ __global__ void heads_merge_kernel(const float* __restrict__ O, float* __restric
   out[((long long)b * T + t) * H * AD + h * AD + i] = O[(((long long)b * H + h) * T + t) * AD + i];
 }
 
-// ---- fused tensor-core flash attention (mma.sync m16n8k16 bf16 for QK^T and PV, fp32 softmax/accumulate) ----
-// Inputs are the rotated/split tensors of rope_split_fa_kernel: Qr, Kr, Vb bf16 [BH][T][64] (q pre-scaled
-// by 1/8; bf16 q/k cost 1.2e-3 of DiT output error on O(1) outputs, measured against the fp32 oracle).  One CTA = 64 queries of one (batch, head); 4 warps x 16 query rows.
+// ---- fused tensor-core flash attention (mma.sync m16n8k16 fp16 for QK^T and PV, fp32 softmax/accumulate) ----
+// Inputs are the rotated/split tensors of rope_split_fa_kernel: Qr, Kr, Vb fp16 [BH][T][64] (q pre-scaled by 1/8).
+// fp16 since round 2: the same 10-bit mantissa as the tf32 GEMMs around it (round 1 used bf16 q/k/v/p: 8 bits, 1.2e-3 of
+// DiT output error on O(1) outputs against the fp32 oracle); q, k, v of a normalised transformer stay far inside fp16 range.  One CTA = 64 queries of one (batch, head); 4 warps x 16 query rows.
 // K/V tiles of 64 keys are staged in shared memory (row pitches 272 B / 144 B keep ldmatrix conflict
 // free); scores, softmax statistics and the output accumulator never leave registers.
 __global__ void rope_split_fa_kernel(const float* __restrict__ qkv, const float* __restrict__ rope,
-                                     __nv_bfloat16* __restrict__ Qr, __nv_bfloat16* __restrict__ Kr,
-                                     __nv_bfloat16* __restrict__ Vb, int T, int H) {
+                                     __half* __restrict__ Qr, __half* __restrict__ Kr,
+                                     __half* __restrict__ Vb, int T, int H) {
   const int t = blockIdx.x, h = blockIdx.y, b = blockIdx.z, i = threadIdx.x;  // 64 threads
   const int ld = 3 * H * AD;
   const float* row = qkv + ((long long)b * T + t) * ld;
@@ -381,11 +389,11 @@ __global__ void rope_split_fa_kernel(const float* __restrict__ qkv, const float*
     const float cs = rope[((long long)t * (AD / 2) + i) * 2], sn = rope[((long long)t * (AD / 2) + i) * 2 + 1];
     const float q0 = row[h * AD + 2 * i], q1 = row[h * AD + 2 * i + 1];
     const float k0 = row[H * AD + h * AD + 2 * i], k1 = row[H * AD + h * AD + 2 * i + 1];
-    *(__nv_bfloat162*)(Qr + (bh * T + t) * AD + 2 * i) =
-        __floats2bfloat162_rn((q0 * cs - q1 * sn) * 0.125f, (q1 * cs + q0 * sn) * 0.125f);
-    *(__nv_bfloat162*)(Kr + (bh * T + t) * AD + 2 * i) = __floats2bfloat162_rn(k0 * cs - k1 * sn, k1 * cs + k0 * sn);
+    *(__half2*)(Qr + (bh * T + t) * AD + 2 * i) =
+        __floats2half2_rn((q0 * cs - q1 * sn) * 0.125f, (q1 * cs + q0 * sn) * 0.125f);
+    *(__half2*)(Kr + (bh * T + t) * AD + 2 * i) = __floats2half2_rn(k0 * cs - k1 * sn, k1 * cs + k0 * sn);
   }
-  Vb[(bh * T + t) * AD + i] = __float2bfloat16_rn(row[2 * H * AD + h * AD + i]);
+  Vb[(bh * T + t) * AD + i] = __float2half_rn(row[2 * H * AD + h * AD + i]);
 }
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -402,9 +410,9 @@ __device__ __forceinline__ void mma_tf32_1688(float (&c)[4], uint32_t a0, uint32
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ void mma_bf16_16816_fa(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+__device__ __forceinline__ void mma_f16_16816_fa(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                                   uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
@@ -413,27 +421,28 @@ __device__ __forceinline__ uint32_t tf32_rn(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return r;
 }
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
   return *(uint32_t*)&v;
 }
 
 constexpr int FQ = 64, FK = 64;
 constexpr int VPITCH = 72;   // bf16 per K / V row in smem (144 B: ldmatrix rows land in distinct bank groups)
-__global__ void __launch_bounds__(128) flash_attn_tc_kernel(const __nv_bfloat16* __restrict__ Qr,
-                                                            const __nv_bfloat16* __restrict__ Kr,
-                                                            const __nv_bfloat16* __restrict__ Vb,
-                                                            float* __restrict__ out, int T, int H) {
+__global__ void __launch_bounds__(128) flash_attn_tc_kernel(const __half* __restrict__ Qr,
+                                                            const __half* __restrict__ Kr,
+                                                            const __half* __restrict__ Vb,
+                                                            float* __restrict__ out, int T, int H,
+                                                            __half* __restrict__ out16) {
   // K/V tiles are double buffered: cp.async fills tile i+1 while the tensor cores work on tile i
-  __shared__ __align__(16) __nv_bfloat16 Ks2[2][FK * VPITCH];
-  __shared__ __align__(16) __nv_bfloat16 Vs2[2][FK * VPITCH];
+  __shared__ __align__(16) __half Ks2[2][FK * VPITCH];
+  __shared__ __align__(16) __half Vs2[2][FK * VPITCH];
   const int bh = blockIdx.y, q0 = blockIdx.x * FQ;
   const int b = bh / H, h = bh % H;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
-  const __nv_bfloat16* Qb = Qr + (long long)bh * T * AD;
-  const __nv_bfloat16* Kb = Kr + (long long)bh * T * AD;
-  const __nv_bfloat16* Vbb = Vb + (long long)bh * T * AD;
+  const __half* Qb = Qr + (long long)bh * T * AD;
+  const __half* Kb = Kr + (long long)bh * T * AD;
+  const __half* Vbb = Vb + (long long)bh * T * AD;
   // Q fragments (bf16, m16n8k16 A operand) of this warp's 16 rows: 4 k-steps of 16 dims
   uint32_t qa[4][4];
   {
@@ -493,8 +502,8 @@ __global__ void __launch_bounds__(128) flash_attn_tc_kernel(const __nv_bfloat16*
         uint32_t b0, b1, b2, b3;
         const uint32_t addr = ks_base + (uint32_t)(((j * 8 + (lane & 7)) * VPITCH + kp * 32 + (lane >> 3) * 8) * 2);
         ldsm_x4(addr, b0, b1, b2, b3);
-        mma_bf16_16816_fa(sc[j], qa[2 * kp][0], qa[2 * kp][1], qa[2 * kp][2], qa[2 * kp][3], b0, b1);
-        mma_bf16_16816_fa(sc[j], qa[2 * kp + 1][0], qa[2 * kp + 1][1], qa[2 * kp + 1][2], qa[2 * kp + 1][3], b2, b3);
+        mma_f16_16816_fa(sc[j], qa[2 * kp][0], qa[2 * kp][1], qa[2 * kp][2], qa[2 * kp][3], b0, b1);
+        mma_f16_16816_fa(sc[j], qa[2 * kp + 1][0], qa[2 * kp + 1][1], qa[2 * kp + 1][2], qa[2 * kp + 1][3], b2, b3);
       }
     }
     // mask keys beyond T, online softmax for rows g (c0,c1) and g+8 (c2,c3)
@@ -522,8 +531,8 @@ __global__ void __launch_bounds__(128) flash_attn_tc_kernel(const __nv_bfloat16*
       const float p2 = __expf(sc[j][2] - mn1), p3 = __expf(sc[j][3] - mn1);
       rs0 += p0 + p1;
       rs1 += p2 + p3;
-      pa[j][0] = pack_bf16(p0, p1);
-      pa[j][1] = pack_bf16(p2, p3);
+      pa[j][0] = pack_h2(p0, p1);
+      pa[j][1] = pack_h2(p2, p3);
     }
     rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1);
     rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
@@ -546,8 +555,8 @@ __global__ void __launch_bounds__(128) flash_attn_tc_kernel(const __nv_bfloat16*
         const int mi = lane >> 3;
         const uint32_t addr = vs_base + (uint32_t)(((kb * 16 + (mi & 1) * 8 + (lane & 7)) * VPITCH + dp * 16 + (mi >> 1) * 8) * 2);
         ldsm_x4_trans(addr, v0, v1, v2, v3);
-        mma_bf16_16816_fa(o[2 * dp], a0, a1, a2, a3, v0, v1);
-        mma_bf16_16816_fa(o[2 * dp + 1], a0, a1, a2, a3, v2, v3);
+        mma_f16_16816_fa(o[2 * dp], a0, a1, a2, a3, v0, v1);
+        mma_f16_16816_fa(o[2 * dp + 1], a0, a1, a2, a3, v2, v3);
       }
     }
     __syncthreads();   // every warp is done with this tile's buffer
@@ -557,8 +566,15 @@ __global__ void __launch_bounds__(128) flash_attn_tc_kernel(const __nv_bfloat16*
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int d = j * 8 + 2 * t4;
-    if (r0 < T) *(float2*)(out + ((long long)b * T + r0) * H * AD + h * AD + d) = make_float2(o[j][0] * i0, o[j][1] * i0);
-    if (r1 < T) *(float2*)(out + ((long long)b * T + r1) * H * AD + h * AD + d) = make_float2(o[j][2] * i1, o[j][3] * i1);
+    const long long a0 = ((long long)b * T + r0) * H * AD + h * AD + d, a1 = ((long long)b * T + r1) * H * AD + h * AD + d;
+    if (out) {
+      if (r0 < T) *(float2*)(out + a0) = make_float2(o[j][0] * i0, o[j][1] * i0);
+      if (r1 < T) *(float2*)(out + a1) = make_float2(o[j][2] * i1, o[j][3] * i1);
+    }
+    if (out16) {
+      if (r0 < T) *(__half2*)(out16 + a0) = __floats2half2_rn(o[j][0] * i0, o[j][1] * i0);
+      if (r1 < T) *(__half2*)(out16 + a1) = __floats2half2_rn(o[j][2] * i1, o[j][3] * i1);
+    }
   }
 }
 
@@ -571,15 +587,15 @@ __global__ void __launch_bounds__(128) flash_attn_tc_kernel(const __nv_bfloat16*
   } while (0)
 
 void layernorm(idx_engine* e, const float* x, float* y, int B, int T, int C, const float* w, const float* b,
-               float eps, const float* scale, const float* shift, int mod_stride) {
+               float eps, const float* scale, const float* shift, int mod_stride, __half* y16) {
   const long long rows = (long long)B * T;
-  rownorm_kernel<0><<<(unsigned)((rows + 7) / 8), 256, 0, e->stream>>>(x, y, rows, T, C, w, b, eps, scale, shift, mod_stride);
+  rownorm_kernel<0><<<(unsigned)((rows + 7) / 8), 256, 0, e->stream>>>(x, y, rows, T, C, w, b, eps, scale, shift, mod_stride, y16);
   LAUNCH_CHECK(e);
 }
 void rmsnorm_adaln(idx_engine* e, const float* x, float* y, int B, int T, int C, const float* nw, const float* mw,
-                   const float* mb, int mod_stride, float eps) {
+                   const float* mb, int mod_stride, float eps, __half* y16) {
   const long long rows = (long long)B * T;
-  rownorm_kernel<1><<<(unsigned)((rows + 7) / 8), 256, 0, e->stream>>>(x, y, rows, T, C, nw, nullptr, eps, mw, mb, mod_stride);
+  rownorm_kernel<1><<<(unsigned)((rows + 7) / 8), 256, 0, e->stream>>>(x, y, rows, T, C, nw, nullptr, eps, mw, mb, mod_stride, y16);
   LAUNCH_CHECK(e);
 }
 void groupnorm1_mish(idx_engine* e, const float* x, float* y, int B, int T, int C, const float* w, const float* b,
@@ -608,17 +624,17 @@ void embedding_rows(idx_engine* e, const float* table, const int* ids, float* ou
   embedding_kernel<<<grid, 128, 0, e->stream>>>(table, ids, out, C, nrows, e->dev_flag);
   LAUNCH_CHECK(e);
 }
-void swiglu(idx_engine* e, const float* ab, float* y, long long rows, int N) {
-  swiglu_kernel<<<(unsigned)((rows * N + 255) / 256), 256, 0, e->stream>>>(ab, y, rows, N);
+void swiglu(idx_engine* e, const float* ab, float* y, long long rows, int N, __half* y16) {
+  swiglu_kernel<<<(unsigned)((rows * N + 255) / 256), 256, 0, e->stream>>>(ab, y, rows, N, y16);
   LAUNCH_CHECK(e);
 }
-void wn_gate(idx_engine* e, const float* xin, const float* g, int g_stride, float* y, int B, int T, int N) {
+void wn_gate(idx_engine* e, const float* xin, const float* g, int g_stride, float* y, int B, int T, int N, __half* y16) {
   dim3 grid((unsigned)(((long long)T * N + 255) / 256), 1, B);
-  wn_gate_kernel<<<grid, 256, 0, e->stream>>>(xin, g, g_stride, y, T, N);
+  wn_gate_kernel<<<grid, 256, 0, e->stream>>>(xin, g, g_stride, y, T, N, y16);
   LAUNCH_CHECK(e);
 }
-void copy_cols(idx_engine* e, const float* src, int lds, float* dst, int ldo, int col0, long long rows, int C) {
-  copy_cols_kernel<<<(unsigned)((rows * C + 255) / 256), 256, 0, e->stream>>>(src, lds, dst, ldo, col0, rows, C);
+void copy_cols(idx_engine* e, const float* src, int lds, float* dst, int ldo, int col0, long long rows, int C, __half* dst16) {
+  copy_cols_kernel<<<(unsigned)((rows * C + 255) / 256), 256, 0, e->stream>>>(src, lds, dst, ldo, col0, rows, C, dst16);
   LAUNCH_CHECK(e);
 }
 void bcast_cols(idx_engine* e, const float* vec, float* dst, int ldo, int col0, int B, int T, int C) {
@@ -634,10 +650,10 @@ void fill_zero(idx_engine* e, float* x, long long n) {
   zero_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(x, n);
   LAUNCH_CHECK(e);
 }
-void reflect_pad_rows(idx_engine* e, const float* x, float* y, int B, int T, int C, int left, int right) {
+void reflect_pad_rows(idx_engine* e, const float* x, float* y, int B, int T, int C, int left, int right, __half* y16) {
   const int Tout = T + left + right;
   dim3 grid((C + 127) / 128, Tout, B);
-  reflect_pad_kernel<<<grid, 128, 0, e->stream>>>(x, y, T, C, left, Tout);
+  reflect_pad_kernel<<<grid, 128, 0, e->stream>>>(x, y, T, C, left, Tout, y16);
   LAUNCH_CHECK(e);
 }
 void rope_table(idx_engine* e, float* tab, int T, int hd) {
@@ -645,22 +661,23 @@ void rope_table(idx_engine* e, float* tab, int T, int hd) {
   LAUNCH_CHECK(e);
 }
 void attention_rope(idx_engine* e, const float* qkv, float* out, int B, int T, int H, const float* rope,
-                    const int* lens) {
+                    const int* lens, __half* out16) {
   static const bool unfused = getenv("IDX_ATTN_UNFUSED") != nullptr;
   if (gemm_default_backend(e) == 0 && lens == nullptr && !unfused) {
     // fused tensor-core flash attention: rotate/split once, then one kernel per layer
     const size_t mark = e->arena.off;
     const long long BH = (long long)B * H;
-    __nv_bfloat16* Qr = (__nv_bfloat16*)e->arena.alloc((size_t)BH * T * AD * 2);
-    __nv_bfloat16* Kr = (__nv_bfloat16*)e->arena.alloc((size_t)BH * T * AD * 2);
-    __nv_bfloat16* Vb = (__nv_bfloat16*)e->arena.alloc((size_t)BH * T * AD * 2);
+    __half* Qr = (__half*)e->arena.alloc((size_t)BH * T * AD * 2);
+    __half* Kr = (__half*)e->arena.alloc((size_t)BH * T * AD * 2);
+    __half* Vb = (__half*)e->arena.alloc((size_t)BH * T * AD * 2);
     rope_split_fa_kernel<<<dim3(T, H, B), AD, 0, e->stream>>>(qkv, rope, Qr, Kr, Vb, T, H);
     LAUNCH_CHECK(e);
-    flash_attn_tc_kernel<<<dim3((T + FQ - 1) / FQ, (unsigned)BH), 128, 0, e->stream>>>(Qr, Kr, Vb, out, T, H);
+    flash_attn_tc_kernel<<<dim3((T + FQ - 1) / FQ, (unsigned)BH), 128, 0, e->stream>>>(Qr, Kr, Vb, out, T, H, out16);
     LAUNCH_CHECK(e);
     e->arena.off = mark;
     return;
   }
+  IDX_CHECK(out16 == nullptr, IDX_ERR_STATE, "attention_rope: an fp16 output exists only on the fused tensor-core path");
   if (gemm_default_backend(e) == 0 && lens == nullptr && T >= 128) {
     // tensor-core path: rotate/split -> S = Q K^T (tcgen05) -> row softmax -> O = P V (tcgen05) -> merge
     const size_t mark = e->arena.off;

@@ -154,6 +154,9 @@ extern "C" int idx_set_option(idx_engine* e, const char* name, int value) {
   if (n == "gemm_backend") {
     IDX_CHECK(value >= 0 && value <= 1, IDX_ERR_ARG, "gemm_backend: 0 = auto (tcgen05 tf32 where applicable), 1 = SIMT fp32");
     e->gemm_backend = value;       // per engine: another handle (another GPU, another thread) keeps its own
+  } else if (n == "tail_f16") {
+    IDX_CHECK(value >= 0 && value <= 1, IDX_ERR_ARG, "tail_f16: 1 = fp16 GEMM operands on the tensor-core path (default), 0 = tf32 over fp32 storage");
+    e->tail_f16 = value;
   } else {
     throw IdxError(IDX_ERR_ARG, "unknown option: " + n);
   }
@@ -161,7 +164,13 @@ extern "C" int idx_set_option(idx_engine* e, const char* name, int value) {
 }
 
 void conv_gemm(idx_engine* e, const ConvGemm& g) {
-  IDX_CHECK(g.A && g.out && g.M > 0 && g.N > 0 && g.K > 0, IDX_ERR_ARG, "conv_gemm: bad arguments");
+  IDX_CHECK((g.A || g.A16) && g.out && g.M > 0 && g.N > 0 && g.K > 0, IDX_ERR_ARG, "conv_gemm: bad arguments");
+  if (g.A16 && g.Wk16) {       // fp16 operands exist only for the tensor-core kernel
+    IDX_CHECK(gemm_tc_supported(g), IDX_ERR_ARG, "conv_gemm: fp16 operands with a shape the tensor-core kernel does not take");
+    gemm_tc_launch(e, g);
+    return;
+  }
+  IDX_CHECK(g.A != nullptr, IDX_ERR_ARG, "conv_gemm: fp32 operand missing");
   static const bool force_simt = getenv("IDX_FORCE_SIMT") != nullptr;
   if (e->force_backend == 2) {
     IDX_CHECK(g.Wk && !g.reflect, IDX_ERR_ARG, "conv_gemm: tensor-core path not applicable");
@@ -263,6 +272,40 @@ ConvGemm gemm_of(const PackedW& w, const float* A, int B, int T, float* out) {
   return g;
 }
 
+ConvGemm gemm_of16(const PackedW& w, const __half* A16, int B, int T, float* out) {
+  ConvGemm g = gemm_of(w, nullptr, B, T, out);
+  IDX_CHECK(w.wk16, IDX_ERR_STATE, "gemm_of16: the weight has no fp16 copy (pack_half)");
+  g.A16 = A16; g.Wk16 = w.wk16;
+  return g;
+}
+
+namespace {
+__global__ void to_half_kernel(const float* __restrict__ x, __half* __restrict__ y, long long n) {
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (i + 1 < n) *(__half2*)(y + i) = __floats2half2_rn(x[i], x[i + 1]);
+  else if (i < n) y[i] = __float2half_rn(x[i]);
+}
+}  // namespace
+
+void to_half(idx_engine* e, const float* x, __half* y, long long n) {
+  if (n <= 0) return;
+  to_half_kernel<<<(unsigned)((n / 2 + 256) / 256), 256, 0, e->stream>>>(x, y, n);
+  IDX_CUDA(cudaGetLastError());
+  e->launches++;
+}
+
+void pack_half(idx_engine* e, WeightPool& pool, PackedW& w) {
+  if (w.wk16 || !w.wk) return;
+  const size_t n = (size_t)w.N * w.K * w.taps;
+  w.wk16 = (__half*)pool.alloc((n + 1) / 2 + 4);
+  to_half(e, w.wk, w.wk16, (long long)n);
+}
+
+bool tail_half(const idx_engine* e) {
+  static const bool off = getenv("IDX_TAIL_F16") && atoi(getenv("IDX_TAIL_F16")) == 0;
+  return !off && e->tail_f16 && e->gemm_backend == 0 && e->force_backend == 0;
+}
+
 namespace {
 __global__ void kmajor_to_simt_kernel(const float* wk, float* ws, int N, int KT) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -282,7 +325,7 @@ extern "C" int idx_debug_conv_gemm(idx_engine* e, const float* A, int B, int Tin
   IDX_CHECK(e && A && wk && out, IDX_ERR_ARG, "null argument");
   IDX_CUDA(cudaSetDevice(e->device));
   const size_t na = (size_t)B * Tin * K, nw = (size_t)N * taps * K, no = (size_t)B * out_elems_per_batch;
-  e->ensure_arena(4 * (na + 2 * nw + 2 * no + (size_t)N) + (1 << 20));
+  e->ensure_arena(4 * (2 * na + 3 * nw + 2 * no + (size_t)N) + (1 << 20));
   e->arena.reset();
   float* dA = e->arena.get<float>(na);
   float* dWk = e->arena.get<float>(nw);
@@ -301,6 +344,14 @@ extern "C" int idx_debug_conv_gemm(idx_engine* e, const float* A, int B, int Tin
   g.A = dA; g.B = B; g.Tin = Tin; g.K = K; g.W = dWs; g.Wk = dWk; g.taps = taps; g.dil = dil; g.pad = pad;
   g.M = M; g.N = N; g.bias = dBias; g.biasN = biasN; g.act = act; g.res = dRes; g.accum = accum; g.scale = scale;
   g.out = dOut; g.out_off = out_off; g.ldo = ldo; g.out_valid = out_valid; g.out_batch_stride = out_elems_per_batch;
+  if (backend == 3) {          // fp16 operands on the tensor cores: convert A and the K-major weights on the device
+    __half* dA16 = (__half*)e->arena.get<float>(na / 2 + 4);
+    __half* dW16 = (__half*)e->arena.get<float>(nw / 2 + 4);
+    to_half(e, dA, dA16, (long long)na);
+    to_half(e, dWk, dW16, (long long)nw);
+    g.A16 = dA16; g.Wk16 = dW16;
+    backend = 0;
+  }
   e->force_backend = backend;
   try {
     conv_gemm(e, g);

@@ -3,6 +3,7 @@
 // rows are time steps, so every Conv1d / Linear is a (multi-tap) GEMM with K = C contiguous.
 #pragma once
 #include "engine.h"
+#include <cuda_fp16.h>
 #include <string>
 #include <vector>
 
@@ -18,6 +19,10 @@ struct ConvGemm {
   int lda = 0;                   // row stride of A in elements; 0 → K
   const float* W = nullptr;   // [taps][K][N]  (N contiguous)  — SIMT layout
   const float* Wk = nullptr;  // [N][taps*K]   (K contiguous)  — tensor-core layout (optional)
+  // fp16 operand path (tcgen05 kind::f16): both set -> the tensor-core kernel reads these instead of A / Wk (same shapes,
+  // strides given in ELEMENTS as for the fp32 operands).  Written by the producing kernel of A / converted once at init.
+  const __half* A16 = nullptr;
+  const __half* Wk16 = nullptr;
   long long w_batch_stride = 0;  // elements between the Wk matrices of consecutive batch entries (0: shared)
   int ldw = 0;                   // row stride of Wk in elements; 0 → taps*K
   int taps = 1, dil = 1, pad = 0, reflect = 0;
@@ -48,10 +53,10 @@ void transpose_btc_to_bct(idx_engine* e, const float* in, float* out, int B, int
 // ---------------------------------------------------------------- normalisation / pointwise --
 // y = LayerNorm(x) [* w + b] [ * (1 + scale[b]) + shift[b] ]   rows of C, x/y [B][T][C]
 void layernorm(idx_engine* e, const float* x, float* y, int B, int T, int C, const float* w,
-               const float* b, float eps, const float* scale, const float* shift, int mod_stride);
+               const float* b, float eps, const float* scale, const float* shift, int mod_stride, __half* y16 = nullptr);
 // y = mw[b] * (x * rsqrt(mean(x^2)+eps) * nw) + mb[b]          (AdaptiveLayerNorm over RMSNorm)
 void rmsnorm_adaln(idx_engine* e, const float* x, float* y, int B, int T, int C, const float* nw,
-                   const float* mw, const float* mb, int mod_stride, float eps);
+                   const float* mw, const float* mb, int mod_stride, float eps, __half* y16 = nullptr);
 // GroupNorm(1 group) over each sample's [T][C] block, affine per channel, followed by Mish
 void groupnorm1_mish(idx_engine* e, const float* x, float* y, int B, int T, int C, const float* w,
                      const float* b, float eps);
@@ -63,11 +68,11 @@ void nearest_interp(idx_engine* e, const float* x, float* y, int B, int Tin, int
 // out[t][:] = table[ids[t]][:]
 void embedding_rows(idx_engine* e, const float* table, const int* ids, float* out, int n, int C, int nrows);
 // y = silu(a) * b where ab [rows][2*N] holds a | b side by side
-void swiglu(idx_engine* e, const float* ab, float* y, long long rows, int N);
+void swiglu(idx_engine* e, const float* ab, float* y, long long rows, int N, __half* y16 = nullptr);
 // y = tanh(a + ga[b]) * sigmoid(c + gc[b]),  xin [B][T][2N] = a | c ; g [B][*] with stride
-void wn_gate(idx_engine* e, const float* xin, const float* g, int g_stride, float* y, int B, int T, int N);
+void wn_gate(idx_engine* e, const float* xin, const float* g, int g_stride, float* y, int B, int T, int N, __half* y16 = nullptr);
 // copy a [rows][C] block into columns [col0, col0+C) of a [rows][ldo] matrix (concat by columns)
-void copy_cols(idx_engine* e, const float* src, int lds, float* dst, int ldo, int col0, long long rows, int C);
+void copy_cols(idx_engine* e, const float* src, int lds, float* dst, int ldo, int col0, long long rows, int C, __half* dst16 = nullptr);
 // broadcast a per-batch vector [B][C] over T rows into columns of dst
 void bcast_cols(idx_engine* e, const float* vec, float* dst, int ldo, int col0, int B, int T, int C);
 // y = silu(x)
@@ -76,19 +81,21 @@ void silu_inplace(idx_engine* e, float* x, long long n);
 void rope_table(idx_engine* e, float* tab, int T, int hd);
 // full (non-causal) attention with key-length mask and interleaved-pair RoPE on q,k.
 // qkv [B][T][3*H*64] (q | k | v), out [B][T][H*64]; lens [B] valid keys (device ints) or null
+// out16 (tensor-core flash path only): the result as fp16 (the operand of the output projection); out may then be null
 void attention_rope(idx_engine* e, const float* qkv, float* out, int B, int T, int H, const float* rope,
-                    const int* lens);
+                    const int* lens, __half* out16 = nullptr);
 // x[b][t][c] (+)= ... CFG + Euler: x += dt * ((1+r) * v[0] - r * v[1]); rows t < P zeroed. x,v: [T][C]
 void cfg_euler(idx_engine* e, float* x, const float* v_cond, const float* v_uncond, float dt, float rate,
                int T, int C, int P);
 void fill_zero(idx_engine* e, float* x, long long n);
 // y[b][i][:] = x[b][reflect(i - left)][:], i in [0, T + left + right)   (F.pad mode='reflect')
-void reflect_pad_rows(idx_engine* e, const float* x, float* y, int B, int T, int C, int left, int right);
+void reflect_pad_rows(idx_engine* e, const float* x, float* y, int B, int T, int C, int left, int right, __half* y16 = nullptr);
 
 // ------------------------------------------------------------------------ packed weights --
 struct PackedW {
   float* wsimt = nullptr;  // [taps][K][N]
   float* wk = nullptr;     // [N][taps*K]
+  __half* wk16 = nullptr;  // [N][taps*K] fp16 copy of wk (made on demand by pack_half)
   const float* bias = nullptr;
   int N = 0, K = 0, taps = 1, dil = 1;
 };
@@ -105,3 +112,11 @@ PackedW pack_conv1d(idx_engine* e, WeightPool& pool, const std::string& name, in
                     int rows = -1);
 // convenience: D = A·W^T (+bias) for a channels-last activation with optional epilogue fields preset in g
 ConvGemm gemm_of(const PackedW& w, const float* A, int B, int T, float* out);
+// same GEMM with fp16 operands: A16 is the fp16 image of the activation (the fp32 pointer may be null)
+ConvGemm gemm_of16(const PackedW& w, const __half* A16, int B, int T, float* out);
+// fp16 copy of a K-major weight matrix (w.wk must exist); idempotent
+void pack_half(idx_engine* e, WeightPool& pool, PackedW& w);
+// fp32 -> fp16 (round to nearest), n elements
+void to_half(idx_engine* e, const float* x, __half* y, long long n);
+// true when the engine runs the tail with fp16 GEMM operands (tensor-core back end and not disabled by IDX_TAIL_F16=0)
+bool tail_half(const idx_engine* e);

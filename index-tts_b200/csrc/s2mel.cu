@@ -223,6 +223,10 @@ extern "C" int idx_s2mel_init(idx_engine* e, const idx_s2mel_config* cfg) {
   }
   s->lr_out = pack_linear(e, s->pool, R + "model." + std::to_string(3 * cfg->lr_convs));
   IDX_CUDA(cudaStreamSynchronize(e->stream));
+  // fp16 K-major copies for the tensor-core path with fp16 operands (DiT + WaveNet GEMMs; made once)
+  for (auto* v : {&s->wqkv, &s->wo, &s->w13, &s->w2, &s->skip_in, &s->wn_in, &s->wn_res, &s->wn_skip})
+    for (auto& w : *v) pack_half(e, s->pool, w);
+  for (auto* w : {&s->skip_linear, &s->conv1, &s->res_proj, &s->fl_linear, &s->conv2}) pack_half(e, s->pool, *w);
   s->has_s2mel = true;
   IDX_API_END(e)
 }
@@ -306,6 +310,9 @@ void length_regulate_dev(idx_engine* e, S2melState* s, const float* d_S, int n_i
 
 struct DitBuffers {
   float *h[16], *a, *qkv, *att, *ff, *cat, *xres, *wy, *wpad, *wxin, *wacts, *wout, *z, *v, *rope;
+  // fp16 images of the GEMM operands (tail_half mode): written by the kernel that produces the operand
+  __half *a16 = nullptr, *att16 = nullptr, *ffh16 = nullptr, *cat16 = nullptr, *xres16 = nullptr, *wpad16 = nullptr,
+         *wacts16 = nullptr, *z16 = nullptr, *wy16 = nullptr;
   int* lens;
 };
 
@@ -321,35 +328,39 @@ static void dit_eval(idx_engine* e, S2melState* s, DitBuffers& b, int Bn, int T,
     g.a_bcast = x_bcast; g.res = C0;
     conv_gemm(e, g);
   }
+  const bool hf = b.a16 != nullptr;     // fp16 GEMM operands (alloc_dit decides; see ops.h tail_half)
+  auto G = [&](const PackedW& w, const float* A32, const __half* A16, int Bb, int Tt, float* out) {
+    return hf ? gemm_of16(w, A16, Bb, Tt, out) : gemm_of(w, A32, Bb, Tt, out);
+  };
   float* h = b.h[0];
   int nskip = 0;
   float* skips[16];
   for (int l = 0; l < Dn; ++l) {
     if (l > Dn / 2) {   // layers_receive_skip (gpt_fast/model.py:166-167)
       float* sk = skips[--nskip];
-      copy_cols(e, h, H, b.cat, 2 * H, 0, (long long)Bn * T, H);
-      copy_cols(e, sk, H, b.cat, 2 * H, H, (long long)Bn * T, H);
+      copy_cols(e, h, H, hf ? nullptr : b.cat, 2 * H, 0, (long long)Bn * T, H, b.cat16);
+      copy_cols(e, sk, H, hf ? nullptr : b.cat, 2 * H, H, (long long)Bn * T, H, b.cat16);
       float* hn = b.h[8 + (l & 1)];
-      conv_gemm(e, gemm_of(s->skip_in[l], b.cat, Bn, T, hn));
+      conv_gemm(e, G(s->skip_in[l], b.cat, b.cat16, Bn, T, hn));
       h = hn;
     }
-    rmsnorm_adaln(e, h, b.a, Bn, T, H, s->attn_norm[l].norm_w, mod + s->attn_norm[l].mod_off,
-                  mod + s->attn_norm[l].mod_off + H, 0, 1e-5f);
-    conv_gemm(e, gemm_of(s->wqkv[l], b.a, Bn, T, b.qkv));
-    attention_rope(e, b.qkv, b.att, Bn, T, nh, b.rope, b.lens);
+    rmsnorm_adaln(e, h, hf ? nullptr : b.a, Bn, T, H, s->attn_norm[l].norm_w, mod + s->attn_norm[l].mod_off,
+                  mod + s->attn_norm[l].mod_off + H, 0, 1e-5f, b.a16);
+    conv_gemm(e, G(s->wqkv[l], b.a, b.a16, Bn, T, b.qkv));
+    attention_rope(e, b.qkv, hf ? nullptr : b.att, Bn, T, nh, b.rope, b.lens, b.att16);
     // layer output buffer: emitted skips (l < Dn/2) keep their own buffer
     float* hout = (l < Dn / 2) ? b.h[1 + l] : b.h[10 + (l & 1)];
     {
-      ConvGemm g = gemm_of(s->wo[l], b.att, Bn, T, hout);
+      ConvGemm g = G(s->wo[l], b.att, b.att16, Bn, T, hout);
       g.res = h;
       conv_gemm(e, g);
     }
-    rmsnorm_adaln(e, hout, b.a, Bn, T, H, s->ffn_norm[l].norm_w, mod + s->ffn_norm[l].mod_off,
-                  mod + s->ffn_norm[l].mod_off + H, 0, 1e-5f);
-    conv_gemm(e, gemm_of(s->w13[l], b.a, Bn, T, b.ff));
-    swiglu(e, b.ff, b.qkv, (long long)Bn * T, s->inter);
+    rmsnorm_adaln(e, hout, hf ? nullptr : b.a, Bn, T, H, s->ffn_norm[l].norm_w, mod + s->ffn_norm[l].mod_off,
+                  mod + s->ffn_norm[l].mod_off + H, 0, 1e-5f, b.a16);
+    conv_gemm(e, G(s->w13[l], b.a, b.a16, Bn, T, b.ff));
+    swiglu(e, b.ff, hf ? nullptr : b.qkv, (long long)Bn * T, s->inter, b.ffh16);
     {
-      ConvGemm g = gemm_of(s->w2[l], b.qkv, Bn, T, hout);
+      ConvGemm g = G(s->w2[l], b.qkv, b.ffh16, Bn, T, hout);
       g.res = hout;
       conv_gemm(e, g);
     }
@@ -359,40 +370,43 @@ static void dit_eval(idx_engine* e, S2melState* s, DitBuffers& b, int Bn, int T,
   rmsnorm_adaln(e, h, b.a, Bn, T, H, s->final_norm.norm_w, mod + s->final_norm.mod_off,
                 mod + s->final_norm.mod_off + H, 0, 1e-5f);
   // long skip: x_res = skip_linear(cat[h, x])   (dit.py:242-243)
-  copy_cols(e, b.a, H, b.cat, H + C, 0, (long long)Bn * T, H);
+  copy_cols(e, b.a, H, hf ? nullptr : b.cat, H + C, 0, (long long)Bn * T, H, b.cat16);
   for (int bi = 0; bi < Bn; ++bi)
-    copy_cols(e, x_bcast ? x_t : x_t + (size_t)bi * T * C, C, b.cat + (size_t)bi * T * (H + C), H + C, H, T, C);
-  conv_gemm(e, gemm_of(s->skip_linear, b.cat, Bn, T, b.xres));
-  conv_gemm(e, gemm_of(s->conv1, b.xres, Bn, T, b.wy));
+    copy_cols(e, x_bcast ? x_t : x_t + (size_t)bi * T * C, C, hf ? nullptr : b.cat + (size_t)bi * T * (H + C), H + C, H, T, C,
+              hf ? b.cat16 + (size_t)bi * T * (H + C) : nullptr);
+  conv_gemm(e, G(s->skip_linear, b.cat, b.cat16, Bn, T, b.xres));
+  if (hf) to_half(e, b.xres, b.xres16, (long long)Bn * T * H);          // operand of conv1 and res_projection
+  conv_gemm(e, G(s->conv1, b.xres, b.xres16, Bn, T, b.wy));
   // WaveNet (wavenet.py:132-166), masks are all-ones for full-length sequences
   fill_zero(e, b.wout, (long long)Bn * T * WH);
   for (int i = 0; i < NL; ++i) {
     // SConv1d pad_mode='reflect' (encodec.py:196-229): materialise the reflected halo rows so the
     // conv is a plain zero-pad-free multi-tap GEMM (tensor-core path; TMA cannot reflect)
     const int kk = s->wn_in[i].taps, pl = (kk - 1) - (kk - 1) / 2, pr = (kk - 1) / 2;
-    reflect_pad_rows(e, b.wy, b.wpad, Bn, T, WH, pl, pr);
-    ConvGemm gi = gemm_of(s->wn_in[i], b.wpad, Bn, T + kk - 1, b.wxin);
+    reflect_pad_rows(e, b.wy, hf ? nullptr : b.wpad, Bn, T, WH, pl, pr, b.wpad16);
+    ConvGemm gi = G(s->wn_in[i], b.wpad, b.wpad16, Bn, T + kk - 1, b.wxin);
     gi.pad = 0; gi.M = T;
     conv_gemm(e, gi);
-    wn_gate(e, b.wxin, wncond + (size_t)i * 2 * WH, 0, b.wacts, Bn, T, WH);
+    wn_gate(e, b.wxin, wncond + (size_t)i * 2 * WH, 0, hf ? nullptr : b.wacts, Bn, T, WH, b.wacts16);
     if (i < NL - 1) {
-      ConvGemm gr = gemm_of(s->wn_res[i], b.wacts, Bn, T, b.wy);
+      ConvGemm gr = G(s->wn_res[i], b.wacts, b.wacts16, Bn, T, b.wy);
       gr.res = b.wy;
       conv_gemm(e, gr);
     }
-    ConvGemm gs = gemm_of(s->wn_skip[i], b.wacts, Bn, T, b.wout);
+    ConvGemm gs = G(s->wn_skip[i], b.wacts, b.wacts16, Bn, T, b.wout);
     gs.accum = 1;
     conv_gemm(e, gs);
   }
   {
-    ConvGemm g = gemm_of(s->res_proj, b.xres, Bn, T, b.wout);   // + res_projection(x_res)
+    ConvGemm g = G(s->res_proj, b.xres, b.xres16, Bn, T, b.wout);   // + res_projection(x_res)
     g.accum = 1;
     conv_gemm(e, g);
   }
   // FinalLayer: modulate(LN(x), shift, scale) -> linear ; then conv2 (1x1)
-  layernorm(e, b.wout, b.z, Bn, T, WH, nullptr, nullptr, 1e-6f, flmod + WH, flmod, 0);
-  conv_gemm(e, gemm_of(s->fl_linear, b.z, Bn, T, b.wy));
-  conv_gemm(e, gemm_of(s->conv2, b.wy, Bn, T, b.v));
+  layernorm(e, b.wout, hf ? nullptr : b.z, Bn, T, WH, nullptr, nullptr, 1e-6f, flmod + WH, flmod, 0, b.z16);
+  conv_gemm(e, G(s->fl_linear, b.z, b.z16, Bn, T, b.wy));
+  if (hf) to_half(e, b.wy, b.wy16, (long long)Bn * T * WH);
+  conv_gemm(e, G(s->conv2, b.wy, b.wy16, Bn, T, b.v));
 }
 
 static void alloc_dit(idx_engine* e, S2melState* s, DitBuffers& b, int Bn, int T) {
@@ -415,6 +429,13 @@ static void alloc_dit(idx_engine* e, S2melState* s, DitBuffers& b, int Bn, int T
   b.v = e->arena.get<float>(bt * C);
   b.rope = e->arena.get<float>((size_t)T * 64);
   b.lens = nullptr;
+  static const bool unfused = getenv("IDX_ATTN_UNFUSED") != nullptr;
+  if (tail_half(e) && !unfused && H % 8 == 0 && WH % 8 == 0 && (H + C) % 8 == 0 && s->inter % 8 == 0) {
+    auto hb = [&](size_t n) { return (__half*)e->arena.alloc(n * sizeof(__half) + 16); };
+    b.a16 = hb(bt * H); b.att16 = hb(bt * H); b.ffh16 = hb(bt * s->inter); b.cat16 = hb(bt * 2 * H);
+    b.xres16 = hb(bt * H); b.wpad16 = hb((size_t)Bn * (T + 8) * WH); b.wacts16 = hb(bt * WH); b.z16 = hb(bt * WH);
+    b.wy16 = hb(bt * WH);
+  }
   rope_table(e, b.rope, T, 64);
 }
 static size_t dit_arena_bytes(const S2melState* s, int Bn, int T) {
@@ -422,7 +443,8 @@ static size_t dit_arena_bytes(const S2melState* s, int Bn, int T) {
   const size_t bt = (size_t)Bn * T;
   const size_t Tp = (size_t)((T + 3) & ~3);
   const size_t attn = 4 * (size_t)Bn * c.heads * (3 * (size_t)T * 64 + 64 * Tp + (size_t)T * Tp) + 8 * 256;
-  return attn + 4 * (bt * c.hidden * (12 + 1 + 3 + 1 + 2 + 1) + bt * 3 * s->inter + bt * c.wn_hidden * 7 + (size_t)Bn * 8 * c.wn_hidden + bt * c.in_channels +
+  const size_t half_bytes = 2 * (bt * c.hidden * 5 + bt * s->inter + bt * c.wn_hidden * 4 + (size_t)Bn * 8 * c.wn_hidden) + 16 * 512;
+  return attn + half_bytes + 4 * (bt * c.hidden * (12 + 1 + 3 + 1 + 2 + 1) + bt * 3 * s->inter + bt * c.wn_hidden * 7 + (size_t)Bn * 8 * c.wn_hidden + bt * c.in_channels +
               (size_t)T * 64) + 64 * 256;
 }
 

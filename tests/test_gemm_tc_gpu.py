@@ -51,6 +51,12 @@ def test_tc_matches_simt_and_fp64(engine, B, Tin, K, N, taps, dil, pad):
     print(f"tc max err {err.max():.2e} (ref max {np.abs(ref).max():.2f}, bound {2e-3 * mag.max():.2e}); "
           f"rel rms {np.sqrt((err ** 2).mean()) / np.sqrt((ref ** 2).mean()):.2e}")
     assert np.all(err <= 2e-3 * mag + 1e-5)
+    # fp16 operands (tcgen05 kind::f16, the round-2 tail path): same 10-bit mantissa, same bound; needs K % 8 == 0
+    if K % 8 == 0:
+        h = engine.debug_conv_gemm(A, wk, taps, dil, pad, bias=bias, backend=3).reshape(B, Tin, N)
+        errh = np.abs(h - ref)
+        print(f"fp16-operand tc max err {errh.max():.2e}; rel rms {np.sqrt((errh ** 2).mean()) / np.sqrt((ref ** 2).mean()):.2e}")
+        assert np.all(errh <= 2e-3 * mag + 1e-5)
 
 
 def test_tc_epilogues_and_transposed_mapping(engine):

@@ -37,17 +37,22 @@ def test_golden_is_the_committed_one():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("backend,name", [(0, "benchmarked precision (tensor-core GEMMs)"), (1, "strict fp32 SIMT back end")])
-def test_full_cfg2_tail_within_north_star_rms(engine, backend, name):
+@pytest.mark.parametrize("backend,f16,name", [(0, 1, "benchmarked precision (tensor cores, fp16 operands)"),
+                                              (0, 0, "tensor cores, tf32 over fp32 storage (round 1)"),
+                                              (1, 1, "strict fp32 SIMT back end")])
+def test_full_cfg2_tail_within_north_star_rms(engine, backend, f16, name):
     g = np.load(GOLD)
     _load_full(engine)
     codes, pc, ref_mel, style, z, F = make_inputs()
     args = (codes[0].numpy().astype(np.int32), pc[0].numpy(), ref_mel[0].numpy(), style[0].numpy(), z[0].numpy(), F, 25, 0.7)
     engine.set_option("gemm_backend", backend)
+    engine.set_option("tail_f16", f16)
     try:
         res = engine.codes_to_wav(*args, want_wav=True, want_pcm16=True, want_mel=True)
+        res = engine.codes_to_wav(*args, want_wav=True, want_pcm16=True, want_mel=True)      # second call: warm timings
     finally:
         engine.set_option("gemm_backend", 0)
+        engine.set_option("tail_f16", 1)
     wav = np.clip(np.asarray(res["wav"]).reshape(-1), -1.0, 1.0)
     ref = g["wav"]
     assert wav.shape == ref.shape and np.isfinite(wav).all()
