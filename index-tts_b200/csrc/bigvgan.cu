@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(256) snake_act_kernel(const float* __restrict_
                                                         const float* __restrict__ ea,
                                                         const float* __restrict__ ib, int T, int C,
                                                         int CB, Taps taps, __half* __restrict__ y16) {
+  pdl_wait();
   const int b = blockIdx.z;
   const int lanes_t = 256 / CB;
   const int c = blockIdx.x * CB + threadIdx.x % CB;
@@ -354,8 +355,7 @@ static void run_act(idx_engine* e, const BigvganState* s, const ActP& a, const f
   const int lanes_t = 256 / CB;
   constexpr int TT = 32;
   dim3 grid((C + CB - 1) / CB, (T + lanes_t * TT - 1) / (lanes_t * TT), B);
-  snake_act_kernel<TT><<<grid, 256, 0, e->stream>>>(x, y, a.ea, a.ib, T, C, CB, s->taps, y16);
-  IDX_CUDA(cudaGetLastError());
+  launch_pdl(e, snake_act_kernel<TT>, grid, dim3(256), 0, x, y, (const float*)a.ea, (const float*)a.ib, T, C, CB, s->taps, y16);
   e->launches++;
 }
 

@@ -58,6 +58,7 @@ struct TcParams {
   int accum; float scale;
   float* out; long long out_batch_stride, out_off, out_valid; int ldo;
   int stages;
+  int epi; __half* out16; const float* aux; int aux_stride;
 };
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_128B: start address (>>4), LBO (unused for
@@ -107,6 +108,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above overlapped with the previous kernel of the stream (programmatic dependent launch); from here on
+  // this grid reads what that kernel wrote
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -166,11 +171,71 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t r[32];
       ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       ptx::tmem_ld_wait();
+      if (p.epi == EPI_NONE) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(r[j]);
+      }
       __syncwarp();
       const int n = n0 + c0 + lane;
-      if (n < p.N) {
+      if (p.epi != EPI_NONE) {
+        // fused pair epilogues, thread = accumulator row (the TMEM lane it just read): both columns of every pair are in this
+        // thread's registers, no transpose and no shuffle; each thread writes 16 or 32 fp16 values = whole 32-byte sectors.
+        // (N is a multiple of 32 for these GEMMs: whole 32-column chunks only.)
+        const int row = mrow0 + lane;
+        if (row < p.M) {
+          const int nb = n0 + c0;                                // first column of this chunk
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + nb + j) : 0.f);
+          if (p.epi == EPI_ROPE) {
+            const int HD = 64, Hh = p.aux_stride, HW = Hh * HD;
+            const int which = nb / HW, hh = (nb % HW) / HD, d0 = nb % HD;      // q | k | v, head, first dim of the chunk
+            __half* dst = p.out16 + (size_t)which * ((size_t)gridDim.z * Hh * p.M * HD) + (((size_t)b * Hh + hh) * (size_t)p.M + row) * HD + d0;
+            uint32_t o[16];
+            if (which < 2) {
+              const float4* tab = (const float4*)(p.aux + ((size_t)row * (HD / 2) + (d0 >> 1)) * 2);   // (cos, sin) pairs
+              const float sc = (which == 0) ? 0.125f : 1.0f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 t4 = __ldg(tab + i);
+                const float a0 = v[4 * i], a1 = v[4 * i + 1], b0 = v[4 * i + 2], b1 = v[4 * i + 3];
+                __half2 h0 = __floats2half2_rn((a0 * t4.x - a1 * t4.y) * sc, (a1 * t4.x + a0 * t4.y) * sc);
+                __half2 h1 = __floats2half2_rn((b0 * t4.z - b1 * t4.w) * sc, (b1 * t4.z + b0 * t4.w) * sc);
+                o[2 * i] = *(uint32_t*)&h0;
+                o[2 * i + 1] = *(uint32_t*)&h1;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                o[i] = *(uint32_t*)&h;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ((uint4*)dst)[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+          } else {
+            const int NH = p.N >> 1, j0 = nb >> 1;
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float r0, r1;
+              if (p.epi == EPI_SWIGLU) {                          // F.silu(w1 x) * (w3 x)
+                r0 = __fdividef(v[4 * i], 1.f + __expf(-v[4 * i])) * v[4 * i + 1];
+                r1 = __fdividef(v[4 * i + 2], 1.f + __expf(-v[4 * i + 2])) * v[4 * i + 3];
+              } else {                                            // fused_add_tanh_sigmoid_multiply
+                const float* ga = p.aux + (size_t)b * p.aux_stride + j0 + 2 * i;
+                r0 = tanhf(v[4 * i] + __ldg(ga)) * __fdividef(1.f, 1.f + __expf(-(v[4 * i + 1] + __ldg(ga + NH))));
+                r1 = tanhf(v[4 * i + 2] + __ldg(ga + 1)) * __fdividef(1.f, 1.f + __expf(-(v[4 * i + 3] + __ldg(ga + NH + 1))));
+              }
+              __half2 h = __floats2half2_rn(r0, r1);
+              o[i] = *(uint32_t*)&h;
+            }
+            uint4* dst = (uint4*)(p.out16 + ((size_t)b * p.M + row) * NH + j0);
+            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+        }
+      } else if (n < p.N) {
         const float bv = p.bias ? __ldg(p.bias + (n % biasN)) : 0.f;
         const float cs = (p.colscale ? __ldg(p.colscale + n) : 1.f);
         const long long flat0 = p.out_off + (long long)mrow0 * p.ldo + n;     // row rr adds rr*ldo
@@ -280,6 +345,10 @@ void launch_bn(idx_engine* e, const ConvGemm& g, const CUtensorMap& tmA, const C
   p.out_batch_stride = g.out_batch_stride ? g.out_batch_stride : (long long)g.M * g.N;
   p.out_off = g.out_off;
   p.out_valid = g.out_valid ? g.out_valid : (long long)g.M * p.ldo;
+  p.epi = g.epi; p.out16 = g.out16; p.aux = g.aux; p.aux_stride = g.aux_stride;
+  if (g.epi != EPI_NONE)
+    IDX_CHECK(g.out16 && g.N % 32 == 0 && !g.res && !g.accum && g.act == ACT_NONE && (g.epi == EPI_SWIGLU || g.aux), IDX_ERR_ARG,
+              "conv_gemm: bad fused-epilogue arguments");
   constexpr int STAGE = BM * BKB + BN * BKB;
   const int n_iters = p.taps * p.n_kchunks;
   static const int occ = getenv("IDX_GEMM_OCC") ? atoi(getenv("IDX_GEMM_OCC")) : 2;
@@ -294,12 +363,223 @@ void launch_bn(idx_engine* e, const ConvGemm& g, const CUtensorMap& tmA, const C
     e->attr_done |= bit;
   }
   dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.B);
-  gemm_tc_kernel<BN, EB><<<grid, 192, smem, e->stream>>>(tmA, tmB, p);
-  IDX_CUDA(cudaGetLastError());
+  launch_pdl(e, gemm_tc_kernel<BN, EB>, grid, dim3(192), smem, tmA, tmB, p);
   e->launches++;
 }
 
+
+// ================================================================================================================
+// tcgen05 flash attention for the DiT (full attention, head dim 64, fp16 operands, fp32 softmax and accumulation).
+//   gpt_fast/model.py:293-303 (F.scaled_dot_product_attention over all T keys; q arrives pre-scaled by 1/8 and
+//   rotated — EPI_ROPE above).
+// One CTA = 128 queries of one (batch, head).  TMEM: S [128 lanes x 128 cols fp32] | O [x 64] | P [x 64: 128 fp16 per
+// row packed two per column] = 256 columns, so two CTAs share an SM and fill each other's bubbles.
+//   warp 0      TMA: Q tile once, then K_j / V_j tiles of 128 keys into a 2-stage ring (SWIZZLE_128B rows of 64 fp16);
+//   warp 1      one thread issues S = Q K_j^T (4 x tcgen05.mma M128 N128 K16, both operands K-major in shared memory) and,
+//               once the softmax warps have stored P_j, O (+)= P_j V_j (8 x M128 N64 K16: A = P from TENSOR MEMORY,
+//               B = V straight from its [key][dim] rows = MN-major operand);
+//   warps 2..5  thread = query row = TMEM lane: online softmax in the log2 domain (two passes over S in TMEM: row max,
+//               then exp2 / row sum / fp16 pack -> tcgen05.st P), rescale of O when the row max moved, final O / l.
+// The legacy mma.sync flash kernel (nn_ops.cu) ran at the mma.sync ceiling of this part (~170 TFLOP/s); here the exp
+// throughput (MUFU) is the bound, as in every Blackwell attention kernel.
+constexpr int FA_Q = 128, FA_K = 128, FA_D = 64;
+struct FaParams { int T, H; float* out; __half* out16; };
+
+__global__ void __launch_bounds__(192, 2)
+fa5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+           const FaParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int TILE = FA_K * FA_D * 2;                  // 16 KB: 128 rows x 128 bytes
+  unsigned char* sQ = base;
+  unsigned char* sK = base + TILE;                       // [2][TILE]
+  unsigned char* sV = base + 3 * TILE;                   // [2][TILE]
+  uint64_t* bars = (uint64_t*)(base + 5 * TILE);
+  uint64_t *q_full = bars, *kv_full = bars + 1, *kv_empty = bars + 3, *s_full = bars + 5, *p_full = bars + 6, *o_full = bars + 7;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y, q0 = blockIdx.x * FA_Q;
+  const int T = p.T, ntiles = (T + FA_K - 1) / FA_K;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&kv_full[s], 1); ptx::mbar_init(&kv_empty[s], 1); }
+    ptx::mbar_init(s_full, 1);
+    ptx::mbar_init(p_full, 128);
+    ptx::mbar_init(o_full, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, 256);
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::tcgen05_fence_after();
+  const uint32_t tm = *tmem_slot;
+  const uint32_t tS = tm, tO = tm + 128, tP = tm + 192;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::prefetch_tensormap(&tmQ); ptx::prefetch_tensormap(&tmK); ptx::prefetch_tensormap(&tmV);
+      ptx::mbar_arrive_expect_tx(q_full, TILE);
+      ptx::tma_load_3d(sQ, &tmQ, q_full, 0, q0, bh);
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j & 1;
+        ptx::mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1u);
+        ptx::mbar_arrive_expect_tx(&kv_full[s], 2 * TILE);
+        ptx::tma_load_3d(sK + s * TILE, &tmK, &kv_full[s], 0, j * FA_K, bh);
+        ptx::tma_load_3d(sV + s * TILE, &tmV, &kv_full[s], 0, j * FA_K, bh);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // D = f32, A = B = f16; S: N = 128 keys, both K-major; PV: N = 64 dims, B (V) MN-major (bit 16)
+      const uint32_t idesc_s = (1u << 4) | ((uint32_t)(FA_K >> 3) << 17) | ((uint32_t)(FA_Q >> 4) << 24);
+      const uint32_t idesc_o = (1u << 4) | (1u << 16) | ((uint32_t)(FA_D >> 3) << 17) | ((uint32_t)(FA_Q >> 4) << 24);
+      ptx::mbar_wait(q_full, 0);
+      const uint64_t dq = make_desc(ptx::smem_u32(sQ));
+      for (int j = 0; j < ntiles; ++j) {
+        const int s = j & 1;
+        ptx::mbar_wait(&kv_full[s], (j >> 1) & 1u);
+        ptx::tcgen05_fence_after();
+        const uint64_t dk = make_desc(ptx::smem_u32(sK + s * TILE));
+#pragma unroll
+        for (int k = 0; k < FA_D / 16; ++k) ptx::umma_f16(tS, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k > 0 ? 1u : 0u);
+        ptx::umma_commit(s_full);                       // tracks every MMA issued so far: S_j ready AND O += P_{j-1} V_{j-1} done
+        ptx::mbar_wait(p_full, j & 1u);                 // P_j is in tensor memory, O has been rescaled
+        ptx::tcgen05_fence_after();
+        const uint64_t dv = make_desc(ptx::smem_u32(sV + s * TILE));
+#pragma unroll
+        for (int k = 0; k < FA_K / 16; ++k)             // 16 keys per MMA: 8 packed P columns, 16 V rows = 2048 bytes
+          ptx::umma_f16_ts(tO, tP + (uint32_t)(8 * k), dv + (uint64_t)(128 * k), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        ptx::umma_commit(&kv_empty[s]);                 // K_j / V_j consumed
+      }
+      ptx::umma_commit(o_full);
+    }
+  } else {
+    const int qd = warp & 3;                            // TMEM lane quarter of this warp
+    const int row = qd * 32 + lane;                     // query row inside the tile = TMEM lane
+    const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+    const float LOG2E = 1.4426950408889634f;
+    float m = -INFINITY, l = 0.f;                       // running row max (log2 domain) and row sum
+    for (int j = 0; j < ntiles; ++j) {
+      ptx::mbar_wait(s_full, j & 1u);
+      ptx::tcgen05_fence_after();
+      const int kbase = j * FA_K;
+      // pass A: row max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < FA_K; c += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(tS + lane_off + (uint32_t)c, r);
+        ptx::tmem_ld_wait();
+        const int nvalid = T - (kbase + c);             // keys beyond T (zero-filled rows of the last tile) are masked
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, i < nvalid ? __uint_as_float(r[i]) : -INFINITY);
+      }
+      const float mn = fmaxf(m, mx * LOG2E);
+      const float corr = exp2f(m - mn);                 // 0 at the first tile (m = -inf)
+      float rs = 0.f;
+      // pass B: p = 2^(s log2e - mn), fp16 pairs -> P (tensor memory)
+#pragma unroll 1
+      for (int c = 0; c < FA_K; c += 32) {
+        uint32_t r[32], pk[16];
+        ptx::tmem_ld_32x32b_x32(tS + lane_off + (uint32_t)c, r);
+        ptx::tmem_ld_wait();
+        const int nvalid = T - (kbase + c);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = (2 * i < nvalid) ? exp2f(fmaf(__uint_as_float(r[2 * i]), LOG2E, -mn)) : 0.f;
+          const float p1 = (2 * i + 1 < nvalid) ? exp2f(fmaf(__uint_as_float(r[2 * i + 1]), LOG2E, -mn)) : 0.f;
+          rs += p0 + p1;
+          __half2 h = __floats2half2_rn(p0, p1);
+          pk[i] = *(uint32_t*)&h;
+        }
+        // the 16 packed columns (32 keys) of this chunk
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
+                tP + lane_off + (uint32_t)(c >> 1)),
+            "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]), "r"(pk[8]), "r"(pk[9]),
+            "r"(pk[10]), "r"(pk[11]), "r"(pk[12]), "r"(pk[13]), "r"(pk[14]), "r"(pk[15])
+            : "memory");
+      }
+      l = l * corr + rs;
+      if (j > 0 && __any_sync(0xffffffffu, corr != 1.f)) {     // warp-uniform: tcgen05.ld / st are warp-collective
+        // the row max moved: O (complete up to tile j-1: s_full tracks that MMA too) is rescaled in tensor memory
+#pragma unroll 1
+        for (int c = 0; c < FA_D; c += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(tO + lane_off + (uint32_t)c, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
+          ptx::tmem_st_32x32b_x32(tO + lane_off + (uint32_t)c, r);
+        }
+      }
+      m = mn;
+      ptx::tmem_st_wait();
+      ptx::tcgen05_fence_before();
+      ptx::mbar_arrive(p_full);
+    }
+    // epilogue: O / l -> fp16 (operand of the output projection) and / or fp32, [B][T][H*64]
+    ptx::mbar_wait(o_full, 0);
+    ptx::tcgen05_fence_after();
+    const int t = q0 + row;
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    const int b = bh / p.H, h = bh % p.H;
+    const size_t o = ((size_t)b * T + t) * (size_t)p.H * FA_D + (size_t)h * FA_D;
+#pragma unroll 1
+    for (int c = 0; c < FA_D; c += 32) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(tO + lane_off + (uint32_t)c, r);
+      ptx::tmem_ld_wait();
+      if (t < T) {
+        if (p.out16) {
+          uint32_t hh[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            __half2 h2 = __floats2half2_rn(__uint_as_float(r[2 * i]) * inv, __uint_as_float(r[2 * i + 1]) * inv);
+            hh[i] = *(uint32_t*)&h2;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ((uint4*)(p.out16 + o + c))[i] = make_uint4(hh[4 * i], hh[4 * i + 1], hh[4 * i + 2], hh[4 * i + 3]);
+        }
+        if (p.out) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            ((float4*)(p.out + o + c))[i] = make_float4(__uint_as_float(r[4 * i]) * inv, __uint_as_float(r[4 * i + 1]) * inv,
+                                                        __uint_as_float(r[4 * i + 2]) * inv, __uint_as_float(r[4 * i + 3]) * inv);
+        }
+      }
+    }
+    ptx::tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc(tm, 256);
+  }
+}
+
 }  // namespace
+
+// tcgen05 flash attention on the rotated / split fp16 tensors Qr | Kr | Vb [B*H][T][64] (see fa5_kernel)
+void flash_attention_tc5(idx_engine* e, const __half* Qr, const __half* Kr, const __half* Vb, float* out, __half* out16,
+                         int B, int T, int H) {
+  const int BH = B * H;
+  cuuint64_t dims[3] = {(cuuint64_t)FA_D, (cuuint64_t)T, (cuuint64_t)BH};
+  cuuint64_t str[2] = {(cuuint64_t)FA_D * 2, (cuuint64_t)T * FA_D * 2};
+  cuuint32_t box[3] = {FA_D, FA_K, 1};
+  CUtensorMap tq = make_map(Qr, 3, dims, str, box, true), tk = make_map(Kr, 3, dims, str, box, true), tv = make_map(Vb, 3, dims, str, box, true);
+  FaParams p;
+  p.T = T; p.H = H; p.out = out; p.out16 = out16;
+  const size_t smem = 5 * (size_t)(FA_K * FA_D * 2) + 1024 + 128;
+  if (!(e->attr_done & (1u << 20))) {
+    IDX_CUDA(cudaFuncSetAttribute(fa5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    e->attr_done |= 1u << 20;
+  }
+  launch_pdl(e, fa5_kernel, dim3((T + FA_Q - 1) / FA_Q, BH), dim3(192), smem, tq, tk, tv, p);
+  e->launches++;
+}
 
 bool gemm_tc_supported(const ConvGemm& g) {
   static const bool off = getenv("IDX_NO_TC") != nullptr;

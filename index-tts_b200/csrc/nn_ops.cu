@@ -25,6 +25,7 @@ __global__ void rownorm_kernel(const float* __restrict__ x, float* __restrict__ 
                                int C, const float* __restrict__ w, const float* __restrict__ b, float eps,
                                const float* __restrict__ m0, const float* __restrict__ m1, int mod_stride,
                                __half* __restrict__ y16) {
+  pdl_wait();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -128,6 +129,7 @@ __global__ void embedding_kernel(const float* __restrict__ table, const int* __r
 }
 
 __global__ void swiglu_kernel(const float* __restrict__ ab, float* __restrict__ y, long long rows, int N, __half* __restrict__ y16) {
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * N) return;
   const long long r = i / N;
@@ -138,6 +140,7 @@ __global__ void swiglu_kernel(const float* __restrict__ ab, float* __restrict__ 
 
 __global__ void wn_gate_kernel(const float* __restrict__ xin, const float* __restrict__ g, int g_stride,
                                float* __restrict__ y, int T, int N, __half* __restrict__ y16) {
+  pdl_wait();
   // fused_add_tanh_sigmoid_multiply (s2mel/modules/commons.py:132-141)
   const int bi = blockIdx.z;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,6 +155,7 @@ __global__ void wn_gate_kernel(const float* __restrict__ xin, const float* __res
 
 __global__ void copy_cols_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldo,
                                  int col0, long long rows, int C, __half* __restrict__ dst16) {
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * C) return;
   const long long r = i / C;
@@ -173,6 +177,7 @@ __global__ void silu_kernel(float* x, long long n) {
 }
 __global__ void reflect_pad_kernel(const float* __restrict__ x, float* __restrict__ y, int T, int C, int left,
                                    int Tout, __half* __restrict__ y16) {
+  pdl_wait();
   const int bi = blockIdx.z, i = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -182,6 +187,7 @@ __global__ void reflect_pad_kernel(const float* __restrict__ x, float* __restric
   put(y, y16, ((long long)bi * Tout + i) * C + c, x[((long long)bi * T + t) * C + c]);
 }
 __global__ void zero_kernel(float* x, long long n) {
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) x[i] = 0.f;
 }
@@ -197,6 +203,7 @@ __global__ void rope_table_kernel(float* tab, int T, int hd) {
 }
 __global__ void cfg_euler_kernel(float* x, const float* vc, const float* vu, float dt, float rate, int T,
                                  int C, int P) {
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)T * C) return;
   const int t = (int)(i / C);
@@ -381,6 +388,7 @@ __global__ void heads_merge_kernel(const float* __restrict__ O, float* __restric
 __global__ void rope_split_fa_kernel(const float* __restrict__ qkv, const float* __restrict__ rope,
                                      __half* __restrict__ Qr, __half* __restrict__ Kr,
                                      __half* __restrict__ Vb, int T, int H) {
+  pdl_wait();
   const int t = blockIdx.x, h = blockIdx.y, b = blockIdx.z, i = threadIdx.x;  // 64 threads
   const int ld = 3 * H * AD;
   const float* row = qkv + ((long long)b * T + t) * ld;
@@ -433,6 +441,7 @@ __global__ void __launch_bounds__(128) flash_attn_tc_kernel(const __half* __rest
                                                             const __half* __restrict__ Vb,
                                                             float* __restrict__ out, int T, int H,
                                                             __half* __restrict__ out16) {
+  pdl_wait();
   // K/V tiles are double buffered: cp.async fills tile i+1 while the tensor cores work on tile i
   __shared__ __align__(16) __half Ks2[2][FK * VPITCH];
   __shared__ __align__(16) __half Vs2[2][FK * VPITCH];
@@ -589,13 +598,13 @@ __global__ void __launch_bounds__(128) flash_attn_tc_kernel(const __half* __rest
 void layernorm(idx_engine* e, const float* x, float* y, int B, int T, int C, const float* w, const float* b,
                float eps, const float* scale, const float* shift, int mod_stride, __half* y16) {
   const long long rows = (long long)B * T;
-  rownorm_kernel<0><<<(unsigned)((rows + 7) / 8), 256, 0, e->stream>>>(x, y, rows, T, C, w, b, eps, scale, shift, mod_stride, y16);
+  launch_pdl(e, rownorm_kernel<0>, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, x, y, rows, T, C, w, b, eps, scale, shift, mod_stride, y16);
   LAUNCH_CHECK(e);
 }
 void rmsnorm_adaln(idx_engine* e, const float* x, float* y, int B, int T, int C, const float* nw, const float* mw,
                    const float* mb, int mod_stride, float eps, __half* y16) {
   const long long rows = (long long)B * T;
-  rownorm_kernel<1><<<(unsigned)((rows + 7) / 8), 256, 0, e->stream>>>(x, y, rows, T, C, nw, nullptr, eps, mw, mb, mod_stride, y16);
+  launch_pdl(e, rownorm_kernel<1>, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, x, y, rows, T, C, nw, (const float*)nullptr, eps, mw, mb, mod_stride, y16);
   LAUNCH_CHECK(e);
 }
 void groupnorm1_mish(idx_engine* e, const float* x, float* y, int B, int T, int C, const float* w, const float* b,
@@ -625,16 +634,16 @@ void embedding_rows(idx_engine* e, const float* table, const int* ids, float* ou
   LAUNCH_CHECK(e);
 }
 void swiglu(idx_engine* e, const float* ab, float* y, long long rows, int N, __half* y16) {
-  swiglu_kernel<<<(unsigned)((rows * N + 255) / 256), 256, 0, e->stream>>>(ab, y, rows, N, y16);
+  launch_pdl(e, swiglu_kernel, dim3((unsigned)((rows * N + 255) / 256)), dim3(256), 0, ab, y, rows, N, y16);
   LAUNCH_CHECK(e);
 }
 void wn_gate(idx_engine* e, const float* xin, const float* g, int g_stride, float* y, int B, int T, int N, __half* y16) {
   dim3 grid((unsigned)(((long long)T * N + 255) / 256), 1, B);
-  wn_gate_kernel<<<grid, 256, 0, e->stream>>>(xin, g, g_stride, y, T, N, y16);
+  launch_pdl(e, wn_gate_kernel, grid, dim3(256), 0, xin, g, g_stride, y, T, N, y16);
   LAUNCH_CHECK(e);
 }
 void copy_cols(idx_engine* e, const float* src, int lds, float* dst, int ldo, int col0, long long rows, int C, __half* dst16) {
-  copy_cols_kernel<<<(unsigned)((rows * C + 255) / 256), 256, 0, e->stream>>>(src, lds, dst, ldo, col0, rows, C, dst16);
+  launch_pdl(e, copy_cols_kernel, dim3((unsigned)((rows * C + 255) / 256)), dim3(256), 0, src, lds, dst, ldo, col0, rows, C, dst16);
   LAUNCH_CHECK(e);
 }
 void bcast_cols(idx_engine* e, const float* vec, float* dst, int ldo, int col0, int B, int T, int C) {
@@ -647,13 +656,13 @@ void silu_inplace(idx_engine* e, float* x, long long n) {
   LAUNCH_CHECK(e);
 }
 void fill_zero(idx_engine* e, float* x, long long n) {
-  zero_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(x, n);
+  launch_pdl(e, zero_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, x, n);
   LAUNCH_CHECK(e);
 }
 void reflect_pad_rows(idx_engine* e, const float* x, float* y, int B, int T, int C, int left, int right, __half* y16) {
   const int Tout = T + left + right;
   dim3 grid((C + 127) / 128, Tout, B);
-  reflect_pad_kernel<<<grid, 128, 0, e->stream>>>(x, y, T, C, left, Tout, y16);
+  launch_pdl(e, reflect_pad_kernel, grid, dim3(128), 0, x, y, T, C, left, Tout, y16);
   LAUNCH_CHECK(e);
 }
 void rope_table(idx_engine* e, float* tab, int T, int hd) {
@@ -670,9 +679,9 @@ void attention_rope(idx_engine* e, const float* qkv, float* out, int B, int T, i
     __half* Qr = (__half*)e->arena.alloc((size_t)BH * T * AD * 2);
     __half* Kr = (__half*)e->arena.alloc((size_t)BH * T * AD * 2);
     __half* Vb = (__half*)e->arena.alloc((size_t)BH * T * AD * 2);
-    rope_split_fa_kernel<<<dim3(T, H, B), AD, 0, e->stream>>>(qkv, rope, Qr, Kr, Vb, T, H);
+    launch_pdl(e, rope_split_fa_kernel, dim3(T, H, B), dim3(AD), 0, qkv, rope, Qr, Kr, Vb, T, H);
     LAUNCH_CHECK(e);
-    flash_attn_tc_kernel<<<dim3((T + FQ - 1) / FQ, (unsigned)BH), 128, 0, e->stream>>>(Qr, Kr, Vb, out, T, H, out16);
+    launch_pdl(e, flash_attn_tc_kernel, dim3((T + FQ - 1) / FQ, (unsigned)BH), dim3(128), 0, (const __half*)Qr, (const __half*)Kr, (const __half*)Vb, out, T, H, out16);
     LAUNCH_CHECK(e);
     e->arena.off = mark;
     return;
@@ -715,8 +724,18 @@ void attention_rope(idx_engine* e, const float* qkv, float* out, int B, int T, i
   attention_kernel<<<grid, 256, smem, e->stream>>>(qkv, out, T, H, rope, lens);
   LAUNCH_CHECK(e);
 }
+void flash_attention_split(idx_engine* e, const __half* Qr, const __half* Kr, const __half* Vb, float* out, __half* out16,
+                           int B, int T, int H) {
+  static const bool fa5 = !(getenv("IDX_FA5") && atoi(getenv("IDX_FA5")) == 0);
+  if (fa5) {
+    flash_attention_tc5(e, Qr, Kr, Vb, out, out16, B, T, H);
+    return;
+  }
+  launch_pdl(e, flash_attn_tc_kernel, dim3((T + FQ - 1) / FQ, (unsigned)((long long)B * H)), dim3(128), 0, Qr, Kr, Vb, out, T, H, out16);
+  LAUNCH_CHECK(e);
+}
 void cfg_euler(idx_engine* e, float* x, const float* v_cond, const float* v_uncond, float dt, float rate, int T,
                int C, int P) {
-  cfg_euler_kernel<<<(unsigned)(((long long)T * C + 255) / 256), 256, 0, e->stream>>>(x, v_cond, v_uncond, dt, rate, T, C, P);
+  launch_pdl(e, cfg_euler_kernel, dim3((unsigned)(((long long)T * C + 255) / 256)), dim3(256), 0, x, v_cond, v_uncond, dt, rate, T, C, P);
   LAUNCH_CHECK(e);
 }

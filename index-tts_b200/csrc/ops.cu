@@ -164,7 +164,8 @@ extern "C" int idx_set_option(idx_engine* e, const char* name, int value) {
 }
 
 void conv_gemm(idx_engine* e, const ConvGemm& g) {
-  IDX_CHECK((g.A || g.A16) && g.out && g.M > 0 && g.N > 0 && g.K > 0, IDX_ERR_ARG, "conv_gemm: bad arguments");
+  IDX_CHECK((g.A || g.A16) && (g.out || g.out16) && g.M > 0 && g.N > 0 && g.K > 0, IDX_ERR_ARG, "conv_gemm: bad arguments");
+  IDX_CHECK(g.epi == EPI_NONE || (g.A16 && g.Wk16), IDX_ERR_ARG, "conv_gemm: fused pair epilogues exist on the fp16 tensor-core path only");
   if (g.A16 && g.Wk16) {       // fp16 operands exist only for the tensor-core kernel
     IDX_CHECK(gemm_tc_supported(g), IDX_ERR_ARG, "conv_gemm: fp16 operands with a shape the tensor-core kernel does not take");
     gemm_tc_launch(e, g);
@@ -281,6 +282,7 @@ ConvGemm gemm_of16(const PackedW& w, const __half* A16, int B, int T, float* out
 
 namespace {
 __global__ void to_half_kernel(const float* __restrict__ x, __half* __restrict__ y, long long n) {
+  pdl_wait();
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 2;
   if (i + 1 < n) *(__half2*)(y + i) = __floats2half2_rn(x[i], x[i + 1]);
   else if (i < n) y[i] = __float2half_rn(x[i]);
@@ -289,9 +291,40 @@ __global__ void to_half_kernel(const float* __restrict__ x, __half* __restrict__
 
 void to_half(idx_engine* e, const float* x, __half* y, long long n) {
   if (n <= 0) return;
-  to_half_kernel<<<(unsigned)((n / 2 + 256) / 256), 256, 0, e->stream>>>(x, y, n);
-  IDX_CUDA(cudaGetLastError());
+  launch_pdl(e, to_half_kernel, dim3((unsigned)((n / 2 + 256) / 256)), dim3(256), 0, x, y, n);
   e->launches++;
+}
+
+namespace {
+__global__ void interleave_half_kernel(const float* __restrict__ wk, __half* __restrict__ dst, int N, long long KT) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * KT) return;
+  const int r = (int)(i / KT);
+  const long long k = i % KT;
+  const int src = (r & 1) ? (N / 2 + (r >> 1)) : (r >> 1);
+  dst[i] = __float2half_rn(wk[(long long)src * KT + k]);
+}
+__global__ void interleave_bias_kernel(const float* __restrict__ b, float* __restrict__ dst, int N) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < N) dst[r] = b[(r & 1) ? (N / 2 + (r >> 1)) : (r >> 1)];
+}
+}  // namespace
+
+__half* pack_half_interleaved(idx_engine* e, WeightPool& pool, const PackedW& w, float** bias_out) {
+  IDX_CHECK(w.wk && w.N % 2 == 0, IDX_ERR_ARG, "pack_half_interleaved: needs a K-major weight with an even row count");
+  const long long KT = (long long)w.K * w.taps, n = (long long)w.N * KT;
+  __half* dst = (__half*)pool.alloc((size_t)(n + 1) / 2 + 4);
+  interleave_half_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(w.wk, dst, w.N, KT);
+  IDX_CUDA(cudaGetLastError());
+  if (bias_out) {
+    *bias_out = nullptr;
+    if (w.bias) {
+      *bias_out = pool.alloc(w.N);
+      interleave_bias_kernel<<<(w.N + 255) / 256, 256, 0, e->stream>>>(w.bias, *bias_out, w.N);
+      IDX_CUDA(cudaGetLastError());
+    }
+  }
+  return dst;
 }
 
 void pack_half(idx_engine* e, WeightPool& pool, PackedW& w) {

@@ -4,9 +4,12 @@
 #pragma once
 #include "engine.h"
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include <string>
+#include <utility>
 #include <vector>
 
+enum { EPI_NONE = 0, EPI_SWIGLU = 1, EPI_WNGATE = 2, EPI_ROPE = 3 };
 enum { ACT_NONE = 0, ACT_GELU_ERF = 1, ACT_SILU = 2, ACT_MISH = 3, ACT_GELU_TANH = 4, ACT_RELU = 5 };
 
 // D[b][m][j] = epi( sum_{tap} sum_{k} A[b][m + tap*dil - pad][k] * W[tap][k][j] )
@@ -23,6 +26,15 @@ struct ConvGemm {
   // strides given in ELEMENTS as for the fp32 operands).  Written by the producing kernel of A / converted once at init.
   const __half* A16 = nullptr;
   const __half* Wk16 = nullptr;
+  // fused pair epilogues of the tensor-core kernel (fp16 results straight into the operand of the next GEMM / the attention):
+  //   EPI_SWIGLU : columns (2j, 2j+1) = (w1 x, w3 x)_j (weight rows interleaved at pack time) -> out16[row][j] = silu(a) * b
+  //   EPI_WNGATE : columns (2j, 2j+1) = (a_j, c_j) of the WaveNet in_layer -> out16[row][j] = tanh(a + g[b][j]) * sigmoid(c + g[b][N/2 + j])
+  //   EPI_ROPE   : columns = q | k | v of the fused wqkv: interleaved-pair RoPE (table aux [T][32][2]) on q (x 1/8) and k, v as is,
+  //                written head-major as fp16 Qr | Kr | Vb [B*H][T][64] (out16 = Qr; the three tensors are contiguous)
+  int epi = 0;
+  __half* out16 = nullptr;
+  const float* aux = nullptr;      // EPI_WNGATE: g [B][aux_stride] ; EPI_ROPE: rope table
+  int aux_stride = 0;              // EPI_WNGATE: floats per batch entry of g ; EPI_ROPE: heads
   long long w_batch_stride = 0;  // elements between the Wk matrices of consecutive batch entries (0: shared)
   int ldw = 0;                   // row stride of Wk in elements; 0 → taps*K
   int taps = 1, dil = 1, pad = 0, reflect = 0;
@@ -49,6 +61,28 @@ inline int gemm_default_backend(const idx_engine* e) { return e->gemm_backend; }
 // [B][C][T] <-> [B][T][C]
 void transpose_bct_to_btc(idx_engine* e, const float* in, float* out, int B, int C, int T);
 void transpose_btc_to_bct(idx_engine* e, const float* in, float* out, int B, int T, int C);
+
+// ------------------------------------------------------------- programmatic dependent launch --
+// The tail is ~4000 short kernels per utterance.  Kernels launched through launch_pdl() carry the programmatic-stream-
+// serialization attribute: their CTAs may be scheduled while the previous kernel of the stream is still draining, so launch
+// latency and the kernel's own prologue (barrier init, TMEM allocation, descriptor prefetch) overlap with it.  Such a kernel
+// executes pdl_wait() — every thread — before it touches global memory, and pdl_trigger() as soon as it has nothing left that
+// the NEXT kernel could disturb (the next kernel's own pdl_wait still waits for this grid to finish completely).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(idx_engine* e, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+  static const bool off = getenv("IDX_PDL") && atoi(getenv("IDX_PDL")) == 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = e->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = off ? 0 : 1;
+  IDX_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+}
+#endif
 
 // ---------------------------------------------------------------- normalisation / pointwise --
 // y = LayerNorm(x) [* w + b] [ * (1 + scale[b]) + shift[b] ]   rows of C, x/y [B][T][C]
@@ -116,6 +150,15 @@ ConvGemm gemm_of(const PackedW& w, const float* A, int B, int T, float* out);
 ConvGemm gemm_of16(const PackedW& w, const __half* A16, int B, int T, float* out);
 // fp16 copy of a K-major weight matrix (w.wk must exist); idempotent
 void pack_half(idx_engine* e, WeightPool& pool, PackedW& w);
+// fp16 K-major copy of w.wk with the two halves of the output rows interleaved (row 2j = row j, row 2j+1 = row N/2 + j): the
+// weight layout of the EPI_SWIGLU / EPI_WNGATE pair epilogues; bias_out (optional) receives the bias interleaved the same way
+__half* pack_half_interleaved(idx_engine* e, WeightPool& pool, const PackedW& w, float** bias_out);
+// the fused flash attention on already rotated / split fp16 tensors Qr | Kr | Vb [B*H][T][64] (what EPI_ROPE writes)
+void flash_attention_split(idx_engine* e, const __half* Qr, const __half* Kr, const __half* Vb, float* out, __half* out16,
+                           int B, int T, int H);
+// the same on tcgen05 (gemm_tc.cu: S and O in tensor memory, P fed back as a tensor-memory operand)
+void flash_attention_tc5(idx_engine* e, const __half* Qr, const __half* Kr, const __half* Vb, float* out, __half* out16,
+                         int B, int T, int H);
 // fp32 -> fp16 (round to nearest), n elements
 void to_half(idx_engine* e, const float* x, __half* y, long long n);
 // true when the engine runs the tail with fp16 GEMM operands (tensor-core back end and not disabled by IDX_TAIL_F16=0)

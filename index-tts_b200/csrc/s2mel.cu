@@ -60,6 +60,9 @@ struct S2melState {
   PackedW te_mlp0, te_mlp2, te2_mlp0, te2_mlp2, wn_cond;
   const float *te_freqs = nullptr, *te2_freqs = nullptr;
   std::vector<PackedW> wn_in, wn_res, wn_skip;
+  // fused-epilogue weight layouts of the fp16 path (rows of the two halves interleaved): w1|w3 and the WaveNet in_layers
+  std::vector<__half*> w13_i16, wn_in_i16;
+  std::vector<float*> wn_in_bias_i;
   int mod_width = 0;
   // length regulator
   PackedW lr_in_proj, lr_out;
@@ -227,6 +230,13 @@ extern "C" int idx_s2mel_init(idx_engine* e, const idx_s2mel_config* cfg) {
   for (auto* v : {&s->wqkv, &s->wo, &s->w13, &s->w2, &s->skip_in, &s->wn_in, &s->wn_res, &s->wn_skip})
     for (auto& w : *v) pack_half(e, s->pool, w);
   for (auto* w : {&s->skip_linear, &s->conv1, &s->res_proj, &s->fl_linear, &s->conv2}) pack_half(e, s->pool, *w);
+  s->w13_i16.clear(); s->wn_in_i16.clear(); s->wn_in_bias_i.clear();
+  for (auto& w : s->w13) s->w13_i16.push_back(pack_half_interleaved(e, s->pool, w, nullptr));
+  for (auto& w : s->wn_in) {
+    float* bi = nullptr;
+    s->wn_in_i16.push_back(pack_half_interleaved(e, s->pool, w, &bi));
+    s->wn_in_bias_i.push_back(bi);
+  }
   s->has_s2mel = true;
   IDX_API_END(e)
 }
@@ -312,7 +322,7 @@ struct DitBuffers {
   float *h[16], *a, *qkv, *att, *ff, *cat, *xres, *wy, *wpad, *wxin, *wacts, *wout, *z, *v, *rope;
   // fp16 images of the GEMM operands (tail_half mode): written by the kernel that produces the operand
   __half *a16 = nullptr, *att16 = nullptr, *ffh16 = nullptr, *cat16 = nullptr, *xres16 = nullptr, *wpad16 = nullptr,
-         *wacts16 = nullptr, *z16 = nullptr, *wy16 = nullptr;
+         *wacts16 = nullptr, *z16 = nullptr, *wy16 = nullptr, *qkv16 = nullptr;     // qkv16: Qr | Kr | Vb [B*H][T][64] each
   int* lens;
 };
 
@@ -329,6 +339,7 @@ static void dit_eval(idx_engine* e, S2melState* s, DitBuffers& b, int Bn, int T,
     conv_gemm(e, g);
   }
   const bool hf = b.a16 != nullptr;     // fp16 GEMM operands (alloc_dit decides; see ops.h tail_half)
+  static const bool fused = !(getenv("IDX_TAIL_FUSED") && atoi(getenv("IDX_TAIL_FUSED")) == 0);   // pair epilogues (A/B switch)
   auto G = [&](const PackedW& w, const float* A32, const __half* A16, int Bb, int Tt, float* out) {
     return hf ? gemm_of16(w, A16, Bb, Tt, out) : gemm_of(w, A32, Bb, Tt, out);
   };
@@ -346,8 +357,17 @@ static void dit_eval(idx_engine* e, S2melState* s, DitBuffers& b, int Bn, int T,
     }
     rmsnorm_adaln(e, h, hf ? nullptr : b.a, Bn, T, H, s->attn_norm[l].norm_w, mod + s->attn_norm[l].mod_off,
                   mod + s->attn_norm[l].mod_off + H, 0, 1e-5f, b.a16);
-    conv_gemm(e, G(s->wqkv[l], b.a, b.a16, Bn, T, b.qkv));
-    attention_rope(e, b.qkv, hf ? nullptr : b.att, Bn, T, nh, b.rope, b.lens, b.att16);
+    if (hf && fused) {
+      // wqkv with the RoPE / 1/8 scale / head split in its epilogue: fp16 Qr | Kr | Vb go straight to the flash attention
+      ConvGemm g = gemm_of16(s->wqkv[l], b.a16, Bn, T, nullptr);
+      g.epi = EPI_ROPE; g.out16 = b.qkv16; g.aux = b.rope; g.aux_stride = nh;
+      conv_gemm(e, g);
+      const size_t one = (size_t)Bn * nh * T * 64;
+      flash_attention_split(e, b.qkv16, b.qkv16 + one, b.qkv16 + 2 * one, nullptr, b.att16, Bn, T, nh);
+    } else {
+      conv_gemm(e, G(s->wqkv[l], b.a, b.a16, Bn, T, b.qkv));
+      attention_rope(e, b.qkv, hf ? nullptr : b.att, Bn, T, nh, b.rope, b.lens, b.att16);
+    }
     // layer output buffer: emitted skips (l < Dn/2) keep their own buffer
     float* hout = (l < Dn / 2) ? b.h[1 + l] : b.h[10 + (l & 1)];
     {
@@ -357,8 +377,14 @@ static void dit_eval(idx_engine* e, S2melState* s, DitBuffers& b, int Bn, int T,
     }
     rmsnorm_adaln(e, hout, hf ? nullptr : b.a, Bn, T, H, s->ffn_norm[l].norm_w, mod + s->ffn_norm[l].mod_off,
                   mod + s->ffn_norm[l].mod_off + H, 0, 1e-5f, b.a16);
-    conv_gemm(e, G(s->w13[l], b.a, b.a16, Bn, T, b.ff));
-    swiglu(e, b.ff, hf ? nullptr : b.qkv, (long long)Bn * T, s->inter, b.ffh16);
+    if (hf && fused) {
+      ConvGemm g = gemm_of16(s->w13[l], b.a16, Bn, T, nullptr);       // SwiGLU in the epilogue (w1 / w3 rows interleaved)
+      g.Wk16 = s->w13_i16[l]; g.bias = nullptr; g.epi = EPI_SWIGLU; g.out16 = b.ffh16;
+      conv_gemm(e, g);
+    } else {
+      conv_gemm(e, G(s->w13[l], b.a, b.a16, Bn, T, b.ff));
+      swiglu(e, b.ff, hf ? nullptr : b.qkv, (long long)Bn * T, s->inter, b.ffh16);
+    }
     {
       ConvGemm g = G(s->w2[l], b.qkv, b.ffh16, Bn, T, hout);
       g.res = hout;
@@ -386,8 +412,14 @@ static void dit_eval(idx_engine* e, S2melState* s, DitBuffers& b, int Bn, int T,
     reflect_pad_rows(e, b.wy, hf ? nullptr : b.wpad, Bn, T, WH, pl, pr, b.wpad16);
     ConvGemm gi = G(s->wn_in[i], b.wpad, b.wpad16, Bn, T + kk - 1, b.wxin);
     gi.pad = 0; gi.M = T;
-    conv_gemm(e, gi);
-    wn_gate(e, b.wxin, wncond + (size_t)i * 2 * WH, 0, hf ? nullptr : b.wacts, Bn, T, WH, b.wacts16);
+    if (hf && fused) {        // the gate in the epilogue (tanh / sigmoid halves interleaved): fp16 acts, no [T][2 WH] round trip
+      gi.Wk16 = s->wn_in_i16[i]; gi.bias = s->wn_in_bias_i[i]; gi.out = nullptr;
+      gi.epi = EPI_WNGATE; gi.out16 = b.wacts16; gi.aux = wncond + (size_t)i * 2 * WH; gi.aux_stride = 0;
+      conv_gemm(e, gi);
+    } else {
+      conv_gemm(e, gi);
+      wn_gate(e, b.wxin, wncond + (size_t)i * 2 * WH, 0, hf ? nullptr : b.wacts, Bn, T, WH, b.wacts16);
+    }
     if (i < NL - 1) {
       ConvGemm gr = G(s->wn_res[i], b.wacts, b.wacts16, Bn, T, b.wy);
       gr.res = b.wy;
@@ -435,6 +467,7 @@ static void alloc_dit(idx_engine* e, S2melState* s, DitBuffers& b, int Bn, int T
     b.a16 = hb(bt * H); b.att16 = hb(bt * H); b.ffh16 = hb(bt * s->inter); b.cat16 = hb(bt * 2 * H);
     b.xres16 = hb(bt * H); b.wpad16 = hb((size_t)Bn * (T + 8) * WH); b.wacts16 = hb(bt * WH); b.z16 = hb(bt * WH);
     b.wy16 = hb(bt * WH);
+    b.qkv16 = hb(3 * bt * H);
   }
   rope_table(e, b.rope, T, 64);
 }
@@ -443,7 +476,7 @@ static size_t dit_arena_bytes(const S2melState* s, int Bn, int T) {
   const size_t bt = (size_t)Bn * T;
   const size_t Tp = (size_t)((T + 3) & ~3);
   const size_t attn = 4 * (size_t)Bn * c.heads * (3 * (size_t)T * 64 + 64 * Tp + (size_t)T * Tp) + 8 * 256;
-  const size_t half_bytes = 2 * (bt * c.hidden * 5 + bt * s->inter + bt * c.wn_hidden * 4 + (size_t)Bn * 8 * c.wn_hidden) + 16 * 512;
+  const size_t half_bytes = 2 * (bt * c.hidden * 8 + bt * s->inter + bt * c.wn_hidden * 4 + (size_t)Bn * 8 * c.wn_hidden) + 16 * 512;
   return attn + half_bytes + 4 * (bt * c.hidden * (12 + 1 + 3 + 1 + 2 + 1) + bt * 3 * s->inter + bt * c.wn_hidden * 7 + (size_t)Bn * 8 * c.wn_hidden + bt * c.in_channels +
               (size_t)T * 64) + 64 * 256;
 }
