@@ -41,6 +41,18 @@ CFM_STEPS, CFG_RATE = 25, 0.7
 AUDIO_S_PER_TOKEN = 2 * 1.72 * 256 / 22050.0
 
 
+def ncu_traffic():
+    """DRAM bytes per decode step of the dominant kernel, from the committed ncu capture summary (tests/tools/ncu_metrics.py
+    turns the .ncu-rep of `ncu --set full` into this JSON); null when no capture has been committed for this kernel."""
+    p = os.path.join(ROOT, "profiles", "r02_gpt_decode1_ncu.json")
+    try:
+        d = json.load(open(p))
+        return float(d["dram_bytes_per_step"]), (f"dram__bytes_read.sum + dram__bytes_write.sum of one gpt_decode1_kernel launch / "
+                                                 f"{d['steps_per_launch']} steps, ncu --set full, profiles/r02_gpt_decode1_ncu.json")
+    except Exception:
+        return None, "no committed ncu capture of this kernel"
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -526,11 +538,9 @@ def main():
         "config": config_block(world),
         "stage_ms_per_step": {"gpt": g_ms / K, "cfm": c_ms / K, "bigvgan": v_ms / K,
                               "other": (t_dev * 1000 - g_ms - c_ms - v_ms) / K},
-        "roofline": {"kernel": "gpt_fused_kernel (decode step)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+        "roofline": {"kernel": "gpt_decode1_kernel (one decode step of the batch-1 decode kernel)", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                      "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": 965.2e6, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per decode step of "
-                                                         "gpt_fused_kernel<1,40> (32-step launch / 32), ncu --set full, "
-                                                         "profiles/r01_gpt_fused_ncu.md",
+                     "traffic": ncu_traffic()[0], "traffic_note": ncu_traffic()[1],
                      "peak_source": which,
                      "us_per_decode_step": step_us,
                      "algorithmic_bytes_per_step": w_bytes + kv_bytes},

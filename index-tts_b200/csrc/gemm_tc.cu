@@ -465,43 +465,29 @@ fa5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
       ptx::mbar_wait(s_full, j & 1u);
       ptx::tcgen05_fence_after();
       const int kbase = j * FA_K;
-      // pass A: row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < FA_K; c += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(tS + lane_off + (uint32_t)c, r);
-        ptx::tmem_ld_wait();
-        const int nvalid = T - (kbase + c);             // keys beyond T (zero-filled rows of the last tile) are masked
+      // the whole S row of this thread (128 keys) in registers: four tensor-memory loads in flight, one wait
+      uint32_t r[FA_K];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, i < nvalid ? __uint_as_float(r[i]) : -INFINITY);
-      }
+      for (int c = 0; c < FA_K; c += 32) ptx::tmem_ld_32x32b_x32(tS + lane_off + (uint32_t)c, r + c);
+      ptx::tmem_ld_wait();
+      const int nvalid = T - kbase;                     // keys beyond T (zero-filled rows of the last tile) are masked
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < FA_K; ++i) mx = fmaxf(mx, i < nvalid ? __uint_as_float(r[i]) : -INFINITY);
       const float mn = fmaxf(m, mx * LOG2E);
       const float corr = exp2f(m - mn);                 // 0 at the first tile (m = -inf)
       float rs = 0.f;
-      // pass B: p = 2^(s log2e - mn), fp16 pairs -> P (tensor memory)
-#pragma unroll 1
-      for (int c = 0; c < FA_K; c += 32) {
-        uint32_t r[32], pk[16];
-        ptx::tmem_ld_32x32b_x32(tS + lane_off + (uint32_t)c, r);
-        ptx::tmem_ld_wait();
-        const int nvalid = T - (kbase + c);
+      // p = 2^(s log2e - mn), packed to fp16 pairs in place: r[i] <- (p[2i], p[2i+1])
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float p0 = (2 * i < nvalid) ? exp2f(fmaf(__uint_as_float(r[2 * i]), LOG2E, -mn)) : 0.f;
-          const float p1 = (2 * i + 1 < nvalid) ? exp2f(fmaf(__uint_as_float(r[2 * i + 1]), LOG2E, -mn)) : 0.f;
-          rs += p0 + p1;
-          __half2 h = __floats2half2_rn(p0, p1);
-          pk[i] = *(uint32_t*)&h;
-        }
-        // the 16 packed columns (32 keys) of this chunk
-        asm volatile(
-            "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
-                tP + lane_off + (uint32_t)(c >> 1)),
-            "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]), "r"(pk[8]), "r"(pk[9]),
-            "r"(pk[10]), "r"(pk[11]), "r"(pk[12]), "r"(pk[13]), "r"(pk[14]), "r"(pk[15])
-            : "memory");
+      for (int i = 0; i < FA_K / 2; ++i) {
+        const float p0 = (2 * i < nvalid) ? exp2f(fmaf(__uint_as_float(r[2 * i]), LOG2E, -mn)) : 0.f;
+        const float p1 = (2 * i + 1 < nvalid) ? exp2f(fmaf(__uint_as_float(r[2 * i + 1]), LOG2E, -mn)) : 0.f;
+        rs += p0 + p1;
+        __half2 h = __floats2half2_rn(p0, p1);
+        r[i] = *(uint32_t*)&h;
       }
+      ptx::tmem_st_32x32b_x32(tP + lane_off, r);
+      ptx::tmem_st_32x32b_x32(tP + lane_off + 32u, r + 32);
       l = l * corr + rs;
       if (j > 0 && __any_sync(0xffffffffu, corr != 1.f)) {     // warp-uniform: tcgen05.ld / st are warp-collective
         // the row max moved: O (complete up to tile j-1: s_full tracks that MMA too) is rescaled in tensor memory

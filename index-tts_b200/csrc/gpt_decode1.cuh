@@ -36,7 +36,7 @@ constexpr int TROWS = 16;       // weight rows per MMA tile
 constexpr int NBAR = 8;         // phase barrier slots
 constexpr int MAXIT = 4;        // (column tile, K segment) items per phase
 constexpr int RED1_MMA = MAXIT * NCW * 16;                 // per-warp partial sums of the phase's tiles
-constexpr int RED1_FLOATS = RED1_MMA + 48 + 64 + NCW * PART_STRIDE;   // + LayerNorm statistics + head scores + attention merge
+constexpr int RED1_FLOATS = 2 * RED1_MMA + 48 + 64 + NCW * PART_STRIDE;   // the MMA partials are double-buffered by phase parity   // + LayerNorm statistics + head scores + attention merge
 
 __device__ __forceinline__ int split_rows(int n, int nt, int j) { return (n * (j + 1)) / nt - (n * j) / nt; }
 __device__ __forceinline__ int split_begin(int n, int nt, int j) { return (n * j) / nt; }
@@ -61,7 +61,7 @@ struct Phase1 {
 struct Smem1 {
   __nv_bfloat16* ring;  // [R][D]
   __nv_bfloat16* xs;    // [FF] GEMV input row (bf16, plain layout)
-  float* red;           // [RED1_MMA] K-split partial sums (disjoint regions: no barrier is needed between the phases' uses)
+  float* red;           // [2][RED1_MMA] K-split partial sums, by phase parity: phase n + 1 may write while the epilogue of phase n reads
   float* red_ln;        // [48] LayerNorm statistics (two sets)
   float* cs;            // [64] processed scores of this CTA's head columns
   float* red_att;       // [NCW][66] attention merge / sampler scratch
@@ -82,7 +82,7 @@ struct Smem1 {
 // NIT (the number of tiles) is a template parameter: with a run-time bound the compiler kept the fragment arrays in local
 // memory (an STL after every LDSM, an LDL before every HMMA: 5400 cycles for a two-tile phase instead of ~500).
 template <int D, int NIT>
-__device__ __forceinline__ void mma_items_n(const Smem1& sm, const Phase1& ph, int row0, unsigned phase_idx, int R, int warp, int lane,
+__device__ __forceinline__ void mma_items_n(const Smem1& sm, float* red, const Phase1& ph, int row0, unsigned phase_idx, int R, int warp, int lane,
                                             long long* st, int dbg) {
   constexpr int KS = (D / 16) / NCW;
   const uint32_t ring_base = ptx::smem_u32(sm.ring);
@@ -137,8 +137,8 @@ __device__ __forceinline__ void mma_items_n(const Smem1& sm, const Phase1& ph, i
 #pragma unroll
     for (int i = 0; i < NIT; ++i)
     {
-      sm.red[(i * NCW + warp) * 16 + g] = acc[i][0];
-      sm.red[(i * NCW + warp) * 16 + g + 8] = acc[i][2];
+      red[(i * NCW + warp) * 16 + g] = acc[i][0];
+      red[(i * NCW + warp) * 16 + g + 8] = acc[i][2];
     }
   }
   ptx::named_bar_sync(1, NCT);
@@ -146,14 +146,16 @@ __device__ __forceinline__ void mma_items_n(const Smem1& sm, const Phase1& ph, i
 }
 
 template <int D>
-__device__ __forceinline__ void mma_items(const Smem1& sm, const Phase1& ph, int row0, unsigned phase_idx, int R, int warp, int lane,
+__device__ __forceinline__ float* mma_items(const Smem1& sm, const Phase1& ph, int row0, unsigned phase_idx, int R, int warp, int lane,
                                           long long* st = nullptr, int dbg = 0) {
+  float* red = sm.red + (phase_idx & 1u) * RED1_MMA;
   switch (ph.nitems) {       // CTA-uniform
-    case 1: mma_items_n<D, 1>(sm, ph, row0, phase_idx, R, warp, lane, st, dbg); break;
-    case 2: mma_items_n<D, 2>(sm, ph, row0, phase_idx, R, warp, lane, st, dbg); break;
-    case 3: mma_items_n<D, 3>(sm, ph, row0, phase_idx, R, warp, lane, st, dbg); break;
-    default: mma_items_n<D, 4>(sm, ph, row0, phase_idx, R, warp, lane, st, dbg); break;
+    case 1: mma_items_n<D, 1>(sm, red, ph, row0, phase_idx, R, warp, lane, st, dbg); break;
+    case 2: mma_items_n<D, 2>(sm, red, ph, row0, phase_idx, R, warp, lane, st, dbg); break;
+    case 3: mma_items_n<D, 3>(sm, red, ph, row0, phase_idx, R, warp, lane, st, dbg); break;
+    default: mma_items_n<D, 4>(sm, red, ph, row0, phase_idx, R, warp, lane, st, dbg); break;
   }
+  return red;
 }
 
 __device__ __forceinline__ float red_sum(const float* red, int item, int row) {
@@ -296,7 +298,7 @@ __global__ void __launch_bounds__(NCT, 1) gpt_decode1_kernel(const GptParams p) 
     sm.ring = (__nv_bfloat16*)q;  q += (size_t)R * D * 2;
     sm.xs = (__nv_bfloat16*)q;    q += (size_t)FF * 2;
     sm.red = (float*)q;           q += sizeof(float) * RED1_FLOATS;
-    sm.red_ln = sm.red + RED1_MMA;
+    sm.red_ln = sm.red + 2 * RED1_MMA;
     sm.cs = sm.red_ln + 48;
     sm.red_att = sm.cs + 64;
     sm.full = (uint64_t*)q;       q += sizeof(uint64_t) * NBAR;
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(NCT, 1) gpt_decode1_kernel(const GptParams p) 
     const float* lnB = sm.lnp + 2 * D;
     const int rr = p.round_bf16;
     const int spin_x = warp * (NPL * 4) + (cta * 37 + warp * 13) % (NPL * 4);      // the word this warp spins on (inside its own slice)
-    const int spin_f = (cta * 41 + warp * 97) % FF;                                // same for the gelu(fc) words
+    const int spin_f = ((cta * 5 + warp) % NSEG) * D + warp * (D / NCW) + (cta * 41) % (D / NCW);   // same for the gelu(fc) words (inside this warp's slices)
     const bool nowait = (p.dbg & 4) != 0;      // diagnostics only: polls do not wait (results are garbage, timing = no dependencies)
     int feed = __ldcg(p.tok + b);
     const bool already_done = __ldcg(p.finished + b) != 0;
@@ -418,8 +420,13 @@ __global__ void __launch_bounds__(NCT, 1) gpt_decode1_kernel(const GptParams p) 
       if (cons_row >= R) cons_row -= R;
       ++cons_tile;
       fill -= tot;
-      issue_fitting();
+      if ((p.dbg & 8) || tix == cons_tile) issue_fitting();   // nothing prefetched (head / first phases of a step): issue at once; dbg 8 = always
     };
+    // The freed rows are refilled a little later — right after this CTA's NEXT hand-over poll has completed: at the release
+    // point all 148 CTAs would start their 60-90 KB bulk copies together, exactly when the epilogue stores and the polls of
+    // the hand-over (the latency-critical traffic) are in flight; the ring holds two to three phases, so the weights issued
+    // one poll later still arrive long before they are consumed.
+    auto refill = [&]() { if (!(p.dbg & 8)) issue_fitting(); };
     issue_fitting();                  // initial fill
 
     for (int step = 0; step < p.nsteps && !already_done; ++step) {
@@ -461,20 +468,22 @@ __global__ void __launch_bounds__(NCT, 1) gpt_decode1_kernel(const GptParams p) 
           }
           prefetch_ln(1, p.ln2_w + (size_t)l * D, p.ln2_b + (size_t)l * D);   // for P4 (drained there)
           G2(1);
+          refill();
           ln_block<NPL>(v, lnA, lnA + D, sm.red_ln, warp, lane);
           G2(2);
 #pragma unroll
           for (int j = 0; j < NPL / 8; ++j) sm.xs[warp * (NPL * 4) + lane + 32 * j] = __float2bfloat16_rn(v[j]);
         }
-        ptx::named_bar_sync(1, NCT);
+        // no CTA barrier: a warp's MMAs read exactly the k-slice of xs this warp has just written (k-steps warp*KS ..)
+        __syncwarp();
         {
-          mma_items<D>(sm, ph_q, cons_row, cons_tile, R, warp, lane, f2 ? f2 + 3 : nullptr, p.dbg);
+          const float* redp = mma_items<D>(sm, ph_q, cons_row, cons_tile, R, warp, lane, f2 ? f2 + 3 : nullptr, p.dbg);
           advance(ph_q);
           if (tid < nq) {
             const int cl = tid;
             int j = 0;
             while (j + 1 < sc.ntq && cl >= split_begin(nq, sc.ntq, j + 1)) ++j;
-            const float a = red_sum(sm.red, j, cl - split_begin(nq, sc.ntq, j));
+            const float a = red_sum(redp, j, cl - split_begin(nq, sc.ntq, j));
             const float v = rnd(a + sm.bias_s[l * bstride + cl], rr);
             const int c = q0 + cl;
             if (c < D) {
@@ -660,8 +669,10 @@ __global__ void __launch_bounds__(NCT, 1) gpt_decode1_kernel(const GptParams p) 
           float v[NPL / 8];
           poll_slice<NPL / 8>(p.ot, warp * (NPL * 4) + lane, ep_oproj, v, spin_x, nowait);
           G2(11);
+          refill();
 #pragma unroll
           for (int j = 0; j < NPL / 8; ++j) sm.xs[warp * (NPL * 4) + lane + 32 * j] = __float2bfloat16_rn(v[j]);
+          __syncwarp();          // own k-slice only: no CTA barrier
         } else {
           // one warp per head, all loads of a head (nsplit x (m, l, o[lane], o[lane + 32])) in flight together
           for (int h = warp; h < H; h += NCW) {
@@ -703,14 +714,15 @@ __global__ void __launch_bounds__(NCT, 1) gpt_decode1_kernel(const GptParams p) 
             sm.xs[h * HD + 32 + lane] = __float2bfloat16_rn(ob * inv);
           }
           G2(11);
+          refill();
+          ptx::named_bar_sync(1, NCT);     // heads are not aligned with the warps' k-slices here
         }
-        ptx::named_bar_sync(1, NCT);
         {
-          mma_items<D>(sm, ph_o, cons_row, cons_tile, R, warp, lane, f2 ? f2 + 12 : nullptr, p.dbg);
+          const float* redp = mma_items<D>(sm, ph_o, cons_row, cons_tile, R, warp, lane, f2 ? f2 + 12 : nullptr, p.dbg);
           advance(ph_o);
           if (tid < no) {
             // the residual stream is fp32 even on the bf16 path (trap P12): only the branch is rounded
-            const float o = rnd(red_sum(sm.red, 0, tid) + sm.bias_s[l * bstride + nq + tid], rr);
+            const float o = rnd(red_sum(redp, 0, tid) + sm.bias_s[l * bstride + nq + tid], rr);
             const float xn = sm.xres[tid] + o;
             sm.xres[tid] = xn;
             st_tagged(p.xt + o0 + tid, xn, ep_oproj);
@@ -725,21 +737,22 @@ __global__ void __launch_bounds__(NCT, 1) gpt_decode1_kernel(const GptParams p) 
           float v[NPL / 8];
           poll_slice<NPL / 8>(p.xt, warp * (NPL * 4) + lane, ep_oproj, v, spin_x, nowait);
           G2(16);
+          refill();
           cp_async_wait_all();   // ln_2 parameters prefetched in P1 (ln_block's own CTA barrier publishes them)
           ln_block<NPL>(v, lnB, lnB + D, sm.red_ln, warp, lane);
           G2(17);
 #pragma unroll
           for (int j = 0; j < NPL / 8; ++j) sm.xs[warp * (NPL * 4) + lane + 32 * j] = __float2bfloat16_rn(v[j]);
         }
-        ptx::named_bar_sync(1, NCT);
+        __syncwarp();
         {
-          mma_items<D>(sm, ph_f, cons_row, cons_tile, R, warp, lane, f2 ? f2 + 18 : nullptr, p.dbg);
+          const float* redp = mma_items<D>(sm, ph_f, cons_row, cons_tile, R, warp, lane, f2 ? f2 + 18 : nullptr, p.dbg);
           advance(ph_f);
           if (tid < nf) {
             const int cl = tid;
             int j = 0;
             while (j + 1 < sc.ntf && cl >= split_begin(nf, sc.ntf, j + 1)) ++j;
-            const float a = red_sum(sm.red, j, cl - split_begin(nf, sc.ntf, j));
+            const float a = red_sum(redp, j, cl - split_begin(nf, sc.ntf, j));
             const float f = rnd(a + sm.bias_s[l * bstride + nq + no + cl], rr);
             const __nv_bfloat16 fv = __float2bfloat16_rn(gelu_new(f, rr));
             asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p.ft + f0 + cl),
@@ -751,8 +764,17 @@ __global__ void __launch_bounds__(NCT, 1) gpt_decode1_kernel(const GptParams p) 
         // ---------------- P5: proj + residual ----------------
         if (l + 1 == L) prefetch_ln(1, p.fn_w, p.fn_b);   // final_norm for the head
         {
-          constexpr int CPR = FF / 8, NCH = (CPR + NCT - 1) / NCT;
-          uint4 lo[NCH], hi[NCH];
+          // every warp polls exactly the gelu(fc) words of ITS k-slices (k-steps warp*KS .. of each of the NSEG segments),
+          // repacks them to bf16 in xs and goes straight to its MMAs: no CTA barrier between the hand-over and the MMAs
+          constexpr int CW = (D / NCW) / 8;                 // 8-word chunks per warp per K-segment
+          constexpr int NCHW = (NSEG * CW + 31) / 32;       // chunks per lane
+          uint4 lo[NCHW], hi[NCHW];
+          int cidx[NCHW];
+#pragma unroll
+          for (int q = 0; q < NCHW; ++q) {
+            const int i = lane + 32 * q;
+            cidx[q] = (i < NSEG * CW) ? (i / CW) * (D / 8) + warp * CW + (i % CW) : -1;
+          }
           const unsigned want = f_tag << 16;
           unsigned spins = 0;
           bool ok;
@@ -766,10 +788,9 @@ __global__ void __launch_bounds__(NCT, 1) gpt_decode1_kernel(const GptParams p) 
           do {
             ok = true;
 #pragma unroll
-            for (int q = 0; q < NCH; ++q) {
-              const int c = tid + q * NCT;
-              if (c < CPR) {
-                const unsigned* src = p.ft + (size_t)c * 8;
+            for (int q = 0; q < NCHW; ++q) {
+              if (cidx[q] >= 0) {
+                const unsigned* src = p.ft + (size_t)cidx[q] * 8;
                 asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
                              : "=r"(lo[q].x), "=r"(lo[q].y), "=r"(lo[q].z), "=r"(lo[q].w) : "l"(src) : "memory");
                 asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
@@ -777,8 +798,8 @@ __global__ void __launch_bounds__(NCT, 1) gpt_decode1_kernel(const GptParams p) 
               }
             }
 #pragma unroll
-            for (int q = 0; q < NCH; ++q) {
-              if (tid + q * NCT < CPR)
+            for (int q = 0; q < NCHW; ++q) {
+              if (cidx[q] >= 0)
                 ok &= ((lo[q].x & 0xffff0000u) == want) & ((lo[q].y & 0xffff0000u) == want) &
                       ((lo[q].z & 0xffff0000u) == want) & ((lo[q].w & 0xffff0000u) == want) &
                       ((hi[q].x & 0xffff0000u) == want) & ((hi[q].y & 0xffff0000u) == want) &
@@ -787,23 +808,23 @@ __global__ void __launch_bounds__(NCT, 1) gpt_decode1_kernel(const GptParams p) 
             if (++spins > (1u << 26)) __trap();
           } while (!ok && !nowait);
           G2(22);
+          refill();
 #pragma unroll
-          for (int q = 0; q < NCH; ++q) {
-            const int c = tid + q * NCT;
-            if (c < CPR)
-              ((uint4*)sm.xs)[c] = make_uint4((lo[q].x & 0xffffu) | (lo[q].y << 16), (lo[q].z & 0xffffu) | (lo[q].w << 16),
-                                              (hi[q].x & 0xffffu) | (hi[q].y << 16), (hi[q].z & 0xffffu) | (hi[q].w << 16));
+          for (int q = 0; q < NCHW; ++q) {
+            if (cidx[q] >= 0)
+              ((uint4*)sm.xs)[cidx[q]] = make_uint4((lo[q].x & 0xffffu) | (lo[q].y << 16), (lo[q].z & 0xffffu) | (lo[q].w << 16),
+                                                     (hi[q].x & 0xffffu) | (hi[q].y << 16), (hi[q].z & 0xffffu) | (hi[q].w << 16));
           }
-          cp_async_wait_all();     // the LayerNorm parameters prefetched in P4
+          cp_async_wait_all();     // the LayerNorm parameters prefetched in P4 (published by the barrier that ends the MMAs)
         }
-        ptx::named_bar_sync(1, NCT);
+        __syncwarp();
         {
-          mma_items<D>(sm, ph_p, cons_row, cons_tile, R, warp, lane, f2 ? f2 + 23 : nullptr, p.dbg);
+          const float* redp = mma_items<D>(sm, ph_p, cons_row, cons_tile, R, warp, lane, f2 ? f2 + 23 : nullptr, p.dbg);
           advance(ph_p);
           if (tid < no) {
             float a = 0.f;
 #pragma unroll
-            for (int s = 0; s < NSEG; ++s) a += red_sum(sm.red, s, tid);
+            for (int s = 0; s < NSEG; ++s) a += red_sum(redp, s, tid);
             const float o = rnd(a + sm.bias_s[l * bstride + nq + no + nf + tid], rr);
             const float xn = sm.xres[tid] + o;
             sm.xres[tid] = xn;
@@ -818,23 +839,24 @@ __global__ void __launch_bounds__(NCT, 1) gpt_decode1_kernel(const GptParams p) 
       {
         float v[NPL / 8];
         poll_slice<NPL / 8>(p.xt, warp * (NPL * 4) + lane, ep_head, v, spin_x, nowait);
+        refill();
         ln_block<NPL>(v, lnA, lnA + D, sm.red_ln, warp, lane);
         ln_block<NPL>(v, lnB, lnB + D, sm.red_ln + 3 * NCW, warp, lane);
 #pragma unroll
         for (int j = 0; j < NPL / 8; ++j) sm.xs[warp * (NPL * 4) + lane + 32 * j] = __float2bfloat16_rn(v[j]);
       }
-      ptx::named_bar_sync(1, NCT);
+      __syncwarp();
       prefetch_ln(0, p.ln1_w, p.ln1_b);      // layer 0 of the next step (buffer A is free: both LNs above are done)
       int token = 0;
       {
-        mma_items<D>(sm, ph_h, cons_row, cons_tile, R, warp, lane);
+        const float* redp = mma_items<D>(sm, ph_h, cons_row, cons_tile, R, warp, lane);
         advance(ph_h);
         float* cs = sm.cs;
         if (tid < nh) {
           const int cl = tid;
           int j = 0;
           while (j + 1 < sc.nth && cl >= split_begin(nh, sc.nth, j + 1)) ++j;
-          const float lg = rnd(red_sum(sm.red, j, cl - split_begin(nh, sc.nth, j)) + sm.bias_s[L * bstride + cl], rr);
+          const float lg = rnd(red_sum(redp, j, cl - split_begin(nh, sc.nth, j)) + sm.bias_s[L * bstride + cl], rr);
           const int i = h0 + cl;
           if (p.logits_dump) p.logits_dump[((size_t)b * p.max_new + k) * V + i] = lg;
           if (p.do_sample) {
