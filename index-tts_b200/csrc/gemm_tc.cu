@@ -194,7 +194,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t o[16];
             if (which < 2) {
               const float4* tab = (const float4*)(p.aux + ((size_t)row * (HD / 2) + (d0 >> 1)) * 2);   // (cos, sin) pairs
-              const float sc = (which == 0) ? 0.125f : 1.0f;
+              const float sc = (which == 0) ? p.scale : 1.0f;      // 1/8 (x log2 e when the tcgen05 flash kernel consumes q)
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const float4 t4 = __ldg(tab + i);
@@ -383,6 +383,11 @@ void launch_bn(idx_engine* e, const ConvGemm& g, const CUtensorMap& tmA, const C
 // The legacy mma.sync flash kernel (nn_ops.cu) ran at the mma.sync ceiling of this part (~170 TFLOP/s); here the exp
 // throughput (MUFU) is the bound, as in every Blackwell attention kernel.
 constexpr int FA_Q = 128, FA_K = 128, FA_D = 64;
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 struct FaParams { int T, H; float* out; __half* out16; };
 
 __global__ void __launch_bounds__(192, 2)
@@ -459,7 +464,6 @@ fa5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
     const int qd = warp & 3;                            // TMEM lane quarter of this warp
     const int row = qd * 32 + lane;                     // query row inside the tile = TMEM lane
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-    const float LOG2E = 1.4426950408889634f;
     float m = -INFINITY, l = 0.f;                       // running row max (log2 domain) and row sum
     for (int j = 0; j < ntiles; ++j) {
       ptx::mbar_wait(s_full, j & 1u);
@@ -470,22 +474,33 @@ fa5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
 #pragma unroll
       for (int c = 0; c < FA_K; c += 32) ptx::tmem_ld_32x32b_x32(tS + lane_off + (uint32_t)c, r + c);
       ptx::tmem_ld_wait();
+      // (ncu of the first version: 2200 warp instructions per tile per softmax warp — per element a masked max, an FMA, the
+      // accurate exp2f sequence, two adds — made the kernel issue-bound at the speed of the mma.sync one.  Now the scores
+      // arrive in the log2 domain (q is pre-scaled by log2(e)/8 in EPI_ROPE), exp2 is the bare MUFU, and only the last
+      // key tile pays for masking.)
       const int nvalid = T - kbase;                     // keys beyond T (zero-filled rows of the last tile) are masked
-      float mx = -INFINITY;
+      if (nvalid < FA_K) {
 #pragma unroll
-      for (int i = 0; i < FA_K; ++i) mx = fmaxf(mx, i < nvalid ? __uint_as_float(r[i]) : -INFINITY);
-      const float mn = fmaxf(m, mx * LOG2E);
-      const float corr = exp2f(m - mn);                 // 0 at the first tile (m = -inf)
-      float rs = 0.f;
-      // p = 2^(s log2e - mn), packed to fp16 pairs in place: r[i] <- (p[2i], p[2i+1])
+        for (int i = 0; i < FA_K; ++i)
+          if (i >= nvalid) r[i] = 0xff800000u;          // -inf
+      }
+      float mx = __uint_as_float(r[0]);
+#pragma unroll
+      for (int i = 1; i < FA_K; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+      const float mn = fmaxf(m, mx);
+      const float corr = ex2_approx(m - mn);            // 0 at the first tile (m = -inf)
+      float rs0 = 0.f, rs1 = 0.f;
+      // p = 2^(s - mn), packed to fp16 pairs in place: r[i] <- (p[2i], p[2i+1])
 #pragma unroll
       for (int i = 0; i < FA_K / 2; ++i) {
-        const float p0 = (2 * i < nvalid) ? exp2f(fmaf(__uint_as_float(r[2 * i]), LOG2E, -mn)) : 0.f;
-        const float p1 = (2 * i + 1 < nvalid) ? exp2f(fmaf(__uint_as_float(r[2 * i + 1]), LOG2E, -mn)) : 0.f;
-        rs += p0 + p1;
+        const float p0 = ex2_approx(__uint_as_float(r[2 * i]) - mn);
+        const float p1 = ex2_approx(__uint_as_float(r[2 * i + 1]) - mn);
+        rs0 += p0;
+        rs1 += p1;
         __half2 h = __floats2half2_rn(p0, p1);
         r[i] = *(uint32_t*)&h;
       }
+      const float rs = rs0 + rs1;
       ptx::tmem_st_32x32b_x32(tP + lane_off, r);
       ptx::tmem_st_32x32b_x32(tP + lane_off + 32u, r + 32);
       l = l * corr + rs;

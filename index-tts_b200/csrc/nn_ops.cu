@@ -724,10 +724,14 @@ void attention_rope(idx_engine* e, const float* qkv, float* out, int B, int T, i
   attention_kernel<<<grid, 256, smem, e->stream>>>(qkv, out, T, H, rope, lens);
   LAUNCH_CHECK(e);
 }
+static bool fa5_on() {
+  static const bool on = !(getenv("IDX_FA5") && atoi(getenv("IDX_FA5")) == 0);
+  return on;
+}
+float flash_attention_q_scale() { return fa5_on() ? 0.125f * 1.4426950408889634f : 0.125f; }
 void flash_attention_split(idx_engine* e, const __half* Qr, const __half* Kr, const __half* Vb, float* out, __half* out16,
                            int B, int T, int H) {
-  static const bool fa5 = !(getenv("IDX_FA5") && atoi(getenv("IDX_FA5")) == 0);
-  if (fa5) {
+  if (fa5_on()) {
     flash_attention_tc5(e, Qr, Kr, Vb, out, out16, B, T, H);
     return;
   }

@@ -156,6 +156,8 @@ __half* pack_half_interleaved(idx_engine* e, WeightPool& pool, const PackedW& w,
 // the fused flash attention on already rotated / split fp16 tensors Qr | Kr | Vb [B*H][T][64] (what EPI_ROPE writes)
 void flash_attention_split(idx_engine* e, const __half* Qr, const __half* Kr, const __half* Vb, float* out, __half* out16,
                            int B, int T, int H);
+// scale EPI_ROPE must apply to q for flash_attention_split: 1/8, times log2(e) when the tcgen05 kernel (exp2 softmax) is on
+float flash_attention_q_scale();
 // the same on tcgen05 (gemm_tc.cu: S and O in tensor memory, P fed back as a tensor-memory operand)
 void flash_attention_tc5(idx_engine* e, const __half* Qr, const __half* Kr, const __half* Vb, float* out, __half* out16,
                          int B, int T, int H);
