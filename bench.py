@@ -167,8 +167,9 @@ WORKLOAD = ("IndexTTS-2.5 infer_v2_5 batch=1 per GPU: 10 s reference (P=861), 32
 
 # -------------------------------------------------------------------------- cpu arm --
 DTYPE = ("bf16 GPT (bf16 weights/activations, fp32 accumulate, fp32 residual stream = the reference's use_bf16 autocast) + "
-         "tf32 tensor-core GEMMs over fp32 storage (codec, length regulator, DiT/WaveNet, BigVGAN; fp32 accumulate) + "
-         "bf16 mma.sync attention in the DiT (fp32 softmax)")
+         "tail on tcgen05 with fp16 operands (kind::f16: DiT / WaveNet / BigVGAN-resblock GEMMs and the DiT flash attention; "
+         "fp32 accumulate, fp32 softmax, fp32 residual streams and pointwise math) and tf32 over fp32 storage for the small "
+         "rest (codec, length regulator, K=80 input convs, ConvTranspose upsamplers)")
 
 
 def config_block(world):
@@ -220,19 +221,26 @@ def cpu_reference_full(threads):
 
 
 def host_threads():
-    return max(1, min(os.cpu_count() or 1, 64))
+    """Threads for the CPU arm: the cores this process may run on (cgroup / affinity aware), at most 32 — the r1/r2 boxes
+    showed 64 torch threads on a 128-logical-core host SLOWER than 8 real cores for this workload."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 32))
 
 
 def run_reference(args, rank, world):
     """`--impl reference`: the reference's own (CPU, fp32) implementation of the path — the oracle port; the reference
     itself cannot be built offline — on the box's host cores, SAME config, metric and unit as the
-    B200 arm.  --steps / --warmup are honoured; only if the projected run would exceed IDX_REF_BUDGET_S (default 1500 s,
-    inside the driver's limit) are the timed steps cut, and the line then says how many actually ran."""
+    B200 arm.  Every step is the FULL config-2 utterance (~1 minute of CPU work), so --steps / --warmup are honoured only
+    as far as IDX_REF_BUDGET_S allows (default 600 s: "the whole run ends within a few minutes"); the line reports the
+    steps that actually ran and says that the request was cut."""
     if rank != 0:
         return
     threads = host_threads()
     once = cpu_reference_full(threads)
-    budget = float(os.environ.get("IDX_REF_BUDGET_S", "1500"))
+    budget = float(os.environ.get("IDX_REF_BUDGET_S", "600"))
     t_start = time.perf_counter()
     W, K = max(0, args.warmup), max(1, args.steps)
     t_first, _ = once()                                   # first warm-up step doubles as the cost probe
