@@ -2112,8 +2112,13 @@ extern "C" int idx_gpt_init(idx_engine* e, const idx_gpt_config* cfg) {
   IDX_CHECK(e && cfg, IDX_ERR_ARG, "null argument");
   IDX_CUDA(cudaSetDevice(e->device));
   if (e->gpt) { gpt_destroy(e->gpt); e->gpt = nullptr; }
-  GptState* g = new GptState();
-  e->gpt = g;
+  // built into a local state and published only on success: a failed init must not leave a half-built e->gpt that passes the
+  // "idx_gpt_init has not been called" guards
+  struct Guard {
+    GptState* g; idx_engine* e; bool ok = false;
+    ~Guard() { if (ok) e->gpt = g; else gpt_destroy(g); }
+  } guard{new GptState(), e};
+  GptState* g = guard.g;
   g->cfg = *cfg;
   const int L = cfg->layers, D = cfg->model_dim, H = cfg->heads, V = cfg->number_mel_codes;
   const int FF = 4 * D;
@@ -2129,6 +2134,7 @@ extern "C" int idx_gpt_init(idx_engine* e, const idx_gpt_config* cfg) {
     IDX_CUDA(cudaEventCreate(&g->ev1));
     IDX_CUDA(cudaEventCreate(&g->ev2));
     IDX_CUDA(cudaStreamSynchronize(e->stream));
+    guard.ok = true;
     return IDX_OK;
   }
 
@@ -2333,6 +2339,7 @@ extern "C" int idx_gpt_init(idx_engine* e, const idx_gpt_config* cfg) {
   IDX_CUDA(cudaEventCreate(&g->ev1));
   IDX_CUDA(cudaEventCreate(&g->ev2));
   IDX_CUDA(cudaStreamSynchronize(e->stream));
+  guard.ok = true;
   IDX_API_END(e)
 }
 
