@@ -171,6 +171,14 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
                : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// 16-byte copy that writes zeros when !valid (src-size 0; the address must still be a valid one)
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ptx::smem_u32(smem_dst)), "l"(gsrc), "r"(valid ? 16 : 0)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
   unsigned v;
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -1249,6 +1257,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gpt_fused_kernel(const GptParams 
 }
 
 #include "gpt_decode1.cuh"
+#include "gpt_decode8.cuh"
 
 // -------------------------------------------------------------------- packing kernel --
 struct PackUnit {
@@ -1844,6 +1853,8 @@ struct GptState {
   unsigned* pflag = nullptr;
   // second-generation batch-1 decode kernel
   int v2 = 0, ring_rows = 0;
+  int v8 = 0, ring_rows8 = 0;       // gpt_decode8_kernel (2..8 sequences per group)
+  size_t smem_v8 = 0;
   size_t smem_v2 = 0;
   __nv_bfloat16* wstream1 = nullptr;
   long long* stream_off1 = nullptr;
@@ -2101,6 +2112,24 @@ static void launch_decode1(idx_engine* e, GptState* g, GptParams& p) {
   g->last_launches++;
 }
 
+// 2..8 sequences per group on the tile / ring structure (gpt_decode8.cuh)
+static size_t smem_bytes_v8(int D, int R, int bias_cap, int ocap, int V) {
+  return (size_t)R * D * 2 + (size_t)B8 * D * 2 + sizeof(float) * (size_t)(RED8_FLOATS + NCW * PART_STRIDE) + 8 * (size_t)NBAR +
+         5 * sizeof(Phase1) + 32 + 4 * (size_t)bias_cap + 4 * (size_t)B8 * ocap + 4 * (size_t)((V + 31) / 32) + 16 +
+         sizeof(float) * 4 * (size_t)D + 64;
+}
+static void launch_decode8(idx_engine* e, GptState* g, GptParams& p) {
+  p.bias_cap = g->bias_cap;
+  p.ocap = g->ocap;
+  p.ring_rows = g->ring_rows8;
+  IDX_CUDA(cudaMemsetAsync(g->barrier, 0, (32 + 256) * sizeof(unsigned), e->stream));
+  void* args[] = {(void*)&p};
+  const void* fn = (p.D / 32 == 40) ? (const void*)gpt_decode8_kernel<40> : (const void*)gpt_decode8_kernel<8>;
+  IDX_CUDA(cudaLaunchCooperativeKernel(fn, dim3(g->G), dim3(NCT), args, g->smem_v8, e->stream));
+  e->launches++;
+  g->last_launches++;
+}
+
 template <int BT>
 static void set_smem_attr(int npl, size_t bytes) {
   if (npl == 40) IDX_CUDA(cudaFuncSetAttribute(gpt_fused_kernel<BT, 40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -2266,6 +2295,21 @@ extern "C" int idx_gpt_init(idx_engine* e, const idx_gpt_config* cfg) {
       IDX_CUDA(cudaMemcpyAsync(g->stream_off1, off1.data(), (G + 1) * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
       IDX_CUDA(cudaStreamSynchronize(e->stream));
       cudaFree(d_u1);
+      // the 8-row decode kernel shares the row stream; its ring is smaller (8 activation rows and 8-wide partial sums in shared memory)
+      g->v8 = (H % 2 == 0) && 8 * (H / 2) <= G && !(getenv("IDX_GPT_V8") && atoi(getenv("IDX_GPT_V8")) == 0);
+      if (g->v8) {
+        int R8 = 0;
+        while (smem_bytes_v8(D, R8 + 1, g->bias_cap, g->ocap, V) <= (size_t)dev_smem - 1024) ++R8;
+        if (getenv("IDX_GPT_RING")) R8 = std::min(R8, atoi(getenv("IDX_GPT_RING")));
+        if (R8 >= std::max(std::max(mq, mf), std::max((FF / D) * mo, mh))) {
+          g->ring_rows8 = R8;
+          g->smem_v8 = smem_bytes_v8(D, R8, g->bias_cap, g->ocap, V);
+          if (D / 32 == 40) IDX_CUDA(cudaFuncSetAttribute(gpt_decode8_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_v8));
+          else IDX_CUDA(cudaFuncSetAttribute(gpt_decode8_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_v8));
+        } else {
+          g->v8 = 0;
+        }
+      }
       g->ot = galloc<uint2>(g, (size_t)D);
       g->partt = galloc<uint2>(g, (size_t)H * 7 * PART_STRIDE);
       g->cand = galloc<uint2>(g, 2 * (size_t)G);
@@ -2711,6 +2755,7 @@ extern "C" int idx_gpt_generate(idx_engine* e, const idx_gpt_request* reqs, int 
     p.step0 = steps_done;
     p.nsteps = std::min(SPL, max_new - steps_done);
     if (BT == 1 && g->v2) launch_decode1(e, g, p);
+    else if (BT == 8 && g->v8) launch_decode8(e, g, p);
     else launch_fused_bt(e, g, p, BT);
     IDX_CUDA(cudaMemcpyAsync(h_done, g->done, 4, cudaMemcpyDeviceToHost, e->stream));
     IDX_CUDA(cudaStreamSynchronize(e->stream));

@@ -386,6 +386,8 @@ __global__ void __launch_bounds__(NCT, 1) gpt_decode1_kernel(const GptParams p) 
     const int rr = p.round_bf16;
     const int spin_x = warp * (NPL * 4) + (cta * 37 + warp * 13) % (NPL * 4);      // the word this warp spins on (inside its own slice)
     const int spin_f = ((cta * 5 + warp) % NSEG) * D + warp * (D / NCW) + (cta * 41) % (D / NCW);   // same for the gelu(fc) words (inside this warp's slices)
+    const int split_at = ((p.dbg >> 16) & 0xff) ? ((p.dbg >> 16) & 0xff) * 32 : 640;     // IDX_GPT_DBG bits 16-23 / 24-30: experiment knobs
+    const int split_len = ((p.dbg >> 24) & 0x7f) ? ((p.dbg >> 24) & 0x7f) * 32 : 320;
     const bool nowait = (p.dbg & 4) != 0;      // diagnostics only: polls do not wait (results are garbage, timing = no dependencies)
     int feed = __ldcg(p.tok + b);
     const bool already_done = __ldcg(p.finished + b) != 0;
@@ -434,7 +436,8 @@ __global__ void __launch_bounds__(NCT, 1) gpt_decode1_kernel(const GptParams p) 
       const int posidx = (k == 0 || p.pos_plain) ? k : k + 1;   // P1: mel position k+1 with the KV cache
       const int pos = plen + k;                       // position of this token in the cache
       const int ctx = pos + 1;
-      const int nsplit = (ctx <= 640) ? 1 : min(7, (ctx + 319) / 320);
+      // key splits: one CTA per head up to split_at keys, then ceil(ctx / split_len) CTAs per head (at most 7)
+      const int nsplit = (ctx <= split_at) ? 1 : min(7, (ctx + split_len - 1) / split_len);
       if (step == 0) prefetch_ln(0, p.ln1_w, p.ln1_b);
       // ---- input row: mel_emb[feed] + mel_pos[posidx], built locally by every CTA (no hand-over) ----
       float v0[NPL / 8];
