@@ -353,20 +353,34 @@ __global__ void __launch_bounds__(NCT, 1) gpt_decode1_kernel(const GptParams p) 
     size_t uoff = 0;                  // stream row of that phase inside the step's stream
     unsigned cons_tile = 0;           // phases consumed
     int cons_row = 0;                 // ring row of the next phase to consume
-    auto issue_fitting = [&]() {
+    // A phase may be issued in instalments (mbarrier.expect_tx for all but the last, which arrives) and one call issues at
+    // most `cap` rows: see gpt_decode8.cuh — bursts of 148 x 60-150 KB bulk copies delay the latency-critical hand-over traffic.
+    // Measured over 256 steps (us / step): whole phases only 445.2; instalments, no cap 433.1; cap 24: 432.8; cap 18: 425.5; cap 12: 436.5.
+    constexpr int MINPART = 4;
+    const int cap = ((p.dbg >> 8) & 0xff) ? ((p.dbg >> 8) & 0xff) : 18;
+    int part = 0;                     // rows of phase pidx already issued
+    auto issue_fitting = [&](int budget = 0) {
       if (!is_prod) return;
-      while (pstep < p.nsteps && tix - cons_tile < (unsigned)NBAR) {
-        const int n = sc.rows(pidx);
-        if (fill + n > R) break;
+      if (budget <= 0) budget = cap;
+      while (pstep < p.nsteps && tix - cons_tile < (unsigned)NBAR && budget > 0) {
+        const int n = sc.rows(pidx) - part;
+        const int avail = min(R - fill, budget);
+        const bool last = avail >= n;
+        const int m = last ? n : avail;
+        if (!last && m < MINPART) break;
         uint64_t* bar = &sm.full[tix % NBAR];
-        ptx::mbar_arrive_expect_tx(bar, (uint32_t)n * D * 2);
-        const int n1 = min(n, R - wpos);
+        if (last) ptx::mbar_arrive_expect_tx(bar, (uint32_t)m * D * 2);
+        else ptx::mbar_expect_tx(bar, (uint32_t)m * D * 2);
+        const int n1 = min(m, R - wpos);
         ptx::bulk_g2s(sm.ring + (size_t)wpos * D, wbase + uoff * D, (uint32_t)n1 * D * 2, bar, pol);
-        if (n1 < n) ptx::bulk_g2s(sm.ring, wbase + (uoff + n1) * D, (uint32_t)(n - n1) * D * 2, bar, pol);
-        wpos += n;
+        if (n1 < m) ptx::bulk_g2s(sm.ring, wbase + (uoff + n1) * D, (uint32_t)(m - n1) * D * 2, bar, pol);
+        wpos += m;
         if (wpos >= R) wpos -= R;
-        fill += n;
-        uoff += n;
+        fill += m;
+        uoff += m;
+        budget -= m;
+        if (!last) { part += m; break; }
+        part = 0;
         ++tix;
         if (++pidx == pps) { pidx = 0; uoff = 0; ++pstep; }
       }
@@ -422,14 +436,14 @@ __global__ void __launch_bounds__(NCT, 1) gpt_decode1_kernel(const GptParams p) 
       if (cons_row >= R) cons_row -= R;
       ++cons_tile;
       fill -= tot;
-      if ((p.dbg & 8) || tix == cons_tile) issue_fitting();   // nothing prefetched (head / first phases of a step): issue at once; dbg 8 = always
+      if ((p.dbg & 8) || tix == cons_tile) issue_fitting(max(cap, sc.rows(pidx) - part));   // the phase consumed next is not (completely) issued: all of it at once; dbg 8 = always
     };
     // The freed rows are refilled a little later — right after this CTA's NEXT hand-over poll has completed: at the release
     // point all 148 CTAs would start their 60-90 KB bulk copies together, exactly when the epilogue stores and the polls of
     // the hand-over (the latency-critical traffic) are in flight; the ring holds two to three phases, so the weights issued
     // one poll later still arrive long before they are consumed.
     auto refill = [&]() { if (!(p.dbg & 8)) issue_fitting(); };
-    issue_fitting();                  // initial fill
+    issue_fitting(R);                 // initial fill
 
     for (int step = 0; step < p.nsteps && !already_done; ++step) {
       const int k = p.step0 + step;
@@ -971,8 +985,10 @@ __global__ void __launch_bounds__(NCT, 1) gpt_decode1_kernel(const GptParams p) 
       if (fin) break;
     }
     // drain: bulk copies issued beyond what was consumed must land before the CTA exits
-    if (is_prod)
+    if (is_prod) {
+      if (part > 0) { ptx::mbar_arrive(&sm.full[tix % NBAR]); ++tix; }     // a partly issued phase: close it so that its bytes can be waited for
       for (unsigned n = cons_tile; n < tix; ++n) ptx::mbar_wait(&sm.full[n % NBAR], (n / NBAR) & 1u);
+    }
   }
   __syncthreads();
 }
