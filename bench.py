@@ -578,7 +578,7 @@ def main():
     if job5 is not None:
         line["config5"] = {k: job5[k] for k in ("value", "unit", "scaling", "rtf", "ms_per_step", "config", "per_rank", "lpt_imbalance",
                                                 "gpu_launches")}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # the CPU leg is reported at N = 1 only (tier contract ④)
         try:
             threads = host_threads()
             tcpu, st = cpu_reference_full(threads)()
