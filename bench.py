@@ -234,13 +234,13 @@ def run_reference(args, rank, world):
     """`--impl reference`: the reference's own (CPU, fp32) implementation of the path — the oracle port; the reference
     itself cannot be built offline — on the box's host cores, SAME config, metric and unit as the
     B200 arm.  Every step is the FULL config-2 utterance (~1 minute of CPU work), so --steps / --warmup are honoured only
-    as far as IDX_REF_BUDGET_S allows (default 600 s: "the whole run ends within a few minutes"); the line reports the
+    as far as IDX_REF_BUDGET_S allows (default 300 s: "the whole run ends within a few minutes"); the line reports the
     steps that actually ran and says that the request was cut."""
     if rank != 0:
         return
     threads = host_threads()
     once = cpu_reference_full(threads)
-    budget = float(os.environ.get("IDX_REF_BUDGET_S", "600"))
+    budget = float(os.environ.get("IDX_REF_BUDGET_S", "300"))
     t_start = time.perf_counter()
     W, K = max(0, args.warmup), max(1, args.steps)
     t_first, _ = once()                                   # first warm-up step doubles as the cost probe
